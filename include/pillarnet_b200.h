@@ -1,0 +1,245 @@
+/*
+ * libpillarnet_b200 — C ABI of the B200-native (sm_100a) PillarNet point->BEV hot path.
+ *
+ * Drop-in boundary for the reference's native operators (all citations relative to the
+ * PillarNet-LTS tree):
+ *   det3d/ops/pillar_ops/src/pillar_api.cpp:10-21     (pybind module `pillar_cuda`, 7 wrappers)
+ *   det3d/ops/iou3d_nms/src/iou3d_nms_api.cpp:11-19   (pybind module `iou3d_nms_cuda`)
+ *   spconv.pytorch SubMConv2d / SparseConv2d          (external dependency, not vendored)
+ *   torch.nn.Conv2d / ConvTranspose2d (cuDNN)         (dense BEV neck / head)
+ *
+ * Conventions
+ *   - plain C: POD arguments only (device pointers, ints, floats, a cudaStream_t passed as void*);
+ *   - the caller owns all memory (outputs and scratch); sizes come from the pn_*_bytes() helpers;
+ *   - every call is asynchronous on `stream`, never synchronises the host, keeps no global state
+ *     besides a cached device-property lookup, and is CUDA-graph capturable;
+ *   - returns PN_OK (0) or a PN_ERR_* code; pn_last_error() gives a message. Never exit()s
+ *     (the reference does: pillar_ops_gpu.cu:53-57, iou3d_nms.cpp:14-25).
+ *   - row counts that only the device knows (number of pillars, number of active sites) are passed
+ *     as `const int*` device scalars next to a host-side capacity; kernels are sized by the capacity
+ *     and exit early past the device count.
+ */
+#ifndef PILLARNET_B200_H_
+#define PILLARNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN_OK 0
+#define PN_ERR_INVALID_ARG 1
+#define PN_ERR_CUDA 2
+#define PN_ERR_WORKSPACE 3
+#define PN_ERR_UNSUPPORTED 4
+
+typedef void* pn_stream_t; /* cudaStream_t */
+
+/* element types for conv activations / weights */
+#define PN_F32 0
+#define PN_BF16 1
+
+int pn_abi_version(void);
+const char* pn_last_error(void);
+/* multiProcessorCount of the current device (148 on B200); <0 on error. */
+int pn_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Dynamic pillarization.
+ * Replaces DynamicPFE.forward's coordinate/mask code (models/readers/dynamic_pillar_encoder.py:33-47),
+ * pillar_cuda.create_point_pillar_index_stack_wrapper (pillar_ops.cpp:15-36, pillar_ops_gpu.cu:13-39),
+ * the torch.cumsum + .item() rank pass (pillar_utils.py:43-45),
+ * pillar_cuda.create_pillar_indices_wrapper (pillar_ops.cpp:39-55, pillar_ops_gpu.cu:60-78) and
+ * pillar_cuda.gather_indice_wrapper (group_ops_gpu.cu:8-17).
+ *
+ *   points        (n_points, point_dim) f32, frames concatenated in order
+ *   frame_offsets (n_frames+1) i32 device; frame b owns rows [off[b], off[b+1])
+ *   cell coords   cx = (int)floorf((x - x0) * inv_pillar) with inv_pillar = 1.0f/(float)pillar_size:
+ *                 this is what the reference's CUDA expression evaluates (torch scalar division).
+ *   occ_words     (ceil(B*H*W/32)) u32, written: bit c set <=> cell c = b*H*W + cy*W + cx occupied
+ *   word_prefix   (same length) i32, written: exclusive popcount prefix of occ_words
+ *   pillar_coords (m_cap,3) i32 [b, cy, cx], ascending cell order  == reference pillar_indices
+ *   point_pillar  (n_points) i32: pillar rank of each point, -1 for out-of-range points.
+ *                 point_pillar[point_pillar >= 0] == reference point_pillar_indices (order kept).
+ *   num_pillars   (1) i32 device
+ * scratch: pn_pillarize_scratch_bytes(n_frames,H,W).
+ */
+size_t pn_mask_words(int n_frames, int H, int W);
+size_t pn_pillarize_scratch_bytes(int n_frames, int H, int W);
+int pn_pillarize(const float* points, int point_dim, const int* frame_offsets, int n_points,
+                 int n_frames, int H, int W, float x0, float y0, float inv_pillar,
+                 uint32_t* occ_words, int* word_prefix, int* pillar_coords, int m_cap,
+                 int* point_pillar, int* num_pillars, void* scratch, size_t scratch_bytes,
+                 pn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) PFN (Linear -> BatchNorm1d(eval, folded to scale/shift) -> ReLU) fused with scatter-max.
+ * Replaces PillarQueryAndGroup's centre/offset features (pillar_utils.py:51-56, gather_feature
+ * group_ops_gpu.cu:20-33), PillarMaxPooling.shared_mlps (pillar_modules.py:26-33,71) and
+ * pillar_cuda.scatter_max_wrapper (scatter_ops.cpp:7-24, scatter_ops_gpu.cu:13-36).
+ *
+ *   per point: cx recomputed from x as in pn_pillarize (equals pillar_indices[:,2] of its pillar);
+ *              ctr = (float)cx*pillar + offset   (mul, add rounded separately, as the reference);
+ *              f = [x-ctr_x, y-ctr_y, p[0..point_dim)]            (2+point_dim values)
+ *              h[c] = max(0, dot(weight[c,:], f) * scale[c] + shift[c])
+ *   out[m,c] = max over points of pillar m (>= 0 by construction; reference zero-inits out)
+ *   weight (c_out, 2+point_dim) f32 row-major (== nn.Linear.weight); scale/shift (c_out) f32.
+ *   out_f32 (m_cap, c_out) f32 ; out_bf16 optional (may be NULL) same shape, bf16 copy for the
+ *   tensor-core backbone.  arg (m_cap, c_out) i32 optional (NULL for inference): index of a
+ *   point attaining the max (lowest point id; the reference's is racy, scatter_ops_gpu.cu:33-35).
+ *   c_out must be 32 or 64.
+ */
+int pn_pfn_scatter_max(const float* points, int point_dim, int n_points, const int* point_pillar,
+                       const int* num_pillars, int m_cap, float x0, float y0, float inv_pillar,
+                       float pillar_size, float x_offset, float y_offset, const float* weight,
+                       const float* scale, const float* shift, int c_out, float* out_f32,
+                       void* out_bf16, int* arg, pn_stream_t stream);
+
+/* Backward of scatter-max (scatter_ops_gpu.cu:38-45): grad_src[arg[m,c]] = grad_out[m,c]. */
+int pn_scatter_max_grad(const float* grad_out, const int* arg, const int* num_pillars, int m_cap,
+                        int c_out, float* grad_src, pn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Rulebooks (replace spconv's indice-pair generation).
+ * Output-stationary neighbour tables: nbr[o*9 + ky*3+kx] = input row or -1.
+ *  - submanifold 3x3 (SubMConv2d, backbones/base.py:38-52): input site (y+ky-1, x+kx-1), same frame;
+ *  - strided 3x3 s2 p1 (SparseConv2d, PillarResNet.py:87,95,103): Ho = (H+2-3)/2+1, output site
+ *    active iff any input at (2oy-1+ky, 2ox-1+kx); output rows in ascending b*Ho*Wo+oy*Wo+ox order.
+ */
+int pn_rulebook_subm3x3(const uint32_t* occ_words, const int* word_prefix, const int* coords,
+                        const int* num_rows, int m_cap, int H, int W, int* nbr, pn_stream_t stream);
+
+size_t pn_rulebook_down_scratch_bytes(int n_frames, int H_out, int W_out);
+int pn_rulebook_down3x3s2(const uint32_t* in_words, const int* in_prefix, const int* in_coords,
+                          const int* in_num_rows, int in_m_cap, int n_frames, int H_in, int W_in,
+                          uint32_t* out_words, int* out_prefix, int* out_coords, int* out_num_rows,
+                          int out_m_cap, int* nbr, void* scratch, size_t scratch_bytes,
+                          pn_stream_t stream);
+
+/* Static gather tables for the dense BEV convs (NHWC rows = b*H*W + y*W + x), computed once per shape:
+ *   mode 0: 3x3 stride s pad 1 (Conv2d / ZeroPad2d+valid conv), taps 9
+ *   mode 1: ConvTranspose2d(k=2,s=2): taps 4, exactly one valid tap (dy*2+dx) per output pixel. */
+int pn_dense_nbr_table(int mode, int n_frames, int H_in, int W_in, int stride, int* nbr,
+                       pn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) Gather-GEMM convolution (sparse SubM / strided sparse / dense 3x3 / transposed 2x2).
+ *   out[o, coff + n] = act( (sum_t sum_c in[nbr[o,t], c] * weight[n, t*cin + c]) * scale[n] + shift[n]
+ *                           + residual[o, n] )
+ * weight layout [cout][taps*cin] == spconv 2.x (Cout,kH,kW,Cin) (torchie/trainer/checkpoint.py:78-87).
+ * impl PN_IMPL_SIMT  : fp32 FMA reference path (any dtype combination below);
+ * impl PN_IMPL_TCGEN05: bf16 operands, fp32 accumulation in TMEM; weight must be K-padded to a
+ *                       multiple of 64 (k_pad) — see pn_conv_pack_weight_bf16.
+ */
+#define PN_IMPL_SIMT 0
+#define PN_IMPL_TCGEN05 1
+
+typedef struct pn_conv_args {
+  const void* in;        /* (rows_in, in_ld) channels-last */
+  int in_dtype;          /* PN_F32 | PN_BF16 */
+  int in_ld;
+  const int* nbr;        /* (rows_cap, taps) or NULL => identity with taps == 1 */
+  int taps;
+  const void* weight;    /* [cout][k_pad] of in_dtype */
+  int k_pad;             /* >= taps*cin, row stride of weight in elements */
+  const float* scale;    /* (cout) or NULL */
+  const float* shift;    /* (cout) or NULL */
+  const void* residual;  /* (rows, res_ld) of out_dtype or NULL */
+  int res_ld;
+  void* out;             /* (rows, out_ld) */
+  int out_dtype;
+  int out_ld;
+  int out_coff;
+  int relu;
+  const int* num_rows;   /* device row count or NULL => rows_cap */
+  int rows_cap;
+  int cin;
+  int cout;
+} pn_conv_args;
+
+int pn_conv_gather(const pn_conv_args* args, int impl, pn_stream_t stream);
+
+/* f32 -> bf16 weight packing with zero padding of K to k_pad (multiple of 64). */
+int pn_conv_pack_weight_bf16(const float* w_f32, int cout, int k, int k_pad, void* w_bf16,
+                             pn_stream_t stream);
+/* rows x cols cast (first *num_rows rows when num_rows != NULL). */
+int pn_cast_f32_to_bf16(const float* in, int in_ld, void* out, int out_ld, int cols,
+                        const int* num_rows, int rows_cap, pn_stream_t stream);
+int pn_cast_bf16_to_f32(const void* in, int in_ld, float* out, int out_ld, int cols,
+                        const int* num_rows, int rows_cap, pn_stream_t stream);
+
+/* SparseConvTensor.dense() (spconv) in NHWC: out[(b*H+y)*W+x, coff..coff+C) = feat[rank] or 0. */
+int pn_sparse_to_dense(const void* feat, int dtype, int feat_ld, const uint32_t* occ_words,
+                       const int* word_prefix, int n_frames, int H, int W, int C, void* out,
+                       int out_ld, int out_coff, pn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (5) CenterHead decode + NMS.
+ * Replaces CenterHead.predict / post_processing (bbox_heads/center_head.py:216-413),
+ * rotate_nms_pcdet / rotate_class_nms_pcdet (core/bbox/box_torch_ops.py:296-359),
+ * iou3d_nms_cuda.nms_gpu (ops/iou3d_nms/src/iou3d_nms.cpp:113-159 + iou3d_nms_kernel.cu:104-324)
+ * and circle_nms (core/utils/circle_nms_jit.py:4-28).
+ *
+ * A "segment" is one independent NMS problem: (frame, task) for use_rotate_nms / circular_nms,
+ * (frame, task, class) for use_multi_class_nms.  Segment id = frame*segs_per_frame + seg_in_frame.
+ */
+typedef struct pn_task_args {
+  const float* maps;   /* (B*H*W, ld) f32 NHWC: all head outputs of this task packed per pixel */
+  int ld;
+  int off_reg, off_height, off_dim, off_rot, off_vel, off_iou, off_hm; /* channel offsets, -1 = absent */
+  int num_cls;
+  int H, W;
+  int stride;          /* task stride (tasks[i].stride) */
+  int seg_base;        /* first segment (within a frame) owned by this task */
+  int per_class;       /* 1 => one segment per class (use_multi_class_nms) */
+} pn_task_args;
+
+/* Stage A: per pixel sigmoid/max/threshold/range test; appends (score,pixel) keys to its segment.
+ *   cand_keys (n_frames*segs_per_frame, cand_cap) u64 ; cand_count (n_frames*segs_per_frame) i32 (zeroed by caller)
+ *   key = (bits(rect_score) << 32) | (0xFFFFFFFF - pixel)   => descending key order == score desc, pixel asc
+ */
+int pn_decode_candidates(const pn_task_args* task, int n_frames, int segs_per_frame,
+                         float score_thr, const float* center_range6 /*host, may be NULL*/,
+                         float pillar_size, float x0, float y0, const float* rectifier /*host, per class*/,
+                         unsigned long long* cand_keys, int cand_cap, int* cand_count,
+                         pn_stream_t stream);
+
+/* Stage B: per segment top-`pre_max` selection + sort, decode of the surviving boxes.
+ *   seg_pre_max (segs_per_frame) host ints.
+ *   sorted_boxes (n_segs, pre_cap, 12) f32: [x,y,z,w,l,h,vx,vy,rot, score, rect_score, label]
+ *   sorted_count (n_segs) i32
+ */
+int pn_select_topk(const pn_task_args* task, int n_frames, int segs_per_frame,
+                   const int* seg_pre_max /*host*/, float pillar_size, float x0, float y0,
+                   const float* rectifier /*host, per class*/,
+                   const unsigned long long* cand_keys, int cand_cap, const int* cand_count,
+                   float* sorted_boxes, int pre_cap, int* sorted_count, pn_stream_t stream);
+
+/* Stage C+D: suppression matrix (upper triangle) + greedy sweep on device.
+ *   mode 0: rotated BEV IoU > thr (iou3d_nms_kernel.cu:104-234 arithmetic incl. MARGIN/EPS)
+ *   mode 1: circle: dist^2 <= thr (circle_nms_jit.py:23-26)
+ *   seg_thr / seg_post_max: (segs_per_frame) host arrays.
+ *   mask scratch: pn_nms_scratch_bytes(n_segs, pre_cap)
+ *   keep_idx (n_segs, post_cap) i32: positions in sorted order; keep_count (n_segs) i32
+ *   det_out  (n_segs, post_cap, 11) f32: [box9, score, label] of kept boxes (vx,vy = 0 when absent)
+ */
+size_t pn_nms_scratch_bytes(int n_segs, int pre_cap);
+int pn_nms(int mode, int n_frames, int segs_per_frame, const float* seg_thr /*host*/,
+           const int* seg_post_max /*host*/, const int* seg_use_rectified /*host or NULL*/,
+           const float* sorted_boxes, int pre_cap, const int* sorted_count, void* scratch,
+           size_t scratch_bytes, int* keep_idx, int post_cap, int* keep_count, float* det_out,
+           pn_stream_t stream);
+
+/* Standalone drop-ins for iou3d_nms_cuda (boxes (n,7) f32 [x,y,z,dx,dy,dz,heading], device). */
+int pn_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* iou,
+                     pn_stream_t stream);
+/* keep (n) i32 device, num_keep (1) i32 device; boxes must already be score-sorted (as nms_gpu). */
+int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t scratch_bytes,
+                   int* keep, int* num_keep, pn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PILLARNET_B200_H_ */

@@ -1,0 +1,183 @@
+"""PillarNet sparse 2D ResNet encoders behind det3d's backbone interface.
+
+Mirrors det3d/models/backbones/PillarResNet.py:8-309 (PillarResNet18S/18/34S/34: same constructor,
+same module tree => same state_dict keys, `backbone_channels` / `backbone_strides`) and
+det3d/models/backbones/base.py:145-213 (Sparse2DBasicBlockV / Sparse2DBasicBlock).  Every
+conv+BN(+ReLU)(+residual) is one gather-GEMM launch (ops.conv_gather) with the epilogue fused; the
+rulebook of a stage is built once (spconv's `indice_key` cache) and shared by its SubM convs.
+"""
+import torch
+from torch import nn
+
+from . import config, ops
+from .layers import (DenseMap, SparseConv2d, SparseReLU, SparseSequential, SubMConv2d,
+                     build_norm_layer, dense_conv3x3, lower, run_conv)
+from .registry import BACKBONES
+from .sparse import SparseConvTensor
+
+
+def conv2D3x3(in_planes, out_planes, stride=1, dilation=1, indice_key=None, bias=True):
+    """backbones/base.py:38-63."""
+    assert stride >= 1
+    if stride == 1:
+        return SubMConv2d(in_planes, out_planes, 3, stride=1, dilation=dilation, padding=dilation,
+                          bias=bias, indice_key=indice_key)
+    return SparseConv2d(in_planes, out_planes, 3, stride=stride, dilation=dilation, padding=dilation,
+                        bias=bias, indice_key=indice_key)
+
+
+def _subm(sp, seq, relu, residual=None):
+    """SparseSequential(SubMConv2d, BN[, SparseReLU]) as one launch."""
+    conv, bn = seq[0], seq[1]
+    t = sp.table
+    lw = lower(conv, bn)
+    out = run_conv(sp.feat, lw, t.subm_nbr(), 9, conv.in_channels, conv.out_channels, t.cap, num=t.num,
+                   relu=relu, residual=residual)
+    return SparseConvTensor(out, t, sp.spatial_shape, sp.batch_size)
+
+
+class Sparse2DBasicBlockV(nn.Module):
+    expansion = 1
+
+    def __init__(self, planes, norm_cfg=None, indice_key=None):
+        super().__init__()
+        if norm_cfg is None:
+            norm_cfg = dict(type="BN1d", momentum=0.01, eps=1e-3)
+        bias = norm_cfg is not None
+        self.conv0 = SparseSequential(conv2D3x3(planes, planes, indice_key=indice_key, bias=bias),
+                                      build_norm_layer(norm_cfg, planes)[1])
+        self.conv1 = SparseSequential(conv2D3x3(planes, planes, indice_key=indice_key, bias=bias),
+                                      build_norm_layer(norm_cfg, planes)[1], SparseReLU())
+        self.conv2 = SparseSequential(conv2D3x3(planes, planes, indice_key=indice_key, bias=bias),
+                                      build_norm_layer(norm_cfg, planes)[1])
+        self.relu = nn.ReLU()
+
+    def forward(self, x):
+        x = _subm(x, self.conv0, relu=False)
+        out = _subm(x, self.conv1, relu=True)
+        return _subm(out, self.conv2, relu=True, residual=x.feat)  # relu(bn(conv) + identity)
+
+
+class Sparse2DBasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, planes, norm_cfg=None, indice_key=None):
+        super().__init__()
+        if norm_cfg is None:
+            norm_cfg = dict(type="BN1d", momentum=0.01, eps=1e-3)
+        bias = norm_cfg is not None
+        self.conv1 = SparseSequential(conv2D3x3(planes, planes, indice_key=indice_key, bias=bias),
+                                      build_norm_layer(norm_cfg, planes)[1], SparseReLU())
+        self.conv2 = SparseSequential(conv2D3x3(planes, planes, indice_key=indice_key, bias=bias),
+                                      build_norm_layer(norm_cfg, planes)[1])
+        self.relu = nn.ReLU()
+
+    def forward(self, x):
+        out = _subm(x, self.conv1, relu=True)
+        return _subm(out, self.conv2, relu=True, residual=x.feat)
+
+
+def _run_stage(sp, stage):
+    """Runs one `convN` SparseSequential: optional [SparseConv2d, BN, SparseReLU] head then blocks."""
+    mods = list(stage)
+    i = 0
+    if isinstance(mods[0], SparseConv2d):
+        conv, bn = mods[0], mods[1]
+        out_table, nbr = ops.rulebook_down3x3s2(sp.table)
+        lw = lower(conv, bn)
+        feat = run_conv(sp.feat, lw, nbr, 9, conv.in_channels, conv.out_channels, out_table.cap,
+                        num=out_table.num, relu=True)
+        sp = SparseConvTensor(feat, out_table, (out_table.H, out_table.W), sp.batch_size)
+        i = 3
+    for m in mods[i:]:
+        sp = m(sp)
+    return sp
+
+
+def post_act_block_dense(in_channels, kernel_size, stride=1, padding=0, dilation=1, norm_cfg=None):
+    """backbones/base.py:100-108."""
+    return nn.Sequential(
+        nn.Conv2d(in_channels, in_channels, kernel_size, stride, padding=padding, dilation=dilation, bias=False),
+        build_norm_layer(norm_cfg, in_channels)[1],
+        SparseReLU(),
+    )
+
+
+class _PillarResNet(nn.Module):
+    """Shared constructor/forward; subclasses give the block counts and whether conv5 exists."""
+    BLOCKS = (1, 2, 2, 2)   # extra Sparse2DBasicBlocks in conv1 (after BlockV), then blocks in conv2..4
+    DENSE = True
+
+    def __init__(self, in_channels=32, **kwargs):
+        super().__init__()
+        c = in_channels
+        norm_cfg = dict(type="BN1d", momentum=0.01, eps=1e-3)
+        self.conv1 = SparseSequential(
+            Sparse2DBasicBlockV(c, norm_cfg=norm_cfg, indice_key="res1"),
+            *[Sparse2DBasicBlock(c, norm_cfg=norm_cfg, indice_key="res1") for _ in range(self.BLOCKS[0])])
+
+        def down(cin, cout, n, key):
+            return SparseSequential(
+                SparseConv2d(cin, cout, 3, 2, padding=1, bias=False),
+                build_norm_layer(norm_cfg, cout)[1],
+                SparseReLU(),
+                *[Sparse2DBasicBlock(cout, norm_cfg=norm_cfg, indice_key=key) for _ in range(n)])
+
+        self.conv2 = down(c, c * 2, self.BLOCKS[1], "res2")
+        self.conv3 = down(c * 2, c * 4, self.BLOCKS[2], "res3")
+        self.conv4 = down(c * 4, c * 8, self.BLOCKS[3], "res4")
+        self.backbone_channels = {"conv1": 32, "conv2": 64, "conv3": 128, "conv4": 256}
+        self.backbone_strides = {"conv1": 1, "conv2": 2, "conv3": 4, "conv4": 8}
+        if self.DENSE:
+            norm_cfg2 = dict(type="BN", momentum=0.01, eps=1e-3)
+            self.conv5 = nn.Sequential(
+                nn.Conv2d(256, 256, 3, 2, padding=1, bias=False),
+                build_norm_layer(norm_cfg2, 256)[1],
+                nn.ReLU(),
+                post_act_block_dense(256, 3, padding=1, norm_cfg=norm_cfg2),
+                post_act_block_dense(256, 3, padding=1, norm_cfg=norm_cfg2),
+            )
+            self.backbone_channels["conv5"] = 256
+            self.backbone_strides["conv5"] = 16
+
+    def forward(self, sp_tensor):
+        x1 = _run_stage(sp_tensor, self.conv1)
+        x2 = _run_stage(x1, self.conv2)
+        x3 = _run_stage(x2, self.conv3)
+        x4 = _run_stage(x3, self.conv4)
+        feats = {"conv1": x1, "conv2": x2, "conv3": x3, "conv4": x4}
+        if self.DENSE:
+            # x_conv4.dense() lands in the left half of a 2C-wide buffer so the neck's channel concat
+            # (necks/rpn.py:201-205) needs no copy: the up-sampled branch writes the right half.
+            t = x4.table
+            C = x4.feat.shape[1]
+            cat_rows = torch.empty(t.B * t.H * t.W, 2 * C, dtype=x4.feat.dtype, device=x4.feat.device)
+            x4.dense_nhwc(out=cat_rows, out_coff=0)
+            d4 = DenseMap(cat_rows, t.B, t.H, t.W, C, 0)
+            c5 = self.conv5
+            d5 = dense_conv3x3(d4, c5[0], c5[1], relu=True, stride=2)
+            d5 = dense_conv3x3(d5, c5[3][0], c5[3][1], relu=True)
+            d5 = dense_conv3x3(d5, c5[4][0], c5[4][1], relu=True)
+            feats["conv4"] = d4.nchw()
+            feats["conv5"] = d5.nchw()
+        return feats
+
+
+@BACKBONES.register_module
+class PillarResNet18S(_PillarResNet):
+    BLOCKS, DENSE = (1, 2, 2, 2), False
+
+
+@BACKBONES.register_module
+class PillarResNet18(_PillarResNet):
+    BLOCKS, DENSE = (1, 2, 2, 2), True
+
+
+@BACKBONES.register_module
+class PillarResNet34S(_PillarResNet):
+    BLOCKS, DENSE = (2, 4, 6, 3), False
+
+
+@BACKBONES.register_module
+class PillarResNet34(_PillarResNet):
+    BLOCKS, DENSE = (2, 4, 6, 3), True

@@ -1,0 +1,29 @@
+"""Global numeric mode of the conv path.
+
+"fp32": fp32 activations/weights, fp32 FMA kernels (PN_IMPL_SIMT) — the 1e-3 parity mode.
+"bf16": bf16 activations/weights, fp32 accumulation in TMEM on tcgen05 (PN_IMPL_TCGEN05) — the fast mode.
+"""
+import torch
+
+from ._lib import PN_IMPL_SIMT, PN_IMPL_TCGEN05
+
+_precision = "bf16"
+
+
+def set_precision(p):
+    global _precision
+    if p not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _precision = p
+
+
+def get_precision():
+    return _precision
+
+
+def act_dtype():
+    return torch.float32 if _precision == "fp32" else torch.bfloat16
+
+
+def conv_impl():
+    return PN_IMPL_SIMT if _precision == "fp32" else PN_IMPL_TCGEN05

@@ -1,0 +1,626 @@
+// CenterHead decode, top-K selection and device-resident rotated / circle NMS for sm_100a.
+//
+// Reference path being replaced (PillarNet-LTS):
+//   det3d/models/bbox_heads/center_head.py:216-350   predict (sigmoid/exp/atan2/meshgrid decode)
+//   det3d/models/bbox_heads/center_head.py:352-413   post_processing (score/range mask, NMS dispatch)
+//   det3d/core/bbox/box_torch_ops.py:296-359         rotate_nms_pcdet / rotate_class_nms_pcdet
+//   det3d/ops/iou3d_nms/src/iou3d_nms.cpp:113-159    nms_gpu (cudaMalloc + D2H + CPU sweep per call)
+//   det3d/ops/iou3d_nms/src/iou3d_nms_kernel.cu:280-324  nms_kernel
+//   det3d/core/utils/circle_nms_jit.py:4-28          circle_nms (numba, CPU)
+//
+// Everything stays on the device: candidates are appended with one atomic per surviving pixel, each
+// NMS segment is selected/sorted by one CTA, the suppression matrix is built only for the upper
+// triangle and only for pairs that survive a conservative disjointness test, and the greedy sweep
+// runs in one warp with the removal bit-vector spread across lanes.
+#include "common.cuh"
+#include "rotated_iou.cuh"
+
+namespace {
+
+using pn_iou::BoxGeom;
+
+constexpr int kBoxRec = 12;   // sorted_boxes record: x y z w l h vx vy rot score rect label
+constexpr int kDetRec = 11;   // det_out record: box9 score label
+constexpr int kSelThreads = 1024;
+constexpr int kSelSmemKeys = 4096;
+
+struct TaskDev {
+  const float* maps;
+  int ld, off_reg, off_height, off_dim, off_rot, off_vel, off_iou, off_hm, num_cls, H, W, stride,
+      seg_base, per_class;
+};
+
+struct Pix {
+  float score, rect, x, y, z;
+  int label;
+};
+
+// sigmoid exactly as ATen's CUDA kernel: 1 / (1 + exp(-x)) in fp32 with precise expf and IEEE divide.
+__device__ __forceinline__ float sigmoid_ref(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// score/label (first max wins, as torch.max), rectified score, decoded centre.
+// center_head.py:257-264 (hm, iou), :306-315 (xs, ys), :366 (max), box_torch_ops.py:301 (rectify).
+__device__ __forceinline__ Pix decode_pixel(const TaskDev& t, const float* __restrict__ row, int i,
+                                            int j, float ps, float x0, float y0,
+                                            const float* __restrict__ rect_r) {
+  Pix p;
+  float best = sigmoid_ref(row[t.off_hm]);
+  int lab = 0;
+  for (int k = 1; k < t.num_cls; ++k) {
+    const float s = sigmoid_ref(row[t.off_hm + k]);
+    if (s > best) { best = s; lab = k; }
+  }
+  p.score = best;
+  p.label = lab;
+  float iou = 1.0f;
+  if (t.off_iou >= 0) {
+    iou = __fmul_rn(__fadd_rn(row[t.off_iou], 1.0f), 0.5f);
+    iou = fminf(fmaxf(iou, 0.0f), 1.0f);
+  }
+  const float r = rect_r ? rect_r[lab] : 0.0f;
+  if (r == 0.0f) {
+    p.rect = best;  // pow(s, 1) * pow(iou, 0) == s (ATen special-cases exponents 1 and 0)
+  } else {
+    p.rect = __fmul_rn(powf(best, 1.0f - r), powf(iou, r));
+  }
+  // xs = (j + reg_x) * stride * pillar_size + x0 : four separately rounded fp32 steps
+  const float fs = (float)t.stride;
+  p.x = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn((float)j, row[t.off_reg]), fs), ps), x0);
+  p.y = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn((float)i, row[t.off_reg + 1]), fs), ps), y0);
+  p.z = row[t.off_height];
+  return p;
+}
+
+struct DecodeParams {
+  TaskDev t;
+  int n_frames, segs_per_frame;
+  float score_thr;
+  int use_range;
+  float range[6];
+  float ps, x0, y0;
+  int use_rect;
+  float rect[8];
+};
+
+__global__ void __launch_bounds__(256)
+k_decode_candidates(DecodeParams P, unsigned long long* __restrict__ keys, int cand_cap,
+                    int* __restrict__ counts) {
+  const TaskDev& t = P.t;
+  const int hw = t.H * t.W;
+  const long long total = (long long)P.n_frames * hw;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(g / hw), pix = (int)(g - (long long)b * hw);
+    const int i = pix / t.W, j = pix - i * t.W;
+    const float* row = t.maps + g * t.ld;
+    // cheap early-out on the raw logit: sigmoid is monotone, so a pixel whose largest logit maps
+    // to a score <= thr can never pass; evaluated with the same sigmoid to keep the decision exact.
+    const Pix p = decode_pixel(t, row, i, j, P.ps, P.x0, P.y0, P.use_rect ? P.rect : nullptr);
+    bool ok = p.score > P.score_thr;
+    if (P.use_range) {
+      ok = ok && p.x >= P.range[0] && p.y >= P.range[1] && p.z >= P.range[2] &&
+           p.x <= P.range[3] && p.y <= P.range[4] && p.z <= P.range[5];
+    }
+    if (!ok) continue;
+    const int seg = b * P.segs_per_frame + t.seg_base + (t.per_class ? p.label : 0);
+    const int slot = atomicAdd(counts + seg, 1);
+    if (slot < cand_cap) {
+      keys[(long long)seg * cand_cap + slot] =
+          ((unsigned long long)__float_as_uint(p.rect) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)pix);
+    }
+  }
+}
+
+// ---- per-segment selection + sort ---------------------------------------------------------------
+
+__device__ void bitonic_sort_desc(unsigned long long* s, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s[i], b = s[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) { s[i] = b; s[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct SelectParams {
+  TaskDev t;
+  int n_frames, segs_per_frame;
+  int seg_lo, seg_hi;  // this task owns segs [seg_lo, seg_hi) within a frame
+  int pre_max[8];      // indexed by seg - seg_lo
+  float ps, x0, y0;
+  int use_rect;
+  float rect[8];
+};
+
+__global__ void __launch_bounds__(kSelThreads)
+k_select_topk(SelectParams P, const unsigned long long* __restrict__ keys_all, int cand_cap,
+              const int* __restrict__ counts, float* __restrict__ sorted_boxes, int pre_cap,
+              int* __restrict__ sorted_count) {
+  __shared__ unsigned long long s_keys[kSelSmemKeys];
+  __shared__ int s_hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_need, s_fill;
+  const TaskDev& t = P.t;
+  const int nseg_task = P.seg_hi - P.seg_lo;
+  const int b = blockIdx.x / nseg_task;
+  const int sl = blockIdx.x - b * nseg_task;
+  const int seg = b * P.segs_per_frame + P.seg_lo + sl;
+  const int K = min(min(P.pre_max[sl], pre_cap), kSelSmemKeys);
+  const int n = min(counts[seg], cand_cap);
+  const unsigned long long* keys = keys_all + (long long)seg * cand_cap;
+  int m;  // number of keys staged in smem
+  if (n <= kSelSmemKeys) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = keys[i];
+    m = n;
+  } else {
+    // MSB-first radix select of the K-th largest key (keys are unique), then gather keys >= it.
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_need = K; }
+    __syncthreads();
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      const unsigned long long hi_mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = keys[i];
+        if ((k & hi_mask) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 0xFF)], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int need = s_need, d = 255;
+        for (; d > 0; --d) {
+          if (s_hist[d] >= need) break;
+          need -= s_hist[d];
+        }
+        s_need = need;
+        s_prefix = prefix | ((unsigned long long)d << shift);
+      }
+      __syncthreads();
+    }
+    const unsigned long long kth = s_prefix;
+    if (threadIdx.x == 0) s_fill = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long k = keys[i];
+      if (k >= kth) {
+        const int slot = atomicAdd(&s_fill, 1);
+        if (slot < kSelSmemKeys) s_keys[slot] = k;
+      }
+    }
+    __syncthreads();
+    m = min(s_fill, kSelSmemKeys);
+  }
+  int p2 = 1;
+  while (p2 < m) p2 <<= 1;
+  for (int i = m + threadIdx.x; i < p2; i += blockDim.x) s_keys[i] = 0ull;
+  __syncthreads();
+  bitonic_sort_desc(s_keys, p2);
+  const int cnt = min(m, K);
+  if (threadIdx.x == 0) sorted_count[seg] = cnt;
+  const int hw = t.H * t.W;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const unsigned long long k = s_keys[i];
+    const int pix = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+    const int ii = pix / t.W, jj = pix - ii * t.W;
+    const float* row = t.maps + ((long long)b * hw + pix) * t.ld;
+    const Pix p = decode_pixel(t, row, ii, jj, P.ps, P.x0, P.y0, P.use_rect ? P.rect : nullptr);
+    float* o = sorted_boxes + ((long long)seg * pre_cap + i) * kBoxRec;
+    o[0] = p.x;
+    o[1] = p.y;
+    o[2] = p.z;
+    // dim = exp(clamp(dim, -1.2, 3.2))  (center_head.py:259)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) o[3 + d] = expf(fminf(fmaxf(row[t.off_dim + d], -1.2f), 3.2f));
+    o[6] = t.off_vel >= 0 ? row[t.off_vel] : 0.f;
+    o[7] = t.off_vel >= 0 ? row[t.off_vel + 1] : 0.f;
+    o[8] = atan2f(row[t.off_rot], row[t.off_rot + 1]);  // atan2(rot_sin, rot_cos), :266-267,306
+    o[9] = p.score;
+    o[10] = p.rect;
+    o[11] = (float)p.label;
+  }
+}
+
+// ---- NMS ----------------------------------------------------------------------------------------
+
+constexpr int kGeomFloats = 18;
+
+__device__ __forceinline__ void store_geom(float* g, const BoxGeom& q) {
+  g[0] = q.cx; g[1] = q.cy;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { g[2 + k] = q.px[k]; g[6 + k] = q.py[k]; }
+  g[10] = q.ic; g[11] = q.is; g[12] = q.mx; g[13] = q.my; g[14] = q.area;
+}
+__device__ __forceinline__ void load_geom(const float* g, BoxGeom& q) {
+  q.cx = g[0]; q.cy = g[1];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { q.px[k] = g[2 + k]; q.py[k] = g[6 + k]; }
+  q.ic = g[10]; q.is = g[11]; q.mx = g[12]; q.my = g[13]; q.area = g[14];
+}
+
+// geometry of the box in pcdet convention: to_pcdet (iou3d_nms_utils.py:30-34) swaps w/l and maps
+// heading -> -rot - pi/2 (neg, then one fp32 subtract of float(pi/2)).
+__global__ void __launch_bounds__(256)
+k_nms_geom(const float* __restrict__ sorted_boxes, int pre_cap, const int* __restrict__ sorted_count,
+           int n_segs, float* __restrict__ geom) {
+  const long long total = (long long)n_segs * pre_cap;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int seg = (int)(g / pre_cap), i = (int)(g - (long long)seg * pre_cap);
+    if (i >= sorted_count[seg]) continue;
+    const float* bx = sorted_boxes + g * kBoxRec;
+    BoxGeom q;
+    const float heading = __fsub_rn(-bx[8], 1.57079632679489661923f);
+    pn_iou::make_geom(bx[0], bx[1], bx[4], bx[3], heading, q);
+    store_geom(geom + g * kGeomFloats, q);
+  }
+}
+
+// 64x64 tile of the suppression matrix; upper triangle only (tile row <= tile col), matching the
+// bits the reference's host sweep actually reads (iou3d_nms.cpp:139-156).
+struct MaskParams {
+  int mode;  // 0 rotated IoU, 1 circle
+  int segs_per_frame;
+  float thr[16];
+};
+
+__global__ void __launch_bounds__(64)
+k_nms_mask(MaskParams P, const float* __restrict__ sorted_boxes, const float* __restrict__ geom,
+           int pre_cap, const int* __restrict__ sorted_count, unsigned long long* __restrict__ mask) {
+  const int seg = blockIdx.z;
+  const int n = sorted_count[seg];
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
+  const int col_blocks = pre_cap / 64;
+  __shared__ float s_col[64 * kGeomFloats];
+  __shared__ unsigned short s_pairs[64 * 64];
+  __shared__ int s_npairs;
+  __shared__ unsigned int s_bits[64][2];
+  const int tid = threadIdx.x;
+  const float thr = P.thr[seg % P.segs_per_frame];
+  const int rows = min(64, n - rb * 64), cols = min(64, n - cb * 64);
+  const long long base = (long long)seg * pre_cap;
+  if (tid == 0) s_npairs = 0;
+  s_bits[tid][0] = 0u;
+  s_bits[tid][1] = 0u;
+  if (P.mode == 0) {
+    for (int i = tid; i < cols * kGeomFloats; i += 64)
+      s_col[i] = geom[(base + cb * 64) * kGeomFloats + i];
+  } else {
+    for (int i = tid; i < cols; i += 64) {
+      s_col[i * 2] = sorted_boxes[(base + cb * 64 + i) * kBoxRec + 0];
+      s_col[i * 2 + 1] = sorted_boxes[(base + cb * 64 + i) * kBoxRec + 1];
+    }
+  }
+  __syncthreads();
+  if (P.mode == 1) {
+    // circle_nms: (float32 difference)^2 summed in float64, compared with <= thresh
+    if (tid < rows) {
+      const float xi = sorted_boxes[(base + rb * 64 + tid) * kBoxRec + 0];
+      const float yi = sorted_boxes[(base + rb * 64 + tid) * kBoxRec + 1];
+      unsigned long long bits = 0ull;
+      const int start = (rb == cb) ? tid + 1 : 0;
+      for (int c = start; c < cols; ++c) {
+        const double dx = (double)__fsub_rn(xi, s_col[c * 2]);
+        const double dy = (double)__fsub_rn(yi, s_col[c * 2 + 1]);
+        if (dx * dx + dy * dy <= (double)thr) bits |= 1ull << c;
+      }
+      mask[(base + rb * 64 + tid) * col_blocks + cb] = bits;
+    }
+    return;
+  }
+  BoxGeom a;
+  if (tid < rows) {
+    load_geom(geom + (base + rb * 64 + tid) * kGeomFloats, a);
+    const int start = (rb == cb) ? tid + 1 : 0;
+    for (int c = start; c < cols; ++c) {
+      BoxGeom bq;
+      bq.cx = s_col[c * kGeomFloats + 0];
+      bq.cy = s_col[c * kGeomFloats + 1];
+      bq.mx = s_col[c * kGeomFloats + 12];
+      bq.my = s_col[c * kGeomFloats + 13];
+      if (!pn_iou::surely_disjoint(a, bq)) {
+        const int slot = atomicAdd(&s_npairs, 1);
+        s_pairs[slot] = (unsigned short)((tid << 6) | c);
+      }
+    }
+  }
+  __syncthreads();
+  const int np = s_npairs;
+  for (int q = tid; q < np; q += 64) {
+    const int r = s_pairs[q] >> 6, c = s_pairs[q] & 63;
+    BoxGeom ra, cbx;
+    load_geom(geom + (base + rb * 64 + r) * kGeomFloats, ra);
+    load_geom(s_col + c * kGeomFloats, cbx);
+    if (pn_iou::iou_bev(ra, cbx) > thr) atomicOr(&s_bits[r][c >> 5], 1u << (c & 31));
+  }
+  __syncthreads();
+  if (tid < rows)
+    mask[(base + rb * 64 + tid) * col_blocks + cb] =
+        ((unsigned long long)s_bits[tid][1] << 32) | s_bits[tid][0];
+}
+
+struct SweepParams {
+  int segs_per_frame;
+  int post_max[16];
+  int use_rect[16];
+};
+
+// One warp per segment.  Lane l owns removal word l (pre_cap <= 2048).  Per 64-box block: the
+// diagonal tile is resolved serially from shared memory, then the rows of the boxes kept in this
+// block are OR-ed into the lanes' words with independent, coalesced loads.
+__global__ void __launch_bounds__(32)
+k_nms_sweep(SweepParams P, const float* __restrict__ sorted_boxes, int pre_cap,
+            const int* __restrict__ sorted_count, const unsigned long long* __restrict__ mask,
+            int* __restrict__ keep_idx, int post_cap, int* __restrict__ keep_count,
+            float* __restrict__ det_out) {
+  const int seg = blockIdx.x, lane = threadIdx.x;
+  const int n = sorted_count[seg];
+  const int col_blocks = pre_cap / 64;
+  const int post = min(P.post_max[seg % P.segs_per_frame], post_cap);
+  const int use_rect = P.use_rect[seg % P.segs_per_frame];
+  const long long base = (long long)seg * pre_cap;
+  __shared__ unsigned long long s_diag[64];
+  __shared__ int s_keep[2048];
+  unsigned long long remv = 0ull;
+  int kept = 0;
+  const int nblk = (n + 63) / 64;
+  for (int blk = 0; blk < nblk && kept < post; ++blk) {
+    const int rows = min(64, n - blk * 64);
+    for (int r = lane; r < 64; r += 32)
+      s_diag[r] = r < rows ? mask[(base + blk * 64 + r) * col_blocks + blk] : 0ull;
+    __syncwarp();
+    unsigned long long cur = __shfl_sync(0xffffffffu, remv, blk);
+    unsigned long long kept_bits = 0ull;
+    int kept_here = 0;
+    for (int r = 0; r < rows; ++r) {
+      if (!((cur >> r) & 1ull)) {
+        if (kept + kept_here < post) {
+          kept_bits |= 1ull << r;
+          if (lane == 0) s_keep[kept + kept_here] = blk * 64 + r;
+          ++kept_here;
+        }
+        cur |= s_diag[r];
+      }
+    }
+    kept += kept_here;
+    if (lane > blk && lane < col_blocks) {
+      unsigned long long acc = 0ull;
+      unsigned long long bits = kept_bits;
+      while (bits) {
+        const int r = __ffsll((long long)bits) - 1;
+        bits &= bits - 1;
+        acc |= mask[(base + blk * 64 + r) * col_blocks + lane];
+      }
+      remv |= acc;
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+  if (lane == 0) keep_count[seg] = kept;
+  for (int k = lane; k < kept; k += 32) {
+    const int i = s_keep[k];
+    keep_idx[(long long)seg * post_cap + k] = i;
+    const float* bx = sorted_boxes + (base + i) * kBoxRec;
+    float* o = det_out + ((long long)seg * post_cap + k) * kDetRec;
+#pragma unroll
+    for (int d = 0; d < 9; ++d) o[d] = bx[d];
+    o[9] = use_rect ? bx[10] : bx[9];
+    o[10] = bx[11];
+  }
+}
+
+// ---- standalone iou3d_nms_cuda drop-ins ---------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+k_boxes_iou(const float* __restrict__ A, int na, const float* __restrict__ B, int nb,
+            float* __restrict__ out) {
+  const long long total = (long long)na * nb;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(g / nb), j = (int)(g - (long long)i * nb);
+    BoxGeom a, b;
+    pn_iou::make_geom(A[i * 7], A[i * 7 + 1], A[i * 7 + 3], A[i * 7 + 4], A[i * 7 + 6], a);
+    pn_iou::make_geom(B[j * 7], B[j * 7 + 1], B[j * 7 + 3], B[j * 7 + 4], B[j * 7 + 6], b);
+    out[g] = pn_iou::iou_bev(a, b);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_boxes7_to_records(const float* __restrict__ boxes, int n, float* __restrict__ rec,
+                    float* __restrict__ geom, int* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *count = n;
+  if (i >= n) return;
+  const float* b = boxes + i * 7;
+  float* o = rec + (long long)i * kBoxRec;
+  for (int d = 0; d < kBoxRec; ++d) o[d] = 0.f;
+  o[0] = b[0]; o[1] = b[1]; o[2] = b[2];
+  BoxGeom q;
+  pn_iou::make_geom(b[0], b[1], b[3], b[4], b[6], q);
+  store_geom(geom + (long long)i * kGeomFloats, q);
+}
+
+inline int grid_for(long long work, int threads) {
+  const int sms = pn_detail::sm_count();
+  long long g = PN_DIVUP(work, (long long)threads);
+  const long long cap = (long long)(sms > 0 ? sms : 148) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+TaskDev to_dev(const pn_task_args* t) {
+  TaskDev d;
+  d.maps = t->maps; d.ld = t->ld; d.off_reg = t->off_reg; d.off_height = t->off_height;
+  d.off_dim = t->off_dim; d.off_rot = t->off_rot; d.off_vel = t->off_vel; d.off_iou = t->off_iou;
+  d.off_hm = t->off_hm; d.num_cls = t->num_cls; d.H = t->H; d.W = t->W; d.stride = t->stride;
+  d.seg_base = t->seg_base; d.per_class = t->per_class;
+  return d;
+}
+
+inline int round_up64(int v) { return (v + 63) / 64 * 64; }
+
+struct NmsScratch {
+  float* geom;
+  unsigned long long* mask;
+};
+inline size_t geom_bytes(int n_segs, int pre_cap) {
+  return ((size_t)n_segs * pre_cap * kGeomFloats * sizeof(float) + 255) / 256 * 256;
+}
+inline size_t mask_bytes(int n_segs, int pre_cap) {
+  return (size_t)n_segs * pre_cap * (pre_cap / 64) * sizeof(unsigned long long);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pn_decode_candidates(const pn_task_args* task, int n_frames, int segs_per_frame,
+                         float score_thr, const float* center_range6, float pillar_size, float x0,
+                         float y0, const float* rectifier, unsigned long long* cand_keys,
+                         int cand_cap, int* cand_count, pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(task && task->maps && cand_keys && cand_count && cand_cap > 0 && n_frames >= 1);
+  PN_REQUIRE(task->num_cls >= 1 && task->num_cls <= 8 && task->H > 0 && task->W > 0);
+  PN_REQUIRE(task->off_reg >= 0 && task->off_height >= 0 && task->off_dim >= 0 && task->off_rot >= 0 &&
+             task->off_hm >= 0);
+  DecodeParams P;
+  P.t = to_dev(task);
+  P.n_frames = n_frames;
+  P.segs_per_frame = segs_per_frame;
+  P.score_thr = score_thr;
+  P.use_range = center_range6 != nullptr;
+  for (int i = 0; i < 6; ++i) P.range[i] = center_range6 ? center_range6[i] : 0.f;
+  P.ps = pillar_size; P.x0 = x0; P.y0 = y0;
+  P.use_rect = rectifier != nullptr;
+  for (int i = 0; i < 8; ++i) P.rect[i] = (rectifier && i < task->num_cls) ? rectifier[i] : 0.f;
+  const long long total = (long long)n_frames * task->H * task->W;
+  k_decode_candidates<<<grid_for(total, 256), 256, 0, stream>>>(P, cand_keys, cand_cap, cand_count);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+int pn_select_topk(const pn_task_args* task, int n_frames, int segs_per_frame,
+                   const int* seg_pre_max, float pillar_size, float x0, float y0,
+                   const float* rectifier, const unsigned long long* cand_keys, int cand_cap,
+                   const int* cand_count, float* sorted_boxes, int pre_cap, int* sorted_count,
+                   pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(task && task->maps && seg_pre_max && cand_keys && cand_count && sorted_boxes && sorted_count);
+  PN_REQUIRE(pre_cap > 0 && pre_cap <= kSelSmemKeys && n_frames >= 1);
+  SelectParams P;
+  P.t = to_dev(task);
+  P.n_frames = n_frames;
+  P.segs_per_frame = segs_per_frame;
+  P.seg_lo = task->seg_base;
+  P.seg_hi = task->seg_base + (task->per_class ? task->num_cls : 1);
+  PN_REQUIRE(P.seg_hi - P.seg_lo <= 8 && P.seg_hi <= segs_per_frame);
+  for (int i = 0; i < 8; ++i) P.pre_max[i] = 0;
+  for (int s = P.seg_lo; s < P.seg_hi; ++s) P.pre_max[s - P.seg_lo] = seg_pre_max[s];
+  P.ps = pillar_size; P.x0 = x0; P.y0 = y0;
+  P.use_rect = rectifier != nullptr;
+  for (int i = 0; i < 8; ++i) P.rect[i] = (rectifier && i < task->num_cls) ? rectifier[i] : 0.f;
+  const int blocks = n_frames * (P.seg_hi - P.seg_lo);
+  k_select_topk<<<blocks, kSelThreads, 0, stream>>>(P, cand_keys, cand_cap, cand_count, sorted_boxes,
+                                                    pre_cap, sorted_count);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+size_t pn_nms_scratch_bytes(int n_segs, int pre_cap) {
+  const int pc = round_up64(pre_cap);
+  return geom_bytes(n_segs, pc) + mask_bytes(n_segs, pc);
+}
+
+int pn_nms(int mode, int n_frames, int segs_per_frame, const float* seg_thr,
+           const int* seg_post_max, const int* seg_use_rectified, const float* sorted_boxes,
+           int pre_cap, const int* sorted_count, void* scratch, size_t scratch_bytes, int* keep_idx,
+           int post_cap, int* keep_count, float* det_out, pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(mode == 0 || mode == 1);
+  PN_REQUIRE(seg_thr && seg_post_max && sorted_boxes && sorted_count && scratch && keep_idx &&
+             keep_count && det_out);
+  PN_REQUIRE(n_frames >= 1 && segs_per_frame >= 1 && segs_per_frame <= 16);
+  PN_REQUIRE(pre_cap > 0 && pre_cap % 64 == 0 && pre_cap <= 2048 && post_cap > 0 && post_cap <= 2048);
+  const int n_segs = n_frames * segs_per_frame;
+  if (scratch_bytes < pn_nms_scratch_bytes(n_segs, pre_cap)) return PN_ERR_WORKSPACE;
+  float* geom = (float*)scratch;
+  unsigned long long* mask = (unsigned long long*)((char*)scratch + geom_bytes(n_segs, pre_cap));
+  MaskParams M;
+  M.mode = mode;
+  M.segs_per_frame = segs_per_frame;
+  SweepParams S;
+  S.segs_per_frame = segs_per_frame;
+  for (int i = 0; i < 16; ++i) {
+    M.thr[i] = i < segs_per_frame ? seg_thr[i] : 0.f;
+    S.post_max[i] = i < segs_per_frame ? seg_post_max[i] : 0;
+    S.use_rect[i] = (i < segs_per_frame && seg_use_rectified) ? seg_use_rectified[i] : 0;
+  }
+  if (mode == 0) {
+    k_nms_geom<<<grid_for((long long)n_segs * pre_cap, 256), 256, 0, stream>>>(
+        sorted_boxes, pre_cap, sorted_count, n_segs, geom);
+    PN_CHECK_LAUNCH();
+  }
+  dim3 grid(pre_cap / 64, pre_cap / 64, n_segs);
+  k_nms_mask<<<grid, 64, 0, stream>>>(M, sorted_boxes, geom, pre_cap, sorted_count, mask);
+  PN_CHECK_LAUNCH();
+  k_nms_sweep<<<n_segs, 32, 0, stream>>>(S, sorted_boxes, pre_cap, sorted_count, mask, keep_idx,
+                                         post_cap, keep_count, det_out);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+int pn_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* iou,
+                     pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(boxes_a && boxes_b && iou && na >= 0 && nb >= 0);
+  if (na == 0 || nb == 0) return PN_OK;
+  k_boxes_iou<<<grid_for((long long)na * nb, 256), 256, 0, stream>>>(boxes_a, na, boxes_b, nb, iou);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+// scratch layout: records (n_cap*12 f32) | geom+mask as pn_nms | det (n_cap*11 f32) | counts (2 i32)
+int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t scratch_bytes,
+                   int* keep, int* num_keep, pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(boxes && scratch && keep && num_keep && n >= 0 && n <= 2048);
+  if (n == 0) {
+    PN_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int), stream));
+    return PN_OK;
+  }
+  const int cap = round_up64(n);
+  const size_t rec_b = ((size_t)cap * kBoxRec * sizeof(float) + 255) / 256 * 256;
+  const size_t nms_b = (pn_nms_scratch_bytes(1, cap) + 255) / 256 * 256;
+  const size_t det_b = ((size_t)cap * kDetRec * sizeof(float) + 255) / 256 * 256;
+  if (scratch_bytes < rec_b + nms_b + det_b + 256) return PN_ERR_WORKSPACE;
+  char* p = (char*)scratch;
+  float* rec = (float*)p;
+  void* nms_s = p + rec_b;
+  float* det = (float*)(p + rec_b + nms_b);
+  int* cnt = (int*)(p + rec_b + nms_b + det_b);
+  float* geom = (float*)nms_s;
+  unsigned long long* mask = (unsigned long long*)((char*)nms_s + geom_bytes(1, cap));
+  k_boxes7_to_records<<<PN_DIVUP(n, 256), 256, 0, stream>>>(boxes, n, rec, geom, cnt);
+  PN_CHECK_LAUNCH();
+  MaskParams M;
+  M.mode = 0; M.segs_per_frame = 1;
+  SweepParams S;
+  S.segs_per_frame = 1;
+  for (int i = 0; i < 16; ++i) { M.thr[i] = thr; S.post_max[i] = cap; S.use_rect[i] = 0; }
+  dim3 grid(cap / 64, cap / 64, 1);
+  k_nms_mask<<<grid, 64, 0, stream>>>(M, rec, geom, cap, cnt, mask);
+  PN_CHECK_LAUNCH();
+  k_nms_sweep<<<1, 32, 0, stream>>>(S, rec, cap, cnt, mask, keep, cap, num_keep, det);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+}  // extern "C"

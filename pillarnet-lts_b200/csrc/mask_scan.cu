@@ -1,0 +1,149 @@
+#include "mask_scan.cuh"
+
+#include <mutex>
+#include <string>
+
+namespace pn_detail {
+
+static thread_local std::string g_last_error;
+
+int fail(cudaError_t e) {
+  g_last_error = std::string("CUDA error: ") + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
+  return PN_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  cached = n;
+  return n;
+}
+
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+// ---- kernels ---------------------------------------------------------------------------------
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  // 256 threads: warp shuffle scan + one smem hop.
+  __shared__ int warp_sums[kScanThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  int warp_off = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    int s = warp_sums[w];
+    if (w < warp) warp_off += s;
+    tot += s;
+  }
+  __syncthreads();
+  *total = tot;
+  return warp_off + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_tile_sums(const uint32_t* __restrict__ words, long long n_words, int* __restrict__ tile_sums) {
+  const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kWordsPerThread;
+  int c = 0;
+  if (base + kWordsPerThread <= n_words) {
+    const uint4* p = reinterpret_cast<const uint4*>(words + base);
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    c = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) +
+        __popc(b.z) + __popc(b.w);
+  } else {
+    for (int i = 0; i < kWordsPerThread; ++i)
+      if (base + i < n_words) c += __popc(__ldg(words + base + i));
+  }
+  int tot;
+  (void)block_exclusive_scan(c, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_tile_offsets(const int* __restrict__ tile_sums, int n_tiles, int* __restrict__ tile_offsets,
+               int* __restrict__ num_out) {
+  int carry = 0;
+  for (int base = 0; base < n_tiles; base += kScanThreads) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_tiles ? tile_sums[i] : 0;
+    int tot;
+    const int ex = block_exclusive_scan(v, &tot);
+    if (i < n_tiles) tile_offsets[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) *num_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_emit(const uint32_t* __restrict__ words, long long n_words, const int* __restrict__ tile_offsets,
+       int cells_per_frame, int W, int* __restrict__ prefix, int* __restrict__ coords, int m_cap) {
+  const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kWordsPerThread;
+  uint32_t w[kWordsPerThread];
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < kWordsPerThread; ++i) {
+    w[i] = (base + i < n_words) ? __ldg(words + base + i) : 0u;
+    c += __popc(w[i]);
+  }
+  int tot;
+  int run = tile_offsets[blockIdx.x] + block_exclusive_scan(c, &tot);
+#pragma unroll
+  for (int i = 0; i < kWordsPerThread; ++i) {
+    if (base + i < n_words) prefix[base + i] = run;
+    uint32_t bits = w[i];
+    while (bits && coords != nullptr) {
+      const int bit = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (run < m_cap) {
+        const long long cell = (base + i) * 32 + bit;
+        const int b = (int)(cell / cells_per_frame);
+        const int r = (int)(cell - (long long)b * cells_per_frame);
+        const int y = r / W;
+        int* o = coords + 3ll * run;
+        o[0] = b;
+        o[1] = y;
+        o[2] = r - y * W;
+      }
+      ++run;
+    }
+    if (coords == nullptr) run += __popc(w[i]);
+  }
+}
+
+int mask_scan_emit(const uint32_t* words, int* prefix, long long n_words, int cells_per_frame,
+                   int W, int* coords, int m_cap, int* num_out, void* scratch,
+                   size_t scratch_bytes, cudaStream_t stream) {
+  if (n_words <= 0) return PN_ERR_INVALID_ARG;
+  if (scratch_bytes < scan_scratch_bytes(n_words)) return PN_ERR_WORKSPACE;
+  const int n_tiles = scan_tiles(n_words);
+  int* tile_sums = reinterpret_cast<int*>(scratch);
+  int* tile_offsets = tile_sums + (n_tiles + 1);
+  k_tile_sums<<<n_tiles, kScanThreads, 0, stream>>>(words, n_words, tile_sums);
+  PN_CHECK_LAUNCH();
+  k_tile_offsets<<<1, kScanThreads, 0, stream>>>(tile_sums, n_tiles, tile_offsets, num_out);
+  PN_CHECK_LAUNCH();
+  k_emit<<<n_tiles, kScanThreads, 0, stream>>>(words, n_words, tile_offsets, cells_per_frame, W,
+                                               prefix, coords, m_cap);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+}  // namespace pn_detail
+
+extern "C" {
+int pn_abi_version(void) { return 1; }
+const char* pn_last_error(void) { return pn_detail::last_error_cstr(); }
+int pn_device_sm_count(void) { return pn_detail::sm_count(); }
+size_t pn_mask_words(int n_frames, int H, int W) {
+  return (size_t)pn_detail::n_words((long long)n_frames * H * W);
+}
+}

@@ -1,0 +1,227 @@
+"""Parameter containers and the fused conv(+BN+ReLU+residual) runner shared by backbone/neck/head.
+
+The containers keep the reference's parameter names and layouts so checkpoints load unchanged
+(det3d/torchie/trainer/checkpoint.py:67-137): sparse conv weights are
+(Cout,kH,kW,Cin) as in spconv 2.x, dense convs are plain nn.Conv2d / nn.ConvTranspose2d /
+nn.BatchNorm{1,2}d modules used as *containers* — their torch forward is never called on the
+product path; the math runs in libpillarnet_b200 through ops.conv_gather.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import config, ops
+
+
+class SparseReLU(nn.ReLU):
+    """spconv.pytorch.SparseReLU stand-in (backbones/base.py:3-4,96,105): marker module; the ReLU is
+    fused into the producing conv's epilogue."""
+
+
+class _SparseConvBase(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1,
+                 bias=True, indice_key=None):
+        super().__init__()
+        if kernel_size != 3 or dilation != 1:
+            raise NotImplementedError("only 3x3, dilation 1 sparse convs are on the PillarNet hot path")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding, self.indice_key = kernel_size, stride, padding, indice_key
+        # spconv 2.x layout (Cout, kH, kW, Cin); checkpoint.py:78-87
+        self.weight = nn.Parameter(torch.empty(out_channels, kernel_size, kernel_size, in_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in = self.in_channels * self.kernel_size * self.kernel_size
+            bound = 1 / math.sqrt(fan_in)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def weight_2d(self):
+        return self.weight.detach().reshape(self.out_channels, -1)
+
+
+class SubMConv2d(_SparseConvBase):
+    """spconv.pytorch.SubMConv2d container (backbones/base.py:43-52)."""
+
+
+class SparseConv2d(_SparseConvBase):
+    """spconv.pytorch.SparseConv2d container (PillarResNet.py:87,95,103); stride 2, padding 1."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=2, padding=1, dilation=1,
+                 bias=False, indice_key=None):
+        if stride != 2 or padding != 1:
+            raise NotImplementedError("only stride 2 / padding 1 strided sparse convs are supported")
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, bias, indice_key)
+
+
+class SparseSequential(nn.Sequential):
+    """spconv.pytorch.SparseSequential container: children keep their integer names."""
+
+
+class Sequential(nn.Sequential):
+    """det3d.models.utils.Sequential (models/utils/misc.py:21-95): nn.Sequential with .add()."""
+
+    def add(self, module, name=None):
+        if name is None:
+            name = str(len(self._modules))
+        self.add_module(name, module)
+
+
+def build_norm_layer(cfg, num_features):
+    """det3d/models/utils/norm.py:68-109 for the types the PillarNet configs use."""
+    cfg = dict(cfg)
+    t = cfg.pop("type")
+    cfg.setdefault("eps", 1e-5)
+    if t == "BN":
+        layer = nn.BatchNorm2d(num_features, **cfg)
+    elif t == "BN1d":
+        layer = nn.BatchNorm1d(num_features, **cfg)
+    else:
+        raise NotImplementedError(f"norm type {t}")
+    return t.lower(), layer
+
+
+# ---- lowering: conv (+bias) + BN(eval) -> packed weight, per-channel scale/shift -----------------
+
+def _versions(*tensors):
+    return tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
+
+
+def weight_matrix(conv):
+    """(Cout, taps*Cin) fp32 matrix in tap-major/channel-minor order for any supported container."""
+    if isinstance(conv, _SparseConvBase):
+        return conv.weight.detach().reshape(conv.out_channels, -1)
+    if isinstance(conv, nn.ConvTranspose2d):
+        # weight (Cin,Cout,2,2): out(2y+dy,2x+dx,o) = sum_c in(y,x,c) W[c,o,dy,dx]; tap = dy*2+dx
+        return conv.weight.detach().permute(1, 2, 3, 0).reshape(conv.out_channels, -1)
+    if isinstance(conv, nn.Conv2d):
+        return conv.weight.detach().permute(0, 2, 3, 1).reshape(conv.out_channels, -1)
+    raise TypeError(type(conv))
+
+
+def fold_affine(conv_bias, bn, cout, device):
+    """y = conv*scale + shift with eval-mode BN folded: scale = g/sqrt(var+eps), shift = b + (bias-mean)*scale."""
+    if bn is not None:
+        inv = torch.rsqrt(bn.running_var.detach().double() + bn.eps)
+        g = bn.weight.detach().double() if bn.weight is not None else torch.ones_like(inv)
+        b = bn.bias.detach().double() if bn.bias is not None else torch.zeros_like(inv)
+        scale = g * inv
+        shift = b - bn.running_mean.detach().double() * scale
+        if conv_bias is not None:
+            shift = shift + conv_bias.detach().double() * scale
+    else:
+        scale = torch.ones(cout, dtype=torch.float64, device=device)
+        shift = conv_bias.detach().double() if conv_bias is not None else torch.zeros(cout, dtype=torch.float64, device=device)
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+class Lowered:
+    __slots__ = ("weight", "k_pad", "scale", "shift", "key")
+
+
+def lower(conv, bn, precision=None):
+    """Cached (per module, per precision) packed weight + folded affine; refreshed when a parameter or
+    running statistic changes (tensor._version), e.g. after load_state_dict or an optimiser step."""
+    precision = precision or config.get_precision()
+    bias = getattr(conv, "bias", None)
+    key = (precision,) + _versions(conv.weight, bias,
+                                   *(() if bn is None else (bn.weight, bn.bias, bn.running_mean, bn.running_var)))
+    cache = conv.__dict__.setdefault("_pn_lowered", {})
+    hit = cache.get(precision)
+    if hit is not None and hit.key == key:
+        return hit
+    if bn is not None and bn.training:
+        raise NotImplementedError("training-mode (batch statistics) BN is lowered by the training path only")
+    w2d = weight_matrix(conv).float().contiguous()
+    lw = Lowered()
+    if precision == "bf16":
+        lw.weight = ops.pack_weight_bf16(w2d)
+    else:
+        lw.weight = w2d
+    lw.k_pad = lw.weight.shape[1]
+    lw.scale, lw.shift = fold_affine(bias, bn, w2d.shape[0], w2d.device)
+    lw.key = key
+    cache[precision] = lw
+    return lw
+
+
+def lower_group(convs, bns, precision=None):
+    """Horizontal fusion: several convs reading the same input become one conv with concatenated Cout."""
+    precision = precision or config.get_precision()
+    parts = [lower(c, b, precision) for c, b in zip(convs, bns)]
+    key = tuple(p.key for p in parts)
+    holder = convs[0].__dict__.setdefault("_pn_group", {})
+    hit = holder.get(precision)
+    if hit is not None and hit.key == key:
+        return hit
+    lw = Lowered()
+    lw.weight = torch.cat([p.weight for p in parts], 0).contiguous()
+    lw.k_pad = lw.weight.shape[1]
+    lw.scale = torch.cat([p.scale for p in parts]).contiguous()
+    lw.shift = torch.cat([p.shift for p in parts]).contiguous()
+    lw.key = key
+    holder[precision] = lw
+    return lw
+
+
+def run_conv(x2d, lw, nbr, taps, cin, cout, rows_cap, *, num=None, relu=False, residual=None, out=None,
+             out_coff=0, out_dtype=None, in_ld=None, in_ptr_offset=0):
+    """One fused conv launch on channels-last rows."""
+    if out is None:
+        out = torch.empty(rows_cap, cout, dtype=out_dtype or x2d.dtype, device=x2d.device)
+    ops.conv_gather(x2d, lw.weight, nbr, taps, cin, cout, out, in_ld=in_ld, k_pad=lw.k_pad, scale=lw.scale,
+                    shift=lw.shift, residual=residual, out_coff=out_coff, relu=relu, num=num,
+                    rows_cap=rows_cap, impl=config.conv_impl(), in_ptr_offset=in_ptr_offset)
+    return out
+
+
+class DenseMap:
+    """Channels-last dense BEV map: rows (B*H*W, ld) with the logical channels at [coff, coff+C)."""
+
+    __slots__ = ("rows", "B", "H", "W", "C", "coff")
+
+    def __init__(self, rows, B, H, W, C, coff=0):
+        self.rows, self.B, self.H, self.W, self.C, self.coff = rows, B, H, W, C, coff
+
+    def nchw(self):
+        """(B,C,H,W) view (channels_last strides), the reference's dense layout."""
+        v = self.rows.view(self.B, self.H, self.W, -1)[..., self.coff:self.coff + self.C].permute(0, 3, 1, 2)
+        v._pn_dense = self  # lets the next module recover the NHWC rows without a copy
+        return v
+
+    @staticmethod
+    def from_nchw(t):
+        d = getattr(t, "_pn_dense", None)
+        if d is not None:
+            return d
+        B, C, H, W = t.shape
+        rows = t.permute(0, 2, 3, 1).contiguous().view(B * H * W, C)
+        if rows.dtype != config.act_dtype():
+            rows = rows.to(config.act_dtype())
+        return DenseMap(rows, B, H, W, C)
+
+
+def dense_conv3x3(x, conv, bn, relu=True, stride=1, out=None, out_coff=0, out_dtype=None):
+    """3x3 pad-1 dense conv (also ZeroPad2d(1)+valid conv, necks/rpn.py:172-176) on a DenseMap."""
+    Ho, Wo = (x.H + 2 - 3) // stride + 1, (x.W + 2 - 3) // stride + 1
+    nbr = ops.dense_nbr_table(0, x.B, x.H, x.W, stride, x.rows.device)
+    lw = lower(conv, bn)
+    cout = conv.out_channels
+    rows_cap = x.B * Ho * Wo
+    o = run_conv(x.rows, lw, nbr, 9, x.C, cout, rows_cap, relu=relu, out=out, out_coff=out_coff,
+                 out_dtype=out_dtype, in_ld=x.rows.stride(0), in_ptr_offset=x.coff)
+    return DenseMap(o, x.B, Ho, Wo, cout, out_coff)
+
+
+def dense_deconv2x2(x, conv, bn, relu=True, out=None, out_coff=0):
+    """ConvTranspose2d(k=2,s=2)+BN+ReLU (necks/rpn.py:150-154) as a 4-tap gather conv."""
+    nbr = ops.dense_nbr_table(1, x.B, x.H, x.W, 2, x.rows.device)
+    lw = lower(conv, bn)
+    cout = conv.out_channels
+    rows_cap = x.B * 4 * x.H * x.W
+    o = run_conv(x.rows, lw, nbr, 4, x.C, cout, rows_cap, relu=relu, out=out, out_coff=out_coff,
+                 in_ld=x.rows.stride(0), in_ptr_offset=x.coff)
+    return DenseMap(o, x.B, 2 * x.H, 2 * x.W, cout, out_coff)

@@ -1,0 +1,283 @@
+"""Functional wrappers over the C ABI (one Python function per pn_* entry point).
+
+All functions are asynchronous on torch's current CUDA stream, allocate their outputs with torch
+(caller-owned memory, as the ABI requires) and never synchronise the host, so a whole forward pass
+built from them can be captured in a CUDA graph.  Row counts only the device knows stay on the device
+(`num` tensors) next to host capacities.
+"""
+import ctypes
+from ctypes import byref, c_float, c_int, c_size_t, c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import (PN_BF16, PN_F32, PN_IMPL_SIMT, PN_IMPL_TCGEN05, ConvArgs, TaskArgs, check, farr,
+                   iarr, ptr, require_cuda, stream_ptr)
+
+_DT = {torch.float32: PN_F32, torch.bfloat16: PN_BF16}
+
+
+def _i32(*shape, device):
+    return torch.empty(*shape, dtype=torch.int32, device=device)
+
+
+class RankTable:
+    """Occupancy bitmask + popcount prefix of one (B,H,W) raster and its active rows.
+
+    coords (cap,3) int32 [b,y,x] in ascending cell order; num: device int32 scalar (1,) ; cap: host.
+    """
+
+    __slots__ = ("words", "prefix", "coords", "num", "cap", "B", "H", "W", "_nbr_subm")
+
+    def __init__(self, words, prefix, coords, num, cap, B, H, W):
+        self.words, self.prefix, self.coords, self.num = words, prefix, coords, num
+        self.cap, self.B, self.H, self.W = cap, B, H, W
+        self._nbr_subm = None
+
+    def count(self):
+        """host sync: number of active rows"""
+        return min(int(self.num.item()), self.cap)
+
+    def subm_nbr(self):
+        """cached 3x3 submanifold neighbour table (cap,9) int32 (the `indice_key` cache of spconv)."""
+        if self._nbr_subm is None:
+            self._nbr_subm = rulebook_subm3x3(self)
+        return self._nbr_subm
+
+
+def pillarize(points, frame_offsets, n_frames, H, W, x0, y0, pillar_size, m_cap=None):
+    """points (N,D) f32 cuda (frames concatenated), frame_offsets (B+1,) int32 cuda.
+
+    Returns (RankTable, point_pillar (N,) int32).  See pn_pillarize in include/pillarnet_b200.h.
+    """
+    lib = _lib.load()
+    require_cuda(points, frame_offsets)
+    if points.dtype != torch.float32 or points.dim() != 2:
+        raise RuntimeError("points must be (N,D) float32")
+    if frame_offsets.dtype != torch.int32 or frame_offsets.numel() != n_frames + 1:
+        raise RuntimeError("frame_offsets must be (B+1,) int32")
+    dev = points.device
+    N, D = points.shape
+    if m_cap is None:
+        m_cap = max(1, min(N, n_frames * H * W))
+    nw = lib.pn_mask_words(n_frames, H, W)
+    words = _i32(nw, device=dev)
+    prefix = _i32(nw, device=dev)
+    coords = _i32(m_cap, 3, device=dev)
+    point_pillar = _i32(max(N, 1), device=dev)
+    num = _i32(1, device=dev)
+    sb = lib.pn_pillarize_scratch_bytes(n_frames, H, W)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
+    # the reference's CUDA expression divides by multiplying with the fp32 reciprocal
+    inv = (torch.tensor(1.0, dtype=torch.float32) / torch.tensor(pillar_size, dtype=torch.float32)).item()
+    check(lib.pn_pillarize(ptr(points), D, ptr(frame_offsets), N, n_frames, H, W,
+                           c_float(_f32(x0)), c_float(_f32(y0)), c_float(inv), ptr(words), ptr(prefix),
+                           ptr(coords), m_cap, ptr(point_pillar), ptr(num), ptr(scratch), c_size_t(sb),
+                           stream_ptr()), "pn_pillarize")
+    return RankTable(words, prefix, coords, num, m_cap, n_frames, H, W), point_pillar[:N]
+
+
+def _f32(v):
+    """round a Python double to fp32 the way torch does for scalar operands"""
+    return torch.tensor(float(v), dtype=torch.float32).item()
+
+
+def pfn_scatter_max(points, point_pillar, table, x0, y0, pillar_size, x_offset, y_offset, weight,
+                    scale, shift, want_bf16=False, want_arg=False):
+    """Fused offset features + Linear + affine(BN) + ReLU + per-pillar max. Returns (f32, bf16|None, arg|None)."""
+    lib = _lib.load()
+    require_cuda(points, point_pillar, weight, scale, shift)
+    N, D = points.shape
+    C = weight.shape[0]
+    if weight.shape[1] != D + 2:
+        raise RuntimeError(f"PFN weight must be (C,{D + 2})")
+    dev = points.device
+    out = torch.empty(table.cap, C, dtype=torch.float32, device=dev)
+    out_bf = torch.empty(table.cap, C, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    arg = _i32(table.cap, C, device=dev) if want_arg else None
+    inv = (torch.tensor(1.0, dtype=torch.float32) / torch.tensor(pillar_size, dtype=torch.float32)).item()
+    check(lib.pn_pfn_scatter_max(ptr(points), D, N, ptr(point_pillar), ptr(table.num), table.cap,
+                                 c_float(_f32(x0)), c_float(_f32(y0)), c_float(inv),
+                                 c_float(_f32(pillar_size)), c_float(_f32(x_offset)),
+                                 c_float(_f32(y_offset)), ptr(weight), ptr(scale), ptr(shift), C,
+                                 ptr(out), ptr(out_bf), ptr(arg), stream_ptr()), "pn_pfn_scatter_max")
+    return out, out_bf, arg
+
+
+def scatter_max_grad(grad_out, arg, table, n_points):
+    lib = _lib.load()
+    require_cuda(grad_out, arg)
+    C = grad_out.shape[1]
+    grad_src = torch.zeros(n_points, C, dtype=torch.float32, device=grad_out.device)
+    check(lib.pn_scatter_max_grad(ptr(grad_out), ptr(arg), ptr(table.num), table.cap, C, ptr(grad_src),
+                                  stream_ptr()), "pn_scatter_max_grad")
+    return grad_src
+
+
+def rulebook_subm3x3(table):
+    lib = _lib.load()
+    nbr = _i32(table.cap, 9, device=table.coords.device)
+    check(lib.pn_rulebook_subm3x3(ptr(table.words), ptr(table.prefix), ptr(table.coords), ptr(table.num),
+                                  table.cap, table.H, table.W, ptr(nbr), stream_ptr()),
+          "pn_rulebook_subm3x3")
+    return nbr
+
+
+def rulebook_down3x3s2(table, out_cap=None):
+    """Strided 3x3/s2/p1 rulebook. Returns (out RankTable, nbr (out_cap,9) int32 into input rows)."""
+    lib = _lib.load()
+    dev = table.coords.device
+    Ho, Wo = (table.H + 2 - 3) // 2 + 1, (table.W + 2 - 3) // 2 + 1
+    if out_cap is None:
+        out_cap = max(1, min(table.cap, table.B * Ho * Wo))
+    nw = lib.pn_mask_words(table.B, Ho, Wo)
+    words, prefix = _i32(nw, device=dev), _i32(nw, device=dev)
+    coords = _i32(out_cap, 3, device=dev)
+    num = _i32(1, device=dev)
+    nbr = _i32(out_cap, 9, device=dev)
+    sb = lib.pn_rulebook_down_scratch_bytes(table.B, Ho, Wo)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
+    check(lib.pn_rulebook_down3x3s2(ptr(table.words), ptr(table.prefix), ptr(table.coords),
+                                    ptr(table.num), table.cap, table.B, table.H, table.W, ptr(words),
+                                    ptr(prefix), ptr(coords), ptr(num), out_cap, ptr(nbr), ptr(scratch),
+                                    c_size_t(sb), stream_ptr()), "pn_rulebook_down3x3s2")
+    return RankTable(words, prefix, coords, num, out_cap, table.B, Ho, Wo), nbr
+
+
+_dense_nbr_cache = {}
+
+
+def dense_nbr_table(mode, n_frames, H, W, stride, device):
+    """Static gather table for dense NHWC convs; cached per (mode,B,H,W,stride,device)."""
+    key = (mode, n_frames, H, W, stride, str(device))
+    t = _dense_nbr_cache.get(key)
+    if t is None:
+        lib = _lib.load()
+        if mode == 0:
+            Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+            t = _i32(n_frames * Ho * Wo, 9, device=device)
+        else:
+            t = _i32(n_frames * 4 * H * W, 4, device=device)
+        check(lib.pn_dense_nbr_table(mode, n_frames, H, W, stride, ptr(t), stream_ptr()),
+              "pn_dense_nbr_table")
+        _dense_nbr_cache[key] = t
+    return t
+
+
+def conv_gather(inp, weight, nbr, taps, cin, cout, out, *, in_ld=None, k_pad=None, scale=None,
+                shift=None, residual=None, res_ld=None, out_ld=None, out_coff=0, relu=False, num=None,
+                rows_cap=None, impl=PN_IMPL_SIMT, in_ptr_offset=0):
+    """out[o, coff:coff+cout] = act((sum_t W_t . in[nbr[o,t]]) * scale + shift + residual).
+
+    `inp`/`out` are 2-D channels-last tensors (possibly wider than cin/cout: in_ld/out_ld are the
+    row strides in elements; in_ptr_offset selects a channel slice of the input)."""
+    lib = _lib.load()
+    a = ConvArgs()
+    es = inp.element_size()
+    a.inp = c_void_p(inp.data_ptr() + in_ptr_offset * es)
+    a.in_dtype = _DT[inp.dtype]
+    a.in_ld = in_ld if in_ld is not None else inp.stride(0)
+    a.nbr = ptr(nbr).value
+    a.taps = taps
+    if weight.dtype != inp.dtype:
+        raise RuntimeError("weight dtype must match the input dtype")
+    a.weight = weight.data_ptr()
+    a.k_pad = k_pad if k_pad is not None else weight.stride(0)
+    a.scale = ptr(scale).value
+    a.shift = ptr(shift).value
+    a.residual = ptr(residual).value
+    a.res_ld = res_ld if res_ld is not None else (residual.stride(0) if residual is not None else 0)
+    a.out = out.data_ptr()
+    a.out_dtype = _DT[out.dtype]
+    a.out_ld = out_ld if out_ld is not None else out.stride(0)
+    a.out_coff = out_coff
+    a.relu = 1 if relu else 0
+    a.num_rows = ptr(num).value
+    a.rows_cap = rows_cap if rows_cap is not None else out.shape[0]
+    a.cin, a.cout = cin, cout
+    if residual is not None and residual.dtype != out.dtype:
+        raise RuntimeError("residual dtype must match the output dtype")
+    check(lib.pn_conv_gather(byref(a), impl, stream_ptr()), "pn_conv_gather")
+    return out
+
+
+def pack_weight_bf16(w_f32_2d, k_pad=None):
+    """(Cout,K) f32 -> (Cout,k_pad) bf16 with K zero-padded to a multiple of 64."""
+    lib = _lib.load()
+    require_cuda(w_f32_2d)
+    cout, k = w_f32_2d.shape
+    if k_pad is None:
+        k_pad = (k + 63) // 64 * 64
+    out = torch.empty(cout, k_pad, dtype=torch.bfloat16, device=w_f32_2d.device)
+    check(lib.pn_conv_pack_weight_bf16(ptr(w_f32_2d), cout, k, k_pad, ptr(out), stream_ptr()),
+          "pn_conv_pack_weight_bf16")
+    return out
+
+
+def cast_rows(inp, dtype, num=None):
+    lib = _lib.load()
+    rows, cols = inp.shape
+    out = torch.empty(rows, cols, dtype=dtype, device=inp.device)
+    if inp.dtype == torch.float32 and dtype == torch.bfloat16:
+        fn, name = lib.pn_cast_f32_to_bf16, "pn_cast_f32_to_bf16"
+    elif inp.dtype == torch.bfloat16 and dtype == torch.float32:
+        fn, name = lib.pn_cast_bf16_to_f32, "pn_cast_bf16_to_f32"
+    else:
+        raise RuntimeError("unsupported cast")
+    check(fn(ptr(inp), inp.stride(0), ptr(out), out.stride(0), cols, ptr(num), rows, stream_ptr()), name)
+    return out
+
+
+def sparse_to_dense(feat, table, C, out=None, out_coff=0):
+    """NHWC densify: returns (B*H*W, out_ld) tensor whose [coff,coff+C) columns hold the features."""
+    lib = _lib.load()
+    n_cells = table.B * table.H * table.W
+    if out is None:
+        out = torch.empty(n_cells, C, dtype=feat.dtype, device=feat.device)
+    check(lib.pn_sparse_to_dense(ptr(feat), _DT[feat.dtype], feat.stride(0), ptr(table.words),
+                                 ptr(table.prefix), table.B, table.H, table.W, C, ptr(out),
+                                 out.stride(0), out_coff, stream_ptr()), "pn_sparse_to_dense")
+    return out
+
+
+def make_task_args(maps, offsets, num_cls, H, W, stride, seg_base, per_class):
+    t = TaskArgs()
+    t.maps = maps.data_ptr()
+    t.ld = maps.stride(0)
+    t.off_reg = offsets.get("reg", -1)
+    t.off_height = offsets.get("height", -1)
+    t.off_dim = offsets.get("dim", -1)
+    t.off_rot = offsets.get("rot", -1)
+    t.off_vel = offsets.get("vel", -1)
+    t.off_iou = offsets.get("iou", -1)
+    t.off_hm = offsets.get("hm", -1)
+    t.num_cls, t.H, t.W, t.stride = num_cls, H, W, stride
+    t.seg_base, t.per_class = seg_base, 1 if per_class else 0
+    return t
+
+
+def boxes_iou_bev(boxes_a, boxes_b):
+    """drop-in for iou3d_nms_cuda.boxes_iou_bev_gpu (iou3d_nms.cpp:90-110)."""
+    lib = _lib.load()
+    require_cuda(boxes_a, boxes_b)
+    out = torch.empty(boxes_a.shape[0], boxes_b.shape[0], dtype=torch.float32, device=boxes_a.device)
+    check(lib.pn_boxes_iou_bev(ptr(boxes_a), boxes_a.shape[0], ptr(boxes_b), boxes_b.shape[0], ptr(out),
+                               stream_ptr()), "pn_boxes_iou_bev")
+    return out
+
+
+def nms_rotated(boxes, thr):
+    """drop-in for iou3d_nms_cuda.nms_gpu (iou3d_nms.cpp:113-159): boxes (n,7) already score-sorted.
+
+    Returns (keep int32 (n,), num_keep int32 (1,)) on the device (no host round trip)."""
+    lib = _lib.load()
+    require_cuda(boxes)
+    n = boxes.shape[0]
+    cap = max(64, (n + 63) // 64 * 64)
+    sb = (cap * 12 * 4 + 256) + (lib.pn_nms_scratch_bytes(1, cap) + 256) + (cap * 11 * 4 + 256) + 512
+    scratch = torch.empty(sb, dtype=torch.uint8, device=boxes.device)
+    keep = _i32(cap, device=boxes.device)
+    num = _i32(1, device=boxes.device)
+    check(lib.pn_nms_rotated(ptr(boxes), n, c_float(thr), ptr(scratch), c_size_t(sb), ptr(keep), ptr(num),
+                             stream_ptr()), "pn_nms_rotated")
+    return keep, num

@@ -1,0 +1,103 @@
+"""Dynamic pillar feature encoder: det3d's `DynamicPFE` reader and `PillarMaxPooling` op module.
+
+Interface mirrors det3d/models/readers/dynamic_pillar_encoder.py:8-50 and
+det3d/ops/pillar_ops/pillar_modules.py:8-74 (same constructor kwargs, same attribute and parameter
+names: reader.pfn_layers.shared_mlps.{0.weight, 1.*}); the computation is two C-ABI calls
+(pn_pillarize, pn_pfn_scatter_max) instead of ~50 torch/extension launches and 4 host syncs.
+"""
+import torch
+from torch import nn
+
+from . import config, ops
+from .registry import READERS
+from .sparse import SparseConvTensor
+
+
+def bev_spatial_shape(pillar_size, point_cloud_range):
+    """det3d/ops/pillar_ops/pillar_utils.py:7-10."""
+    W = round((point_cloud_range[3] - point_cloud_range[0]) / pillar_size)
+    H = round((point_cloud_range[4] - point_cloud_range[1]) / pillar_size)
+    return int(H), int(W)
+
+
+class PillarMaxPooling(nn.Module):
+    def __init__(self, mlps, pillar_size, point_cloud_range, activation="relu"):
+        super().__init__()
+        if activation != "relu":
+            raise NotImplementedError("only ReLU is fused (all PillarNet configs use it)")
+        if len(mlps) != 2:
+            raise NotImplementedError("the fused PFN supports one Linear+BN+ReLU layer (num_filters=(C,))")
+        self.pillar_size = pillar_size
+        self.point_cloud_range = list(point_cloud_range)
+        self.height, self.width = bev_spatial_shape(pillar_size, point_cloud_range)
+        # offsets formed in double as pillar_utils.py:19-20
+        self.x_offset = pillar_size / 2.0 + point_cloud_range[0]
+        self.y_offset = pillar_size / 2.0 + point_cloud_range[1]
+        self.shared_mlps = nn.Sequential(
+            nn.Linear(mlps[0], mlps[1], bias=False),
+            nn.BatchNorm1d(mlps[1], momentum=0.01, eps=1e-3),
+            nn.ReLU(),
+        )
+        nn.init.kaiming_normal_(self.shared_mlps[0].weight)  # pillar_modules.py:35-54
+
+    def folded(self):
+        """(weight (C,7) f32, scale (C), shift (C)) with eval BN folded; cached on parameter versions."""
+        lin, bn = self.shared_mlps[0], self.shared_mlps[1]
+        key = tuple((t.data_ptr(), t._version) for t in
+                    (lin.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var))
+        hit = self.__dict__.get("_pn_folded")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        if bn.training:
+            raise NotImplementedError("training-mode PFN is handled by the training path")
+        inv = torch.rsqrt(bn.running_var.detach().double() + bn.eps)
+        scale = (bn.weight.detach().double() * inv)
+        shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+        val = (lin.weight.detach().float().contiguous(), scale.float().contiguous(), shift.float().contiguous())
+        self.__dict__["_pn_folded"] = (key, val)
+        return val
+
+    def forward(self, points, frame_offsets, batch_size):
+        """points (N,D) f32 concatenated frames; frame_offsets (B+1,) int32 device."""
+        table, point_pillar = ops.pillarize(points, frame_offsets, batch_size, self.height, self.width,
+                                            self.point_cloud_range[0], self.point_cloud_range[1],
+                                            self.pillar_size)
+        w, scale, shift = self.folded()
+        want_bf16 = config.get_precision() == "bf16"
+        f32, bf16, _ = ops.pfn_scatter_max(points, point_pillar, table, self.point_cloud_range[0],
+                                           self.point_cloud_range[1], self.pillar_size, self.x_offset,
+                                           self.y_offset, w, scale, shift, want_bf16=want_bf16)
+        sp = SparseConvTensor(bf16 if want_bf16 else f32, table, (self.height, self.width), batch_size)
+        sp.features_f32 = f32
+        sp.point_pillar = point_pillar
+        return sp
+
+
+@READERS.register_module
+class DynamicPFE(nn.Module):
+    def __init__(self, in_channels=5, num_filters=(32,), pillar_size=0.1,
+                 pc_range=(0, -40, -3, 70.4, 40, 1)):
+        super().__init__()
+        self.pillar_size = pillar_size
+        self.pc_range = pc_range
+        assert len(num_filters) > 0
+        num_filters = [2 + in_channels] + list(num_filters)
+        self.pfn_layers = PillarMaxPooling(mlps=num_filters, pillar_size=pillar_size,
+                                           point_cloud_range=pc_range)
+        self.height, self.width = self.pfn_layers.height, self.pfn_layers.width
+
+    def forward(self, data, **kwargs):
+        """data["points"]: list of B (Ni,D) f32 CUDA tensors (det3d) or a pre-batched
+        (points (N,D), frame_offsets (B+1,) int32) pair under data["points_batched"]."""
+        if "points_batched" in data:
+            points, offsets = data["points_batched"]
+            B = offsets.numel() - 1
+        else:
+            pts = data["points"]
+            B = len(pts)
+            counts = [0]
+            for p in pts:
+                counts.append(counts[-1] + p.shape[0])
+            points = pts[0] if B == 1 else torch.cat(pts, 0)
+            offsets = torch.tensor(counts, dtype=torch.int32).to(points.device, non_blocking=True)
+        return self.pfn_layers(points.contiguous(), offsets, B)
