@@ -160,6 +160,9 @@ typedef struct pn_conv_args {
 } pn_conv_args;
 
 int pn_conv_gather(const pn_conv_args* args, int impl, pn_stream_t stream);
+/* sizeof() of the two argument structs, so a foreign binding can verify its layout. */
+size_t pn_sizeof_conv_args(void);
+size_t pn_sizeof_task_args(void);
 
 /* f32 -> bf16 weight packing with zero padding of K to k_pad (multiple of 64). */
 int pn_conv_pack_weight_bf16(const float* w_f32, int cout, int k, int k_pad, void* w_bf16,

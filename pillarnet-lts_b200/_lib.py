@@ -63,6 +63,8 @@ SIGNATURES = {
                                       c_void_p, c_size_t, c_void_p]),
     "pn_dense_nbr_table": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pn_conv_gather": (c_int, [POINTER(ConvArgs), c_int, c_void_p]),
+    "pn_sizeof_conv_args": (c_size_t, []),
+    "pn_sizeof_task_args": (c_size_t, []),
     "pn_conv_pack_weight_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pn_cast_f32_to_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pn_cast_bf16_to_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),

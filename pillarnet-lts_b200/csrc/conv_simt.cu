@@ -195,6 +195,9 @@ int pn_conv_gather(const pn_conv_args* a, int impl, pn_stream_t stream_) {
   return launch_simt<float, __nv_bfloat16>(a, stream);
 }
 
+size_t pn_sizeof_conv_args(void) { return sizeof(pn_conv_args); }
+size_t pn_sizeof_task_args(void) { return sizeof(pn_task_args); }
+
 int pn_conv_pack_weight_bf16(const float* w_f32, int cout, int k, int k_pad, void* w_bf16,
                              pn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;

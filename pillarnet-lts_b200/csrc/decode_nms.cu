@@ -93,8 +93,6 @@ k_decode_candidates(DecodeParams P, unsigned long long* __restrict__ keys, int c
     const int b = (int)(g / hw), pix = (int)(g - (long long)b * hw);
     const int i = pix / t.W, j = pix - i * t.W;
     const float* row = t.maps + g * t.ld;
-    // cheap early-out on the raw logit: sigmoid is monotone, so a pixel whose largest logit maps
-    // to a score <= thr can never pass; evaluated with the same sigmoid to keep the decision exact.
     const Pix p = decode_pixel(t, row, i, j, P.ps, P.x0, P.y0, P.use_rect ? P.rect : nullptr);
     bool ok = p.score > P.score_thr;
     if (P.use_range) {
@@ -274,7 +272,7 @@ __global__ void __launch_bounds__(64)
 k_nms_mask(MaskParams P, const float* __restrict__ sorted_boxes, const float* __restrict__ geom,
            int pre_cap, const int* __restrict__ sorted_count, unsigned long long* __restrict__ mask) {
   const int seg = blockIdx.z;
-  const int n = sorted_count[seg];
+  const int n = min(sorted_count[seg], pre_cap);
   const int rb = blockIdx.y, cb = blockIdx.x;
   if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
   const int col_blocks = pre_cap / 64;
@@ -352,23 +350,23 @@ struct SweepParams {
   int use_rect[16];
 };
 
-// One warp per segment.  Lane l owns removal word l (pre_cap <= 2048).  Per 64-box block: the
-// diagonal tile is resolved serially from shared memory, then the rows of the boxes kept in this
-// block are OR-ed into the lanes' words with independent, coalesced loads.
+// One warp per segment.  Removal word w (64 boxes) lives in lane w%32, slot w/32 (pre_cap <= 4096).
+// Per 64-box block: the diagonal tile is resolved serially from shared memory, then the rows of the
+// boxes kept in this block are OR-ed into the lanes' words with independent, coalesced loads.
 __global__ void __launch_bounds__(32)
 k_nms_sweep(SweepParams P, const float* __restrict__ sorted_boxes, int pre_cap,
             const int* __restrict__ sorted_count, const unsigned long long* __restrict__ mask,
             int* __restrict__ keep_idx, int post_cap, int* __restrict__ keep_count,
             float* __restrict__ det_out) {
   const int seg = blockIdx.x, lane = threadIdx.x;
-  const int n = sorted_count[seg];
+  const int n = min(sorted_count[seg], pre_cap);
   const int col_blocks = pre_cap / 64;
   const int post = min(P.post_max[seg % P.segs_per_frame], post_cap);
   const int use_rect = P.use_rect[seg % P.segs_per_frame];
   const long long base = (long long)seg * pre_cap;
   __shared__ unsigned long long s_diag[64];
-  __shared__ int s_keep[2048];
-  unsigned long long remv = 0ull;
+  __shared__ int s_keep[4096];
+  unsigned long long remv[2] = {0ull, 0ull};
   int kept = 0;
   const int nblk = (n + 63) / 64;
   for (int blk = 0; blk < nblk && kept < post; ++blk) {
@@ -376,7 +374,7 @@ k_nms_sweep(SweepParams P, const float* __restrict__ sorted_boxes, int pre_cap,
     for (int r = lane; r < 64; r += 32)
       s_diag[r] = r < rows ? mask[(base + blk * 64 + r) * col_blocks + blk] : 0ull;
     __syncwarp();
-    unsigned long long cur = __shfl_sync(0xffffffffu, remv, blk);
+    unsigned long long cur = __shfl_sync(0xffffffffu, blk < 32 ? remv[0] : remv[1], blk & 31);
     unsigned long long kept_bits = 0ull;
     int kept_here = 0;
     for (int r = 0; r < rows; ++r) {
@@ -390,15 +388,19 @@ k_nms_sweep(SweepParams P, const float* __restrict__ sorted_boxes, int pre_cap,
       }
     }
     kept += kept_here;
-    if (lane > blk && lane < col_blocks) {
-      unsigned long long acc = 0ull;
-      unsigned long long bits = kept_bits;
-      while (bits) {
-        const int r = __ffsll((long long)bits) - 1;
-        bits &= bits - 1;
-        acc |= mask[(base + blk * 64 + r) * col_blocks + lane];
+#pragma unroll
+    for (int slot = 0; slot < 2; ++slot) {
+      const int w = lane + 32 * slot;
+      if (w > blk && w < col_blocks) {
+        unsigned long long acc = 0ull;
+        unsigned long long bits = kept_bits;
+        while (bits) {
+          const int r = __ffsll((long long)bits) - 1;
+          bits &= bits - 1;
+          acc |= mask[(base + blk * 64 + r) * col_blocks + w];
+        }
+        remv[slot] |= acc;
       }
-      remv |= acc;
     }
     __syncwarp();
   }
@@ -548,7 +550,7 @@ int pn_nms(int mode, int n_frames, int segs_per_frame, const float* seg_thr,
   PN_REQUIRE(seg_thr && seg_post_max && sorted_boxes && sorted_count && scratch && keep_idx &&
              keep_count && det_out);
   PN_REQUIRE(n_frames >= 1 && segs_per_frame >= 1 && segs_per_frame <= 16);
-  PN_REQUIRE(pre_cap > 0 && pre_cap % 64 == 0 && pre_cap <= 2048 && post_cap > 0 && post_cap <= 2048);
+  PN_REQUIRE(pre_cap > 0 && pre_cap % 64 == 0 && pre_cap <= 4096 && post_cap > 0 && post_cap <= 4096);
   const int n_segs = n_frames * segs_per_frame;
   if (scratch_bytes < pn_nms_scratch_bytes(n_segs, pre_cap)) return PN_ERR_WORKSPACE;
   float* geom = (float*)scratch;
@@ -591,7 +593,7 @@ int pn_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb,
 int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t scratch_bytes,
                    int* keep, int* num_keep, pn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  PN_REQUIRE(boxes && scratch && keep && num_keep && n >= 0 && n <= 2048);
+  PN_REQUIRE(boxes && scratch && keep && num_keep && n >= 0 && n <= 4096);
   if (n == 0) {
     PN_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int), stream));
     return PN_OK;

@@ -1,0 +1,149 @@
+"""Generates the committed golden vectors by EXECUTING the reference's own code in the build container.
+
+Run:  python tests/golden/make_golden.py      (needs /root/reference and oracle/_ref; see _ref_import.py)
+
+Fixtures (all small .npz):
+  iou_pairs.npz          det3d/ops/iou3d_nms/src/iou3d_cpu.cpp:232-250 boxes_iou_bev_cpu on seeded boxes
+  circle_nms.npz         det3d/core/utils/circle_nms_jit.py:4-28 (numba) keep lists
+  head_predict_circle.npz det3d/models/bbox_heads/center_head.py:216-413 CenterHead.predict (circular_nms)
+  neck_head_forward.npz  det3d/models/necks/rpn.py:137-207 RPNV1 + center_head.py:116-127 forward (torch CPU)
+  set_by_task_cfg.json   det3d/core/utils/center_utils.py:229-274 on the Waymo FPN test_cfg
+"""
+import json
+import logging
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import _ref_import  # noqa: E402
+
+_ref_import.setup()
+
+from det3d.core.utils.circle_nms_jit import circle_nms  # noqa: E402
+from det3d.core.utils.center_utils import set_by_task_cfg  # noqa: E402
+from det3d.models.bbox_heads.center_head import CenterHead  # noqa: E402
+from det3d.models.necks.rpn import RPNV1  # noqa: E402
+from det3d.torchie import Config  # noqa: E402
+import det3d.ops.iou3d_nms.iou3d_nms_cuda as iou3d  # noqa: E402
+
+
+def rand_boxes(rng, n, spread=10.0):
+    b = np.zeros((n, 7), np.float32)
+    b[:, 0:2] = rng.uniform(-spread, spread, (n, 2))
+    b[:, 2] = rng.uniform(-1, 1, n)
+    b[:, 3] = rng.uniform(0.3, 5, n)
+    b[:, 4] = rng.uniform(0.3, 2.5, n)
+    b[:, 5] = rng.uniform(0.5, 2, n)
+    b[:, 6] = rng.uniform(-4, 4, n)
+    return b
+
+
+def gen_iou():
+    rng = np.random.default_rng(11)
+    A = rand_boxes(rng, 96)
+    B = rand_boxes(rng, 96)
+    B[:32] = A[:32] + rng.normal(0, 0.05, (32, 7)).astype(np.float32)       # near duplicates
+    B[32:40] = A[32:40]                                                      # identical
+    A[40:56, 3:5] = rng.uniform(0.4, 0.9, (16, 2))                           # pedestrian-sized
+    B[40:56] = A[40:56] + rng.normal(0, 0.02, (16, 7)).astype(np.float32)
+    B[56:60, 6] = A[56:60, 6] + np.float32(np.pi / 2)                        # axis swaps
+    B[56:60, :2] = A[56:60, :2]
+    out = torch.zeros(len(A), len(B))
+    iou3d.boxes_iou_bev_cpu(torch.from_numpy(A), torch.from_numpy(B), out)
+    np.savez_compressed(os.path.join(HERE, "iou_pairs.npz"), a=A, b=B, iou=out.numpy())
+
+
+def gen_circle():
+    rng = np.random.default_rng(12)
+    cases = {}
+    for i, (n, thr) in enumerate([(200, 4.0), (500, 0.85), (64, 0.175)]):
+        d = np.zeros((n, 3), np.float32)
+        d[:, :2] = rng.uniform(-20, 20, (n, 2))
+        d[:, 2] = rng.permutation(n).astype(np.float32) / n * 0.9 + 0.1   # distinct scores
+        keep = np.array(circle_nms(d, thresh=thr), np.int64)
+        cases[f"dets{i}"], cases[f"thr{i}"], cases[f"keep{i}"] = d, np.float64(thr), keep
+    np.savez_compressed(os.path.join(HERE, "circle_nms.npz"), **cases)
+
+
+def gen_predict():
+    rng = np.random.default_rng(13)
+    tasks = [dict(stride=8, class_names=["car"]), dict(stride=8, class_names=["ped", "cone"])]
+    ps, pcr = 0.075, [-54, -54, -5.0, 54, 54, 3.0]
+    head = CenterHead(tasks=[Config(t) for t in tasks], in_channels=[16], code_weights=[1.0] * 10,
+                      common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2)},
+                      share_channel=8, pillar_size=ps, point_cloud_range=pcr, logger=logging.getLogger("g"))
+    B, H, W = 2, 40, 40
+    test_cfg = Config(dict(circular_nms=True, min_radius=[4.0, 0.85],
+                           nms=dict(nms_pre_max_size=[1000, 1000], nms_post_max_size=[83, 83], nms_iou_threshold=0.2),
+                           score_threshold=0.1, post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]))
+    preds, save = [], {}
+    for t, task in enumerate(tasks):
+        K = len(task["class_names"])
+        d = {}
+        for name, c in (("reg", 2), ("height", 1), ("dim", 3), ("rot", 2), ("vel", 2), ("hm", K)):
+            v = rng.normal(0, 0.7, (B, c, H, W)).astype(np.float32)
+            if name == "hm":
+                v = rng.normal(-3.5, 1.5, (B, c, H, W)).astype(np.float32)
+            if name == "reg":
+                v = rng.uniform(0, 1, (B, c, H, W)).astype(np.float32)
+            d[name] = torch.from_numpy(v)
+            save[f"t{t}_{name}"] = v
+        preds.append(d)
+    rets = head.predict({"metadata": [None] * B}, [dict((k, v.clone()) for k, v in p.items()) for p in preds], test_cfg)
+    for b, r in enumerate(rets):
+        save[f"out{b}_boxes"] = r["box3d_lidar"].numpy()
+        save[f"out{b}_scores"] = r["scores"].numpy()
+        save[f"out{b}_labels"] = r["label_preds"].numpy()
+    np.savez_compressed(os.path.join(HERE, "head_predict_circle.npz"), **save)
+
+
+def gen_neck_head():
+    torch.manual_seed(14)
+    tasks = [dict(stride=8, class_names=["car"]), dict(stride=8, class_names=["ped", "cone"])]
+    neck = RPNV1(layer_nums=[1, 2], num_filters=32, in_channels=[32, 32], logger=logging.getLogger("g"))
+    head = CenterHead(tasks=[Config(t) for t in tasks], in_channels=[32], code_weights=[1.0] * 10,
+                      common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2)},
+                      share_channel=16, pillar_size=0.075, point_cloud_range=[-54, -54, -5.0, 54, 54, 3.0],
+                      logger=logging.getLogger("g"))
+    for m in list(neck.modules()) + list(head.modules()):
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.1)
+    neck.eval()
+    head.eval()
+    x4 = torch.randn(2, 32, 12, 12) * (torch.rand(2, 1, 12, 12) > 0.5)
+    x5 = torch.randn(2, 32, 6, 6)
+    with torch.no_grad():
+        bev = neck({"conv4": x4, "conv5": x5})
+        preds = head(bev)
+    save = {"x4": x4.numpy(), "x5": x5.numpy(), "bev": bev[0].numpy()}
+    for k, v in neck.state_dict().items():
+        save["neck." + k] = v.numpy()
+    for k, v in head.state_dict().items():
+        save["head." + k] = v.numpy()
+    for t, p in enumerate(preds):
+        for k, v in p.items():
+            save[f"pred{t}_{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "neck_head_forward.npz"), **save)
+
+
+def gen_cfg():
+    cfg = Config.fromfile("/root/reference/configs/pillarnet/pillarnet34_fpn_centerhead_waymo.py")
+    out = set_by_task_cfg(cfg.test_cfg, [1, 2])
+    with open(os.path.join(HERE, "set_by_task_cfg.json"), "w") as fh:
+        json.dump(json.loads(json.dumps(out)), fh, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    gen_iou()
+    gen_circle()
+    gen_predict()
+    gen_neck_head()
+    gen_cfg()
+    print("golden fixtures written to", HERE)

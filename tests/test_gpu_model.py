@@ -1,0 +1,164 @@
+"""GPU: whole-model parity on a small PillarNet-18 (128x128 pillars), module interfaces included.
+
+fp32 mode vs a dense-equivalent torch restatement (SubM = conv2d * input mask; strided =
+conv2d(stride 2) * max_pool2d(mask); cuDNN with TF32 disabled) driven by the *same* parameters, the
+dense conv5/neck/head being the model's own nn.Conv2d/BatchNorm2d containers run by torch.
+Stated tolerance (north_star): max-abs 1e-3 relative to max|ref| for fp32; bf16 mode: 5e-2 rel-to-max
+on the head maps (bf16 operands through ~40 layers)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.gpu_util import randomize_bn
+
+pytestmark = pytest.mark.gpu
+
+PS, PCR = 0.3, [-19.2, -19.2, -5.0, 19.2, 19.2, 3.0]
+TASKS = [dict(stride=8, class_names=["car"]), dict(stride=8, class_names=["ped", "cone"])]
+
+
+def _model(backbone="PillarResNet18", seed=0):
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200.registry import ConfigDict
+    cfg = dict(
+        type="PillarNet",
+        reader=dict(type="DynamicPFE", in_channels=5, num_filters=(32,), pillar_size=PS, pc_range=PCR),
+        backbone=dict(type=backbone, in_channels=32),
+        neck=dict(type="RPNV1", layer_nums=[1, 1], num_filters=256, in_channels=[256, 256]),
+        bbox_head=dict(type="CenterHead", tasks=TASKS, in_channels=[256], code_weights=[1.0] * 10,
+                       common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2)},
+                       pillar_size=PS, point_cloud_range=PCR))
+    test_cfg = dict(nms=dict(use_rotate_nms=True, nms_pre_max_size=1000, nms_post_max_size=83, nms_iou_threshold=0.2),
+                    rectifier=0, score_threshold=0.1, post_center_limit_range=[-25, -25, -10.0, 25, 25, 10.0])
+    torch.manual_seed(seed)
+    m = P.build_detector(ConfigDict.wrap(cfg), None, ConfigDict.wrap(test_cfg))
+    randomize_bn(m, seed)
+    for t in m.bbox_head.task_heads:
+        t.hm[-1].bias.data.fill_(-0.5)
+    return m.cuda().eval()
+
+
+def _frames(B):
+    from pillarnet_lts_b200 import synth
+    return [torch.from_numpy(synth.make_frame("nuscenes", 60 + i)[::3].copy()).cuda() for i in range(B)]
+
+
+def _bn_eval(x, bn):
+    return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+
+
+def _dense_reference(model, sp):
+    """dense-equivalent torch forward from the reader output to the head maps"""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, (H, W) = sp.batch_size, sp.spatial_shape
+    n = sp.table.count()
+    idx = sp.indices.long()
+    x = torch.zeros(B, 32, H, W, device="cuda")
+    x[idx[:, 0], :, idx[:, 1], idx[:, 2]] = sp.features_f32[:n]
+    mask = torch.zeros(B, 1, H, W, device="cuda")
+    mask[idx[:, 0], 0, idx[:, 1], idx[:, 2]] = 1
+
+    def subm(seq, x, mask, relu, res=None):
+        conv, bn = seq[0], seq[1]
+        y = _bn_eval(F.conv2d(x, conv.weight.permute(0, 3, 1, 2), conv.bias, padding=1), bn)
+        if res is not None:
+            y = y + res
+        if relu:
+            y = F.relu(y)
+        return y * mask
+
+    def block(b, x, mask):
+        if hasattr(b, "conv0"):
+            x = subm(b.conv0, x, mask, False)
+        out = subm(b.conv1, x, mask, True)
+        return subm(b.conv2, out, mask, True, res=x)
+
+    feats = {}
+    for name in ("conv1", "conv2", "conv3", "conv4"):
+        mods = list(getattr(model.backbone, name))
+        i = 0
+        if not hasattr(mods[0], "conv1"):
+            conv, bn = mods[0], mods[1]
+            mask = (F.max_pool2d(mask, 3, 2, 1) > 0).float()
+            x = F.relu(_bn_eval(F.conv2d(x, conv.weight.permute(0, 3, 1, 2), None, stride=2, padding=1), bn)) * mask
+            i = 3
+        for b in mods[i:]:
+            x = block(b, x, mask)
+        feats[name] = x
+    x5 = model.backbone.conv5(feats["conv4"])
+    nk = model.neck
+    up = nk.deblock_5(nk.block_5(x5))
+    bev = nk.block_4(torch.cat([feats["conv4"], up], 1))
+    hd = model.bbox_head
+    share = hd.share_convs[0](bev)
+    preds = []
+    for th in hd.task_heads:
+        preds.append({name: getattr(th, name)(share) for name in th.heads})
+    return feats, x5, bev, preds
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("backbone", ["PillarResNet18", "PillarResNet34"])
+def test_fp32_mode_matches_dense_equivalent_torch(backbone):
+    import pillarnet_lts_b200 as P
+    P.set_precision("fp32")
+    model = _model(backbone)
+    pts = _frames(2)
+    with torch.no_grad():
+        sp = model.reader(dict(points=pts))
+        feats = model.backbone(sp)
+        bev = model.neck(feats)
+        preds = model.bbox_head(bev)
+        rf, r5, rbev, rpreds = _dense_reference(model, sp)
+    torch.cuda.synchronize()
+    for name in ("conv1", "conv2", "conv3"):
+        d = feats[name].dense()
+        assert _rel(d, rf[name]) <= 1e-3, name
+    assert _rel(feats["conv4"], rf["conv4"]) <= 1e-3
+    assert _rel(feats["conv5"], r5) <= 1e-3
+    assert _rel(bev[0], rbev) <= 1e-3
+    for p, rp in zip(preds, rpreds):
+        for k in rp:
+            assert _rel(p[k], rp[k]) <= 1e-3, k
+
+
+def test_bf16_mode_within_stated_tolerance_and_detector_runs():
+    import pillarnet_lts_b200 as P
+    model = _model()
+    pts = _frames(2)
+    with torch.no_grad():
+        P.set_precision("fp32")
+        sp = model.reader(dict(points=pts))
+        _, _, rbev, rpreds = _dense_reference(model, sp)
+        P.set_precision("bf16")
+        bev, _ = model.extract_feat(dict(points=pts))
+        preds = model.bbox_head(bev)
+        dets = model(dict(points=pts, metadata=[{"token": i} for i in range(2)]), return_loss=False)
+    torch.cuda.synchronize()
+    assert _rel(bev[0].float(), rbev) <= 5e-2
+    for p, rp in zip(preds, rpreds):
+        for k in rp:
+            assert _rel(p[k], rp[k]) <= 5e-2, k
+    assert len(dets) == 2
+    for d in dets:
+        assert d["box3d_lidar"].shape[1] == 9 and d["scores"].shape[0] == d["label_preds"].shape[0]
+        assert d["label_preds"].dtype == torch.int64
+
+
+def test_frames_are_independent_batch_equals_single():
+    """frame sharding contract: a frame's detections do not depend on its batch-mates."""
+    import pillarnet_lts_b200 as P
+    P.set_precision("fp32")
+    model = _model()
+    pts = _frames(3)
+    with torch.no_grad():
+        batched = model(dict(points=pts, metadata=[{}] * 3), return_loss=False)
+        singles = [model(dict(points=[p], metadata=[{}]), return_loss=False)[0] for p in pts]
+    for a, b in zip(batched, singles):
+        assert torch.equal(a["label_preds"], b["label_preds"])
+        assert torch.equal(a["box3d_lidar"], b["box3d_lidar"]) and torch.equal(a["scores"], b["scores"])

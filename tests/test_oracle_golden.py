@@ -1,0 +1,71 @@
+"""CPU: the oracle against the committed golden vectors (outputs of the reference's own code, generated
+by tests/golden/make_golden.py) — this is what pins the oracle before it is trusted as the checker."""
+import json
+import os
+
+import numpy as np
+
+from oracle import pillarnet_oracle as O
+
+
+def test_iou_oracle_bit_exact_vs_reference_cpu_twin(golden_dir):
+    g = np.load(os.path.join(golden_dir, "iou_pairs.npz"))
+    mine = O.boxes_iou_bev(g["a"], g["b"])
+    assert (g["iou"] > 0).sum() > 100
+    assert np.array_equal(mine.view(np.int32), g["iou"].view(np.int32))
+
+
+def test_circle_nms_oracle_vs_reference_numba(golden_dir):
+    g = np.load(os.path.join(golden_dir, "circle_nms.npz"))
+    for i in range(3):
+        d, thr, keep = g[f"dets{i}"], float(g[f"thr{i}"]), g[f"keep{i}"]
+        order = O.stable_order_desc(d[:, 2])
+        mine = order[O.nms_circle_sorted(d[order][:, :2], thr)]
+        assert np.array_equal(mine, keep)
+        assert 0 < len(keep) < len(d)
+
+
+def test_predict_oracle_vs_reference_centerhead(golden_dir):
+    """decode + post_processing (circular_nms) vs CenterHead.predict executed from /root/reference."""
+    g = np.load(os.path.join(golden_dir, "head_predict_circle.npz"))
+    ps, pcr = 0.075, [-54, -54, -5.0, 54, 54, 3.0]
+    names = ["reg", "height", "dim", "rot", "vel", "hm"]
+    ncls = [1, 2]
+    min_radius = [4.0, 0.85]
+    B = g["t0_hm"].shape[0]
+    per_frame = [[] for _ in range(B)]
+    for t in range(2):
+        offs, parts, c = {}, [], 0
+        for n in names:
+            v = g[f"t{t}_{n}"].transpose(0, 2, 3, 1)
+            offs[n] = c
+            c += v.shape[-1]
+            parts.append(v)
+        maps = np.concatenate(parts, -1)
+        boxes, hm, iou = O.decode_task(maps, offs, ncls[t], 8, ps, pcr)
+        for b in range(B):
+            cfg = dict(mode="circle", min_radius=min_radius[t], post_max=83, score_threshold=0.1,
+                       post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0])
+            bx, sc, lb = O.post_process_frame(boxes[b], hm[b], iou[b], cfg)
+            per_frame[b].append((bx, sc, lb + sum(ncls[:t])))
+    for b in range(B):
+        bx = np.concatenate([p[0] for p in per_frame[b]])
+        sc = np.concatenate([p[1] for p in per_frame[b]])
+        lb = np.concatenate([p[2] for p in per_frame[b]])
+        assert len(bx) == len(g[f"out{b}_boxes"]) > 10
+        assert np.array_equal(lb, g[f"out{b}_labels"])
+        np.testing.assert_allclose(sc, g[f"out{b}_scores"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(bx, g[f"out{b}_boxes"], rtol=1e-5, atol=1e-5)
+
+
+def test_set_by_task_cfg_vs_reference(golden_dir):
+    import pillarnet_lts_b200  # noqa: F401
+    from pillarnet_lts_b200.detector import set_by_task_cfg
+    with open(os.path.join(golden_dir, "set_by_task_cfg.json")) as fh:
+        want = json.load(fh)
+    cfg = dict(nms=dict(use_multi_class_nms=True, nms_pre_max_size=[2048, 1024, 1024],
+                        nms_post_max_size=[200, 150, 150], nms_iou_threshold=[0.8, 0.55, 0.55]),
+               rectifier=[0., 0., 0.], score_threshold=0.1,
+               post_center_limit_range=[-80, -80, -10.0, 80, 80, 10.0])
+    got = set_by_task_cfg(cfg, [1, 2])
+    assert json.loads(json.dumps(got)) == want
