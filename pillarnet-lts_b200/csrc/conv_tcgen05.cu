@@ -1,5 +1,553 @@
-// placeholder until the tcgen05 implicit-GEMM kernel lands
+// Gather-GEMM convolution on 5th-gen tensor cores (PN_IMPL_TCGEN05) for sm_100a.
+//
+//   out[o, n] = act( (sum_t sum_c in[nbr[o,t], c] * W[n, t*cin + c]) * scale[n] + shift[n] + res[o,n] )
+//
+// Replaces spconv's implicit-GEMM SubMConv2d / SparseConv2d (det3d/models/backbones/base.py:38-63,
+// PillarResNet.py:87,95,103) and the cuDNN 3x3 / transposed-2x2 convs of the dense BEV neck and
+// head (necks/rpn.py:147-207, bbox_heads/center_head.py:27-35,101-112).  Only the dense channel
+// contraction touches the tensor cores; the gather stays a gather.
+//
+// Structure (one persistent CTA per SM, 288 threads, warp-specialised):
+//   warps 0-3  A producers: gather 128 activation rows x 64 channels (bf16, 128 B per row) per
+//              K-chunk with 16-byte cp.async into a 128B-swizzled K-major tile (rows that are
+//              missing in the rulebook are zero-filled by cp.async src-size 0); thread 0 also
+//              issues the TMA load of the weight tile (BLOCK_N x 64, SWIZZLE_128B tensor map) and
+//              arms the stage's mbarrier with the TMA byte count.
+//   warp 8     allocates TMEM (2 x BLOCK_N fp32 columns: double-buffered accumulator); one elected
+//              lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16, kind::f16, bf16 x bf16 -> fp32) and
+//              tcgen05.commit to release smem stages / publish the accumulator.
+//   warps 4-7  epilogue: tcgen05.ld 32 lanes x 32 columns, fused scale/shift (BN+bias), residual,
+//              ReLU, convert, row-contiguous stores; overlaps with the next tile's MMAs.
+// K = taps*cin is walked in 64-element chunks (zero-padded weights), so a chunk may straddle taps
+// (cin = 32) — each 16-byte piece belongs to exactly one tap because cin % 8 == 0.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
-namespace pn_detail {
-int conv_tcgen05(const pn_conv_args*, cudaStream_t) { return PN_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;       // bf16 elements = 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = BLOCK_M * 128;
+constexpr int kProducerThreads = 128;
+constexpr int kEpilogueThreads = 128;
+constexpr int kThreads = 288;
+constexpr int kLag = 2;           // cp.async groups kept in flight per producer thread
+constexpr int kMaxTaps = 9;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (=1, unused for swizzled K-major), [32,46) SBO >> 4
+//   (8 rows x 128 B = 1024 B between row groups), [46,48) version = 1, [61,64) layout = SWIZZLE_128B (2).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = BN.
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+struct KArgs {
+  const __nv_bfloat16* in;
+  int in_ld;
+  const int* nbr;
+  int taps;
+  int n_chunks;  // k_pad / 64
+  const float* scale;
+  const float* shift;
+  const void* residual;
+  int res_ld;
+  void* out;
+  int out_f32;   // 1: float output, 0: bf16
+  int out_ld;
+  int out_coff;
+  int relu;
+  const int* num_rows;
+  int rows_cap;
+  int cin;
+  int cout;
+};
+
+template <int BN, int STAGES>
+struct Smem {
+  alignas(1024) uint8_t a[STAGES][A_STAGE_BYTES];
+  alignas(1024) uint8_t b[STAGES][BN * 128];
+  alignas(8) uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  int nbr[BLOCK_M * kMaxTaps];
+  float scale[BN];
+  float shift[BN];
+};
+
+template <int BN>
+constexpr int tmem_cols() {
+  return 2 * BN < 32 ? 32 : 2 * BN;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const KArgs P) {
+  extern __shared__ uint8_t smem_raw[];
+  using S = Smem<BN, STAGES>;
+  S& sm = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = P.num_rows ? min(*P.num_rows, P.rows_cap) : P.rows_cap;
+  const int n_n_tiles = (P.cout + BN - 1) / BN;
+  const int n_tiles = ((rows + BLOCK_M - 1) / BLOCK_M) * n_n_tiles;
+  constexpr int TCOLS = tmem_cols<BN>();
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&sm.full[s], kProducerThreads + 1);
+        mbar_init(&sm.empty[s], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&sm.tmem_full[i], 1);
+        mbar_init(&sm.tmem_empty[i], kEpilogueThreads);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<TCOLS>(&sm.tmem_base);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp < 4) {
+    // ===================== A producers (+ weight TMA) =====================
+    const int tid = threadIdx.x;
+    const int piece = tid & 7, rg = tid >> 3;
+    const int k_total = P.taps * P.cin;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m_tile = tile / n_n_tiles, n_tile = tile - m_tile * n_n_tiles;
+      const int row0 = m_tile * BLOCK_M;
+      named_bar_sync(1, kProducerThreads);
+      for (int i = tid; i < BLOCK_M * P.taps; i += kProducerThreads) {
+        const int r = i / P.taps, t = i - r * P.taps;
+        const int row = row0 + r;
+        int src = -1;
+        if (row < rows) src = P.nbr ? __ldg(P.nbr + (long long)row * P.taps + t) : row;
+        sm.nbr[i] = src;
+      }
+      named_bar_sync(1, kProducerThreads);
+      for (int kc = 0; kc < P.n_chunks; ++kc, ++g) {
+        const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+        mbar_wait(&sm.empty[s], ph ^ 1u);
+        if (tid == 0) {
+          mbar_arrive_expect_tx(&sm.full[s], BN * 128);
+          tma_load_2d(smem_u32(sm.b[s]), &tmap_w, kc * BLOCK_K, n_tile * BN, &sm.full[s]);
+        }
+        const int k = kc * BLOCK_K + piece * 8;
+        const int t = k / P.cin, c = k - t * P.cin;
+        const bool k_ok = k < k_total;
+        const uint32_t a_base = smem_u32(sm.a[s]);
+#pragma unroll
+        for (int i = 0; i < BLOCK_M / 16; ++i) {
+          const int r = rg + 16 * i;
+          const int src = k_ok ? sm.nbr[r * P.taps + t] : -1;
+          const __nv_bfloat16* gp = P.in + (src >= 0 ? (long long)src * P.in_ld + c : 0);
+          cp_async16(a_base + r * 128 + ((piece ^ (r & 7)) << 4), gp, src >= 0 ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (g >= (uint32_t)kLag) {
+          cp_async_wait<kLag>();
+          fence_proxy_async_smem();
+          mbar_arrive(&sm.full[(g - kLag) % STAGES]);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (uint32_t j = (g >= (uint32_t)kLag ? g - kLag : 0u); j < g; ++j) mbar_arrive(&sm.full[j % STAGES]);
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      uint32_t g = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u, acc_ph = (tcount >> 1) & 1u;
+        mbar_wait(&sm.tmem_empty[acc], acc_ph ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kc = 0; kc < P.n_chunks; ++kc, ++g) {
+          const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+          mbar_wait(&sm.full[s], ph);
+          tcgen05_fence_after();
+          const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(sm.a[s]));
+          const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(sm.b[s]));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&sm.empty[s]);
+        }
+        umma_commit(&sm.tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue =====================
+    const int e = warp - 4;
+    const int etid = threadIdx.x - 4 * 32;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const int m_tile = tile / n_n_tiles, n_tile = tile - m_tile * n_n_tiles;
+      const int n0 = n_tile * BN;
+      const uint32_t acc = tcount & 1u, acc_ph = (tcount >> 1) & 1u;
+      named_bar_sync(2, kEpilogueThreads);
+      for (int i = etid; i < BN; i += kEpilogueThreads) {
+        const int n = n0 + i;
+        sm.scale[i] = (n < P.cout && P.scale) ? __ldg(P.scale + n) : 1.f;
+        sm.shift[i] = (n < P.cout && P.shift) ? __ldg(P.shift + n) : 0.f;
+      }
+      named_bar_sync(2, kEpilogueThreads);
+      mbar_wait(&sm.tmem_full[acc], acc_ph);
+      tcgen05_fence_after();
+      const int row = m_tile * BLOCK_M + e * 32 + lane;
+      const bool row_ok = row < rows;
+      constexpr int CH = BN < 32 ? 16 : 32;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        if (n0 + c0 >= P.cout) break;  // warp-uniform
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * BN + c0;
+        if (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+        tmem_wait_ld();
+        if (row_ok) {
+          const int nvalid = min(CH, P.cout - (n0 + c0));
+          float f[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) f[j] = fmaf(__uint_as_float(v[j]), sm.scale[c0 + j], sm.shift[c0 + j]);
+          const long long ooff = (long long)row * P.out_ld + P.out_coff + n0 + c0;
+          if (P.out_f32) {
+            float* op = reinterpret_cast<float*>(P.out) + ooff;
+            if (P.residual) {
+              const float* rp = reinterpret_cast<const float*>(P.residual) + (long long)row * P.res_ld + n0 + c0;
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (j < nvalid) f[j] += rp[j];
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (nvalid == CH && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4)
+                *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (j < nvalid) op[j] = f[j];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + ooff;
+            if (P.residual) {
+              const __nv_bfloat16* rp =
+                  reinterpret_cast<const __nv_bfloat16*>(P.residual) + (long long)row * P.res_ld + n0 + c0;
+              if (nvalid == CH && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
+#pragma unroll
+                for (int j = 0; j < CH; j += 8) {
+                  const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float2 ff = __bfloat1622float2(h[u]);
+                    f[j + 2 * u] += ff.x;
+                    f[j + 2 * u + 1] += ff.y;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                  if (j < nvalid) f[j] += __bfloat162float(rp[j]);
+              }
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (nvalid == CH && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 8) {
+                uint4 q;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[j + 2 * u], f[j + 2 * u + 1]);
+                *reinterpret_cast<uint4*>(op + j) = q;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (j < nvalid) op[j] = __float2bfloat16_rn(f[j]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&sm.tmem_empty[acc]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tcgen05_fence_after();
+    tmem_dealloc<TCOLS>(tmem_base);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int cout, k_pad, bn;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && cout == o.cout && k_pad == o.k_pad && bn == o.bn;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (size_t)k.cout * 1000003u ^ (size_t)k.k_pad * 10007u ^ (size_t)k.bn;
+  }
+};
+
+// Weight tensor maps are pure functions of (pointer, shape, tile): cache them (encoding costs ~1 us).
+int get_weight_map(const void* w, int cout, int k_pad, int bn, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{w, cout, k_pad, bn};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return PN_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return PN_ERR_UNSUPPORTED;
+  cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)cout};
+  cuuint64_t gstride[1] = {(cuuint64_t)k_pad * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return PN_ERR_CUDA;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+  }
+  *out = m;
+  return PN_OK;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& map, const KArgs& ka, int grid, cudaStream_t stream) {
+  constexpr size_t smem = sizeof(Smem<BN, STAGES>) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PN_CUDA(cudaFuncSetAttribute(k_conv_tc<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  k_conv_tc<BN, STAGES><<<grid, kThreads, smem, stream>>>(map, ka);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+}  // namespace
+
+namespace pn_detail {
+
+int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
+  if (a->in_dtype != PN_BF16) return PN_ERR_UNSUPPORTED;
+  if (a->taps > kMaxTaps) return PN_ERR_UNSUPPORTED;
+  if (a->cin % 8 != 0 || a->in_ld % 8 != 0 || (reinterpret_cast<uintptr_t>(a->in) & 15u) != 0)
+    return PN_ERR_UNSUPPORTED;
+  if (a->k_pad % BLOCK_K != 0 || (reinterpret_cast<uintptr_t>(a->weight) & 15u) != 0) return PN_ERR_UNSUPPORTED;
+  const int bn = a->cout <= 16 ? 16 : a->cout <= 32 ? 32 : a->cout <= 64 ? 64 : a->cout <= 128 ? 128 : 256;
+  CUtensorMap map;
+  int rc = get_weight_map(a->weight, a->cout, a->k_pad, bn, &map);
+  if (rc != PN_OK) return rc;
+  KArgs ka;
+  ka.in = reinterpret_cast<const __nv_bfloat16*>(a->in);
+  ka.in_ld = a->in_ld;
+  ka.nbr = a->nbr;
+  ka.taps = a->taps;
+  ka.n_chunks = a->k_pad / BLOCK_K;
+  ka.scale = a->scale;
+  ka.shift = a->shift;
+  ka.residual = a->residual;
+  ka.res_ld = a->res_ld;
+  ka.out = a->out;
+  ka.out_f32 = a->out_dtype == PN_F32;
+  ka.out_ld = a->out_ld;
+  ka.out_coff = a->out_coff;
+  ka.relu = a->relu;
+  ka.num_rows = a->num_rows;
+  ka.rows_cap = a->rows_cap;
+  ka.cin = a->cin;
+  ka.cout = a->cout;
+  const int sms = sm_count();
+  if (sms <= 0) return PN_ERR_CUDA;
+  const long long tiles_cap = (long long)PN_DIVUP(a->rows_cap, BLOCK_M) * PN_DIVUP(a->cout, bn);
+  const int grid = (int)(tiles_cap < sms ? tiles_cap : sms);
+  switch (bn) {
+    case 16: return launch<16, 6>(map, ka, grid, stream);
+    case 32: return launch<32, 6>(map, ka, grid, stream);
+    case 64: return launch<64, 6>(map, ka, grid, stream);
+    case 128: return launch<128, 5>(map, ka, grid, stream);
+    default: return launch<256, 4>(map, ka, grid, stream);
+  }
+}
+
+}  // namespace pn_detail

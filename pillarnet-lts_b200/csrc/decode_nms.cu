@@ -593,7 +593,8 @@ int pn_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb,
 int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t scratch_bytes,
                    int* keep, int* num_keep, pn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  PN_REQUIRE(boxes && scratch && keep && num_keep && n >= 0 && n <= 4096);
+  PN_REQUIRE(scratch && keep && num_keep && n >= 0 && n <= 4096);
+  PN_REQUIRE(boxes || n == 0);
   if (n == 0) {
     PN_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int), stream));
     return PN_OK;

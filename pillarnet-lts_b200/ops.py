@@ -129,7 +129,8 @@ def rulebook_down3x3s2(table, out_cap=None):
     dev = table.coords.device
     Ho, Wo = (table.H + 2 - 3) // 2 + 1, (table.W + 2 - 3) // 2 + 1
     if out_cap is None:
-        out_cap = max(1, min(table.cap, table.B * Ho * Wo))
+        # every active input can activate up to 4 outputs (2 per axis)
+        out_cap = max(1, min(4 * table.cap, table.B * Ho * Wo))
     nw = lib.pn_mask_words(table.B, Ho, Wo)
     words, prefix = _i32(nw, device=dev), _i32(nw, device=dev)
     coords = _i32(out_cap, 3, device=dev)
