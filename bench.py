@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the PillarNet point->BEV hot path (pillarize -> PFN -> sparse backbone ->
+dense neck/head -> CenterHead decode -> NMS) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W              (N>1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the CPU arm: oracle port on host cores)
+
+A step = one pass of the hot path over one batch of synthetic frames.  Workload at N=1: BASELINE.json
+configs[1], PillarNet-18 nuScenes inference, batch 1 (`--workload nusc18`).  Frames are independent, so
+N>1 shards frames across ranks with no data-path collective (weak scaling, fixed per-GPU work) and one
+fixed-shape NCCL all-gather of the detections at the end of the job.
+
+Prints ONE JSON line on rank 0 (see the keys in main()).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model(workload, device, seed=0):
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200 import configs
+    from pillarnet_lts_b200.registry import ConfigDict
+    cfg = configs.get(workload)
+    torch.manual_seed(seed)
+    model = P.build_detector(ConfigDict.wrap(cfg["model"]), None, ConfigDict.wrap(cfg["test_cfg"]))
+    g = torch.Generator().manual_seed(seed + 1)
+    for m in model.modules():  # non-trivial BN statistics so the folded affine is exercised
+        if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+    return model.to(device).eval(), cfg
+
+
+def make_frames(kind, n, seed0):
+    from pillarnet_lts_b200 import synth
+    return synth.make_batch(kind, n, seed0)
+
+
+# ---------------------------------------------------------------------------------------------------
+def conv_breakdown(engine, reps=3):
+    """Instrumented eager pass: CUDA events around every conv launch and every stage on the launching
+    stream -> per-shape totals; used to name the dominant kernel and measure its duration live."""
+    from pillarnet_lts_b200 import ops
+    recs = []
+    orig = ops.conv_gather
+
+    def timed(inp, weight, nbr, taps, cin, cout, out, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig(inp, weight, nbr, taps, cin, cout, out, **kw)
+        e.record()
+        recs.append((taps, cin, cout, kw.get("rows_cap") or out.shape[0], kw.get("num"), s, e))
+        return r
+
+    model = engine.model
+    stages = {}
+
+    def stage(name, fn):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = fn()
+        e.record()
+        stages.setdefault(name, []).append((s, e))
+        return r
+
+    import pillarnet_lts_b200.layers as layers
+    ops.conv_gather = timed
+    try:
+        with torch.cuda.stream(engine.stream), torch.no_grad():
+            for _ in range(reps):
+                recs_start = len(recs)
+                sp = stage("reader", lambda: model.reader(dict(points_batched=(engine.points, engine.offsets))))
+                feats = stage("backbone", lambda: model.backbone(sp))
+                bev = stage("neck", lambda: model.neck(feats))
+                preds = stage("head", lambda: model.bbox_head(bev))
+                stage("decode_nms", lambda: model.bbox_head.predict_raw(preds, model.test_cfg))
+            engine.stream.synchronize()
+    finally:
+        ops.conv_gather = orig
+    per_pass = recs[recs_start:]
+    shapes = {}
+    for taps, cin, cout, rows_cap, num, s, e in recs:
+        rows = rows_cap if num is None else min(int(num.item()), rows_cap)
+        key = (taps, cin, cout, rows)
+        d = shapes.setdefault(key, dict(us=0.0, n=0))
+        d["us"] += s.elapsed_time(e) * 1e3
+        d["n"] += 1
+    out = []
+    for (taps, cin, cout, rows), d in shapes.items():
+        flop = 2.0 * rows * taps * cin * cout
+        avg = d["us"] / d["n"]
+        out.append(dict(taps=taps, cin=cin, cout=cout, rows=rows, launches_per_pass=d["n"] // reps, avg_us=avg,
+                        tflops=flop / avg / 1e6, total_us_per_pass=d["us"] / reps))
+    out.sort(key=lambda r: -r["total_us_per_pass"])
+    st = {k: float(np.median([s.elapsed_time(e) * 1e3 for s, e in v])) for k, v in stages.items()}
+    return out, st, len(per_pass)
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200 import _lib
+    from pillarnet_lts_b200.engine import InferenceEngine, calibrate_heatmap_bias
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P.set_precision(args.precision)
+    lib = _lib.load()
+    B = args.frames_per_step
+    model, cfg = build_model(args.workload, dev)
+    pool = 8
+    # global frame i -> rank i % world (the reference's DistributedSampler: datasets/loader/sampler.py:93)
+    frames = [make_frames(cfg["synth"], 1, seed0=1000 + (j * world + rank))[0] for j in range(pool * B)]
+    calibrate_heatmap_bias(model, frames[:B], target_cells=args.hm_cells)
+    cap = int(max(sum(len(f) for f in frames[i * B:(i + 1) * B]) for i in range(pool)) * 1.05) + 1024
+    eng = InferenceEngine(model, B, cap, device=dev)
+    n0 = eng.stage_host(frames[:B])
+    eng.upload(n0)
+    eng.prepare(warmup=2)
+    l0 = lib.pn_launch_count()
+    with torch.cuda.stream(eng.stream), torch.no_grad():
+        eng._forward()                      # one eager pass = the kernels one graph replay launches
+    eng.stream.synchronize()
+    launches_per_pass = lib.pn_launch_count() - l0
+
+    # device-resident copies of the frame pool (for the HBM-resident `value` leg)
+    dev_batches = []
+    for i in range(pool):
+        fs = frames[i * B:(i + 1) * B]
+        offs = np.cumsum([0] + [len(f) for f in fs]).astype(np.int32)
+        dev_batches.append((torch.from_numpy(np.concatenate(fs)).to(dev), torch.from_numpy(offs).to(dev)))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident(i):
+        p, o = dev_batches[i % pool]
+        with torch.cuda.stream(eng.stream):
+            eng.points[:p.shape[0]].copy_(p, non_blocking=True)
+            eng.offsets.copy_(o, non_blocking=True)
+        eng.launch()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- value: inputs resident in HBM, L2 flushed between timed steps ----
+    ev = []
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        with torch.cuda.stream(eng.stream):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(eng.stream)
+        step_resident(i)
+        with torch.cuda.stream(eng.stream):
+            e.record(eng.stream)
+        ev.append((s, e))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    gpu_ms = sum(s.elapsed_time(e) for s, e in ev)
+    # ---- e2e: pinned host -> H2D -> graph -> D2H of the detections, every step ----
+    staged = []
+    for i in range(pool):
+        staged.append([torch.from_numpy(f).pin_memory() for f in frames[i * B:(i + 1) * B]])
+    h2d = d2h = 0
+    for i in range(3):
+        eng.infer(staged[i % pool])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        n = eng.stage_host(staged[i % pool])
+        h2d = eng.upload(n)
+        eng.launch()
+        d2h = eng.download()
+        eng.stream.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    last = eng.assemble_host()
+    n_det = int(sum(d["scores"].shape[0] for d in last))
+    # ---- final detection gather (the only collective on the inference path) ----
+    if world > 1:
+        from pillarnet_lts_b200.dist import gather_detections
+        gathered = gather_detections(eng.det_out, eng.keep_count)
+        torch.cuda.synchronize()
+    # max over ranks
+    t = torch.tensor([gpu_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gpu_ms, e2e_ms = t.tolist()
+    frames_total = args.steps * B * world
+    value = frames_total / (gpu_ms / 1e3)
+    e2e_value = frames_total / (e2e_ms / 1e3)
+
+    line = None
+    if rank == 0:
+        peaks = _peaks()
+        breakdown, stages, n_conv = conv_breakdown(eng)
+        top = breakdown[0]
+        flop_total = sum(2.0 * r["rows"] * r["taps"] * r["cin"] * r["cout"] * r["launches_per_pass"] for r in breakdown)
+        roof = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 gather-GEMM conv)",
+                "shape": {k: top[k] for k in ("taps", "cin", "cout", "rows")},
+                "achieved": top["tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": top["tflops"] / peaks["tf_sustained"], "peak_source": peaks["source"] + " (sustained bf16)",
+                "avg_us": top["avg_us"], "share_of_step": top["total_us_per_pass"] / (gpu_ms * 1e3 / args.steps),
+                "traffic": None}
+        cpu = cpu_baseline(args, model, frames[0:B]) if world == 1 and not args.no_cpu_baseline else None
+        line = {
+            "metric": "frames/s (pillarize->PFN->sparse backbone->dense neck/head->decode->NMS)",
+            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": gpu_ms / args.steps, "ms_per_frame": gpu_ms / args.steps / B,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: PillarNet inference, batch {B}/GPU, synthetic "
+                                   f"{cfg['synth']}-shaped frames (~{int(np.mean([len(f) for f in frames]))} pts), "
+                                   f"random-init weights, hm bias calibrated to ~{args.hm_cells} candidate cells/task",
+                       "frames_per_step_per_gpu": B, "l2": "256 MB buffer written between timed steps (L2 flush)",
+                       "cuda_graph": True, "precision": args.precision},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_per_pass * args.steps),
+            "launches_per_step": int(launches_per_pass),
+            "wall_s_timed_region": t_wall,
+            "detections_last_step": n_det,
+            "roofline": roof,
+            "model_tflops": flop_total / (gpu_ms * 1e3 / args.steps) / 1e6,
+            "stages_us": stages,
+            "cpu_baseline": cpu,
+        }
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"breakdown_{args.workload}_n{world}.json"), "w") as fh:
+            json.dump({"convs": breakdown, "stages_us": stages, "conv_launches_per_pass": n_conv}, fh, indent=1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_run(model, frames, steps, warmup):
+    """the oracle port of the whole path on the host cores; returns (seconds per step list, timings)"""
+    import copy
+    from oracle import cpu_path
+    model_cpu = copy.deepcopy(model).cpu().eval()
+    times, tm = [], {}
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        cpu_path.cpu_forward(model_cpu, frames, tm)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, tm
+
+
+def cpu_baseline(args, model, frames):
+    torch.set_num_threads(os.cpu_count() or 1)
+    times, tm = cpu_run(model, frames, steps=2, warmup=1)
+    sec = float(np.median(times))
+    return {"value": len(frames) / sec, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(frames)} full synthetic frame(s) per step, 1 warm-up + 2 timed steps of the oracle "
+                      f"CPU path (numpy pillarize, torch-CPU PFN + dense-equivalent backbone + neck/head, C NMS)",
+            "seconds_per_step": sec, "stage_seconds": tm}
+
+
+def run_reference(args):
+    """--impl reference: the CPU arm. Rank 0 alone runs; other ranks exit 0 without work."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    B = args.frames_per_step
+    model, cfg = build_model(args.workload, torch.device("cpu"))
+    frames = make_frames(cfg["synth"], B, seed0=1000)
+    # bounded: each step is B full frames; steps/warm-up are clamped so the run ends within minutes
+    t0 = time.perf_counter()
+    times, tm = cpu_run(model, frames, steps=1, warmup=0)
+    est = times[0]
+    budget = 150.0
+    steps = max(1, min(args.steps, int(budget / max(est, 1e-3))))
+    warm = max(0, min(args.warmup, 1))
+    times, tm = cpu_run(model, frames, steps=steps, warmup=warm)
+    total = float(np.sum(times))
+    value = steps * B / total
+    line = {
+        "impl": "reference",
+        "metric": "frames/s (pillarize->PFN->sparse backbone->dense neck/head->decode->NMS)",
+        "value": value, "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": steps, "warmup": warm, "steps_requested": args.steps,
+        "ms_per_step": total / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: PillarNet inference, batch {B}, CPU oracle port of the reference "
+                               f"path on the host cores (no GPU)", "frames_per_step_per_gpu": B},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{B} full synthetic frame(s) per step; steps clamped to fit ~{budget:.0f} s",
+                         "stage_seconds": tm},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="nusc18", choices=["nusc18", "nusc34", "waymo34"])
+    ap.add_argument("--frames-per-step", type=int, default=1)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--hm-cells", type=int, default=1500)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; see --impl reference)")
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

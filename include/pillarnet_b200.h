@@ -45,6 +45,8 @@ int pn_abi_version(void);
 const char* pn_last_error(void);
 /* multiProcessorCount of the current device (148 on B200); <0 on error. */
 int pn_device_sm_count(void);
+/* number of kernels this library has launched in this process (memsets not counted). */
+long long pn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * (1) Dynamic pillarization.
@@ -54,7 +56,9 @@ int pn_device_sm_count(void);
  * pillar_cuda.create_pillar_indices_wrapper (pillar_ops.cpp:39-55, pillar_ops_gpu.cu:60-78) and
  * pillar_cuda.gather_indice_wrapper (group_ops_gpu.cu:8-17).
  *
- *   points        (n_points, point_dim) f32, frames concatenated in order
+ *   points        (n_points, point_dim) f32, frames concatenated in order; n_points is a host
+ *                 CAPACITY, the live count is frame_offsets[n_frames] on the device (so a captured
+ *                 CUDA graph serves frames of any size up to the capacity)
  *   frame_offsets (n_frames+1) i32 device; frame b owns rows [off[b], off[b+1])
  *   cell coords   cx = (int)floorf((x - x0) * inv_pillar) with inv_pillar = 1.0f/(float)pillar_size:
  *                 this is what the reference's CUDA expression evaluates (torch scalar division).
@@ -89,10 +93,11 @@ int pn_pillarize(const float* points, int point_dim, const int* frame_offsets, i
  *   out_f32 (m_cap, c_out) f32 ; out_bf16 optional (may be NULL) same shape, bf16 copy for the
  *   tensor-core backbone.  arg (m_cap, c_out) i32 optional (NULL for inference): index of a
  *   point attaining the max (lowest point id; the reference's is racy, scatter_ops_gpu.cu:33-35).
- *   c_out must be 32 or 64.
+ *   c_out must be 32 or 64.  n_points_live: optional device scalar (e.g. frame_offsets + n_frames)
+ *   bounding the live points below the host capacity n_points; NULL = all n_points.
  */
-int pn_pfn_scatter_max(const float* points, int point_dim, int n_points, const int* point_pillar,
-                       const int* num_pillars, int m_cap, float x0, float y0, float inv_pillar,
+int pn_pfn_scatter_max(const float* points, int point_dim, int n_points, const int* n_points_live,
+                       const int* point_pillar, const int* num_pillars, int m_cap, float x0, float y0, float inv_pillar,
                        float pillar_size, float x_offset, float y_offset, const float* weight,
                        const float* scale, const float* shift, int c_out, float* out_f32,
                        void* out_bf16, int* arg, pn_stream_t stream);

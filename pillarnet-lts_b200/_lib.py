@@ -46,12 +46,13 @@ SIGNATURES = {
     "pn_abi_version": (c_int, []),
     "pn_last_error": (c_char_p, []),
     "pn_device_sm_count": (c_int, []),
+    "pn_launch_count": (ctypes.c_longlong, []),
     "pn_mask_words": (c_size_t, [c_int, c_int, c_int]),
     "pn_pillarize_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pn_pillarize": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                              c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_void_p]),
-    "pn_pfn_scatter_max": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_float,
+    "pn_pfn_scatter_max": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
                                    c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pn_scatter_max_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -1,0 +1,73 @@
+"""Model / test configurations of the benchmark workloads, restated as plain dicts.
+
+Values follow the reference's config modules (which are not available on the GPU box):
+  nusc18  : configs/pillarnet/pillarnet_centerhead_nusc.py:6-50,68-81   (PillarNet-18, nuScenes, 10 sweeps)
+  nusc34  : the same with backbone.type = "PillarResNet34" (BASELINE config 4; no such file ships)
+  waymo34 : configs/pillarnet/pillarnet34_fpn_centerhead_waymo.py:4-45,64-79 (PillarNet-34 + RPNG FPN)
+On a machine that has the reference tree, `Config.fromfile(<reference config>)` builds the same models.
+"""
+import copy
+
+
+def _nusc(backbone):
+    tasks = [
+        dict(stride=8, class_names=["car"]),
+        dict(stride=8, class_names=["truck", "construction_vehicle"]),
+        dict(stride=8, class_names=["bus", "trailer"]),
+        dict(stride=8, class_names=["barrier"]),
+        dict(stride=8, class_names=["motorcycle", "bicycle"]),
+        dict(stride=8, class_names=["pedestrian", "traffic_cone"]),
+    ]
+    ps, pcr = 0.075, [-54, -54, -5.0, 54, 54, 3.0]
+    model = dict(
+        type="PillarNet",
+        pretrained=None,
+        reader=dict(type="DynamicPFE", in_channels=5, num_filters=(32,), pillar_size=ps, pc_range=pcr),
+        backbone=dict(type=backbone, in_channels=32),
+        neck=dict(type="RPNV1", layer_nums=[5, 5], num_filters=256, in_channels=[256, 256]),
+        bbox_head=dict(
+            type="CenterHead", tasks=tasks, in_channels=[256],
+            code_weights=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.2, 0.2, 1.0, 1.0],
+            common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2)},
+            reg_iou="GIoU", pillar_size=ps, point_cloud_range=pcr),
+    )
+    test_cfg = dict(
+        nms=dict(use_rotate_nms=True, nms_pre_max_size=1000, nms_post_max_size=83, nms_iou_threshold=0.2),
+        rectifier=0, score_threshold=0.1, double_flip=False,
+        post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0],
+    )
+    return dict(model=model, test_cfg=test_cfg, train_cfg=None, synth="nuscenes", pillar_size=ps, pc_range=pcr)
+
+
+def _waymo34():
+    tasks = [dict(stride=8, class_names=["VEHICLE"]), dict(stride=4, class_names=["PEDESTRIAN", "CYCLIST"])]
+    ps, pcr = 0.1, [-75.2, -75.2, -2, 75.2, 75.2, 4]
+    model = dict(
+        type="PillarNet",
+        reader=dict(type="DynamicPFE", in_channels=5, num_filters=(32,), pillar_size=ps, pc_range=pcr),
+        backbone=dict(type="PillarResNet34", in_channels=32),
+        neck=dict(type="RPNG", layer_nums=[5, 5], num_filters=[256, 128], in_channels=[256, 256, 128]),
+        bbox_head=dict(
+            type="CenterHead", tasks=tasks, in_channels=[256, 128],
+            code_weights=[1.0] * 8,
+            common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "iou": (1, 2)},
+            reg_iou="GIoU", pillar_size=ps, point_cloud_range=pcr),
+    )
+    test_cfg = dict(
+        nms=dict(use_multi_class_nms=True, nms_pre_max_size=[2048, 1024, 1024],
+                 nms_post_max_size=[200, 150, 150], nms_iou_threshold=[0.8, 0.55, 0.55]),
+        rectifier=[0., 0., 0.], score_threshold=0.1,
+        post_center_limit_range=[-80, -80, -10.0, 80, 80, 10.0],
+    )
+    return dict(model=model, test_cfg=test_cfg, train_cfg=None, synth="waymo", pillar_size=ps, pc_range=pcr)
+
+
+WORKLOADS = {
+    "nusc18": lambda: _nusc("PillarResNet18"),
+    "nusc34": lambda: _nusc("PillarResNet34"),
+    "waymo34": _waymo34,
+}
+
+
+def get(name):
+    return copy.deepcopy(WORKLOADS[name]())

@@ -15,6 +15,7 @@
   do {                                                     \
     cudaError_t e__ = cudaGetLastError();                  \
     if (e__ != cudaSuccess) return pn_detail::fail(e__);   \
+    pn_detail::count_launch();                             \
   } while (0)
 
 #define PN_CUDA(call)                                      \
@@ -31,6 +32,7 @@
 namespace pn_detail {
 int fail(cudaError_t e);     // records the CUDA error string, returns PN_ERR_CUDA
 int sm_count();              // cached multiProcessorCount of the current device
+void count_launch();         // bumps the process-wide kernel-launch counter (pn_launch_count)
 
 // Number of 32-bit occupancy words for a (B,H,W) raster.
 __host__ __device__ inline long long n_words(long long cells) { return (cells + 31) >> 5; }

@@ -1,11 +1,16 @@
 #include "mask_scan.cuh"
 
+#include <atomic>
 #include <mutex>
 #include <string>
 
 namespace pn_detail {
 
 static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int fail(cudaError_t e) {
   g_last_error = std::string("CUDA error: ") + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
@@ -143,6 +148,7 @@ extern "C" {
 int pn_abi_version(void) { return 1; }
 const char* pn_last_error(void) { return pn_detail::last_error_cstr(); }
 int pn_device_sm_count(void) { return pn_detail::sm_count(); }
+long long pn_launch_count(void) { return pn_detail::launches(); }
 size_t pn_mask_words(int n_frames, int H, int W) {
   return (size_t)pn_detail::n_words((long long)n_frames * H * W);
 }

@@ -55,8 +55,10 @@ k_mark(const float* __restrict__ pts, int dim, const int* __restrict__ frame_off
        int n_frames, int H, int W, float x0, float y0, float inv, uint32_t* __restrict__ words,
        int* __restrict__ point_cell) {
   extern __shared__ __align__(16) float s_pts[];
+  n_points = min(n_points, __ldg(frame_off + n_frames));  // live count on the device, capacity on the host
   const int first = blockIdx.x * kPtThreads;
   const int count = min(kPtThreads, n_points - first);
+  if (count <= 0) return;
   stage_points(pts, (long long)first * dim, count * dim, s_pts);
   __syncthreads();
   if ((int)threadIdx.x >= count) return;
@@ -76,9 +78,9 @@ k_mark(const float* __restrict__ pts, int dim, const int* __restrict__ frame_off
 
 __global__ void __launch_bounds__(kPtThreads)
 k_rank(const uint32_t* __restrict__ words, const int* __restrict__ prefix, int n_points,
-       int* __restrict__ point_pillar) {
+       const int* __restrict__ n_live, int* __restrict__ point_pillar) {
   const int p = blockIdx.x * kPtThreads + threadIdx.x;
-  if (p >= n_points) return;
+  if (p >= min(n_points, __ldg(n_live))) return;
   const int cell = point_pillar[p];
   if (cell >= 0) point_pillar[p] = pn_rank_of(words, prefix, cell);
 }
@@ -102,7 +104,7 @@ k_zero_rows(float* __restrict__ out, int* __restrict__ arg, const int* __restric
 // order-independent: the result is deterministic, unlike the reference's CAS loop.
 template <int C>
 __global__ void __launch_bounds__(kPtThreads)
-k_pfn_scatter_max(const float* __restrict__ pts, int dim, int n_points,
+k_pfn_scatter_max(const float* __restrict__ pts, int dim, int n_points, const int* __restrict__ n_live,
                   const int* __restrict__ point_pillar, float x0, float y0,
                   float inv, float ps, float xoff, float yoff, const float* __restrict__ weight,
                   const float* __restrict__ scale, const float* __restrict__ shift,
@@ -110,8 +112,10 @@ k_pfn_scatter_max(const float* __restrict__ pts, int dim, int n_points,
   extern __shared__ __align__(16) float s_pts[];
   __shared__ int s_rank[kPtThreads];
   constexpr int R = C / 32;
+  if (n_live) n_points = min(n_points, __ldg(n_live));
   const int first = blockIdx.x * kPtThreads;
   const int count = min(kPtThreads, n_points - first);
+  if (count <= 0) return;
   stage_points(pts, (long long)first * dim, count * dim, s_pts);
   if ((int)threadIdx.x < count) s_rank[threadIdx.x] = __ldg(point_pillar + first + threadIdx.x);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -158,13 +162,13 @@ k_pfn_scatter_max(const float* __restrict__ pts, int dim, int n_points,
 // reference's scatter_arg_max_kernel but exact-compare and tie-broken).
 template <int C>
 __global__ void __launch_bounds__(kPtThreads)
-k_pfn_argmax(const float* __restrict__ pts, int dim, int n_points,
+k_pfn_argmax(const float* __restrict__ pts, int dim, int n_points, const int* __restrict__ n_live,
              const int* __restrict__ point_pillar, float x0, float y0, float inv, float ps,
              float xoff, float yoff, const float* __restrict__ weight,
              const float* __restrict__ scale, const float* __restrict__ shift,
              const float* __restrict__ out, int* __restrict__ arg, int m_cap) {
   const int p = blockIdx.x * (kPtThreads / 32) + (threadIdx.x >> 5);
-  if (p >= n_points) return;
+  if (p >= n_points || (n_live && p >= __ldg(n_live))) return;
   const int rank = __ldg(point_pillar + p);
   if (rank < 0 || rank >= m_cap) return;
   const int lane = threadIdx.x & 31;
@@ -245,14 +249,15 @@ int pn_pillarize(const float* points, int point_dim, const int* frame_offsets, i
                                      num_pillars, scratch, scratch_bytes, stream);
   if (rc != PN_OK) return rc;
   if (n_points > 0) {
-    k_rank<<<blocks, kPtThreads, 0, stream>>>(occ_words, word_prefix, n_points, point_pillar);
+    k_rank<<<blocks, kPtThreads, 0, stream>>>(occ_words, word_prefix, n_points, frame_offsets + n_frames,
+                                              point_pillar);
     PN_CHECK_LAUNCH();
   }
   return PN_OK;
 }
 
-int pn_pfn_scatter_max(const float* points, int point_dim, int n_points, const int* point_pillar,
-                       const int* num_pillars, int m_cap, float x0, float y0,
+int pn_pfn_scatter_max(const float* points, int point_dim, int n_points, const int* n_points_live,
+                       const int* point_pillar, const int* num_pillars, int m_cap, float x0, float y0,
                        float inv_pillar, float pillar_size, float x_offset, float y_offset,
                        const float* weight, const float* scale, const float* shift, int c_out,
                        float* out_f32, void* out_bf16, int* arg, pn_stream_t stream_) {
@@ -272,13 +277,13 @@ int pn_pfn_scatter_max(const float* points, int point_dim, int n_points, const i
     PN_CHECK_LAUNCH();                                                                             \
     if (n_points > 0) {                                                                            \
       k_pfn_scatter_max<C><<<blocks, kPtThreads, smem, stream>>>(                                  \
-          points, point_dim, n_points, point_pillar, x0, y0, inv_pillar, pillar_size,        \
-          x_offset, y_offset, weight, scale, shift, out_f32, m_cap);                               \
+          points, point_dim, n_points, n_points_live, point_pillar, x0, y0, inv_pillar,       \
+          pillar_size, x_offset, y_offset, weight, scale, shift, out_f32, m_cap);                               \
       PN_CHECK_LAUNCH();                                                                           \
       if (arg) {                                                                                   \
         k_pfn_argmax<C><<<PN_DIVUP(n_points, kPtThreads / 32), kPtThreads, 0, stream>>>(           \
-            points, point_dim, n_points, point_pillar, x0, y0, inv_pillar, pillar_size, x_offset,  \
-            y_offset, weight, scale, shift, out_f32, arg, m_cap);                                  \
+            points, point_dim, n_points, n_points_live, point_pillar, x0, y0, inv_pillar,         \
+            pillar_size, x_offset, y_offset, weight, scale, shift, out_f32, arg, m_cap);                                  \
         PN_CHECK_LAUNCH();                                                                         \
       }                                                                                            \
     }                                                                                              \

@@ -1,0 +1,148 @@
+"""Inference engine: the whole point->detections pass as one CUDA graph with device-resident counts.
+
+The reference spends its time on ~500 launches and ~20 host syncs per frame; here the
+forward pass (pn_pillarize ... pn_nms) is sync-free, so it is captured once per (batch, capacity) and
+replayed.  Public API (what bench.py's `e2e` leg times):
+
+    eng = InferenceEngine(model, n_frames=1, points_cap=300_000)
+    dets = eng.infer([points_f32_numpy_or_tensor, ...])      # H2D -> graph -> D2H -> list of dicts
+
+`infer` accepts frames of any size up to the capacity: the live point count travels in the
+frame-offset vector on the device.
+"""
+import numpy as np
+import torch
+
+from . import config
+
+
+class InferenceEngine:
+    def __init__(self, model, n_frames, points_cap, point_dim=5, device=None, use_graph=True):
+        self.model = model.eval()
+        self.B = n_frames
+        self.cap = int(points_cap)
+        self.dev = device or next(model.parameters()).device
+        self.points = torch.zeros(self.cap, point_dim, dtype=torch.float32, device=self.dev)
+        self.offsets = torch.zeros(n_frames + 1, dtype=torch.int32, device=self.dev)
+        self.h_points = torch.zeros(self.cap, point_dim, dtype=torch.float32).pin_memory()
+        self.h_offsets = torch.zeros(n_frames + 1, dtype=torch.int32).pin_memory()
+        self.graph = None
+        self.use_graph = use_graph
+        self.det_out = self.keep_count = self.plan = None
+        self.h_det = self.h_cnt = None
+        self.stream = torch.cuda.Stream(device=self.dev)
+
+    # -- input staging -------------------------------------------------------------------------
+    def stage_host(self, frames):
+        """packs frames into the pinned host buffers; returns the number of points"""
+        assert len(frames) == self.B
+        n = 0
+        self.h_offsets[0] = 0
+        for b, f in enumerate(frames):
+            f = torch.as_tensor(f, dtype=torch.float32)
+            k = f.shape[0]
+            if n + k > self.cap:
+                raise RuntimeError(f"{n + k} points exceed the engine capacity {self.cap}")
+            self.h_points[n:n + k].copy_(f)
+            n += k
+            self.h_offsets[b + 1] = n
+        return n
+
+    def upload(self, n):
+        """async H2D of the staged frames (pinned -> device) on the engine stream"""
+        with torch.cuda.stream(self.stream):
+            self.points[:n].copy_(self.h_points[:n], non_blocking=True)
+            self.offsets.copy_(self.h_offsets, non_blocking=True)
+        return n * self.points.shape[1] * 4 + self.offsets.numel() * 4
+
+    # -- graph ---------------------------------------------------------------------------------
+    def _forward(self):
+        return self.model.forward_device(self.points, self.offsets)
+
+    def prepare(self, warmup=2):
+        """eager warm-up (fills lowering caches, static tables) then capture"""
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            for _ in range(warmup):
+                out = self._forward()
+            self.stream.synchronize()
+            if self.use_graph:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=self.stream):
+                    out = self._forward()
+            self.det_out, self.keep_count, self.plan = out
+        self.h_det = torch.empty(self.det_out.shape, dtype=self.det_out.dtype).pin_memory()
+        self.h_cnt = torch.empty(self.keep_count.shape, dtype=self.keep_count.dtype).pin_memory()
+        self.stream.synchronize()
+        return self
+
+    def launch(self):
+        """one forward pass on the engine stream (no host sync)"""
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self.det_out, self.keep_count, self.plan = self._forward()
+
+    def download(self):
+        with torch.cuda.stream(self.stream):
+            self.h_det.copy_(self.det_out, non_blocking=True)
+            self.h_cnt.copy_(self.keep_count, non_blocking=True)
+        return self.h_det.numel() * 4 + self.h_cnt.numel() * 4
+
+    # -- public API ------------------------------------------------------------------------------
+    def infer(self, frames, metadata=None):
+        if self.det_out is None:
+            self.prepare()
+        n = self.stage_host(frames)
+        self.upload(n)
+        self.launch()
+        self.download()
+        self.stream.synchronize()
+        return self.assemble_host(metadata)
+
+    def assemble_host(self, metadata=None):
+        """detections from the pinned read-back, det3d's structure (center_head.py:332-350,405-409)"""
+        head = self.model.bbox_head
+        plan = self.plan
+        B, S, post_cap = plan["B"], plan["S"], plan["post_cap"]
+        det = self.h_det.view(B, S, post_cap, 11)
+        cnt = self.h_cnt.view(B, S)
+        cls_off, flag = [], 0
+        for k in head.num_classes:
+            cls_off.append(flag)
+            flag += k
+        out = []
+        for b in range(B):
+            boxes, scores, labels = [], [], []
+            for s, seg in enumerate(plan["segs"]):
+                k = int(cnt[b, s])
+                d = det[b, s, :k]
+                boxes.append(d[:, :9] if head.box_n_dim == 9 else torch.cat([d[:, :6], d[:, 8:9]], 1))
+                scores.append(d[:, 9])
+                labels.append(d[:, 10].to(torch.int64) + cls_off[seg["task"]])
+            out.append({"box3d_lidar": torch.cat(boxes), "scores": torch.cat(scores),
+                        "label_preds": torch.cat(labels), "metadata": metadata[b] if metadata else None})
+        return out
+
+
+def calibrate_heatmap_bias(model, frames, target_cells=1500):
+    """Random-init heads give a degenerate candidate count (hm bias -2.19, center_head.py:19,38): shift each
+    task's heat-map bias so that about `target_cells` cells per frame pass the score threshold, which is
+    what a trained model feeds the NMS stage."""
+    import math
+    dev = next(model.parameters()).device
+    thr = float(model.test_cfg["score_threshold"])
+    logit_thr = math.log(thr / (1 - thr))
+    counts = np.cumsum([0] + [len(f) for f in frames]).astype(np.int32)
+    pts = torch.from_numpy(np.concatenate(frames)).to(dev)
+    off = torch.from_numpy(counts).to(dev)
+    with torch.no_grad():
+        bev, _ = model.extract_feat(dict(points_batched=(pts, off)))
+        preds = model.bbox_head(bev)
+        for t, p in enumerate(preds):
+            hm = p["hm"].float().amax(1).reshape(len(frames), -1)
+            k = max(1, min(hm.shape[1] - 1, target_cells))
+            kth = torch.topk(hm, k, dim=1).values[:, -1].mean().item()
+            fc = model.bbox_head.task_heads[t].hm
+            fc[-1].bias.data += (logit_thr - kth)
+    torch.cuda.synchronize()

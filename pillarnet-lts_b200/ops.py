@@ -83,7 +83,7 @@ def _f32(v):
 
 
 def pfn_scatter_max(points, point_pillar, table, x0, y0, pillar_size, x_offset, y_offset, weight,
-                    scale, shift, want_bf16=False, want_arg=False):
+                    scale, shift, want_bf16=False, want_arg=False, n_live=None):
     """Fused offset features + Linear + affine(BN) + ReLU + per-pillar max. Returns (f32, bf16|None, arg|None)."""
     lib = _lib.load()
     require_cuda(points, point_pillar, weight, scale, shift)
@@ -96,7 +96,7 @@ def pfn_scatter_max(points, point_pillar, table, x0, y0, pillar_size, x_offset, 
     out_bf = torch.empty(table.cap, C, dtype=torch.bfloat16, device=dev) if want_bf16 else None
     arg = _i32(table.cap, C, device=dev) if want_arg else None
     inv = (torch.tensor(1.0, dtype=torch.float32) / torch.tensor(pillar_size, dtype=torch.float32)).item()
-    check(lib.pn_pfn_scatter_max(ptr(points), D, N, ptr(point_pillar), ptr(table.num), table.cap,
+    check(lib.pn_pfn_scatter_max(ptr(points), D, N, ptr(n_live), ptr(point_pillar), ptr(table.num), table.cap,
                                  c_float(_f32(x0)), c_float(_f32(y0)), c_float(inv),
                                  c_float(_f32(pillar_size)), c_float(_f32(x_offset)),
                                  c_float(_f32(y_offset)), ptr(weight), ptr(scale), ptr(shift), C,

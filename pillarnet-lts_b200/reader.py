@@ -66,7 +66,8 @@ class PillarMaxPooling(nn.Module):
         want_bf16 = config.get_precision() == "bf16"
         f32, bf16, _ = ops.pfn_scatter_max(points, point_pillar, table, self.point_cloud_range[0],
                                            self.point_cloud_range[1], self.pillar_size, self.x_offset,
-                                           self.y_offset, w, scale, shift, want_bf16=want_bf16)
+                                           self.y_offset, w, scale, shift, want_bf16=want_bf16,
+                                           n_live=frame_offsets[batch_size:])
         sp = SparseConvTensor(bf16 if want_bf16 else f32, table, (self.height, self.width), batch_size)
         sp.features_f32 = f32
         sp.point_pillar = point_pillar
