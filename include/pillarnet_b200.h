@@ -169,6 +169,16 @@ int pn_conv_gather(const pn_conv_args* args, int impl, pn_stream_t stream);
 size_t pn_sizeof_conv_args(void);
 size_t pn_sizeof_task_args(void);
 
+/* Grouped dense 3x3 (pad 1) conv with 1..4 output channels per group, all groups in one launch:
+ * the last conv of every CenterHead branch (center_head.py:34-35).  in: bf16 NHWC rows
+ * (n_frames*H*W, in_ld); group g reads channels [in_coff, in_coff+cin) and writes f32 columns
+ * [out_coff, out_coff+cout) of out (rows, out_ld).  groups: device (n_groups,5) int32
+ * {in_coff, cout, w_off, s_off, out_coff}; wbuf: packed f32 [cout][9][cin] weights + [cout] biases.
+ * cin % 32 == 0.  fp32 accumulation. */
+int pn_conv3x3_small_cout(const void* in, int in_ld, int cin, int n_frames, int H, int W,
+                          const int* groups, int n_groups, const float* wbuf, float* out, int out_ld,
+                          pn_stream_t stream);
+
 /* f32 -> bf16 weight packing with zero padding of K to k_pad (multiple of 64). */
 int pn_conv_pack_weight_bf16(const float* w_f32, int cout, int k, int k_pad, void* w_bf16,
                              pn_stream_t stream);

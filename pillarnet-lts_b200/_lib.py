@@ -66,6 +66,8 @@ SIGNATURES = {
     "pn_conv_gather": (c_int, [POINTER(ConvArgs), c_int, c_void_p]),
     "pn_sizeof_conv_args": (c_size_t, []),
     "pn_sizeof_task_args": (c_size_t, []),
+    "pn_conv3x3_small_cout": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                      c_void_p, c_int, c_void_p]),
     "pn_conv_pack_weight_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pn_cast_f32_to_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pn_cast_bf16_to_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),

@@ -99,9 +99,17 @@ k_decode_candidates(DecodeParams P, unsigned long long* __restrict__ keys, int c
       ok = ok && p.x >= P.range[0] && p.y >= P.range[1] && p.z >= P.range[2] &&
            p.x <= P.range[3] && p.y <= P.range[4] && p.z <= P.range[5];
     }
+    // warp-aggregated append: one atomic per (warp, segment) instead of one per surviving pixel
+    const int seg = ok ? b * P.segs_per_frame + t.seg_base + (t.per_class ? p.label : 0) : -1;
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, seg);
     if (!ok) continue;
-    const int seg = b * P.segs_per_frame + t.seg_base + (t.per_class ? p.label : 0);
-    const int slot = atomicAdd(counts + seg, 1);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counts + seg, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const int slot = base + __popc(peers & ((1u << lane) - 1u));
     if (slot < cand_cap) {
       keys[(long long)seg * cand_cap + slot] =
           ((unsigned long long)__float_as_uint(p.rect) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)pix);
@@ -171,14 +179,24 @@ k_select_topk(SelectParams P, const unsigned long long* __restrict__ keys_all, i
         if ((k & hi_mask) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 0xFF)], 1);
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        int need = s_need, d = 255;
-        for (; d > 0; --d) {
-          if (s_hist[d] >= need) break;
-          need -= s_hist[d];
+      // suffix sums over the 256 bins (Hillis-Steele in smem), then the unique digit d with
+      // S[d] >= need > S[d+1] carries the K-th largest key
+      const int need = s_need;
+      __syncthreads();
+      for (int off = 1; off < 256; off <<= 1) {
+        int v = 0;
+        if (threadIdx.x < 256) v = s_hist[threadIdx.x] + (threadIdx.x + off < 256 ? s_hist[threadIdx.x + off] : 0);
+        __syncthreads();
+        if (threadIdx.x < 256) s_hist[threadIdx.x] = v;
+        __syncthreads();
+      }
+      if (threadIdx.x < 256) {
+        const int d = threadIdx.x;
+        const int above = d < 255 ? s_hist[d + 1] : 0;
+        if (s_hist[d] >= need && above < need) {
+          s_need = need - above;
+          s_prefix = prefix | ((unsigned long long)d << shift);
         }
-        s_need = need;
-        s_prefix = prefix | ((unsigned long long)d << shift);
       }
       __syncthreads();
     }

@@ -57,17 +57,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
 
 __global__ void __launch_bounds__(kScanThreads)
 k_tile_sums(const uint32_t* __restrict__ words, long long n_words, int* __restrict__ tile_sums) {
-  const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kWordsPerThread;
-  int c = 0;
-  if (base + kWordsPerThread <= n_words) {
-    const uint4* p = reinterpret_cast<const uint4*>(words + base);
-    uint4 a = __ldg(p), b = __ldg(p + 1);
-    c = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) +
-        __popc(b.z) + __popc(b.w);
-  } else {
-    for (int i = 0; i < kWordsPerThread; ++i)
-      if (base + i < n_words) c += __popc(__ldg(words + base + i));
-  }
+  const long long w = (long long)blockIdx.x * kScanTile + threadIdx.x;
+  const int c = w < n_words ? __popc(__ldg(words + w)) : 0;
   int tot;
   (void)block_exclusive_scan(c, &tot);
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
@@ -91,36 +82,32 @@ k_tile_offsets(const int* __restrict__ tile_sums, int n_tiles, int* __restrict__
 __global__ void __launch_bounds__(kScanThreads)
 k_emit(const uint32_t* __restrict__ words, long long n_words, const int* __restrict__ tile_offsets,
        int cells_per_frame, int W, int* __restrict__ prefix, int* __restrict__ coords, int m_cap) {
-  const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kWordsPerThread;
-  uint32_t w[kWordsPerThread];
-  int c = 0;
-#pragma unroll
-  for (int i = 0; i < kWordsPerThread; ++i) {
-    w[i] = (base + i < n_words) ? __ldg(words + base + i) : 0u;
-    c += __popc(w[i]);
-  }
+  const long long w = (long long)blockIdx.x * kScanTile + threadIdx.x;
+  uint32_t bits = w < n_words ? __ldg(words + w) : 0u;
   int tot;
-  int run = tile_offsets[blockIdx.x] + block_exclusive_scan(c, &tot);
-#pragma unroll
-  for (int i = 0; i < kWordsPerThread; ++i) {
-    if (base + i < n_words) prefix[base + i] = run;
-    uint32_t bits = w[i];
-    while (bits && coords != nullptr) {
-      const int bit = __ffs(bits) - 1;
-      bits &= bits - 1;
-      if (run < m_cap) {
-        const long long cell = (base + i) * 32 + bit;
-        const int b = (int)(cell / cells_per_frame);
-        const int r = (int)(cell - (long long)b * cells_per_frame);
-        const int y = r / W;
-        int* o = coords + 3ll * run;
-        o[0] = b;
-        o[1] = y;
-        o[2] = r - y * W;
-      }
-      ++run;
+  int run = tile_offsets[blockIdx.x] + block_exclusive_scan(__popc(bits), &tot);
+  if (w < n_words) prefix[w] = run;
+  if (coords == nullptr || bits == 0u) return;
+  // all cells of a word share most of the decomposition: the word never straddles more than 2 rows
+  const int cell0 = (int)(w * 32);
+  int b = cell0 / cells_per_frame;
+  int r = cell0 - b * cells_per_frame;
+  int y = r / W;
+  int x = r - y * W;
+  int prev = 0;
+  while (bits) {
+    const int bit = __ffs(bits) - 1;
+    bits &= bits - 1;
+    x += bit - prev;
+    prev = bit;
+    while (x >= W) { x -= W; if (++y * W >= cells_per_frame) { y = 0; ++b; } }
+    if (run < m_cap) {
+      int* o = coords + 3ll * run;
+      o[0] = b;
+      o[1] = y;
+      o[2] = x;
     }
-    if (coords == nullptr) run += __popc(w[i]);
+    ++run;
   }
 }
 

@@ -9,8 +9,10 @@
 namespace pn_detail {
 
 constexpr int kScanThreads = 256;
-constexpr int kWordsPerThread = 8;
-constexpr int kScanTile = kScanThreads * kWordsPerThread;  // 2048 words = 65536 cells per CTA
+// One word (32 cells) per thread: occupied cells cluster spatially, so giving a thread several words
+// serialises the coordinate emission of a dense region in a few threads (measured: 65 us -> see profiles/).
+constexpr int kWordsPerThread = 1;
+constexpr int kScanTile = kScanThreads * kWordsPerThread;  // 256 words = 8192 cells per CTA
 
 inline int scan_tiles(long long n_words) { return (int)PN_DIVUP(n_words, (long long)kScanTile); }
 // scratch: tile sums + tile offsets

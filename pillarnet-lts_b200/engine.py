@@ -144,5 +144,5 @@ def calibrate_heatmap_bias(model, frames, target_cells=1500):
             k = max(1, min(hm.shape[1] - 1, target_cells))
             kth = torch.topk(hm, k, dim=1).values[:, -1].mean().item()
             fc = model.bbox_head.task_heads[t].hm
-            fc[-1].bias.data += (logit_thr - kth)
+            fc[-1].bias.add_(logit_thr - kth)   # in-place on the Parameter: bumps ._version -> lowering refresh
     torch.cuda.synchronize()

@@ -111,34 +111,83 @@ class CenterHead(nn.Module):
                                  relu=True, in_ld=feat.rows.stride(0), in_ptr_offset=feat.coff)
             slot = {id(e[2]): i for i, e in enumerate(two_level)}
             nbr = ops.dense_nbr_table(0, feat.B, feat.H, feat.W, 1, feat.rows.device)
+            # one packed f32 map for all tasks on this feature; a task's maps are a column slice of it
+            t_off, total = {}, 0
+            for t in tids:
+                t_off[t] = total
+                total += sum(v[0] for v in self.task_heads[t].heads.values())
+            all_rows = torch.empty(feat.rows.shape[0], total, dtype=torch.float32, device=feat.rows.device)
+            fused_final = (inter is not None and inter.dtype == torch.bfloat16 and len(two_level) == len(entries)
+                           and all(e[2][-1].out_channels <= 4 for e in entries)
+                           and two_level[0][2][0].out_channels % 32 == 0)
+            if fused_final:
+                hc = two_level[0][2][0].out_channels
+                groups, wbuf = self._final_groups(fi, entries, slot, t_off, hc)
+                ops.conv3x3_small_cout(inter, inter.stride(0), hc, feat.B, feat.H, feat.W, groups, len(entries),
+                                       wbuf, all_rows)
             for t in tids:
                 th = self.task_heads[t]
                 offsets, c = {}, 0
                 for name in th.heads:
                     offsets[name] = c
                     c += th.heads[name][0]
-                rows = torch.empty(feat.rows.shape[0], c, dtype=torch.float32, device=feat.rows.device)
+                rows = all_rows[:, t_off[t]:t_off[t] + c]
                 for name in th.heads:
+                    if fused_final:
+                        break
                     fc = getattr(th, name)
                     final = fc[-1]
                     if len(fc) == 4:
                         i = slot[id(fc)]
                         hc = fc[0].out_channels
                         run_conv(inter, lower(final, None), nbr, 9, hc, final.out_channels, rows.shape[0],
-                                 out=rows, out_coff=offsets[name], in_ld=inter.stride(0), in_ptr_offset=i * hc)
+                                 out=all_rows, out_coff=t_off[t] + offsets[name], in_ld=inter.stride(0),
+                                 in_ptr_offset=i * hc)
                     else:
                         cur = feat
                         for j in range(0, len(fc) - 1, 3):
                             cur = dense_conv3x3(cur, fc[j], fc[j + 1], relu=True)
                         run_conv(cur.rows, lower(final, None), nbr, 9, cur.C, final.out_channels, rows.shape[0],
-                                 out=rows, out_coff=offsets[name], in_ld=cur.rows.stride(0), in_ptr_offset=cur.coff)
+                                 out=all_rows, out_coff=t_off[t] + offsets[name], in_ld=cur.rows.stride(0),
+                                 in_ptr_offset=cur.coff)
                 pp = PackedPreds()
-                v = rows.view(feat.B, feat.H, feat.W, c)
+                v = all_rows.view(feat.B, feat.H, feat.W, total)[..., t_off[t]:t_off[t] + c]
                 for name in th.heads:
                     pp[name] = v[..., offsets[name]:offsets[name] + th.heads[name][0]].permute(0, 3, 1, 2)
                 pp.rows, pp.offsets, pp.shape = rows, offsets, (feat.B, feat.H, feat.W)
                 rets[t] = pp
         return rets
+
+    def _final_groups(self, fi, entries, slot, t_off, hc):
+        """device descriptors + packed fp32 weights of all final convs on feature `fi` (cached on versions)"""
+        finals = [e[2][-1] for e in entries]
+        key = tuple((f.weight.data_ptr(), f.weight._version, f.bias.data_ptr(), f.bias._version) for f in finals)
+        cache = self.__dict__.setdefault("_pn_final_groups", {})
+        hit = cache.get(fi)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        desc, chunks, off = [], [], 0
+        col = {}
+        for t, name, fc in entries:
+            th = self.task_heads[t]
+            c = 0
+            for nm in th.heads:
+                if nm == name:
+                    break
+                c += th.heads[nm][0]
+            col[id(fc)] = t_off[t] + c
+        for t, name, fc in entries:
+            f = fc[-1]
+            w = f.weight.detach().float().permute(0, 2, 3, 1).reshape(-1)   # [cout][9][cin]
+            b = f.bias.detach().float().reshape(-1)
+            desc.append([slot[id(fc)] * hc, f.out_channels, off, off + w.numel(), col[id(fc)]])
+            chunks += [w, b]
+            off += w.numel() + b.numel()
+        dev = finals[0].weight.device
+        groups = torch.tensor(desc, dtype=torch.int32).to(dev)
+        wbuf = torch.cat(chunks).contiguous()
+        cache[fi] = (key, groups, wbuf)
+        return groups, wbuf
 
     # ------------------------------------------------------------------------------------------
     def _packed(self, preds_dict):

@@ -118,6 +118,15 @@ def fold_affine(conv_bias, bn, cout, device):
     return scale.float().contiguous(), shift.float().contiguous()
 
 
+def invalidate(module):
+    """Drops every cached lowering under `module`.  The caches key on tensor._version, which in-place
+    edits through `.data` do not bump (load_state_dict / optimiser steps / copy_ do) — call this after
+    such an edit."""
+    for m in module.modules():
+        for k in ("_pn_lowered", "_pn_group", "_pn_folded", "_pn_final_groups"):
+            m.__dict__.pop(k, None)
+
+
 class Lowered:
     __slots__ = ("weight", "k_pad", "scale", "shift", "key")
 

@@ -202,6 +202,14 @@ def conv_gather(inp, weight, nbr, taps, cin, cout, out, *, in_ld=None, k_pad=Non
     return out
 
 
+def conv3x3_small_cout(inp, in_ld, cin, n_frames, H, W, groups, n_groups, wbuf, out):
+    """grouped tiny-Cout dense 3x3 conv (all CenterHead final convs in one launch); see the C header."""
+    lib = _lib.load()
+    check(lib.pn_conv3x3_small_cout(ptr(inp), in_ld, cin, n_frames, H, W, ptr(groups), n_groups, ptr(wbuf),
+                                    ptr(out), out.stride(0), stream_ptr()), "pn_conv3x3_small_cout")
+    return out
+
+
 def pack_weight_bf16(w_f32_2d, k_pad=None):
     """(Cout,K) f32 -> (Cout,k_pad) bf16 with K zero-padded to a multiple of 64."""
     lib = _lib.load()

@@ -220,3 +220,36 @@ def test_tcgen05_conv_vs_simt_same_operands(cin, cout, taps_case):
         ops.conv_gather(x, wp, nbr, taps, cin, cout, o, scale=scale, shift=shift, num=num, rows_cap=cap, impl=impl)
     torch.cuda.synchronize()
     assert (o32[1] - o32[0]).abs().max().item() <= 2e-3 * max(1.0, o32[0].abs().max().item())
+
+
+def test_grouped_small_cout_conv_vs_torch():
+    """all CenterHead final convs in one launch (fp32 accumulation on bf16 inputs) vs F.conv2d, tol 1e-4."""
+    from pillarnet_lts_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, H, W, hc = 2, 45, 37, 64
+    couts = [2, 1, 3, 2, 2, 1, 4]
+    G = len(couts)
+    x = torch.randn(B * H * W, G * hc, device="cuda", generator=g).to(torch.bfloat16)
+    ws = [torch.randn(c, hc, 3, 3, device="cuda", generator=g) * 0.1 for c in couts]
+    bs = [torch.randn(c, device="cuda", generator=g) for c in couts]
+    desc, chunks, off, col = [], [], 0, 0
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        wf = w.permute(0, 2, 3, 1).reshape(-1)
+        desc.append([i * hc, w.shape[0], off, off + wf.numel(), col])
+        chunks += [wf, b]
+        off += wf.numel() + b.numel()
+        col += w.shape[0]
+    groups = torch.tensor(desc, dtype=torch.int32).cuda()
+    wbuf = torch.cat(chunks).contiguous()
+    out = torch.full((B * H * W, col + 3), -9.0, device="cuda")
+    ops.conv3x3_small_cout(x, x.stride(0), hc, B, H, W, groups, G, wbuf, out)
+    torch.cuda.synchronize()
+    xin = x.float().view(B, H, W, G * hc).permute(0, 3, 1, 2)
+    c0 = 0
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        want = torch.nn.functional.conv2d(xin[:, i * hc:(i + 1) * hc], w, b, padding=1).permute(0, 2, 3, 1)
+        got = out[:, c0:c0 + w.shape[0]].view(B, H, W, -1)
+        assert (got - want).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
+        c0 += w.shape[0]
+    assert bool((out[:, col:] == -9.0).all())
