@@ -162,6 +162,7 @@ typedef struct pn_conv_args {
   int rows_cap;
   int cin;
   int cout;
+  int rows_hint;         /* expected live rows (tile-shape heuristic only); 0 => rows_cap */
 } pn_conv_args;
 
 int pn_conv_gather(const pn_conv_args* args, int impl, pn_stream_t stream);
@@ -215,23 +216,26 @@ typedef struct pn_task_args {
 } pn_task_args;
 
 /* Stage A: per pixel sigmoid/max/threshold/range test; appends (score,pixel) keys to its segment.
+ * All `n_tasks` (<= 8) tasks of the head go in one launch.
+ *   rectifier: host (n_tasks, 8) floats, per task per class (NULL = all 0)
  *   cand_keys (n_frames*segs_per_frame, cand_cap) u64 ; cand_count (n_frames*segs_per_frame) i32 (zeroed by caller)
  *   key = (bits(rect_score) << 32) | (0xFFFFFFFF - pixel)   => descending key order == score desc, pixel asc
  */
-int pn_decode_candidates(const pn_task_args* task, int n_frames, int segs_per_frame,
+int pn_decode_candidates(const pn_task_args* tasks, int n_tasks, int n_frames, int segs_per_frame,
                          float score_thr, const float* center_range6 /*host, may be NULL*/,
-                         float pillar_size, float x0, float y0, const float* rectifier /*host, per class*/,
+                         float pillar_size, float x0, float y0, const float* rectifier /*host*/,
                          unsigned long long* cand_keys, int cand_cap, int* cand_count,
                          pn_stream_t stream);
 
-/* Stage B: per segment top-`pre_max` selection + sort, decode of the surviving boxes.
+/* Stage B: per segment top-`pre_max` selection + sort, decode of the surviving boxes (one CTA per
+ * segment, every segment of every task and frame in one launch).
  *   seg_pre_max (segs_per_frame) host ints.
  *   sorted_boxes (n_segs, pre_cap, 12) f32: [x,y,z,w,l,h,vx,vy,rot, score, rect_score, label]
  *   sorted_count (n_segs) i32
  */
-int pn_select_topk(const pn_task_args* task, int n_frames, int segs_per_frame,
+int pn_select_topk(const pn_task_args* tasks, int n_tasks, int n_frames, int segs_per_frame,
                    const int* seg_pre_max /*host*/, float pillar_size, float x0, float y0,
-                   const float* rectifier /*host, per class*/,
+                   const float* rectifier /*host (n_tasks,8)*/,
                    const unsigned long long* cand_keys, int cand_cap, const int* cand_count,
                    float* sorted_boxes, int pre_cap, int* sorted_count, pn_stream_t stream);
 

@@ -27,7 +27,7 @@ class ConvArgs(Structure):
         ("out", c_void_p), ("out_dtype", c_int), ("out_ld", c_int), ("out_coff", c_int),
         ("relu", c_int),
         ("num_rows", c_void_p), ("rows_cap", c_int),
-        ("cin", c_int), ("cout", c_int),
+        ("cin", c_int), ("cout", c_int), ("rows_hint", c_int),
     ]
 
 
@@ -73,10 +73,10 @@ SIGNATURES = {
     "pn_cast_bf16_to_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pn_sparse_to_dense": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                    c_int, c_void_p, c_int, c_int, c_void_p]),
-    "pn_decode_candidates": (c_int, [POINTER(TaskArgs), c_int, c_int, c_float, POINTER(c_float),
+    "pn_decode_candidates": (c_int, [POINTER(TaskArgs), c_int, c_int, c_int, c_float, POINTER(c_float),
                                      c_float, c_float, c_float, POINTER(c_float), c_void_p, c_int,
                                      c_void_p, c_void_p]),
-    "pn_select_topk": (c_int, [POINTER(TaskArgs), c_int, c_int, POINTER(c_int), c_float, c_float,
+    "pn_select_topk": (c_int, [POINTER(TaskArgs), c_int, c_int, c_int, POINTER(c_int), c_float, c_float,
                                c_float, POINTER(c_float), c_void_p, c_int, c_void_p, c_void_p, c_int,
                                c_void_p, c_void_p]),
     "pn_nms_scratch_bytes": (c_size_t, [c_int, c_int]),

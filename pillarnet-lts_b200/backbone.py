@@ -26,13 +26,20 @@ def conv2D3x3(in_planes, out_planes, stride=1, dilation=1, indice_key=None, bias
                         bias=bias, indice_key=indice_key)
 
 
+def _rows_hint(table):
+    """Expected active rows of a stage (the live count stays on the device): LiDAR BEV occupancy is
+    ~5 % at full resolution and ~25 % after three stride-2 stages; only steers the conv tile shape."""
+    cells = table.B * table.H * table.W
+    return min(table.cap, max(1, cells // 4))
+
+
 def _subm(sp, seq, relu, residual=None):
     """SparseSequential(SubMConv2d, BN[, SparseReLU]) as one launch."""
     conv, bn = seq[0], seq[1]
     t = sp.table
     lw = lower(conv, bn)
     out = run_conv(sp.feat, lw, t.subm_nbr(), 9, conv.in_channels, conv.out_channels, t.cap, num=t.num,
-                   relu=relu, residual=residual)
+                   relu=relu, residual=residual, rows_hint=_rows_hint(t))
     return SparseConvTensor(out, t, sp.spatial_shape, sp.batch_size)
 
 
@@ -86,7 +93,7 @@ def _run_stage(sp, stage):
         out_table, nbr = ops.rulebook_down3x3s2(sp.table)
         lw = lower(conv, bn)
         feat = run_conv(sp.feat, lw, nbr, 9, conv.in_channels, conv.out_channels, out_table.cap,
-                        num=out_table.num, relu=True)
+                        num=out_table.num, relu=True, rows_hint=_rows_hint(out_table))
         sp = SparseConvTensor(feat, out_table, (out_table.H, out_table.W), sp.batch_size)
         i = 3
     for m in mods[i:]:

@@ -74,17 +74,32 @@ __device__ __forceinline__ void run_group(const __nv_bfloat16* __restrict__ in, 
     for (int j = 0; j < COUT; ++j) acc[q][j] = 0.f;
   for (int c0 = 0; c0 < cin; c0 += CHUNK) {
     __syncthreads();
-    // stage halo: half-warp per pixel, lane -> channel pair (64 contiguous bytes per pixel)
+    // stage halo: half-warp per pixel, lane -> channel pair (64 contiguous bytes per pixel).
+    // Loads are issued in batches of 8 independent requests per thread before the shared-memory
+    // stores, otherwise each of the 77 iterations waits a full L2 round trip.
     const int half = tid >> 4, pr = tid & 15;
-    for (int px = half; px < HH_ * HW_; px += THREADS / 16) {
-      const int hy = px / HW_, hx = px - hy * HW_;
-      const int gy = y0 + hy - 1, gx = x0 + hx - 1;
-      uint32_t u = 0u;
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        const __nv_bfloat16* p = in + ((long long)(b * H + gy) * W + gx) * in_ld + g.in_coff + c0;
-        u = __ldg(reinterpret_cast<const uint32_t*>(p) + pr);
+    constexpr int kPix = HH_ * HW_, kStep = THREADS / 16, kBatch = 8;
+    for (int px0 = half; px0 < kPix; px0 += kStep * kBatch) {
+      uint32_t u[kBatch];
+      int so[kBatch];
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        const int px = px0 + i * kStep;
+        u[i] = 0u;
+        so[i] = -1;
+        if (px < kPix) {
+          const int hy = px / HW_, hx = px - hy * HW_;
+          const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+          so[i] = pr * (HH_ * RS) + hy * RS + hx;
+          if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const __nv_bfloat16* p = in + ((long long)(b * H + gy) * W + gx) * in_ld + g.in_coff + c0;
+            u[i] = __ldg(reinterpret_cast<const uint32_t*>(p) + pr);
+          }
+        }
       }
-      s_in[pr * (HH_ * RS) + hy * RS + hx] = u;
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i)
+        if (so[i] >= 0) s_in[so[i]] = u[i];
     }
     // stage weights of this channel chunk: s_w[tap][pair][j][2] = W[j][tap][c0 + 2*pair + {0,1}]
     for (int i = tid; i < 9 * PAIRS * COUT * 2; i += THREADS) {

@@ -35,7 +35,7 @@ constexpr int A_STAGE_BYTES = BLOCK_M * 128;
 constexpr int kProducerThreads = 128;
 constexpr int kEpilogueThreads = 128;
 constexpr int kThreads = 288;
-constexpr int kLag = 2;           // cp.async groups kept in flight per producer thread
+constexpr int kLag = 3;           // cp.async groups kept in flight per producer thread (<= STAGES-1)
 constexpr int kMaxTaps = 9;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -199,7 +199,7 @@ struct Smem {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
-  int nbr[BLOCK_M * kMaxTaps];
+  int nbr[2][BLOCK_M * kMaxTaps];
   float scale[BN];
   float shift[BN];
 };
@@ -247,18 +247,41 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const KArgs P) {
     const int piece = tid & 7, rg = tid >> 3;
     const int k_total = P.taps * P.cin;
     uint32_t g = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m_tile = tile / n_n_tiles, n_tile = tile - m_tile * n_n_tiles;
+    // The rulebook rows of a tile are fetched one tile ahead into registers and parked in the other
+    // half of sm.nbr, so a tile never starts with an exposed global-memory round trip.
+    constexpr int kNbrPerThread = (BLOCK_M * kMaxTaps + kProducerThreads - 1) / kProducerThreads;
+    const int nbr_elems = BLOCK_M * P.taps;
+    auto fetch_nbr = [&](int tile, int (&regs)[kNbrPerThread]) {
+      const int m_tile = tile / n_n_tiles;
       const int row0 = m_tile * BLOCK_M;
-      named_bar_sync(1, kProducerThreads);
-      for (int i = tid; i < BLOCK_M * P.taps; i += kProducerThreads) {
-        const int r = i / P.taps, t = i - r * P.taps;
-        const int row = row0 + r;
+#pragma unroll
+      for (int q = 0; q < kNbrPerThread; ++q) {
+        const int i = tid + q * kProducerThreads;
         int src = -1;
-        if (row < rows) src = P.nbr ? __ldg(P.nbr + (long long)row * P.taps + t) : row;
-        sm.nbr[i] = src;
+        if (i < nbr_elems && tile < n_tiles) {
+          const int r = i / P.taps, t = i - r * P.taps;
+          const int row = row0 + r;
+          if (row < rows) src = P.nbr ? __ldg(P.nbr + (long long)row * P.taps + t) : row;
+        }
+        regs[q] = src;
       }
-      named_bar_sync(1, kProducerThreads);
+    };
+    auto park_nbr = [&](int buf, const int (&regs)[kNbrPerThread]) {
+#pragma unroll
+      for (int q = 0; q < kNbrPerThread; ++q) {
+        const int i = tid + q * kProducerThreads;
+        if (i < nbr_elems) sm.nbr[buf][i] = regs[q];
+      }
+    };
+    int nbr_regs[kNbrPerThread];
+    fetch_nbr(blockIdx.x, nbr_regs);
+    park_nbr(0, nbr_regs);
+    named_bar_sync(1, kProducerThreads);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      const int m_tile = tile / n_n_tiles, n_tile = tile - m_tile * n_n_tiles;
+      const int* s_nbr = sm.nbr[tl & 1u];
+      fetch_nbr(tile + gridDim.x, nbr_regs);  // next tile's rows: loads in flight during this tile
       for (int kc = 0; kc < P.n_chunks; ++kc, ++g) {
         const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
         mbar_wait(&sm.empty[s], ph ^ 1u);
@@ -273,7 +296,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const KArgs P) {
 #pragma unroll
         for (int i = 0; i < BLOCK_M / 16; ++i) {
           const int r = rg + 16 * i;
-          const int src = k_ok ? sm.nbr[r * P.taps + t] : -1;
+          const int src = k_ok ? s_nbr[r * P.taps + t] : -1;
           const __nv_bfloat16* gp = P.in + (src >= 0 ? (long long)src * P.in_ld + c : 0);
           cp_async16(a_base + r * 128 + ((piece ^ (r & 7)) << 4), gp, src >= 0 ? 16u : 0u);
         }
@@ -284,6 +307,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const KArgs P) {
           mbar_arrive(&sm.full[(g - kLag) % STAGES]);
         }
       }
+      park_nbr((tl + 1u) & 1u, nbr_regs);   // the other buffer: nobody reads it during this tile
+      named_bar_sync(1, kProducerThreads);
     }
     cp_async_wait<0>();
     fence_proxy_async_smem();
@@ -514,7 +539,26 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
   if (a->cin % 8 != 0 || a->in_ld % 8 != 0 || (reinterpret_cast<uintptr_t>(a->in) & 15u) != 0)
     return PN_ERR_UNSUPPORTED;
   if (a->k_pad % BLOCK_K != 0 || (reinterpret_cast<uintptr_t>(a->weight) & 15u) != 0) return PN_ERR_UNSUPPORTED;
-  const int bn = a->cout <= 16 ? 16 : a->cout <= 32 ? 32 : a->cout <= 64 ? 64 : a->cout <= 128 ? 128 : 256;
+  int bn = a->cout <= 16 ? 16 : a->cout <= 32 ? 32 : a->cout <= 64 ? 64 : a->cout <= 128 ? 128 : 256;
+  {
+    // Tile-shape choice.  The kernel is bound by L2->SM bytes (A tile 128 rows + B tile bn rows per
+    // K chunk), so pick the bn that minimises waves x bytes-per-tile; with few row tiles (deep,
+    // low-resolution layers) a narrower N tile lets every SM stream only its slice of the weights.
+    // The live row count is on the device: rows_hint (expected rows) stands in for it when given.
+    const int sms_ = sm_count();
+    const long long rows_est = a->rows_hint > 0 ? a->rows_hint : a->rows_cap;
+    const long long m_tiles = PN_DIVUP(rows_est, (long long)BLOCK_M);
+    if (bn > 64) {
+      long long best_cost = -1;
+      int best = bn;
+      for (int cand = bn; cand >= 64; cand >>= 1) {
+        const long long tiles = m_tiles * PN_DIVUP(a->cout, cand);
+        const long long cost = PN_DIVUP(tiles, (long long)sms_) * (BLOCK_M + cand);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cand; }
+      }
+      bn = best;
+    }
+  }
   CUtensorMap map;
   int rc = get_weight_map(a->weight, a->cout, a->k_pad, bn, &map);
   if (rc != PN_OK) return rc;

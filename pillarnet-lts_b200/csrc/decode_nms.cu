@@ -71,21 +71,25 @@ __device__ __forceinline__ Pix decode_pixel(const TaskDev& t, const float* __res
   return p;
 }
 
+constexpr int kMaxTasks = 8;
+
 struct DecodeParams {
-  TaskDev t;
+  TaskDev t[kMaxTasks];
+  int n_tasks;
   int n_frames, segs_per_frame;
   float score_thr;
   int use_range;
   float range[6];
   float ps, x0, y0;
-  int use_rect;
-  float rect[8];
+  float rect[kMaxTasks][8];
 };
 
+// grid.y = task: all tasks of the head in one launch
 __global__ void __launch_bounds__(256)
-k_decode_candidates(DecodeParams P, unsigned long long* __restrict__ keys, int cand_cap,
-                    int* __restrict__ counts) {
-  const TaskDev& t = P.t;
+k_decode_candidates(const __grid_constant__ DecodeParams P, unsigned long long* __restrict__ keys,
+                    int cand_cap, int* __restrict__ counts) {
+  const TaskDev& t = P.t[blockIdx.y];
+  const float* rect = P.rect[blockIdx.y];
   const int hw = t.H * t.W;
   const long long total = (long long)P.n_frames * hw;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
@@ -93,7 +97,7 @@ k_decode_candidates(DecodeParams P, unsigned long long* __restrict__ keys, int c
     const int b = (int)(g / hw), pix = (int)(g - (long long)b * hw);
     const int i = pix / t.W, j = pix - i * t.W;
     const float* row = t.maps + g * t.ld;
-    const Pix p = decode_pixel(t, row, i, j, P.ps, P.x0, P.y0, P.use_rect ? P.rect : nullptr);
+    const Pix p = decode_pixel(t, row, i, j, P.ps, P.x0, P.y0, rect);
     bool ok = p.score > P.score_thr;
     if (P.use_range) {
       ok = ok && p.x >= P.range[0] && p.y >= P.range[1] && p.z >= P.range[2] &&
@@ -136,28 +140,33 @@ __device__ void bitonic_sort_desc(unsigned long long* s, int n_pow2) {
 }
 
 struct SelectParams {
-  TaskDev t;
+  TaskDev t[kMaxTasks];
+  int n_tasks;
   int n_frames, segs_per_frame;
-  int seg_lo, seg_hi;  // this task owns segs [seg_lo, seg_hi) within a frame
-  int pre_max[8];      // indexed by seg - seg_lo
+  int pre_max[16];     // per segment-in-frame
   float ps, x0, y0;
-  int use_rect;
-  float rect[8];
+  float rect[kMaxTasks][8];
 };
 
 __global__ void __launch_bounds__(kSelThreads)
-k_select_topk(SelectParams P, const unsigned long long* __restrict__ keys_all, int cand_cap,
-              const int* __restrict__ counts, float* __restrict__ sorted_boxes, int pre_cap,
+k_select_topk(const __grid_constant__ SelectParams P, const unsigned long long* __restrict__ keys_all,
+              int cand_cap, const int* __restrict__ counts, float* __restrict__ sorted_boxes, int pre_cap,
               int* __restrict__ sorted_count) {
   __shared__ unsigned long long s_keys[kSelSmemKeys];
   __shared__ int s_hist[256];
   __shared__ unsigned long long s_prefix;
   __shared__ int s_need, s_fill;
-  const TaskDev& t = P.t;
-  const int nseg_task = P.seg_hi - P.seg_lo;
-  const int b = blockIdx.x / nseg_task;
-  const int sl = blockIdx.x - b * nseg_task;
-  const int seg = b * P.segs_per_frame + P.seg_lo + sl;
+  // one CTA per segment of the whole batch (all tasks in one launch)
+  const int seg = blockIdx.x;
+  const int b = seg / P.segs_per_frame;
+  const int sl = seg - b * P.segs_per_frame;
+  int ti = 0;
+  for (int k = 0; k < P.n_tasks; ++k) {
+    const int lo = P.t[k].seg_base, hi = lo + (P.t[k].per_class ? P.t[k].num_cls : 1);
+    if (sl >= lo && sl < hi) ti = k;
+  }
+  const TaskDev& t = P.t[ti];
+  const float* rect = P.rect[ti];
   const int K = min(min(P.pre_max[sl], pre_cap), kSelSmemKeys);
   const int n = min(counts[seg], cand_cap);
   const unsigned long long* keys = keys_all + (long long)seg * cand_cap;
@@ -226,7 +235,7 @@ k_select_topk(SelectParams P, const unsigned long long* __restrict__ keys_all, i
     const int pix = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
     const int ii = pix / t.W, jj = pix - ii * t.W;
     const float* row = t.maps + ((long long)b * hw + pix) * t.ld;
-    const Pix p = decode_pixel(t, row, ii, jj, P.ps, P.x0, P.y0, P.use_rect ? P.rect : nullptr);
+    const Pix p = decode_pixel(t, row, ii, jj, P.ps, P.x0, P.y0, rect);
     float* o = sorted_boxes + ((long long)seg * pre_cap + i) * kBoxRec;
     o[0] = p.x;
     o[1] = p.y;
@@ -502,54 +511,65 @@ inline size_t mask_bytes(int n_segs, int pre_cap) {
 
 extern "C" {
 
-int pn_decode_candidates(const pn_task_args* task, int n_frames, int segs_per_frame,
+int pn_decode_candidates(const pn_task_args* tasks, int n_tasks, int n_frames, int segs_per_frame,
                          float score_thr, const float* center_range6, float pillar_size, float x0,
                          float y0, const float* rectifier, unsigned long long* cand_keys,
                          int cand_cap, int* cand_count, pn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  PN_REQUIRE(task && task->maps && cand_keys && cand_count && cand_cap > 0 && n_frames >= 1);
-  PN_REQUIRE(task->num_cls >= 1 && task->num_cls <= 8 && task->H > 0 && task->W > 0);
-  PN_REQUIRE(task->off_reg >= 0 && task->off_height >= 0 && task->off_dim >= 0 && task->off_rot >= 0 &&
-             task->off_hm >= 0);
+  PN_REQUIRE(tasks && n_tasks >= 1 && n_tasks <= kMaxTasks && cand_keys && cand_count && cand_cap > 0);
+  PN_REQUIRE(n_frames >= 1 && segs_per_frame >= 1 && segs_per_frame <= 16);
   DecodeParams P;
-  P.t = to_dev(task);
+  P.n_tasks = n_tasks;
+  long long max_total = 0;
+  for (int k = 0; k < n_tasks; ++k) {
+    const pn_task_args* task = tasks + k;
+    PN_REQUIRE(task->maps && task->num_cls >= 1 && task->num_cls <= 8 && task->H > 0 && task->W > 0);
+    PN_REQUIRE(task->off_reg >= 0 && task->off_height >= 0 && task->off_dim >= 0 && task->off_rot >= 0 &&
+               task->off_hm >= 0);
+    P.t[k] = to_dev(task);
+    for (int i = 0; i < 8; ++i) P.rect[k][i] = (rectifier && i < task->num_cls) ? rectifier[k * 8 + i] : 0.f;
+    const long long total = (long long)n_frames * task->H * task->W;
+    if (total > max_total) max_total = total;
+  }
   P.n_frames = n_frames;
   P.segs_per_frame = segs_per_frame;
   P.score_thr = score_thr;
   P.use_range = center_range6 != nullptr;
   for (int i = 0; i < 6; ++i) P.range[i] = center_range6 ? center_range6[i] : 0.f;
   P.ps = pillar_size; P.x0 = x0; P.y0 = y0;
-  P.use_rect = rectifier != nullptr;
-  for (int i = 0; i < 8; ++i) P.rect[i] = (rectifier && i < task->num_cls) ? rectifier[i] : 0.f;
-  const long long total = (long long)n_frames * task->H * task->W;
-  k_decode_candidates<<<grid_for(total, 256), 256, 0, stream>>>(P, cand_keys, cand_cap, cand_count);
+  dim3 grid(grid_for(max_total, 256), n_tasks);
+  k_decode_candidates<<<grid, 256, 0, stream>>>(P, cand_keys, cand_cap, cand_count);
   PN_CHECK_LAUNCH();
   return PN_OK;
 }
 
-int pn_select_topk(const pn_task_args* task, int n_frames, int segs_per_frame,
+int pn_select_topk(const pn_task_args* tasks, int n_tasks, int n_frames, int segs_per_frame,
                    const int* seg_pre_max, float pillar_size, float x0, float y0,
                    const float* rectifier, const unsigned long long* cand_keys, int cand_cap,
                    const int* cand_count, float* sorted_boxes, int pre_cap, int* sorted_count,
                    pn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  PN_REQUIRE(task && task->maps && seg_pre_max && cand_keys && cand_count && sorted_boxes && sorted_count);
-  PN_REQUIRE(pre_cap > 0 && pre_cap <= kSelSmemKeys && n_frames >= 1);
+  PN_REQUIRE(tasks && n_tasks >= 1 && n_tasks <= kMaxTasks && seg_pre_max && cand_keys && cand_count &&
+             sorted_boxes && sorted_count);
+  PN_REQUIRE(pre_cap > 0 && pre_cap <= kSelSmemKeys && n_frames >= 1 && segs_per_frame >= 1 &&
+             segs_per_frame <= 16);
   SelectParams P;
-  P.t = to_dev(task);
+  P.n_tasks = n_tasks;
+  int covered = 0;
+  for (int k = 0; k < n_tasks; ++k) {
+    const pn_task_args* task = tasks + k;
+    PN_REQUIRE(task->maps && task->num_cls >= 1 && task->num_cls <= 8);
+    P.t[k] = to_dev(task);
+    for (int i = 0; i < 8; ++i) P.rect[k][i] = (rectifier && i < task->num_cls) ? rectifier[k * 8 + i] : 0.f;
+    covered += task->per_class ? task->num_cls : 1;
+  }
+  PN_REQUIRE(covered == segs_per_frame);
   P.n_frames = n_frames;
   P.segs_per_frame = segs_per_frame;
-  P.seg_lo = task->seg_base;
-  P.seg_hi = task->seg_base + (task->per_class ? task->num_cls : 1);
-  PN_REQUIRE(P.seg_hi - P.seg_lo <= 8 && P.seg_hi <= segs_per_frame);
-  for (int i = 0; i < 8; ++i) P.pre_max[i] = 0;
-  for (int s = P.seg_lo; s < P.seg_hi; ++s) P.pre_max[s - P.seg_lo] = seg_pre_max[s];
+  for (int i = 0; i < 16; ++i) P.pre_max[i] = i < segs_per_frame ? seg_pre_max[i] : 0;
   P.ps = pillar_size; P.x0 = x0; P.y0 = y0;
-  P.use_rect = rectifier != nullptr;
-  for (int i = 0; i < 8; ++i) P.rect[i] = (rectifier && i < task->num_cls) ? rectifier[i] : 0.f;
-  const int blocks = n_frames * (P.seg_hi - P.seg_lo);
-  k_select_topk<<<blocks, kSelThreads, 0, stream>>>(P, cand_keys, cand_cap, cand_count, sorted_boxes,
-                                                    pre_cap, sorted_count);
+  k_select_topk<<<n_frames * segs_per_frame, kSelThreads, 0, stream>>>(P, cand_keys, cand_cap, cand_count,
+                                                                      sorted_boxes, pre_cap, sorted_count);
   PN_CHECK_LAUNCH();
   return PN_OK;
 }

@@ -280,18 +280,22 @@ class CenterHead(nn.Module):
         x0, y0 = ops._f32(self.point_cloud_range[0]), ops._f32(self.point_cloud_range[1])
         pre_arr = iarr([min(s["pre"], pre_cap) for s in segs])
         seg_base = 0
+        tasks_arr = (_lib.TaskArgs * len(packed))()
+        rect_flat = []
         for t, (rows, offsets, (b_, H, W)) in enumerate(packed):
             nseg_t = self.num_classes[t] if plan["multi"] else 1
-            ta = ops.make_task_args(rows, offsets, self.num_classes[t], H, W, self.task_strides[t], seg_base,
-                                    plan["multi"])
-            rect = farr(plan["rects"][t])
-            check(lib.pn_decode_candidates(byref(ta), B, S, c_float(ops._f32(test_cfg["score_threshold"])),
-                                           rng_arr, c_float(ps), c_float(x0), c_float(y0), rect, ptr(keys),
-                                           cand_cap, ptr(cand_count), stream_ptr()), "pn_decode_candidates")
-            check(lib.pn_select_topk(byref(ta), B, S, pre_arr, c_float(ps), c_float(x0), c_float(y0), rect,
-                                     ptr(keys), cand_cap, ptr(cand_count), ptr(sorted_boxes), pre_cap,
-                                     ptr(sorted_count), stream_ptr()), "pn_select_topk")
+            tasks_arr[t] = ops.make_task_args(rows, offsets, self.num_classes[t], H, W, self.task_strides[t],
+                                              seg_base, plan["multi"])
+            r = list(plan["rects"][t])[:8]
+            rect_flat += r + [0.0] * (8 - len(r))
             seg_base += nseg_t
+        rect = farr(rect_flat)
+        check(lib.pn_decode_candidates(tasks_arr, len(packed), B, S, c_float(ops._f32(test_cfg["score_threshold"])),
+                                       rng_arr, c_float(ps), c_float(x0), c_float(y0), rect, ptr(keys),
+                                       cand_cap, ptr(cand_count), stream_ptr()), "pn_decode_candidates")
+        check(lib.pn_select_topk(tasks_arr, len(packed), B, S, pre_arr, c_float(ps), c_float(x0), c_float(y0),
+                                 rect, ptr(keys), cand_cap, ptr(cand_count), ptr(sorted_boxes), pre_cap,
+                                 ptr(sorted_count), stream_ptr()), "pn_select_topk")
         sb = lib.pn_nms_scratch_bytes(n_segs, pre_cap)
         scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
         keep_idx = torch.empty(n_segs, post_cap, dtype=torch.int32, device=dev)

@@ -167,7 +167,7 @@ def dense_nbr_table(mode, n_frames, H, W, stride, device):
 
 def conv_gather(inp, weight, nbr, taps, cin, cout, out, *, in_ld=None, k_pad=None, scale=None,
                 shift=None, residual=None, res_ld=None, out_ld=None, out_coff=0, relu=False, num=None,
-                rows_cap=None, impl=PN_IMPL_SIMT, in_ptr_offset=0):
+                rows_cap=None, impl=PN_IMPL_SIMT, in_ptr_offset=0, rows_hint=0):
     """out[o, coff:coff+cout] = act((sum_t W_t . in[nbr[o,t]]) * scale + shift + residual).
 
     `inp`/`out` are 2-D channels-last tensors (possibly wider than cin/cout: in_ld/out_ld are the
@@ -196,6 +196,7 @@ def conv_gather(inp, weight, nbr, taps, cin, cout, out, *, in_ld=None, k_pad=Non
     a.num_rows = ptr(num).value
     a.rows_cap = rows_cap if rows_cap is not None else out.shape[0]
     a.cin, a.cout = cin, cout
+    a.rows_hint = int(rows_hint)
     if residual is not None and residual.dtype != out.dtype:
         raise RuntimeError("residual dtype must match the output dtype")
     check(lib.pn_conv_gather(byref(a), impl, stream_ptr()), "pn_conv_gather")
