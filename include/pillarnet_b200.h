@@ -125,8 +125,10 @@ int pn_rulebook_down3x3s2(const uint32_t* in_words, const int* in_prefix, const 
 
 /* Static gather tables for the dense BEV convs (NHWC rows = b*H*W + y*W + x), computed once per shape:
  *   mode 0: 3x3 stride s pad 1 (Conv2d / ZeroPad2d+valid conv), taps 9
- *   mode 1: ConvTranspose2d(k=2,s=2): taps 4, exactly one valid tap (dy*2+dx) per output pixel. */
-int pn_dense_nbr_table(int mode, int n_frames, int H_in, int W_in, int stride, int* nbr,
+ *   mode 1: ConvTranspose2d(k=2,s=2): taps 4, exactly one valid tap (dy*2+dx) per output pixel.
+ * pad_flags bit 0: input rows index a zero-padded (H+2,W+2) map; bit 1: output rows do (border rows get
+ * all -1 taps; the conv then zeroes them, see pn_conv_args.out_hp). */
+int pn_dense_nbr_table(int mode, int n_frames, int H_in, int W_in, int stride, int pad_flags, int* nbr,
                        pn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -163,6 +165,7 @@ typedef struct pn_conv_args {
   int cin;
   int cout;
   int rows_hint;         /* expected live rows (tile-shape heuristic only); 0 => rows_cap */
+  int out_hp, out_wp;    /* != 0: output rows are a zero-padded (B,out_hp,out_wp) map; border rows are written as 0 */
 } pn_conv_args;
 
 int pn_conv_gather(const pn_conv_args* args, int impl, pn_stream_t stream);
@@ -175,10 +178,21 @@ size_t pn_sizeof_task_args(void);
  * (n_frames*H*W, in_ld); group g reads channels [in_coff, in_coff+cin) and writes f32 columns
  * [out_coff, out_coff+cout) of out (rows, out_ld).  groups: device (n_groups,5) int32
  * {in_coff, cout, w_off, s_off, out_coff}; wbuf: packed f32 [cout][9][cin] weights + [cout] biases.
- * cin % 32 == 0.  fp32 accumulation. */
-int pn_conv3x3_small_cout(const void* in, int in_ld, int cin, int n_frames, int H, int W,
+ * cin % 32 == 0.  fp32 accumulation.  in_padded != 0: `in` rows index the zero-padded (H+2,W+2) map. */
+int pn_conv3x3_small_cout(const void* in, int in_ld, int cin, int n_frames, int H, int W, int in_padded,
                           const int* groups, int n_groups, const float* wbuf, float* out, int out_ld,
                           pn_stream_t stream);
+
+/* Dense 3x3 stride-1 pad-1 conv + scale/shift + ReLU on a ZERO-PADDED NHWC layout (tensor cores, TMA).
+ * in : bf16 rows (n_frames*(H+2)*(W+2), in_ld), border rows are zeros; channels [in_coff, in_coff+cin)
+ * weight: bf16 [cout][k_pad] (tap-major, k_pad >= 9*cin, multiple of 64) as pn_conv_pack_weight_bf16 makes
+ * out: padded rows again (borders written as zeros; out_compact = 0) or compact rows
+ *      b*H*W + y*W + x (out_compact = 1); bf16 or f32; columns [out_coff, out_coff+cout).
+ * cin % 64 == 0.  tile_hint: 0 = automatic tile shape (1..4 force one; testing only). */
+int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_frames, int H, int W,
+                     const void* weight, int k_pad, int cout, const float* scale, const float* shift,
+                     void* out, int out_dtype, int out_ld, int out_coff, int out_compact, int relu,
+                     int tile_hint, pn_stream_t stream);
 
 /* f32 -> bf16 weight packing with zero padding of K to k_pad (multiple of 64). */
 int pn_conv_pack_weight_bf16(const float* w_f32, int cout, int k, int k_pad, void* w_bf16,
@@ -189,10 +203,11 @@ int pn_cast_f32_to_bf16(const float* in, int in_ld, void* out, int out_ld, int c
 int pn_cast_bf16_to_f32(const void* in, int in_ld, float* out, int out_ld, int cols,
                         const int* num_rows, int rows_cap, pn_stream_t stream);
 
-/* SparseConvTensor.dense() (spconv) in NHWC: out[(b*H+y)*W+x, coff..coff+C) = feat[rank] or 0. */
+/* SparseConvTensor.dense() (spconv) in NHWC: out[(b*H+y)*W+x, coff..coff+C) = feat[rank] or 0.
+ * out_padded != 0: rows index the zero-padded map (b*(H+2)+y+1)*(W+2)+x+1, borders written as 0. */
 int pn_sparse_to_dense(const void* feat, int dtype, int feat_ld, const uint32_t* occ_words,
                        const int* word_prefix, int n_frames, int H, int W, int C, void* out,
-                       int out_ld, int out_coff, pn_stream_t stream);
+                       int out_ld, int out_coff, int out_padded, pn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (5) CenterHead decode + NMS.

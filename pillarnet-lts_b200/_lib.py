@@ -27,7 +27,7 @@ class ConvArgs(Structure):
         ("out", c_void_p), ("out_dtype", c_int), ("out_ld", c_int), ("out_coff", c_int),
         ("relu", c_int),
         ("num_rows", c_void_p), ("rows_cap", c_int),
-        ("cin", c_int), ("cout", c_int), ("rows_hint", c_int),
+        ("cin", c_int), ("cout", c_int), ("rows_hint", c_int), ("out_hp", c_int), ("out_wp", c_int),
     ]
 
 
@@ -62,17 +62,19 @@ SIGNATURES = {
     "pn_rulebook_down3x3s2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                       c_void_p, c_size_t, c_void_p]),
-    "pn_dense_nbr_table": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pn_dense_nbr_table": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pn_conv_gather": (c_int, [POINTER(ConvArgs), c_int, c_void_p]),
     "pn_sizeof_conv_args": (c_size_t, []),
     "pn_sizeof_task_args": (c_size_t, []),
-    "pn_conv3x3_small_cout": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+    "pn_conv3x3_small_cout": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                       c_void_p, c_int, c_void_p]),
+    "pn_conv_dense3x3": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pn_conv_pack_weight_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pn_cast_f32_to_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pn_cast_bf16_to_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pn_sparse_to_dense": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
-                                   c_int, c_void_p, c_int, c_int, c_void_p]),
+                                   c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pn_decode_candidates": (c_int, [POINTER(TaskArgs), c_int, c_int, c_int, c_float, POINTER(c_float),
                                      c_float, c_float, c_float, POINTER(c_float), c_void_p, c_int,
                                      c_void_p, c_void_p]),

@@ -11,7 +11,7 @@ from torch import nn
 
 from . import config, ops
 from .layers import (DenseMap, SparseConv2d, SparseReLU, SparseSequential, SubMConv2d,
-                     build_norm_layer, dense_conv3x3, lower, run_conv)
+                     build_norm_layer, dense_conv3x3, lower, new_dense_rows, run_conv, use_padded_layout)
 from .registry import BACKBONES
 from .sparse import SparseConvTensor
 
@@ -158,9 +158,10 @@ class _PillarResNet(nn.Module):
             # (necks/rpn.py:201-205) needs no copy: the up-sampled branch writes the right half.
             t = x4.table
             C = x4.feat.shape[1]
-            cat_rows = torch.empty(t.B * t.H * t.W, 2 * C, dtype=x4.feat.dtype, device=x4.feat.device)
-            x4.dense_nhwc(out=cat_rows, out_coff=0)
-            d4 = DenseMap(cat_rows, t.B, t.H, t.W, C, 0)
+            pad = 1 if use_padded_layout() else 0
+            cat_rows = new_dense_rows(t.B, t.H, t.W, 2 * C, x4.feat.dtype, x4.feat.device, pad)
+            x4.dense_nhwc(out=cat_rows, out_coff=0, padded=bool(pad))
+            d4 = DenseMap(cat_rows, t.B, t.H, t.W, C, 0, pad)
             c5 = self.conv5
             d5 = dense_conv3x3(d4, c5[0], c5[1], relu=True, stride=2)
             d5 = dense_conv3x3(d5, c5[3][0], c5[3][1], relu=True)

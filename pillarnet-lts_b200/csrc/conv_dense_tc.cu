@@ -1,0 +1,510 @@
+// Dense 3x3 / stride-1 / pad-1 convolution on tcgen05 over a ZERO-PADDED NHWC layout, fully TMA fed.
+//
+// Replaces the cuDNN Conv2d(3x3)+BatchNorm2d+ReLU stacks of the dense BEV path
+// (det3d/models/backbones/PillarResNet.py:110-117 conv5, det3d/models/necks/rpn.py:172-185 blocks,
+// det3d/models/bbox_heads/center_head.py:27-33,101-105 shared + first-level head convs).
+//
+// Layout trick: a (B,H,W,C) map is stored with a one-pixel zero border, flattened to rows
+// q = (b*Hp + y)*Wp + x, Hp = H+2, Wp = W+2.  A 3x3 tap (dy,dx) of output q then reads input row
+// q + (dy-1)*Wp + (dx-1): a CONSTANT row offset, for every pixel including the image border (the
+// border rows are the padding).  So for a tile of 128*MT consecutive q and one 64-channel K chunk, the
+// three taps of a kernel row dy are three windows, shifted by one 128-byte row, of ONE contiguous
+// segment of 128*MT+2 activation rows — loaded once by TMA (SWIZZLE_128B) and addressed by three UMMA
+// descriptors.  Compared with the gather formulation (conv_tcgen05.cu) this reads each activation row
+// 3x instead of 9x per tile and needs no rulebook; with MT = 2 the 256-row CTA also reuses every weight
+// tile for two MMAs, halving weight bytes per FLOP (the kernel is L2->SM-bandwidth bound).
+//
+// Warp roles (256 threads, persistent): warp 0 lane 0 = activation TMA producer, warp 1 lane 0 = weight
+// TMA producer, warp 2 = TMEM owner + MMA issuer, warps 4-7 = epilogue (folded BN/bias, ReLU, zeroed
+// border rows so the output is again a valid padded map — or compact rows for consumers that want
+// un-padded NHWC).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_K = 64;
+constexpr int kThreads = 256;
+constexpr int kEpilogueThreads = 128;
+constexpr int kTailRows = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();  // protocol bug: trap instead of hanging the box
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B descriptor; the start address may sit on any 128-byte row of a 1024-byte
+// aligned tile (window shifted by dx rows): `base_offset` (bits 49-51) carries (addr >> 7) & 7 when
+// mode != 0 (see the probe in tests/test_gpu_dense_conv.py; mode selected at run time).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, int base_offset_mode) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (base_offset_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct DArgs {
+  int cin;         // multiple of 64
+  int in_coff;     // first input channel inside the (rows, in_ld) matrix
+  int cout;
+  int Hp, Wp;      // padded map size
+  int n_pos;       // B*Hp*Wp
+  const float* scale;
+  const float* shift;
+  void* out;
+  int out_f32;
+  int out_ld;
+  int out_coff;
+  int out_compact; // 0: padded rows (borders zeroed); 1: compact rows b*H*W + (y-1)*W + (x-1)
+  int relu;
+  int base_offset_mode;
+};
+
+template <int MT, int BN, int SA, int SB>
+struct DSmem {
+  static constexpr int kSegRows = 128 * MT + kTailRows;
+  alignas(1024) uint8_t a[SA][kSegRows * 128];
+  alignas(1024) uint8_t b[SB][BN * 128];
+  alignas(8) uint64_t full_a[SA];
+  uint64_t empty_a[SA];
+  uint64_t full_b[SB];
+  uint64_t empty_b[SB];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  float scale[BN];
+  float shift[BN];
+};
+
+template <int MT, int BN, int SA, int SB>
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_constant__ CUtensorMap tmap_a_tail,
+             const __grid_constant__ CUtensorMap tmap_w, const DArgs P) {
+  extern __shared__ uint8_t smem_raw[];
+  using S = DSmem<MT, BN, SA, SB>;
+  S& sm = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int M_TILE = 128 * MT;
+  constexpr int ACC_COLS = MT * BN;                       // fp32 columns per tile
+  constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;     // double-buffer the accumulator when TMEM allows
+  constexpr int TCOLS = (NACC * ACC_COLS) < 32 ? 32 : NACC * ACC_COLS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_n_tiles = (P.cout + BN - 1) / BN;
+  const int n_tiles = ((P.n_pos + M_TILE - 1) / M_TILE) * n_n_tiles;
+  const int n_cc = P.cin / BLOCK_K;
+
+  if (warp == 2) {
+    if (lane == 0) {
+      for (int s = 0; s < SA; ++s) { mbar_init(&sm.full_a[s], 1); mbar_init(&sm.empty_a[s], 1); }
+      for (int s = 0; s < SB; ++s) { mbar_init(&sm.full_b[s], 1); mbar_init(&sm.empty_b[s], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], kEpilogueThreads); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<TCOLS>(&sm.tmem_base);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===================== activation segments (TMA) =====================
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m_tile = tile / n_n_tiles;
+        const int q0 = m_tile * M_TILE;
+        for (int cc = 0; cc < n_cc; ++cc) {
+          for (int dy = 0; dy < 3; ++dy, ++g) {
+            const uint32_t s = g % SA, ph = (g / SA) & 1u;
+            mbar_wait(&sm.empty_a[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&sm.full_a[s], (uint32_t)(S::kSegRows * 128));
+            const int row = q0 + (dy - 1) * P.Wp - 1;   // may be negative / past the end: TMA zero-fills
+            const int ch = P.in_coff + cc * BLOCK_K;
+            tma_load_2d(smem_u32(sm.a[s]), &tmap_a_main, ch, row, &sm.full_a[s]);
+            tma_load_2d(smem_u32(sm.a[s]) + M_TILE * 128, &tmap_a_tail, ch, row + M_TILE, &sm.full_a[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== weight tiles (TMA) =====================
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int n_tile = tile % n_n_tiles;
+        for (int cc = 0; cc < n_cc; ++cc) {
+          for (int tap = 0; tap < 9; ++tap, ++g) {
+            const uint32_t s = g % SB, ph = (g / SB) & 1u;
+            mbar_wait(&sm.empty_b[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&sm.full_b[s], (uint32_t)(BN * 128));
+            tma_load_2d(smem_u32(sm.b[s]), &tmap_w, tap * P.cin + cc * BLOCK_K, n_tile * BN, &sm.full_b[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      uint32_t ga = 0, gb = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = NACC == 2 ? (tcount & 1u) : 0u;
+        const uint32_t acc_ph = NACC == 2 ? ((tcount >> 1) & 1u) : (tcount & 1u);
+        mbar_wait(&sm.tmem_empty[acc], acc_ph ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int cc = 0; cc < n_cc; ++cc) {
+          for (int dy = 0; dy < 3; ++dy, ++ga) {
+            const uint32_t sa = ga % SA, pha = (ga / SA) & 1u;
+            mbar_wait(&sm.full_a[sa], pha);
+            for (int dx = 0; dx < 3; ++dx, ++gb) {
+              const uint32_t sb = gb % SB, phb = (gb / SB) & 1u;
+              mbar_wait(&sm.full_b[sb], phb);
+              tcgen05_fence_after();
+              const uint32_t b_addr = smem_u32(sm.b[sb]);
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                const uint32_t a_addr = smem_u32(sm.a[sa]) + (uint32_t)(m * 128 + dx) * 128u;
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                  const uint64_t a_desc = make_desc(a_addr + k * 32, P.base_offset_mode);
+                  const uint64_t b_desc = make_desc(b_addr + k * 32, 0);
+                  umma_bf16(d_tmem + m * BN, a_desc, b_desc, idesc, (cc | dy | dx | k) != 0 ? 1u : 0u);
+                }
+              }
+              umma_commit(&sm.empty_b[sb]);
+            }
+            umma_commit(&sm.empty_a[sa]);
+          }
+        }
+        umma_commit(&sm.tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int e = warp - 4;
+    const int etid = threadIdx.x - 4 * 32;
+    const int hw_p = P.Hp * P.Wp;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const int m_tile = tile / n_n_tiles, n_tile = tile - m_tile * n_n_tiles;
+      const int n0 = n_tile * BN;
+      const uint32_t acc = NACC == 2 ? (tcount & 1u) : 0u;
+      const uint32_t acc_ph = NACC == 2 ? ((tcount >> 1) & 1u) : (tcount & 1u);
+      named_bar_sync(2, kEpilogueThreads);
+      for (int i = etid; i < BN; i += kEpilogueThreads) {
+        const int n = n0 + i;
+        sm.scale[i] = (n < P.cout && P.scale) ? __ldg(P.scale + n) : 1.f;
+        sm.shift[i] = (n < P.cout && P.shift) ? __ldg(P.shift + n) : 0.f;
+      }
+      named_bar_sync(2, kEpilogueThreads);
+      mbar_wait(&sm.tmem_full[acc], acc_ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int q = m_tile * M_TILE + m * 128 + e * 32 + lane;
+        const bool valid = q < P.n_pos;
+        const int b = valid ? q / hw_p : 0;
+        const int r = q - b * hw_p;
+        const int y = r / P.Wp, x = r - y * P.Wp;
+        const bool border = (x == 0) || (x == P.Wp - 1) || (y == 0) || (y == P.Hp - 1);
+        long long orow = q;
+        bool store = valid;
+        if (P.out_compact) {
+          store = valid && !border;
+          orow = ((long long)b * (P.Hp - 2) + (y - 1)) * (P.Wp - 2) + (x - 1);
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (n0 + c0 >= P.cout) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * ACC_COLS + m * BN + c0, v);
+          tmem_wait_ld();
+          if (store) {
+            const int nvalid = min(32, P.cout - (n0 + c0));
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float t = fmaf(__uint_as_float(v[j]), sm.scale[c0 + j], sm.shift[c0 + j]);
+              if (P.relu) t = fmaxf(t, 0.f);
+              f[j] = (border && !P.out_compact) ? 0.f : t;
+            }
+            const long long ooff = orow * P.out_ld + P.out_coff + n0 + c0;
+            if (P.out_f32) {
+              float* op = reinterpret_cast<float*>(P.out) + ooff;
+              if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) op[j] = f[j];
+              }
+            } else {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + ooff;
+              if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 qv;
+                  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&qv);
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[j + 2 * u], f[j + 2 * u + 1]);
+                  *reinterpret_cast<uint4*>(op + j) = qv;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) op[j] = __float2bfloat16_rn(f[j]);
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&sm.tmem_empty[acc]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<TCOLS>(tmem_base);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct Key {
+  const void* ptr;
+  long long rows;
+  int cols, ld, box_rows;
+  bool operator==(const Key& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct KeyHash {
+  size_t operator()(const Key& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (size_t)k.rows * 1000003u ^ (size_t)k.cols * 10007u ^
+           (size_t)k.ld * 131u ^ (size_t)k.box_rows;
+  }
+};
+
+// 2-D bf16 tensor map over a row-major (rows, cols) matrix with row stride ld; box = 64 cols x box_rows.
+int get_map(const void* base, long long rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  Key key{base, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return PN_OK; }
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return PN_ERR_UNSUPPORTED;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return PN_ERR_CUDA;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+  }
+  *out = m;
+  return PN_OK;
+}
+
+template <int MT, int BN, int SA, int SB>
+int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, const DArgs& a, int grid,
+           cudaStream_t stream) {
+  constexpr size_t smem = sizeof(DSmem<MT, BN, SA, SB>) + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    PN_CUDA(cudaFuncSetAttribute(k_conv_dense<MT, BN, SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    configured = true;
+  }
+  k_conv_dense<MT, BN, SA, SB><<<grid, kThreads, smem, stream>>>(ma, mt, mw, a);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_frames, int H, int W,
+                     const void* weight, int k_pad, int cout, const float* scale, const float* shift,
+                     void* out, int out_dtype, int out_ld, int out_coff, int out_compact, int relu,
+                     int tile_hint, pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(in && weight && out && n_frames >= 1 && H > 0 && W > 0 && cout >= 1);
+  PN_REQUIRE(cin % BLOCK_K == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && k_pad % BLOCK_K == 0 && k_pad >= 9 * cin);
+  PN_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15u) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15u) == 0);
+  PN_REQUIRE(out_dtype == PN_F32 || out_dtype == PN_BF16);
+  const int Hp = H + 2, Wp = W + 2;
+  const long long n_pos = (long long)n_frames * Hp * Wp;
+  PN_REQUIRE(n_pos < (1ll << 31));
+  const int sms = pn_detail::sm_count();
+  if (sms <= 0) return PN_ERR_CUDA;
+  // tile shape: minimise waves x per-tap cost, cost = max(load bytes / ~20 B/clk, MMA cycles)
+  struct Cand { int mt, bn; };
+  const Cand cands[4] = {{2, 256}, {1, 256}, {2, 128}, {1, 128}};
+  int best = -1;
+  double best_cost = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int mt = cands[i].mt, bn = cands[i].bn;
+    if (bn > 128 && cout <= 128) continue;
+    const long long tiles = PN_DIVUP(n_pos, (long long)(128 * mt)) * PN_DIVUP(cout, bn);
+    const double waves = (double)PN_DIVUP(tiles, (long long)sms);
+    const double bytes = bn * 128.0 + (128.0 * mt + kTailRows) * 128.0 / 3.0;
+    const double mma = mt * 4.0 * (bn / 2.0);
+    const double per_tap = bytes / 20.0 > mma ? bytes / 20.0 : mma;
+    const double cost = waves * per_tap;
+    if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
+  }
+  if (tile_hint >= 1 && tile_hint <= 4) best = tile_hint - 1;
+  const int mt = cands[best].mt, bn = cands[best].bn;
+  CUtensorMap ma, mtail, mw;
+  int rc = get_map(in, n_pos, in_ld, in_ld, 128 * mt, &ma);
+  if (rc != PN_OK) return rc;
+  rc = get_map(in, n_pos, in_ld, in_ld, kTailRows, &mtail);
+  if (rc != PN_OK) return rc;
+  rc = get_map(weight, cout, k_pad, k_pad, bn, &mw);
+  if (rc != PN_OK) return rc;
+  DArgs a;
+  a.cin = cin; a.in_coff = in_coff; a.cout = cout; a.Hp = Hp; a.Wp = Wp; a.n_pos = (int)n_pos;
+  a.scale = scale; a.shift = shift; a.out = out; a.out_f32 = out_dtype == PN_F32; a.out_ld = out_ld;
+  a.out_coff = out_coff; a.out_compact = out_compact; a.relu = relu;
+  a.base_offset_mode = (tile_hint & 0x100) ? 1 : 0;
+  const long long tiles = PN_DIVUP(n_pos, (long long)(128 * mt)) * PN_DIVUP(cout, bn);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  if (mt == 2 && bn == 256) return launch<2, 256, 2, 4>(ma, mtail, mw, a, grid, stream);
+  if (mt == 1 && bn == 256) return launch<1, 256, 3, 5>(ma, mtail, mw, a, grid, stream);
+  if (mt == 2 && bn == 128) return launch<2, 128, 3, 6>(ma, mtail, mw, a, grid, stream);
+  return launch<1, 128, 4, 8>(ma, mtail, mw, a, grid, stream);
+}
+
+}  // extern "C"

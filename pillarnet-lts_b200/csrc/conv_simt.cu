@@ -29,7 +29,7 @@ k_conv_simt(const TIn* __restrict__ in, int in_ld, const int* __restrict__ nbr, 
             const TIn* __restrict__ weight, int k_pad, const float* __restrict__ scale,
             const float* __restrict__ shift, const TOut* __restrict__ residual, int res_ld,
             TOut* __restrict__ out, int out_ld, int out_coff, int relu,
-            const int* __restrict__ num_rows, int rows_cap, int cin, int cout) {
+            const int* __restrict__ num_rows, int rows_cap, int cin, int cout, int out_hp, int out_wp) {
   __shared__ float sA[TK][TM + 1];
   __shared__ float sW[TK][TN + 1];
   __shared__ int sNbr[TM];
@@ -91,6 +91,12 @@ k_conv_simt(const TIn* __restrict__ in, int in_ld, const int* __restrict__ nbr, 
   for (int i = 0; i < 4; ++i) {
     const int r = row0 + ty * 4 + i;
     if (r >= rows) continue;
+    bool border = false;
+    if (out_wp > 0) {
+      const int q = r % (out_hp * out_wp);
+      const int y = q / out_wp, x = q - y * out_wp;
+      border = x == 0 || x == out_wp - 1 || y == 0 || y == out_hp - 1;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
@@ -101,6 +107,7 @@ k_conv_simt(const TIn* __restrict__ in, int in_ld, const int* __restrict__ nbr, 
       v = fmaf(v, sc, sh);
       if (residual) v += to_f32<TOut>(residual[(long long)r * res_ld + n]);
       if (relu) v = fmaxf(v, 0.f);
+      if (border) v = 0.f;
       out[(long long)r * out_ld + out_coff + n] = from_f32<TOut>(v);
     }
   }
@@ -113,7 +120,7 @@ int launch_simt(const pn_conv_args* a, cudaStream_t stream) {
   k_conv_simt<TIn, TOut><<<grid, THREADS, 0, stream>>>(
       (const TIn*)a->in, a->in_ld, a->nbr, a->taps, (const TIn*)a->weight, a->k_pad, a->scale,
       a->shift, (const TOut*)a->residual, a->res_ld, (TOut*)a->out, a->out_ld, a->out_coff, a->relu,
-      a->num_rows, a->rows_cap, a->cin, a->cout);
+      a->num_rows, a->rows_cap, a->cin, a->cout, a->out_hp, a->out_wp);
   PN_CHECK_LAUNCH();
   return PN_OK;
 }
@@ -143,23 +150,28 @@ k_cast_rows(const TI* __restrict__ in, int in_ld, TO* __restrict__ out, int out_
 }
 
 // Dense-driven densify: one thread per (pixel, 8-byte chunk); absent pixels get zeros, so no memset
-// and every output byte is written exactly once, coalesced along channels.
+// and every output byte is written exactly once, coalesced along channels.  pad = 1: the output rows
+// are the zero-padded (H+2, W+2) map (borders written as zeros).
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_sparse_to_dense(const T* __restrict__ feat, int feat_ld, const uint32_t* __restrict__ words,
-                  const int* __restrict__ prefix, long long n_cells, int C, T* __restrict__ out,
-                  int out_ld, int out_coff) {
+                  const int* __restrict__ prefix, int n_frames, int H, int W, int pad, int C,
+                  T* __restrict__ out, int out_ld, int out_coff) {
   constexpr int V = 8 / sizeof(T);  // elements per 8-byte chunk
   const int chunks = C / V;
-  const long long total = n_cells * chunks;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const long long total = (long long)n_frames * Hp * Wp * chunks;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long cell = i / chunks;
-    const int ch = (int)(i - cell * chunks);
-    const int r = pn_rank_of(words, prefix, (int)cell);
+    const long long pos = i / chunks;
+    const int ch = (int)(i - pos * chunks);
+    const int x = (int)(pos % Wp) - pad, y = (int)((pos / Wp) % Hp) - pad;
+    const int b = (int)(pos / ((long long)Wp * Hp));
+    int r = -1;
+    if (x >= 0 && x < W && y >= 0 && y < H) r = pn_rank_of(words, prefix, (b * H + y) * W + x);
     uint2 v = make_uint2(0u, 0u);
     if (r >= 0) v = *reinterpret_cast<const uint2*>(feat + (long long)r * feat_ld + ch * V);
-    *reinterpret_cast<uint2*>(out + cell * out_ld + out_coff + ch * V) = v;
+    *reinterpret_cast<uint2*>(out + pos * out_ld + out_coff + ch * V) = v;
   }
 }
 
@@ -232,18 +244,19 @@ int pn_cast_bf16_to_f32(const void* in, int in_ld, float* out, int out_ld, int c
 
 int pn_sparse_to_dense(const void* feat, int dtype, int feat_ld, const uint32_t* occ_words,
                        const int* word_prefix, int n_frames, int H, int W, int C, void* out,
-                       int out_ld, int out_coff, pn_stream_t stream_) {
+                       int out_ld, int out_coff, int out_padded, pn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   PN_REQUIRE(feat && occ_words && word_prefix && out && n_frames >= 1 && H > 0 && W > 0 && C > 0);
-  const long long n_cells = (long long)n_frames * H * W;
+  const int pad = out_padded ? 1 : 0;
+  const long long n_cells = (long long)n_frames * (H + 2 * pad) * (W + 2 * pad);
   if (dtype == PN_F32) {
     PN_REQUIRE(C % 2 == 0 && feat_ld % 2 == 0 && out_ld % 2 == 0 && out_coff % 2 == 0);
     k_sparse_to_dense<float><<<grid_for(n_cells * (C / 2), 256), 256, 0, stream>>>(
-        (const float*)feat, feat_ld, occ_words, word_prefix, n_cells, C, (float*)out, out_ld, out_coff);
+        (const float*)feat, feat_ld, occ_words, word_prefix, n_frames, H, W, pad, C, (float*)out, out_ld, out_coff);
   } else if (dtype == PN_BF16) {
     PN_REQUIRE(C % 4 == 0 && feat_ld % 4 == 0 && out_ld % 4 == 0 && out_coff % 4 == 0);
     k_sparse_to_dense<__nv_bfloat16><<<grid_for(n_cells * (C / 4), 256), 256, 0, stream>>>(
-        (const __nv_bfloat16*)feat, feat_ld, occ_words, word_prefix, n_cells, C, (__nv_bfloat16*)out,
+        (const __nv_bfloat16*)feat, feat_ld, occ_words, word_prefix, n_frames, H, W, pad, C, (__nv_bfloat16*)out,
         out_ld, out_coff);
   } else {
     return PN_ERR_INVALID_ARG;

@@ -61,7 +61,7 @@ __device__ __forceinline__ void compute_chunk(const uint32_t* __restrict__ s_in,
 }
 
 template <int COUT>
-__device__ __forceinline__ void run_group(const __nv_bfloat16* __restrict__ in, int in_ld, int cin, int H, int W,
+__device__ __forceinline__ void run_group(const __nv_bfloat16* __restrict__ in, int in_ld, int cin, int H, int W, int pad,
                                           const GroupDesc& g, const float* __restrict__ wbuf,
                                           float* __restrict__ out, int out_ld, uint32_t* s_in, float* s_w,
                                           int b, int y0, int x0) {
@@ -92,7 +92,8 @@ __device__ __forceinline__ void run_group(const __nv_bfloat16* __restrict__ in, 
           const int gy = y0 + hy - 1, gx = x0 + hx - 1;
           so[i] = pr * (HH_ * RS) + hy * RS + hx;
           if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            const __nv_bfloat16* p = in + ((long long)(b * H + gy) * W + gx) * in_ld + g.in_coff + c0;
+            const __nv_bfloat16* p =
+                in + ((long long)(b * (H + 2 * pad) + gy + pad) * (W + 2 * pad) + gx + pad) * in_ld + g.in_coff + c0;
             u[i] = __ldg(reinterpret_cast<const uint32_t*>(p) + pr);
           }
         }
@@ -124,7 +125,7 @@ __device__ __forceinline__ void run_group(const __nv_bfloat16* __restrict__ in, 
 }
 
 __global__ void __launch_bounds__(THREADS)
-k_conv3x3_small(const __nv_bfloat16* __restrict__ in, int in_ld, int cin, int H, int W, int tiles_x,
+k_conv3x3_small(const __nv_bfloat16* __restrict__ in, int in_ld, int cin, int H, int W, int pad, int tiles_x,
                 int tiles_y, const GroupDesc* __restrict__ groups, const float* __restrict__ wbuf,
                 float* __restrict__ out, int out_ld) {
   __shared__ uint32_t s_in[PAIRS * HH_ * RS];
@@ -135,10 +136,10 @@ k_conv3x3_small(const __nv_bfloat16* __restrict__ in, int in_ld, int cin, int H,
   const int r = t - b * tiles_x * tiles_y;
   const int y0 = (r / tiles_x) * TH, x0 = (r % tiles_x) * TW;
   switch (g.cout) {
-    case 1: run_group<1>(in, in_ld, cin, H, W, g, wbuf, out, out_ld, s_in, s_w, b, y0, x0); break;
-    case 2: run_group<2>(in, in_ld, cin, H, W, g, wbuf, out, out_ld, s_in, s_w, b, y0, x0); break;
-    case 3: run_group<3>(in, in_ld, cin, H, W, g, wbuf, out, out_ld, s_in, s_w, b, y0, x0); break;
-    default: run_group<4>(in, in_ld, cin, H, W, g, wbuf, out, out_ld, s_in, s_w, b, y0, x0); break;
+    case 1: run_group<1>(in, in_ld, cin, H, W, pad, g, wbuf, out, out_ld, s_in, s_w, b, y0, x0); break;
+    case 2: run_group<2>(in, in_ld, cin, H, W, pad, g, wbuf, out, out_ld, s_in, s_w, b, y0, x0); break;
+    case 3: run_group<3>(in, in_ld, cin, H, W, pad, g, wbuf, out, out_ld, s_in, s_w, b, y0, x0); break;
+    default: run_group<4>(in, in_ld, cin, H, W, pad, g, wbuf, out, out_ld, s_in, s_w, b, y0, x0); break;
   }
 }
 
@@ -148,7 +149,7 @@ extern "C" {
 
 // groups: device array of n_groups x 5 int32 {in_coff, cout(1..4), w_off, s_off, out_coff};
 // wbuf: packed f32 weights ([cout][9][cin] per group) and shifts.  in: bf16 NHWC rows, out: f32 rows.
-int pn_conv3x3_small_cout(const void* in, int in_ld, int cin, int n_frames, int H, int W,
+int pn_conv3x3_small_cout(const void* in, int in_ld, int cin, int n_frames, int H, int W, int in_padded,
                           const int* groups, int n_groups, const float* wbuf, float* out, int out_ld,
                           pn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -157,7 +158,7 @@ int pn_conv3x3_small_cout(const void* in, int in_ld, int cin, int n_frames, int 
   PN_REQUIRE((reinterpret_cast<uintptr_t>(in) & 3u) == 0);
   const int tiles_x = PN_DIVUP(W, TW), tiles_y = PN_DIVUP(H, TH);
   dim3 grid(n_frames * tiles_x * tiles_y, n_groups);
-  k_conv3x3_small<<<grid, THREADS, 0, stream>>>((const __nv_bfloat16*)in, in_ld, cin, H, W, tiles_x, tiles_y,
+  k_conv3x3_small<<<grid, THREADS, 0, stream>>>((const __nv_bfloat16*)in, in_ld, cin, H, W, in_padded ? 1 : 0, tiles_x, tiles_y,
                                                 reinterpret_cast<const GroupDesc*>(groups), wbuf, out, out_ld);
   PN_CHECK_LAUNCH();
   return PN_OK;

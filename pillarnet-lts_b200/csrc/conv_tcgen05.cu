@@ -35,7 +35,6 @@ constexpr int A_STAGE_BYTES = BLOCK_M * 128;
 constexpr int kProducerThreads = 128;
 constexpr int kEpilogueThreads = 128;
 constexpr int kThreads = 288;
-constexpr int kLag = 3;           // cp.async groups kept in flight per producer thread (<= STAGES-1)
 constexpr int kMaxTaps = 9;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -188,6 +187,7 @@ struct KArgs {
   int rows_cap;
   int cin;
   int cout;
+  int out_hp, out_wp;  // != 0: zero the border rows of a padded output map
 };
 
 template <int BN, int STAGES>
@@ -220,6 +220,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const KArgs P) {
   const int n_n_tiles = (P.cout + BN - 1) / BN;
   const int n_tiles = ((rows + BLOCK_M - 1) / BLOCK_M) * n_n_tiles;
   constexpr int TCOLS = tmem_cols<BN>();
+  // cp.async groups kept in flight per producer thread; the MMA trails the issue point by kLag chunks,
+  // so kLag must leave at least two free stages (measured: lag 3 with 4 stages costs 25 %).
+  constexpr int kLag = STAGES >= 6 ? 3 : 2;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -360,6 +363,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const KArgs P) {
       tcgen05_fence_after();
       const int row = m_tile * BLOCK_M + e * 32 + lane;
       const bool row_ok = row < rows;
+      bool border = false;
+      if (P.out_wp > 0) {
+        const int q = row % (P.out_hp * P.out_wp);
+        const int y = q / P.out_wp, x = q - y * P.out_wp;
+        border = x == 0 || x == P.out_wp - 1 || y == 0 || y == P.out_hp - 1;
+      }
       constexpr int CH = BN < 32 ? 16 : 32;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
@@ -385,6 +394,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const KArgs P) {
             if (P.relu) {
 #pragma unroll
               for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (border) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) f[j] = 0.f;
             }
             if (nvalid == CH && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
 #pragma unroll
@@ -421,6 +434,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const KArgs P) {
             if (P.relu) {
 #pragma unroll
               for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (border) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) f[j] = 0.f;
             }
             if (nvalid == CH && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
 #pragma unroll
@@ -581,6 +598,8 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
   ka.rows_cap = a->rows_cap;
   ka.cin = a->cin;
   ka.cout = a->cout;
+  ka.out_hp = a->out_hp;
+  ka.out_wp = a->out_wp;
   const int sms = sm_count();
   if (sms <= 0) return PN_ERR_CUDA;
   const long long tiles_cap = (long long)PN_DIVUP(a->rows_cap, BLOCK_M) * PN_DIVUP(a->cout, bn);

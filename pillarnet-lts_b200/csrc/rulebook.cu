@@ -73,35 +73,47 @@ k_down_nbr(const uint32_t* __restrict__ in_words, const int* __restrict__ in_pre
   }
 }
 
-// Dense NHWC gather tables (static per shape).
+// Dense NHWC gather tables (static per shape).  pi/po = 1 when the input/output rows index a
+// zero-padded (H+2, W+2) map.
 __global__ void __launch_bounds__(256)
-k_dense_nbr_conv3(int n_frames, int H, int W, int stride, int Ho, int Wo, int* __restrict__ nbr) {
-  const long long total = (long long)n_frames * Ho * Wo * 9;
+k_dense_nbr_conv3(int n_frames, int H, int W, int stride, int Ho, int Wo, int pi, int po,
+                  int* __restrict__ nbr) {
+  const int Hop = Ho + 2 * po, Wop = Wo + 2 * po, Hip = H + 2 * pi, Wip = W + 2 * pi;
+  const long long total = (long long)n_frames * Hop * Wop * 9;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     const long long o = t / 9;
     const int k = (int)(t - o * 9);
-    const int ox = (int)(o % Wo);
-    const int oy = (int)((o / Wo) % Ho);
-    const int b = (int)(o / ((long long)Wo * Ho));
-    const int yy = oy * stride - 1 + k / 3, xx = ox * stride - 1 + k % 3;
-    nbr[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (b * H + yy) * W + xx : -1;
+    const int ox = (int)(o % Wop) - po;
+    const int oy = (int)((o / Wop) % Hop) - po;
+    const int b = (int)(o / ((long long)Wop * Hop));
+    int v = -1;
+    if (ox >= 0 && ox < Wo && oy >= 0 && oy < Ho) {
+      const int yy = oy * stride - 1 + k / 3, xx = ox * stride - 1 + k % 3;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = (b * Hip + yy + pi) * Wip + xx + pi;
+    }
+    nbr[t] = v;
   }
 }
 
 __global__ void __launch_bounds__(256)
-k_dense_nbr_deconv2(int n_frames, int H, int W, int* __restrict__ nbr) {
+k_dense_nbr_deconv2(int n_frames, int H, int W, int pi, int po, int* __restrict__ nbr) {
   const int Ho = 2 * H, Wo = 2 * W;
-  const long long total = (long long)n_frames * Ho * Wo * 4;
+  const int Hop = Ho + 2 * po, Wop = Wo + 2 * po, Hip = H + 2 * pi, Wip = W + 2 * pi;
+  const long long total = (long long)n_frames * Hop * Wop * 4;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     const long long o = t >> 2;
     const int k = (int)(t & 3);
-    const int ox = (int)(o % Wo);
-    const int oy = (int)((o / Wo) % Ho);
-    const int b = (int)(o / ((long long)Wo * Ho));
-    const int tap = (oy & 1) * 2 + (ox & 1);
-    nbr[t] = (k == tap) ? (b * H + (oy >> 1)) * W + (ox >> 1) : -1;
+    const int ox = (int)(o % Wop) - po;
+    const int oy = (int)((o / Wop) % Hop) - po;
+    const int b = (int)(o / ((long long)Wop * Hop));
+    int v = -1;
+    if (ox >= 0 && ox < Wo && oy >= 0 && oy < Ho) {
+      const int tap = (oy & 1) * 2 + (ox & 1);
+      if (k == tap) v = (b * Hip + (oy >> 1) + pi) * Wip + (ox >> 1) + pi;
+    }
+    nbr[t] = v;
   }
 }
 
@@ -162,18 +174,19 @@ int pn_rulebook_down3x3s2(const uint32_t* in_words, const int* in_prefix, const 
   return PN_OK;
 }
 
-int pn_dense_nbr_table(int mode, int n_frames, int H_in, int W_in, int stride, int* nbr,
+int pn_dense_nbr_table(int mode, int n_frames, int H_in, int W_in, int stride, int pad_flags, int* nbr,
                        pn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   PN_REQUIRE(nbr && n_frames >= 1 && H_in > 0 && W_in > 0);
+  const int pi = pad_flags & 1, po = (pad_flags >> 1) & 1;
   if (mode == 0) {
     PN_REQUIRE(stride == 1 || stride == 2);
     const int Ho = (H_in + 2 - 3) / stride + 1, Wo = (W_in + 2 - 3) / stride + 1;
-    const long long total = (long long)n_frames * Ho * Wo * 9;
-    k_dense_nbr_conv3<<<grid_for(total, 256), 256, 0, stream>>>(n_frames, H_in, W_in, stride, Ho, Wo, nbr);
+    const long long total = (long long)n_frames * (Ho + 2 * po) * (Wo + 2 * po) * 9;
+    k_dense_nbr_conv3<<<grid_for(total, 256), 256, 0, stream>>>(n_frames, H_in, W_in, stride, Ho, Wo, pi, po, nbr);
   } else if (mode == 1) {
-    const long long total = (long long)n_frames * H_in * W_in * 16;
-    k_dense_nbr_deconv2<<<grid_for(total, 256), 256, 0, stream>>>(n_frames, H_in, W_in, nbr);
+    const long long total = (long long)n_frames * (2 * H_in + 2 * po) * (2 * W_in + 2 * po) * 4;
+    k_dense_nbr_deconv2<<<grid_for(total, 256), 256, 0, stream>>>(n_frames, H_in, W_in, pi, po, nbr);
   } else {
     return PN_ERR_INVALID_ARG;
   }

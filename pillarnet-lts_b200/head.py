@@ -31,6 +31,13 @@ class PackedPreds(dict):
     shape = None     # (B, H, W)
 
 
+class _GroupConv:
+    """shape-only stand-in passed to dense_conv3x3 together with an already lowered (fused) weight"""
+
+    def __init__(self, out_channels):
+        self.out_channels = out_channels
+
+
 class SepHead(nn.Module):
     def __init__(self, in_channels, heads, head_conv=64, init_bias=-2.19, **kwargs):
         super().__init__(**kwargs)
@@ -103,28 +110,30 @@ class CenterHead(nn.Module):
                        for name in self.task_heads[t].heads]
             two_level = [e for e in entries if len(e[2]) == 4]
             inter = None
+            pad = feat.pad
+            n_pix = feat.B * feat.H * feat.W
             if two_level:
                 lw = lower_group([e[2][0] for e in two_level], [e[2][1] for e in two_level])
                 hc = two_level[0][2][0].out_channels
-                nbr = ops.dense_nbr_table(0, feat.B, feat.H, feat.W, 1, feat.rows.device)
-                inter = run_conv(feat.rows, lw, nbr, 9, feat.C, hc * len(two_level), feat.rows.shape[0],
-                                 relu=True, in_ld=feat.rows.stride(0), in_ptr_offset=feat.coff)
+                # all first-level head convs of all tasks on this feature: one conv, Cout = n_heads*hc
+                inter = dense_conv3x3(feat, _GroupConv(hc * len(two_level)), None, relu=True, lowered=lw)
             slot = {id(e[2]): i for i, e in enumerate(two_level)}
-            nbr = ops.dense_nbr_table(0, feat.B, feat.H, feat.W, 1, feat.rows.device)
+            # gather table of the final convs: reads the (possibly padded) intermediate, writes compact rows
+            nbr = ops.dense_nbr_table(0, feat.B, feat.H, feat.W, 1, feat.rows.device, in_pad=bool(pad), out_pad=False)
             # one packed f32 map for all tasks on this feature; a task's maps are a column slice of it
             t_off, total = {}, 0
             for t in tids:
                 t_off[t] = total
                 total += sum(v[0] for v in self.task_heads[t].heads.values())
-            all_rows = torch.empty(feat.rows.shape[0], total, dtype=torch.float32, device=feat.rows.device)
-            fused_final = (inter is not None and inter.dtype == torch.bfloat16 and len(two_level) == len(entries)
+            all_rows = torch.empty(n_pix, total, dtype=torch.float32, device=feat.rows.device)
+            fused_final = (inter is not None and inter.rows.dtype == torch.bfloat16 and len(two_level) == len(entries)
                            and all(e[2][-1].out_channels <= 4 for e in entries)
                            and two_level[0][2][0].out_channels % 32 == 0)
             if fused_final:
                 hc = two_level[0][2][0].out_channels
                 groups, wbuf = self._final_groups(fi, entries, slot, t_off, hc)
-                ops.conv3x3_small_cout(inter, inter.stride(0), hc, feat.B, feat.H, feat.W, groups, len(entries),
-                                       wbuf, all_rows)
+                ops.conv3x3_small_cout(inter.rows, inter.rows.stride(0), hc, feat.B, feat.H, feat.W, groups,
+                                       len(entries), wbuf, all_rows, in_padded=bool(inter.pad))
             for t in tids:
                 th = self.task_heads[t]
                 offsets, c = {}, 0
@@ -140,14 +149,14 @@ class CenterHead(nn.Module):
                     if len(fc) == 4:
                         i = slot[id(fc)]
                         hc = fc[0].out_channels
-                        run_conv(inter, lower(final, None), nbr, 9, hc, final.out_channels, rows.shape[0],
-                                 out=all_rows, out_coff=t_off[t] + offsets[name], in_ld=inter.stride(0),
+                        run_conv(inter.rows, lower(final, None), nbr, 9, hc, final.out_channels, n_pix,
+                                 out=all_rows, out_coff=t_off[t] + offsets[name], in_ld=inter.rows.stride(0),
                                  in_ptr_offset=i * hc)
                     else:
                         cur = feat
                         for j in range(0, len(fc) - 1, 3):
                             cur = dense_conv3x3(cur, fc[j], fc[j + 1], relu=True)
-                        run_conv(cur.rows, lower(final, None), nbr, 9, cur.C, final.out_channels, rows.shape[0],
+                        run_conv(cur.rows, lower(final, None), nbr, 9, cur.C, final.out_channels, n_pix,
                                  out=all_rows, out_coff=t_off[t] + offsets[name], in_ld=cur.rows.stride(0),
                                  in_ptr_offset=cur.coff)
                 pp = PackedPreds()

@@ -177,60 +177,95 @@ def lower_group(convs, bns, precision=None):
 
 
 def run_conv(x2d, lw, nbr, taps, cin, cout, rows_cap, *, num=None, relu=False, residual=None, out=None,
-             out_coff=0, out_dtype=None, in_ld=None, in_ptr_offset=0, rows_hint=0):
+             out_coff=0, out_dtype=None, in_ld=None, in_ptr_offset=0, rows_hint=0, out_hw_pad=None):
     """One fused conv launch on channels-last rows."""
     if out is None:
         out = torch.empty(rows_cap, cout, dtype=out_dtype or x2d.dtype, device=x2d.device)
     ops.conv_gather(x2d, lw.weight, nbr, taps, cin, cout, out, in_ld=in_ld, k_pad=lw.k_pad, scale=lw.scale,
                     shift=lw.shift, residual=residual, out_coff=out_coff, relu=relu, num=num,
-                    rows_cap=rows_cap, impl=config.conv_impl(), in_ptr_offset=in_ptr_offset, rows_hint=rows_hint)
+                    rows_cap=rows_cap, impl=config.conv_impl(), in_ptr_offset=in_ptr_offset, rows_hint=rows_hint,
+                    out_hw_pad=out_hw_pad)
     return out
 
 
+def use_padded_layout():
+    """bf16 tensor-core mode stores dense BEV maps with a one-pixel zero border (see conv_dense_tc.cu)."""
+    return config.get_precision() == "bf16"
+
+
 class DenseMap:
-    """Channels-last dense BEV map: rows (B*H*W, ld) with the logical channels at [coff, coff+C)."""
+    """Channels-last dense BEV map: rows (B*Hs*Ws, ld) with the logical channels at [coff, coff+C).
+    pad = 1: storage is the zero-bordered map, Hs = H+2, Ws = W+2 (the layout pn_conv_dense3x3 uses)."""
 
-    __slots__ = ("rows", "B", "H", "W", "C", "coff")
+    __slots__ = ("rows", "B", "H", "W", "C", "coff", "pad")
 
-    def __init__(self, rows, B, H, W, C, coff=0):
-        self.rows, self.B, self.H, self.W, self.C, self.coff = rows, B, H, W, C, coff
+    def __init__(self, rows, B, H, W, C, coff=0, pad=0):
+        self.rows, self.B, self.H, self.W, self.C, self.coff, self.pad = rows, B, H, W, C, coff, pad
+
+    @property
+    def n_rows(self):
+        return self.B * (self.H + 2 * self.pad) * (self.W + 2 * self.pad)
 
     def nchw(self):
         """(B,C,H,W) view (channels_last strides), the reference's dense layout."""
-        v = self.rows.view(self.B, self.H, self.W, -1)[..., self.coff:self.coff + self.C].permute(0, 3, 1, 2)
+        p = self.pad
+        v = self.rows.view(self.B, self.H + 2 * p, self.W + 2 * p, -1)
+        if p:
+            v = v[:, 1:-1, 1:-1]
+        v = v[..., self.coff:self.coff + self.C].permute(0, 3, 1, 2)
         v._pn_dense = self  # lets the next module recover the NHWC rows without a copy
         return v
 
     @staticmethod
     def from_nchw(t):
         d = getattr(t, "_pn_dense", None)
-        if d is not None:
+        if d is not None and (d.pad == 1) == use_padded_layout():
             return d
         B, C, H, W = t.shape
-        rows = t.permute(0, 2, 3, 1).contiguous().view(B * H * W, C)
-        if rows.dtype != config.act_dtype():
-            rows = rows.to(config.act_dtype())
-        return DenseMap(rows, B, H, W, C)
+        x = t.permute(0, 2, 3, 1)
+        if x.dtype != config.act_dtype():
+            x = x.to(config.act_dtype())
+        if use_padded_layout():
+            x = torch.nn.functional.pad(x, (0, 0, 1, 1, 1, 1))
+            return DenseMap(x.contiguous().view(B * (H + 2) * (W + 2), C), B, H, W, C, 0, 1)
+        return DenseMap(x.contiguous().view(B * H * W, C), B, H, W, C)
 
 
-def dense_conv3x3(x, conv, bn, relu=True, stride=1, out=None, out_coff=0, out_dtype=None):
-    """3x3 pad-1 dense conv (also ZeroPad2d(1)+valid conv, necks/rpn.py:172-176) on a DenseMap."""
+def new_dense_rows(B, H, W, width, dtype, device, pad):
+    return torch.empty(B * (H + 2 * pad) * (W + 2 * pad), width, dtype=dtype, device=device)
+
+
+def dense_conv3x3(x, conv, bn, relu=True, stride=1, out=None, out_coff=0, out_dtype=None, out_compact=False,
+                  lowered=None):
+    """3x3 pad-1 dense conv (also ZeroPad2d(1)+valid conv, necks/rpn.py:172-176) on a DenseMap.
+    Padded maps + stride 1 run on the TMA-fed dense tensor-core kernel; everything else on the gather conv."""
     Ho, Wo = (x.H + 2 - 3) // stride + 1, (x.W + 2 - 3) // stride + 1
-    nbr = ops.dense_nbr_table(0, x.B, x.H, x.W, stride, x.rows.device)
-    lw = lower(conv, bn)
+    lw = lowered if lowered is not None else lower(conv, bn)
     cout = conv.out_channels
-    rows_cap = x.B * Ho * Wo
-    o = run_conv(x.rows, lw, nbr, 9, x.C, cout, rows_cap, relu=relu, out=out, out_coff=out_coff,
-                 out_dtype=out_dtype, in_ld=x.rows.stride(0), in_ptr_offset=x.coff)
-    return DenseMap(o, x.B, Ho, Wo, cout, out_coff)
+    opad = 0 if out_compact else x.pad
+    if out is None:
+        out = new_dense_rows(x.B, Ho, Wo, cout, out_dtype or x.rows.dtype, x.rows.device, opad)
+    if x.pad and stride == 1 and x.C % 64 == 0 and x.coff % 8 == 0:
+        ops.conv_dense3x3(x.rows, x.coff, x.C, x.B, x.H, x.W, lw.weight, cout, out, scale=lw.scale, shift=lw.shift,
+                          out_coff=out_coff, out_compact=out_compact, relu=relu)
+    else:
+        nbr = ops.dense_nbr_table(0, x.B, x.H, x.W, stride, x.rows.device, in_pad=bool(x.pad), out_pad=bool(opad))
+        rows_cap = x.B * (Ho + 2 * opad) * (Wo + 2 * opad)
+        run_conv(x.rows, lw, nbr, 9, x.C, cout, rows_cap, relu=relu, out=out, out_coff=out_coff,
+                 in_ld=x.rows.stride(0), in_ptr_offset=x.coff,
+                 out_hw_pad=(Ho + 2, Wo + 2) if opad else None)
+    return DenseMap(out, x.B, Ho, Wo, cout, out_coff, opad)
 
 
 def dense_deconv2x2(x, conv, bn, relu=True, out=None, out_coff=0):
     """ConvTranspose2d(k=2,s=2)+BN+ReLU (necks/rpn.py:150-154) as a 4-tap gather conv."""
-    nbr = ops.dense_nbr_table(1, x.B, x.H, x.W, 2, x.rows.device)
+    nbr = ops.dense_nbr_table(1, x.B, x.H, x.W, 2, x.rows.device, in_pad=bool(x.pad), out_pad=bool(x.pad))
     lw = lower(conv, bn)
     cout = conv.out_channels
-    rows_cap = x.B * 4 * x.H * x.W
-    o = run_conv(x.rows, lw, nbr, 4, x.C, cout, rows_cap, relu=relu, out=out, out_coff=out_coff,
-                 in_ld=x.rows.stride(0), in_ptr_offset=x.coff)
-    return DenseMap(o, x.B, 2 * x.H, 2 * x.W, cout, out_coff)
+    Ho, Wo = 2 * x.H, 2 * x.W
+    if out is None:
+        out = new_dense_rows(x.B, Ho, Wo, cout, x.rows.dtype, x.rows.device, x.pad)
+    rows_cap = x.B * (Ho + 2 * x.pad) * (Wo + 2 * x.pad)
+    run_conv(x.rows, lw, nbr, 4, x.C, cout, rows_cap, relu=relu, out=out, out_coff=out_coff,
+             in_ld=x.rows.stride(0), in_ptr_offset=x.coff, out_hw_pad=(Ho + 2, Wo + 2) if x.pad else None)
+    return DenseMap(out, x.B, Ho, Wo, cout, out_coff, x.pad)

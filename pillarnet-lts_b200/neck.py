@@ -12,7 +12,8 @@ import torch
 from torch import nn
 
 from . import config
-from .layers import DenseMap, Sequential, build_norm_layer, dense_conv3x3, dense_deconv2x2
+from .layers import (DenseMap, Sequential, build_norm_layer, dense_conv3x3, dense_deconv2x2, new_dense_rows,
+                     use_padded_layout)
 from .registry import NECKS
 from .sparse import SparseConvTensor
 
@@ -23,9 +24,10 @@ def _to_dense_map(x, cat_room=False):
         t = x.table
         C = x.feat.shape[1]
         width = 2 * C if cat_room else C
-        rows = torch.empty(t.B * t.H * t.W, width, dtype=x.feat.dtype, device=x.feat.device)
-        x.dense_nhwc(out=rows, out_coff=0)
-        return DenseMap(rows, t.B, t.H, t.W, C, 0)
+        pad = 1 if use_padded_layout() else 0
+        rows = new_dense_rows(t.B, t.H, t.W, width, x.feat.dtype, x.feat.device, pad)
+        x.dense_nhwc(out=rows, out_coff=0, padded=bool(pad))
+        return DenseMap(rows, t.B, t.H, t.W, C, 0, pad)
     return DenseMap.from_nchw(x)
 
 
@@ -93,7 +95,7 @@ class RPNV1(_RPNBase):
         up_c = self.deblock_5[0].out_channels
         rows, coff = _cat_buffer(x4, up_c)
         dense_deconv2x2(x, self.deblock_5[0], self.deblock_5[1], relu=True, out=rows, out_coff=coff)
-        cat = DenseMap(rows, x4.B, x4.H, x4.W, x4.C + up_c, 0)
+        cat = DenseMap(rows, x4.B, x4.H, x4.W, x4.C + up_c, 0, x4.pad)
         x = self._run_block(cat, self.block_4)
         return tuple([x.nchw()])
 
@@ -118,7 +120,7 @@ class RPNV2(_RPNBase):
         up_c = self.deblock_4[0].out_channels
         rows, coff = _cat_buffer(x3, up_c)
         dense_deconv2x2(x, self.deblock_4[0], self.deblock_4[1], relu=True, out=rows, out_coff=coff)
-        cat = DenseMap(rows, x3.B, x3.H, x3.W, x3.C + up_c, 0)
+        cat = DenseMap(rows, x3.B, x3.H, x3.W, x3.C + up_c, 0, x3.pad)
         x = self._run_block(cat, self.block_3)
         return tuple([x.nchw()])
 
@@ -150,12 +152,12 @@ class RPNG(_RPNBase):
         up_c = self.top_down_54[0].out_channels
         rows, coff = _cat_buffer(x4, up_c)
         dense_deconv2x2(x5, self.top_down_54[0], self.top_down_54[1], relu=True, out=rows, out_coff=coff)
-        x4o = self._run_block(DenseMap(rows, x4.B, x4.H, x4.W, x4.C + up_c, 0), self.block_4)
+        x4o = self._run_block(DenseMap(rows, x4.B, x4.H, x4.W, x4.C + up_c, 0, x4.pad), self.block_4)
         # head stride 4
         up_c = self.top_down_43[0].out_channels
         rows, coff = _cat_buffer(x3, up_c)
         dense_deconv2x2(x4o, self.top_down_43[0], self.top_down_43[1], relu=True, out=rows, out_coff=coff)
-        x3o = self._run_block(DenseMap(rows, x3.B, x3.H, x3.W, x3.C + up_c, 0), self.block_3)
+        x3o = self._run_block(DenseMap(rows, x3.B, x3.H, x3.W, x3.C + up_c, 0, x3.pad), self.block_3)
         return tuple([x4o.nchw(), x3o.nchw()])
 
 
@@ -192,15 +194,15 @@ class RPNGV2(_RPNBase):
         dt, dev = x4.rows.dtype, x4.rows.device
         # head stride 8
         half = self.reduce_4[0].out_channels
-        rows = torch.empty(x4.B * x4.H * x4.W, 2 * half, dtype=dt, device=dev)
+        rows = new_dense_rows(x4.B, x4.H, x4.W, 2 * half, dt, dev, x4.pad)
         dense_conv3x3(x4, self.reduce_4[0], self.reduce_4[1], relu=True, out=rows, out_coff=0)
         x5 = self._run_block(x5, self.block_5)
         dense_deconv2x2(x5, self.top_down_54[0], self.top_down_54[1], relu=True, out=rows, out_coff=half)
-        x4o = self._run_block(DenseMap(rows, x4.B, x4.H, x4.W, 2 * half, 0), self.block_4)
+        x4o = self._run_block(DenseMap(rows, x4.B, x4.H, x4.W, 2 * half, 0, x4.pad), self.block_4)
         # head stride 4
         half = self.reduce_3[0].out_channels
-        rows = torch.empty(x3.B * x3.H * x3.W, 2 * half, dtype=dt, device=dev)
+        rows = new_dense_rows(x3.B, x3.H, x3.W, 2 * half, dt, dev, x3.pad)
         dense_conv3x3(x3, self.reduce_3[0], self.reduce_3[1], relu=True, out=rows, out_coff=0)
         dense_deconv2x2(x4o, self.top_down_43[0], self.top_down_43[1], relu=True, out=rows, out_coff=half)
-        x3o = self._run_block(DenseMap(rows, x3.B, x3.H, x3.W, 2 * half, 0), self.block_3)
+        x3o = self._run_block(DenseMap(rows, x3.B, x3.H, x3.W, 2 * half, 0, x3.pad), self.block_3)
         return tuple([x4o.nchw(), x3o.nchw()])

@@ -148,18 +148,21 @@ def rulebook_down3x3s2(table, out_cap=None):
 _dense_nbr_cache = {}
 
 
-def dense_nbr_table(mode, n_frames, H, W, stride, device):
-    """Static gather table for dense NHWC convs; cached per (mode,B,H,W,stride,device)."""
-    key = (mode, n_frames, H, W, stride, str(device))
+def dense_nbr_table(mode, n_frames, H, W, stride, device, in_pad=False, out_pad=False):
+    """Static gather table for dense NHWC convs; cached per (mode,B,H,W,stride,padding,device).
+    in_pad/out_pad: the input/output rows index a zero-padded (H+2,W+2) map."""
+    key = (mode, n_frames, H, W, stride, bool(in_pad), bool(out_pad), str(device))
     t = _dense_nbr_cache.get(key)
     if t is None:
         lib = _lib.load()
+        po = 2 if out_pad else 0
         if mode == 0:
             Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
-            t = _i32(n_frames * Ho * Wo, 9, device=device)
+            t = _i32(n_frames * (Ho + po) * (Wo + po), 9, device=device)
         else:
-            t = _i32(n_frames * 4 * H * W, 4, device=device)
-        check(lib.pn_dense_nbr_table(mode, n_frames, H, W, stride, ptr(t), stream_ptr()),
+            t = _i32(n_frames * (2 * H + po) * (2 * W + po), 4, device=device)
+        flags = (1 if in_pad else 0) | (2 if out_pad else 0)
+        check(lib.pn_dense_nbr_table(mode, n_frames, H, W, stride, flags, ptr(t), stream_ptr()),
               "pn_dense_nbr_table")
         _dense_nbr_cache[key] = t
     return t
@@ -167,7 +170,7 @@ def dense_nbr_table(mode, n_frames, H, W, stride, device):
 
 def conv_gather(inp, weight, nbr, taps, cin, cout, out, *, in_ld=None, k_pad=None, scale=None,
                 shift=None, residual=None, res_ld=None, out_ld=None, out_coff=0, relu=False, num=None,
-                rows_cap=None, impl=PN_IMPL_SIMT, in_ptr_offset=0, rows_hint=0):
+                rows_cap=None, impl=PN_IMPL_SIMT, in_ptr_offset=0, rows_hint=0, out_hw_pad=None):
     """out[o, coff:coff+cout] = act((sum_t W_t . in[nbr[o,t]]) * scale + shift + residual).
 
     `inp`/`out` are 2-D channels-last tensors (possibly wider than cin/cout: in_ld/out_ld are the
@@ -197,17 +200,30 @@ def conv_gather(inp, weight, nbr, taps, cin, cout, out, *, in_ld=None, k_pad=Non
     a.rows_cap = rows_cap if rows_cap is not None else out.shape[0]
     a.cin, a.cout = cin, cout
     a.rows_hint = int(rows_hint)
+    a.out_hp, a.out_wp = (out_hw_pad if out_hw_pad is not None else (0, 0))
     if residual is not None and residual.dtype != out.dtype:
         raise RuntimeError("residual dtype must match the output dtype")
     check(lib.pn_conv_gather(byref(a), impl, stream_ptr()), "pn_conv_gather")
     return out
 
 
-def conv3x3_small_cout(inp, in_ld, cin, n_frames, H, W, groups, n_groups, wbuf, out):
+def conv3x3_small_cout(inp, in_ld, cin, n_frames, H, W, groups, n_groups, wbuf, out, in_padded=False):
     """grouped tiny-Cout dense 3x3 conv (all CenterHead final convs in one launch); see the C header."""
     lib = _lib.load()
-    check(lib.pn_conv3x3_small_cout(ptr(inp), in_ld, cin, n_frames, H, W, ptr(groups), n_groups, ptr(wbuf),
+    check(lib.pn_conv3x3_small_cout(ptr(inp), in_ld, cin, n_frames, H, W, 1 if in_padded else 0, ptr(groups),
+                                    n_groups, ptr(wbuf),
                                     ptr(out), out.stride(0), stream_ptr()), "pn_conv3x3_small_cout")
+    return out
+
+
+def conv_dense3x3(inp, in_coff, cin, n_frames, H, W, weight, cout, out, *, scale=None, shift=None, out_coff=0,
+                  out_compact=False, relu=False, tile_hint=0):
+    """3x3/s1/p1 conv on zero-padded NHWC rows (B*(H+2)*(W+2), ld) -> padded (or compact) rows; see the C header."""
+    lib = _lib.load()
+    check(lib.pn_conv_dense3x3(ptr(inp), inp.stride(0), in_coff, cin, n_frames, H, W, ptr(weight), weight.stride(0),
+                               cout, ptr(scale), ptr(shift), ptr(out), _DT[out.dtype], out.stride(0), out_coff,
+                               1 if out_compact else 0, 1 if relu else 0, tile_hint, stream_ptr()),
+          "pn_conv_dense3x3")
     return out
 
 
@@ -238,15 +254,16 @@ def cast_rows(inp, dtype, num=None):
     return out
 
 
-def sparse_to_dense(feat, table, C, out=None, out_coff=0):
-    """NHWC densify: returns (B*H*W, out_ld) tensor whose [coff,coff+C) columns hold the features."""
+def sparse_to_dense(feat, table, C, out=None, out_coff=0, padded=False):
+    """NHWC densify: returns (B*H*W, out_ld) rows whose [coff,coff+C) columns hold the features
+    (padded: (B*(H+2)*(W+2), out_ld) rows of the zero-bordered map)."""
     lib = _lib.load()
-    n_cells = table.B * table.H * table.W
+    n_cells = table.B * (table.H + (2 if padded else 0)) * (table.W + (2 if padded else 0))
     if out is None:
         out = torch.empty(n_cells, C, dtype=feat.dtype, device=feat.device)
     check(lib.pn_sparse_to_dense(ptr(feat), _DT[feat.dtype], feat.stride(0), ptr(table.words),
                                  ptr(table.prefix), table.B, table.H, table.W, C, ptr(out),
-                                 out.stride(0), out_coff, stream_ptr()), "pn_sparse_to_dense")
+                                 out.stride(0), out_coff, 1 if padded else 0, stream_ptr()), "pn_sparse_to_dense")
     return out
 
 

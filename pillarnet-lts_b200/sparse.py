@@ -44,9 +44,10 @@ class SparseConvTensor:
         out._count = self._count
         return out
 
-    def dense_nhwc(self, out=None, out_coff=0):
-        """(B*H*W, C) channels-last densify (zero elsewhere)."""
-        return ops.sparse_to_dense(self.feat, self.table, self.feat.shape[1], out=out, out_coff=out_coff)
+    def dense_nhwc(self, out=None, out_coff=0, padded=False):
+        """(B*H*W, C) channels-last densify (zero elsewhere); padded: the zero-bordered (H+2,W+2) map."""
+        return ops.sparse_to_dense(self.feat, self.table, self.feat.shape[1], out=out, out_coff=out_coff,
+                                   padded=padded)
 
     def dense(self, channels_first=True):
         """(B,C,H,W) tensor as spconv's .dense(); storage is NHWC (a channels_last NCHW view)."""

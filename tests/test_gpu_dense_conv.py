@@ -1,0 +1,73 @@
+"""GPU parity of the padded-layout dense 3x3 tensor-core conv (pn_conv_dense3x3) vs torch F.conv2d on the
+same bf16-rounded operands (fp32 accumulate both sides): 2e-3 rel-to-max for f32 output, one bf16 ulp
+(1e-2 rel-to-max) for bf16 output."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _pad_rows(x_nhwc):
+    """(B,H,W,C) -> zero-padded rows (B*(H+2)*(W+2), C)"""
+    B, H, W, C = x_nhwc.shape
+    p = torch.zeros(B, H + 2, W + 2, C, dtype=x_nhwc.dtype, device=x_nhwc.device)
+    p[:, 1:-1, 1:-1] = x_nhwc
+    return p.view(-1, C).contiguous()
+
+
+def _run(B, H, W, cin, cout, tile_hint, compact, out_dtype, in_extra=0, relu=True):
+    from pillarnet_lts_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H + cin + cout)
+    x = torch.randn(B, H, W, cin + in_extra, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (1.0 / (9 * cin) ** 0.5)
+    wp = ops.pack_weight_bf16(w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous())
+    scale = torch.rand(cout, device="cuda", generator=g) + 0.5
+    shift = torch.randn(cout, device="cuda", generator=g) * 0.1
+    rows = _pad_rows(x)
+    n_out = B * H * W if compact else rows.shape[0]
+    out = torch.full((n_out, cout + 8), 5.0, device="cuda", dtype=out_dtype)
+    ops.conv_dense3x3(rows, in_extra, cin, B, H, W, wp, cout, out, scale=scale, shift=shift, out_coff=8,
+                      out_compact=compact, relu=relu, tile_hint=tile_hint)
+    torch.cuda.synchronize()
+    xin = x[..., in_extra:].float().permute(0, 3, 1, 2)
+    want = F.conv2d(xin, wp[:, :9 * cin].float().view(cout, 3, 3, cin).permute(0, 3, 1, 2), padding=1)
+    want = want * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if relu:
+        want = want.relu()
+    want = want.permute(0, 2, 3, 1)
+    if compact:
+        got = out[:, 8:].float().view(B, H, W, cout)
+    else:
+        full = out[:, 8:].float().view(B, H + 2, W + 2, cout)
+        assert float(full[:, 0].abs().max()) == 0 and float(full[:, -1].abs().max()) == 0
+        assert float(full[:, :, 0].abs().max()) == 0 and float(full[:, :, -1].abs().max()) == 0
+        got = full[:, 1:-1, 1:-1]
+    assert bool((out[:, :8] == 5.0).all())
+    err = (got - want).abs().max().item() / max(1.0, want.abs().max().item())
+    return err
+
+
+def test_descriptor_window_mode_probe():
+    """which UMMA descriptor encoding addresses a row-shifted window of a 128B-swizzled tile"""
+    errs = {}
+    for mode in (0, 0x100):
+        errs[mode] = _run(1, 20, 24, 64, 64, 4 | mode, False, torch.float32)
+    print("dense conv window probe: base_offset=0 err %.3g, base_offset=(addr>>7)&7 err %.3g" % (errs[0], errs[0x100]))
+    assert min(errs.values()) <= 2e-3
+
+
+@pytest.mark.parametrize("tile", [1, 2, 3, 4])
+@pytest.mark.parametrize("B,H,W,cin,cout", [(1, 20, 24, 64, 64), (2, 33, 17, 128, 256), (1, 45, 45, 256, 160)])
+def test_dense_conv_vs_torch(tile, B, H, W, cin, cout):
+    if tile in (1, 2) and cout <= 128:
+        pytest.skip("BN=256 tiles are not offered for cout <= 128")
+    assert _run(B, H, W, cin, cout, tile, False, torch.float32) <= 2e-3
+    assert _run(B, H, W, cin, cout, tile, True, torch.bfloat16, in_extra=64) <= 1e-2
+
+
+def test_dense_conv_auto_tile_full_size():
+    assert _run(1, 180, 180, 256, 256, 0, False, torch.bfloat16) <= 1e-2
+    assert _run(1, 90, 90, 256, 256, 0, False, torch.bfloat16) <= 1e-2
+    assert _run(1, 180, 180, 64, 2304, 0, True, torch.bfloat16, relu=True) <= 1e-2
