@@ -166,6 +166,7 @@ typedef struct pn_conv_args {
   int cout;
   int rows_hint;         /* expected live rows (tile-shape heuristic only); 0 => rows_cap */
   int out_hp, out_wp;    /* != 0: output rows are a zero-padded (B,out_hp,out_wp) map; border rows are written as 0 */
+  int in_rows;           /* allocated rows of `in` (enables the TMA gather4 activation path); 0 = unknown */
 } pn_conv_args;
 
 int pn_conv_gather(const pn_conv_args* args, int impl, pn_stream_t stream);

@@ -27,7 +27,7 @@ class ConvArgs(Structure):
         ("out", c_void_p), ("out_dtype", c_int), ("out_ld", c_int), ("out_coff", c_int),
         ("relu", c_int),
         ("num_rows", c_void_p), ("rows_cap", c_int),
-        ("cin", c_int), ("cout", c_int), ("rows_hint", c_int), ("out_hp", c_int), ("out_wp", c_int),
+        ("cin", c_int), ("cout", c_int), ("rows_hint", c_int), ("out_hp", c_int), ("out_wp", c_int), ("in_rows", c_int),
     ]
 
 

@@ -97,6 +97,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// TMA gather4: four rows (given by index) x 64 channels -> four consecutive 128-byte smem rows
+// (SWIZZLE_128B); rows whose index is outside the tensor are zero-filled.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2,
+                                            int r3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -188,6 +198,7 @@ struct KArgs {
   int cin;
   int cout;
   int out_hp, out_wp;  // != 0: zero the border rows of a padded output map
+  int in_rows;         // allocated rows of `in` (TMA gather path: index >= in_rows reads zeros)
 };
 
 template <int BN, int STAGES>
@@ -209,9 +220,9 @@ constexpr int tmem_cols() {
   return 2 * BN < 32 ? 32 : 2 * BN;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TMA_A>
 __global__ void __launch_bounds__(kThreads, 1)
-k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const KArgs P) {
+k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const KArgs P) {
   extern __shared__ uint8_t smem_raw[];
   using S = Smem<BN, STAGES>;
   S& sm = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -227,7 +238,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const KArgs P) {
   if (warp == 8) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
-        mbar_init(&sm.full[s], kProducerThreads + 1);
+        mbar_init(&sm.full[s], TMA_A ? 1 : kProducerThreads + 1);
         mbar_init(&sm.empty[s], 1);
       }
       for (int i = 0; i < 2; ++i) {
@@ -285,37 +296,67 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const KArgs P) {
       const int m_tile = tile / n_n_tiles, n_tile = tile - m_tile * n_n_tiles;
       const int* s_nbr = sm.nbr[tl & 1u];
       fetch_nbr(tile + gridDim.x, nbr_regs);  // next tile's rows: loads in flight during this tile
-      for (int kc = 0; kc < P.n_chunks; ++kc, ++g) {
-        const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
-        mbar_wait(&sm.empty[s], ph ^ 1u);
-        if (tid == 0) {
-          mbar_arrive_expect_tx(&sm.full[s], BN * 128);
-          tma_load_2d(smem_u32(sm.b[s]), &tmap_w, kc * BLOCK_K, n_tile * BN, &sm.full[s]);
-        }
-        const int k = kc * BLOCK_K + piece * 8;
-        const int t = k / P.cin, c = k - t * P.cin;
-        const bool k_ok = k < k_total;
-        const uint32_t a_base = smem_u32(sm.a[s]);
+      if constexpr (TMA_A) {
+        // one warp feeds the tile: lane l gathers rows 4l..4l+3 of the chunk with one TMA gather4
+        // (cin % 64 == 0, so a 64-channel chunk lies inside one tap); lane 0 also loads the weights.
+        if (warp == 0) {
+          for (int kc = 0; kc < P.n_chunks; ++kc, ++g) {
+            const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+            if (lane == 0) {
+              mbar_wait(&sm.empty[s], ph ^ 1u);
+              mbar_arrive_expect_tx(&sm.full[s], A_STAGE_BYTES + BN * 128);
+              tma_load_2d(smem_u32(sm.b[s]), &tmap_w, kc * BLOCK_K, n_tile * BN, &sm.full[s]);
+            }
+            __syncwarp();
+            const int k = kc * BLOCK_K;
+            const int t = k / P.cin, c = k - t * P.cin;
+            const bool k_ok = k < k_total;
+            int idx[4];
 #pragma unroll
-        for (int i = 0; i < BLOCK_M / 16; ++i) {
-          const int r = rg + 16 * i;
-          const int src = k_ok ? s_nbr[r * P.taps + t] : -1;
-          const __nv_bfloat16* gp = P.in + (src >= 0 ? (long long)src * P.in_ld + c : 0);
-          cp_async16(a_base + r * 128 + ((piece ^ (r & 7)) << 4), gp, src >= 0 ? 16u : 0u);
+            for (int i = 0; i < 4; ++i) {
+              const int src = k_ok ? s_nbr[(4 * lane + i) * P.taps + t] : -1;
+              idx[i] = src >= 0 ? src : P.in_rows;   // out of bounds => zero row
+            }
+            tma_gather4(smem_u32(sm.a[s]) + lane * 512, &tmap_a, c, idx[0], idx[1], idx[2], idx[3], &sm.full[s]);
+          }
+        } else {
+          g += P.n_chunks;
         }
-        cp_async_commit();
-        if (g >= (uint32_t)kLag) {
-          cp_async_wait<kLag>();
-          fence_proxy_async_smem();
-          mbar_arrive(&sm.full[(g - kLag) % STAGES]);
+      } else {
+      for (int kc = 0; kc < P.n_chunks; ++kc, ++g) {
+          const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+          mbar_wait(&sm.empty[s], ph ^ 1u);
+          if (tid == 0) {
+            mbar_arrive_expect_tx(&sm.full[s], BN * 128);
+            tma_load_2d(smem_u32(sm.b[s]), &tmap_w, kc * BLOCK_K, n_tile * BN, &sm.full[s]);
+          }
+          const int k = kc * BLOCK_K + piece * 8;
+          const int t = k / P.cin, c = k - t * P.cin;
+          const bool k_ok = k < k_total;
+          const uint32_t a_base = smem_u32(sm.a[s]);
+#pragma unroll
+          for (int i = 0; i < BLOCK_M / 16; ++i) {
+            const int r = rg + 16 * i;
+            const int src = k_ok ? s_nbr[r * P.taps + t] : -1;
+            const __nv_bfloat16* gp = P.in + (src >= 0 ? (long long)src * P.in_ld + c : 0);
+            cp_async16(a_base + r * 128 + ((piece ^ (r & 7)) << 4), gp, src >= 0 ? 16u : 0u);
+          }
+          cp_async_commit();
+          if (g >= (uint32_t)kLag) {
+            cp_async_wait<kLag>();
+            fence_proxy_async_smem();
+            mbar_arrive(&sm.full[(g - kLag) % STAGES]);
+          }
         }
       }
       park_nbr((tl + 1u) & 1u, nbr_regs);   // the other buffer: nobody reads it during this tile
       named_bar_sync(1, kProducerThreads);
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (uint32_t j = (g >= (uint32_t)kLag ? g - kLag : 0u); j < g; ++j) mbar_arrive(&sm.full[j % STAGES]);
+    if constexpr (!TMA_A) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      for (uint32_t j = (g >= (uint32_t)kLag ? g - kLag : 0u); j < g; ++j) mbar_arrive(&sm.full[j % STAGES]);
+    }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -489,22 +530,26 @@ EncodeTiledFn get_encode_fn() {
 
 struct MapKey {
   const void* ptr;
-  int cout, k_pad, bn;
+  long long rows;
+  int cols, ld, box_rows;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && cout == o.cout && k_pad == o.k_pad && bn == o.bn;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
-    return std::hash<const void*>()(k.ptr) ^ (size_t)k.cout * 1000003u ^ (size_t)k.k_pad * 10007u ^ (size_t)k.bn;
+    return std::hash<const void*>()(k.ptr) ^ (size_t)k.rows * 1000003u ^ (size_t)k.cols * 10007u ^
+           (size_t)k.ld * 131u ^ (size_t)k.box_rows;
   }
 };
 
-// Weight tensor maps are pure functions of (pointer, shape, tile): cache them (encoding costs ~1 us).
-int get_weight_map(const void* w, int cout, int k_pad, int bn, CUtensorMap* out) {
+// bf16 row-major (rows, cols) matrix with row stride ld; box = 64 columns x box_rows, SWIZZLE_128B.
+// Weight tiles use box_rows = BLOCK_N; the gather4 activation map uses box_rows = 1.
+// Maps are pure functions of (pointer, shape, box): cached (encoding costs ~1 us).
+int get_map(const void* base, long long rows, int cols, int ld, int box_rows, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{w, cout, k_pad, bn};
+  MapKey key{base, rows, cols, ld, box_rows};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -515,12 +560,12 @@ int get_weight_map(const void* w, int cout, int k_pad, int bn, CUtensorMap* out)
   }
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return PN_ERR_UNSUPPORTED;
-  cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)cout};
-  cuuint64_t gstride[1] = {(cuuint64_t)k_pad * sizeof(__nv_bfloat16)};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)bn};
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstride, box, estr,
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return PN_ERR_CUDA;
@@ -533,15 +578,17 @@ int get_weight_map(const void* w, int cout, int k_pad, int bn, CUtensorMap* out)
   return PN_OK;
 }
 
-template <int BN, int STAGES>
-int launch(const CUtensorMap& map, const KArgs& ka, int grid, cudaStream_t stream) {
+template <int BN, int STAGES, bool TMA_A>
+int launch(const CUtensorMap& map_w, const CUtensorMap& map_a, const KArgs& ka, int grid, cudaStream_t stream) {
   constexpr size_t smem = sizeof(Smem<BN, STAGES>) + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    PN_CUDA(cudaFuncSetAttribute(k_conv_tc<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PN_CUDA(cudaFuncSetAttribute(k_conv_tc<BN, STAGES, TMA_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
     configured = true;
   }
-  k_conv_tc<BN, STAGES><<<grid, kThreads, smem, stream>>>(map, ka);
+  k_conv_tc<BN, STAGES, TMA_A><<<grid, kThreads, smem, stream>>>(map_w, map_a, ka);
   PN_CHECK_LAUNCH();
   return PN_OK;
 }
@@ -576,9 +623,18 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
       bn = best;
     }
   }
-  CUtensorMap map;
-  int rc = get_weight_map(a->weight, a->cout, a->k_pad, bn, &map);
+  CUtensorMap map, map_a;
+  int rc = get_map(a->weight, a->cout, a->k_pad, a->k_pad, bn, &map);
   if (rc != PN_OK) return rc;
+  // activations through TMA gather4 when a 64-channel chunk never straddles taps and the allocation
+  // size of `in` is known; otherwise 16-byte cp.async gathers
+  const bool tma_a = a->cin % BLOCK_K == 0 && a->in_rows > 0;
+  if (tma_a) {
+    rc = get_map(a->in, a->in_rows, a->cin, a->in_ld, 1, &map_a);
+    if (rc != PN_OK) return rc;
+  } else {
+    map_a = map;
+  }
   KArgs ka;
   ka.in = reinterpret_cast<const __nv_bfloat16*>(a->in);
   ka.in_ld = a->in_ld;
@@ -600,16 +656,26 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
   ka.cout = a->cout;
   ka.out_hp = a->out_hp;
   ka.out_wp = a->out_wp;
+  ka.in_rows = a->in_rows;
   const int sms = sm_count();
   if (sms <= 0) return PN_ERR_CUDA;
   const long long tiles_cap = (long long)PN_DIVUP(a->rows_cap, BLOCK_M) * PN_DIVUP(a->cout, bn);
   const int grid = (int)(tiles_cap < sms ? tiles_cap : sms);
+  if (tma_a) {
+    switch (bn) {
+      case 16: return launch<16, 8, true>(map, map_a, ka, grid, stream);
+      case 32: return launch<32, 8, true>(map, map_a, ka, grid, stream);
+      case 64: return launch<64, 8, true>(map, map_a, ka, grid, stream);
+      case 128: return launch<128, 6, true>(map, map_a, ka, grid, stream);
+      default: return launch<256, 4, true>(map, map_a, ka, grid, stream);
+    }
+  }
   switch (bn) {
-    case 16: return launch<16, 6>(map, ka, grid, stream);
-    case 32: return launch<32, 6>(map, ka, grid, stream);
-    case 64: return launch<64, 6>(map, ka, grid, stream);
-    case 128: return launch<128, 5>(map, ka, grid, stream);
-    default: return launch<256, 4>(map, ka, grid, stream);
+    case 16: return launch<16, 6, false>(map, map_a, ka, grid, stream);
+    case 32: return launch<32, 6, false>(map, map_a, ka, grid, stream);
+    case 64: return launch<64, 6, false>(map, map_a, ka, grid, stream);
+    case 128: return launch<128, 5, false>(map, map_a, ka, grid, stream);
+    default: return launch<256, 4, false>(map, map_a, ka, grid, stream);
   }
 }
 

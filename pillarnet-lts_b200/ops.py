@@ -201,6 +201,7 @@ def conv_gather(inp, weight, nbr, taps, cin, cout, out, *, in_ld=None, k_pad=Non
     a.cin, a.cout = cin, cout
     a.rows_hint = int(rows_hint)
     a.out_hp, a.out_wp = (out_hw_pad if out_hw_pad is not None else (0, 0))
+    a.in_rows = inp.shape[0]
     if residual is not None and residual.dtype != out.dtype:
         raise RuntimeError("residual dtype must match the output dtype")
     check(lib.pn_conv_gather(byref(a), impl, stream_ptr()), "pn_conv_gather")
