@@ -118,7 +118,7 @@ def conv_breakdown(engine, reps=3):
         s.record()
         r = orig(inp, weight, nbr, taps, cin, cout, out, **kw)
         e.record()
-        recs.append((taps, cin, cout, kw.get("rows_cap") or out.shape[0], kw.get("num"), s, e))
+        recs.append((taps, cin, cout, kw.get("rows_cap") or out.shape[0], kw.get("num"), s, e, "k_conv_tc"))
         return r
 
     model = engine.model
@@ -132,8 +132,27 @@ def conv_breakdown(engine, reps=3):
         stages.setdefault(name, []).append((s, e))
         return r
 
-    import pillarnet_lts_b200.layers as layers
+    orig_dense, orig_small = ops.conv_dense3x3, ops.conv3x3_small_cout
+
+    def timed_dense(inp, in_coff, cin, n_frames, H, W, weight, cout, out, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig_dense(inp, in_coff, cin, n_frames, H, W, weight, cout, out, **kw)
+        e.record()
+        # FLOPs counted over real pixels only (the padded border rows are overhead)
+        recs.append((9, cin, cout, n_frames * H * W, None, s, e, "k_conv_dense"))
+        return r
+
+    def timed_small(inp, in_ld, cin, n_frames, H, W, groups, n_groups, wbuf, out, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig_small(inp, in_ld, cin, n_frames, H, W, groups, n_groups, wbuf, out, **kw)
+        e.record()
+        recs.append((9, cin, int(out.shape[1]), n_frames * H * W, None, s, e, "k_conv3x3_small"))
+        return r
+
     ops.conv_gather = timed
+    ops.conv_dense3x3, ops.conv3x3_small_cout = timed_dense, timed_small
     try:
         with torch.cuda.stream(engine.stream), torch.no_grad():
             for _ in range(reps):
@@ -146,19 +165,21 @@ def conv_breakdown(engine, reps=3):
             engine.stream.synchronize()
     finally:
         ops.conv_gather = orig
+        ops.conv_dense3x3, ops.conv3x3_small_cout = orig_dense, orig_small
     per_pass = recs[recs_start:]
     shapes = {}
-    for taps, cin, cout, rows_cap, num, s, e in recs:
+    for taps, cin, cout, rows_cap, num, s, e, kname in recs:
         rows = rows_cap if num is None else min(int(num.item()), rows_cap)
-        key = (taps, cin, cout, rows)
+        key = (taps, cin, cout, rows, kname)
         d = shapes.setdefault(key, dict(us=0.0, n=0))
         d["us"] += s.elapsed_time(e) * 1e3
         d["n"] += 1
     out = []
-    for (taps, cin, cout, rows), d in shapes.items():
+    for (taps, cin, cout, rows, kname), d in shapes.items():
         flop = 2.0 * rows * taps * cin * cout
         avg = d["us"] / d["n"]
-        out.append(dict(taps=taps, cin=cin, cout=cout, rows=rows, launches_per_pass=d["n"] // reps, avg_us=avg,
+        out.append(dict(kernel=kname, taps=taps, cin=cin, cout=cout, rows=rows, launches_per_pass=d["n"] // reps,
+                        avg_us=avg,
                         tflops=flop / avg / 1e6, total_us_per_pass=d["us"] / reps))
     out.sort(key=lambda r: -r["total_us_per_pass"])
     st = {k: float(np.median([s.elapsed_time(e) * 1e3 for s, e in v])) for k, v in stages.items()}
@@ -284,7 +305,7 @@ def run_gpu(args):
         breakdown, stages, n_conv = conv_breakdown(eng)
         top = breakdown[0]
         flop_total = sum(2.0 * r["rows"] * r["taps"] * r["cin"] * r["cout"] * r["launches_per_pass"] for r in breakdown)
-        roof = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 gather-GEMM conv)",
+        roof = {"bound": "tensor", "kernel": top["kernel"] + " (tcgen05 implicit-GEMM conv)",
                 "shape": {k: top[k] for k in ("taps", "cin", "cout", "rows")},
                 "achieved": top["tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": top["tflops"] / peaks["tf_sustained"], "peak_source": peaks["source"] + " (sustained bf16)",
@@ -315,7 +336,8 @@ def run_gpu(args):
             "cpu_baseline": cpu,
         }
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"breakdown_{args.workload}_n{world}.json"), "w") as fh:
+        tag = "_prof" if args.profile_pass else ""
+        with open(os.path.join(ROOT, "gpurun_out", f"breakdown_{args.workload}_n{world}{tag}.json"), "w") as fh:
             json.dump({"convs": breakdown, "stages_us": stages, "conv_launches_per_pass": n_conv}, fh, indent=1)
         print(json.dumps(line), flush=True)
     if world > 1:

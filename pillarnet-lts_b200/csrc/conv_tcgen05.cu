@@ -22,6 +22,7 @@
 // (cin = 32) — each 16-byte piece belongs to exactly one tap because cin % 8 == 0.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -232,8 +233,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   const int n_tiles = ((rows + BLOCK_M - 1) / BLOCK_M) * n_n_tiles;
   constexpr int TCOLS = tmem_cols<BN>();
   // cp.async groups kept in flight per producer thread; the MMA trails the issue point by kLag chunks,
-  // so kLag must leave at least two free stages (measured: lag 3 with 4 stages costs 25 %).
-  constexpr int kLag = STAGES >= 6 ? 3 : 2;
+  // so kLag must leave two free stages (measured: lag 3 with 4 stages costs 25 %).  The gather is
+  // latency bound (~2.5 chunks in flight gave ~30 GB/s per SM), hence as many stages as smem allows.
+  constexpr int kLag = STAGES - 2;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -628,7 +630,13 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
   if (rc != PN_OK) return rc;
   // activations through TMA gather4 when a 64-channel chunk never straddles taps and the allocation
   // size of `in` is known; otherwise 16-byte cp.async gathers
-  const bool tma_a = a->cin % BLOCK_K == 0 && a->in_rows > 0;
+  // Measured on B200: 32 gather4 ops per 16 KB chunk are slower than 1024 cp.async pieces (57 vs 42 us
+  // on the 128-channel stage), so the TMA gather path stays opt-in (PN_CONV_TMA_GATHER=1).
+  static const bool tma_gather_enabled = [] {
+    const char* e = getenv("PN_CONV_TMA_GATHER");
+    return e && e[0] == '1';
+  }();
+  const bool tma_a = tma_gather_enabled && a->cin % BLOCK_K == 0 && a->in_rows > 0;
   if (tma_a) {
     rc = get_map(a->in, a->in_rows, a->cin, a->in_ld, 1, &map_a);
     if (rc != PN_OK) return rc;
@@ -671,10 +679,10 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
     }
   }
   switch (bn) {
-    case 16: return launch<16, 6, false>(map, map_a, ka, grid, stream);
-    case 32: return launch<32, 6, false>(map, map_a, ka, grid, stream);
-    case 64: return launch<64, 6, false>(map, map_a, ka, grid, stream);
-    case 128: return launch<128, 5, false>(map, map_a, ka, grid, stream);
+    case 16: return launch<16, 9, false>(map, map_a, ka, grid, stream);
+    case 32: return launch<32, 9, false>(map, map_a, ka, grid, stream);
+    case 64: return launch<64, 8, false>(map, map_a, ka, grid, stream);
+    case 128: return launch<128, 6, false>(map, map_a, ka, grid, stream);
     default: return launch<256, 4, false>(map, map_a, ka, grid, stream);
   }
 }
