@@ -27,11 +27,16 @@ struct GroupDesc {
   int out_coff;  // first output column
 };
 
+// weights of one (tap, channel pair) are WV floats: [j][2] for j < COUT, zero padded to a multiple of 4 so
+// that they are fetched with broadcast LDS.128 (COUT <= 2: one, COUT 3..4: two) instead of 2*COUT LDS.32
+template <int COUT> struct WVec { static constexpr int value = COUT <= 2 ? 4 : 8; };
+
 template <int COUT>
 __device__ __forceinline__ void compute_chunk(const uint32_t* __restrict__ s_in, const float* __restrict__ s_w,
                                               int ty, int tx4, float (&acc)[4][COUT]) {
-  // s_in[pair][row*RS + col] (bf16x2), s_w[tap][pair][COUT][2]
-#pragma unroll 1
+  constexpr int WV = WVec<COUT>::value;
+  // s_in[pair][row*RS + col] (bf16x2), s_w[tap][pair][WV]
+#pragma unroll 2
   for (int p = 0; p < PAIRS; ++p) {
     const uint32_t* base = s_in + p * (HH_ * RS) + ty * RS + tx4;
     float2 v[3][6];
@@ -46,14 +51,19 @@ __device__ __forceinline__ void compute_chunk(const uint32_t* __restrict__ s_in,
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        const float* w = s_w + ((dy * 3 + dx) * PAIRS + p) * (COUT * 2);
+        float w[WV];
+        const float4* wp = reinterpret_cast<const float4*>(s_w + ((dy * 3 + dx) * PAIRS + p) * WV);
+#pragma unroll
+        for (int i = 0; i < WV / 4; ++i) {
+          const float4 t = wp[i];
+          w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+        }
 #pragma unroll
         for (int j = 0; j < COUT; ++j) {
-          const float wa = w[2 * j], wb = w[2 * j + 1];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            acc[q][j] = fmaf(v[dy][q + dx].x, wa, acc[q][j]);
-            acc[q][j] = fmaf(v[dy][q + dx].y, wb, acc[q][j]);
+            acc[q][j] = fmaf(v[dy][q + dx].x, w[2 * j], acc[q][j]);
+            acc[q][j] = fmaf(v[dy][q + dx].y, w[2 * j + 1], acc[q][j]);
           }
         }
       }
@@ -102,10 +112,12 @@ __device__ __forceinline__ void run_group(const __nv_bfloat16* __restrict__ in, 
       for (int i = 0; i < kBatch; ++i)
         if (so[i] >= 0) s_in[so[i]] = u[i];
     }
-    // stage weights of this channel chunk: s_w[tap][pair][j][2] = W[j][tap][c0 + 2*pair + {0,1}]
-    for (int i = tid; i < 9 * PAIRS * COUT * 2; i += THREADS) {
-      const int e = i & 1, j = (i >> 1) % COUT, pp = (i / (2 * COUT)) % PAIRS, tap = i / (2 * COUT * PAIRS);
-      s_w[i] = __ldg(wbuf + g.w_off + (j * 9 + tap) * cin + c0 + 2 * pp + e);
+    // stage weights of this channel chunk: s_w[tap][pair][WV] = W[j][tap][c0 + 2*pair + {0,1}], zero padded
+    constexpr int WV = WVec<COUT>::value;
+    for (int i = tid; i < 9 * PAIRS * WV; i += THREADS) {
+      const int e = i % WV, pp = (i / WV) % PAIRS, tap = i / (WV * PAIRS);
+      const int j = e >> 1;
+      s_w[i] = j < COUT ? __ldg(wbuf + g.w_off + (j * 9 + tap) * cin + c0 + 2 * pp + (e & 1)) : 0.f;
     }
     __syncthreads();
     compute_chunk<COUT>(s_in, s_w, ty, tx4, acc);
@@ -129,7 +141,7 @@ k_conv3x3_small(const __nv_bfloat16* __restrict__ in, int in_ld, int cin, int H,
                 int tiles_y, const GroupDesc* __restrict__ groups, const float* __restrict__ wbuf,
                 float* __restrict__ out, int out_ld) {
   __shared__ uint32_t s_in[PAIRS * HH_ * RS];
-  __shared__ float s_w[9 * PAIRS * 4 * 2];
+  __shared__ __align__(16) float s_w[9 * PAIRS * 8];
   const GroupDesc g = groups[blockIdx.y];
   const int t = blockIdx.x;
   const int b = t / (tiles_x * tiles_y);

@@ -86,7 +86,13 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
+// Asynchronous arrive: counts as this thread's arrival once all cp.async it issued so far have landed
+// (no commit/wait_group, no blocking) — the pattern CUTLASS's sm100 cp.async+UMMA mainloop uses.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -232,10 +238,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   const int n_n_tiles = (P.cout + BN - 1) / BN;
   const int n_tiles = ((rows + BLOCK_M - 1) / BLOCK_M) * n_n_tiles;
   constexpr int TCOLS = tmem_cols<BN>();
-  // cp.async groups kept in flight per producer thread; the MMA trails the issue point by kLag chunks,
-  // so kLag must leave two free stages (measured: lag 3 with 4 stages costs 25 %).  The gather is
-  // latency bound (~2.5 chunks in flight gave ~30 GB/s per SM), hence as many stages as smem allows.
-  constexpr int kLag = STAGES - 2;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -343,22 +345,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
             const __nv_bfloat16* gp = P.in + (src >= 0 ? (long long)src * P.in_ld + c : 0);
             cp_async16(a_base + r * 128 + ((piece ^ (r & 7)) << 4), gp, src >= 0 ? 16u : 0u);
           }
-          cp_async_commit();
-          if (g >= (uint32_t)kLag) {
-            cp_async_wait<kLag>();
-            fence_proxy_async_smem();
-            mbar_arrive(&sm.full[(g - kLag) % STAGES]);
-          }
+            cp_async_mbar_arrive_noinc(&sm.full[s]);
         }
       }
       park_nbr((tl + 1u) & 1u, nbr_regs);   // the other buffer: nobody reads it during this tile
       named_bar_sync(1, kProducerThreads);
     }
-    if constexpr (!TMA_A) {
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      for (uint32_t j = (g >= (uint32_t)kLag ? g - kLag : 0u); j < g; ++j) mbar_arrive(&sm.full[j % STAGES]);
-    }
+    if constexpr (!TMA_A) cp_async_wait_all();   // nothing of this CTA's may still be in flight at exit
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
