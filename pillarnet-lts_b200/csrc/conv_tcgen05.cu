@@ -33,9 +33,12 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;       // bf16 elements = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * 128;
-constexpr int kProducerThreads = 128;
+constexpr int kProducerThreads = 256;   // 8 warps: the gather is bound by the producers' instruction issue
 constexpr int kEpilogueThreads = 128;
-constexpr int kThreads = 288;
+constexpr int kProducerWarps = kProducerThreads / 32;
+constexpr int kEpilogueWarp0 = kProducerWarps;        // 4 epilogue warps; index % 4 == TMEM lane quarter
+constexpr int kMmaWarp = kProducerWarps + 4;
+constexpr int kThreads = (kMmaWarp + 1) * 32;
 constexpr int kMaxTaps = 9;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -206,6 +209,7 @@ struct KArgs {
   int cout;
   int out_hp, out_wp;  // != 0: zero the border rows of a padded output map
   int in_rows;         // allocated rows of `in` (TMA gather path: index >= in_rows reads zeros)
+  int cin_shift;       // log2(cin) when cin is a power of two, else -1
 };
 
 template <int BN, int STAGES>
@@ -239,7 +243,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   const int n_tiles = ((rows + BLOCK_M - 1) / BLOCK_M) * n_n_tiles;
   constexpr int TCOLS = tmem_cols<BN>();
 
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&sm.full[s], TMA_A ? 1 : kProducerThreads + 1);
@@ -259,11 +263,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   tcgen05_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // ===================== A producers (+ weight TMA) =====================
     const int tid = threadIdx.x;
-    const int piece = tid & 7, rg = tid >> 3;
+    const int piece = tid & 7, rg = tid >> 3;          // rg in [0,32): rows rg + 32*i, i < 4
     const int k_total = P.taps * P.cin;
+    // swizzled destination of this thread's 16-byte piece inside a stage (row & 7 == rg & 7 for all i)
+    const uint32_t dst_off = (uint32_t)rg * 128u + (uint32_t)((piece ^ (rg & 7)) << 4);
+    const uint32_t in_ld_bytes = (uint32_t)P.in_ld * 2u;
+    const char* in_bytes = reinterpret_cast<const char*>(P.in);
     uint32_t g = 0;
     // The rulebook rows of a tile are fetched one tile ahead into registers and parked in the other
     // half of sm.nbr, so a tile never starts with an exposed global-memory round trip.
@@ -335,15 +343,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
             tma_load_2d(smem_u32(sm.b[s]), &tmap_w, kc * BLOCK_K, n_tile * BN, &sm.full[s]);
           }
           const int k = kc * BLOCK_K + piece * 8;
-          const int t = k / P.cin, c = k - t * P.cin;
+          int t, c;
+          if (P.cin_shift >= 0) { t = k >> P.cin_shift; c = k & (P.cin - 1); }
+          else { t = k / P.cin; c = k - t * P.cin; }
           const bool k_ok = k < k_total;
-          const uint32_t a_base = smem_u32(sm.a[s]);
+          const uint32_t dst = smem_u32(sm.a[s]) + dst_off;
+          const int* nb = s_nbr + rg * P.taps + t;
+          const uint32_t coff = (uint32_t)c * 2u;
 #pragma unroll
-          for (int i = 0; i < BLOCK_M / 16; ++i) {
-            const int r = rg + 16 * i;
-            const int src = k_ok ? s_nbr[r * P.taps + t] : -1;
-            const __nv_bfloat16* gp = P.in + (src >= 0 ? (long long)src * P.in_ld + c : 0);
-            cp_async16(a_base + r * 128 + ((piece ^ (r & 7)) << 4), gp, src >= 0 ? 16u : 0u);
+          for (int i = 0; i < BLOCK_M / 32; ++i) {
+            const int src = k_ok ? nb[i * 32 * P.taps] : -1;
+            // 32-bit byte offset (the host checks in_rows*in_ld*2 < 4 GiB); missing neighbour => zero fill
+            const uint32_t off = src >= 0 ? (uint32_t)src * in_ld_bytes + coff : 0u;
+            cp_async16(dst + (uint32_t)i * (32u * 128u), in_bytes + off, src >= 0 ? 16u : 0u);
           }
             cp_async_mbar_arrive_noinc(&sm.full[s]);
         }
@@ -352,7 +364,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
       named_bar_sync(1, kProducerThreads);
     }
     if constexpr (!TMA_A) cp_async_wait_all();   // nothing of this CTA's may still be in flight at exit
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<BN>();
@@ -381,8 +393,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
     __syncwarp();
   } else {
     // ===================== epilogue =====================
-    const int e = warp - 4;
-    const int etid = threadIdx.x - 4 * 32;
+    const int e = warp - kEpilogueWarp0;
+    const int etid = threadIdx.x - kEpilogueWarp0 * 32;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const int m_tile = tile / n_n_tiles, n_tile = tile - m_tile * n_n_tiles;
@@ -498,7 +510,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tcgen05_fence_after();
     tmem_dealloc<TCOLS>(tmem_base);
   }
@@ -658,6 +670,10 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
   ka.out_hp = a->out_hp;
   ka.out_wp = a->out_wp;
   ka.in_rows = a->in_rows;
+  ka.cin_shift = -1;
+  for (int sft = 3; sft < 16; ++sft)
+    if ((1 << sft) == a->cin) ka.cin_shift = sft;
+  if (a->in_rows > 0 && (long long)a->in_rows * a->in_ld * 2 >= (1ll << 32)) return PN_ERR_UNSUPPORTED;
   const int sms = sm_count();
   if (sms <= 0) return PN_ERR_CUDA;
   const long long tiles_cap = (long long)PN_DIVUP(a->rows_cap, BLOCK_M) * PN_DIVUP(a->cout, bn);

@@ -295,7 +295,9 @@ struct MaskParams {
   float thr[16];
 };
 
-__global__ void __launch_bounds__(64)
+constexpr int kMaskThreads = 256;
+
+__global__ void __launch_bounds__(kMaskThreads)
 k_nms_mask(MaskParams P, const float* __restrict__ sorted_boxes, const float* __restrict__ geom,
            int pre_cap, const int* __restrict__ sorted_count, unsigned long long* __restrict__ mask) {
   const int seg = blockIdx.z;
@@ -308,62 +310,63 @@ k_nms_mask(MaskParams P, const float* __restrict__ sorted_boxes, const float* __
   __shared__ int s_npairs;
   __shared__ unsigned int s_bits[64][2];
   const int tid = threadIdx.x;
+  const int row_t = tid & 63, cg = tid >> 6;   // prefilter: thread = (row, group of 16 columns)
   const float thr = P.thr[seg % P.segs_per_frame];
   const int rows = min(64, n - rb * 64), cols = min(64, n - cb * 64);
   const long long base = (long long)seg * pre_cap;
   if (tid == 0) s_npairs = 0;
-  s_bits[tid][0] = 0u;
-  s_bits[tid][1] = 0u;
+  if (tid < 64) { s_bits[tid][0] = 0u; s_bits[tid][1] = 0u; }
   if (P.mode == 0) {
-    for (int i = tid; i < cols * kGeomFloats; i += 64)
+    for (int i = tid; i < cols * kGeomFloats; i += kMaskThreads)
       s_col[i] = geom[(base + cb * 64) * kGeomFloats + i];
   } else {
-    for (int i = tid; i < cols; i += 64) {
+    for (int i = tid; i < cols; i += kMaskThreads) {
       s_col[i * 2] = sorted_boxes[(base + cb * 64 + i) * kBoxRec + 0];
       s_col[i * 2 + 1] = sorted_boxes[(base + cb * 64 + i) * kBoxRec + 1];
     }
   }
   __syncthreads();
+  const int c_lo = max(cg * 16, (rb == cb) ? row_t + 1 : 0), c_hi = min(cg * 16 + 16, cols);
   if (P.mode == 1) {
     // circle_nms: (float32 difference)^2 summed in float64, compared with <= thresh
-    if (tid < rows) {
-      const float xi = sorted_boxes[(base + rb * 64 + tid) * kBoxRec + 0];
-      const float yi = sorted_boxes[(base + rb * 64 + tid) * kBoxRec + 1];
-      unsigned long long bits = 0ull;
-      const int start = (rb == cb) ? tid + 1 : 0;
-      for (int c = start; c < cols; ++c) {
+    if (row_t < rows) {
+      const float xi = sorted_boxes[(base + rb * 64 + row_t) * kBoxRec + 0];
+      const float yi = sorted_boxes[(base + rb * 64 + row_t) * kBoxRec + 1];
+      unsigned int lo = 0u, hi = 0u;
+      for (int c = c_lo; c < c_hi; ++c) {
         const double dx = (double)__fsub_rn(xi, s_col[c * 2]);
         const double dy = (double)__fsub_rn(yi, s_col[c * 2 + 1]);
-        if (dx * dx + dy * dy <= (double)thr) bits |= 1ull << c;
+        if (dx * dx + dy * dy <= (double)thr) { if (c < 32) lo |= 1u << c; else hi |= 1u << (c - 32); }
       }
-      mask[(base + rb * 64 + tid) * col_blocks + cb] = bits;
+      if (lo) atomicOr(&s_bits[row_t][0], lo);
+      if (hi) atomicOr(&s_bits[row_t][1], hi);
     }
-    return;
-  }
-  BoxGeom a;
-  if (tid < rows) {
-    load_geom(geom + (base + rb * 64 + tid) * kGeomFloats, a);
-    const int start = (rb == cb) ? tid + 1 : 0;
-    for (int c = start; c < cols; ++c) {
-      BoxGeom bq;
-      bq.cx = s_col[c * kGeomFloats + 0];
-      bq.cy = s_col[c * kGeomFloats + 1];
-      bq.mx = s_col[c * kGeomFloats + 12];
-      bq.my = s_col[c * kGeomFloats + 13];
-      if (!pn_iou::surely_disjoint(a, bq)) {
-        const int slot = atomicAdd(&s_npairs, 1);
-        s_pairs[slot] = (unsigned short)((tid << 6) | c);
+  } else {
+    if (row_t < rows) {
+      const float* ga = geom + (base + rb * 64 + row_t) * kGeomFloats;
+      BoxGeom a;
+      a.cx = ga[0]; a.cy = ga[1]; a.mx = ga[12]; a.my = ga[13];
+      for (int c = c_lo; c < c_hi; ++c) {
+        BoxGeom bq;
+        bq.cx = s_col[c * kGeomFloats + 0];
+        bq.cy = s_col[c * kGeomFloats + 1];
+        bq.mx = s_col[c * kGeomFloats + 12];
+        bq.my = s_col[c * kGeomFloats + 13];
+        if (!pn_iou::surely_disjoint(a, bq)) {
+          const int slot = atomicAdd(&s_npairs, 1);
+          s_pairs[slot] = (unsigned short)((row_t << 6) | c);
+        }
       }
     }
-  }
-  __syncthreads();
-  const int np = s_npairs;
-  for (int q = tid; q < np; q += 64) {
-    const int r = s_pairs[q] >> 6, c = s_pairs[q] & 63;
-    BoxGeom ra, cbx;
-    load_geom(geom + (base + rb * 64 + r) * kGeomFloats, ra);
-    load_geom(s_col + c * kGeomFloats, cbx);
-    if (pn_iou::iou_bev(ra, cbx) > thr) atomicOr(&s_bits[r][c >> 5], 1u << (c & 31));
+    __syncthreads();
+    const int np = s_npairs;
+    for (int q = tid; q < np; q += kMaskThreads) {
+      const int r = s_pairs[q] >> 6, c = s_pairs[q] & 63;
+      BoxGeom ra, cbx;
+      load_geom(geom + (base + rb * 64 + r) * kGeomFloats, ra);
+      load_geom(s_col + c * kGeomFloats, cbx);
+      if (pn_iou::iou_bev(ra, cbx) > thr) atomicOr(&s_bits[r][c >> 5], 1u << (c & 31));
+    }
   }
   __syncthreads();
   if (tid < rows)
@@ -419,12 +422,22 @@ k_nms_sweep(SweepParams P, const float* __restrict__ sorted_boxes, int pre_cap,
     for (int slot = 0; slot < 2; ++slot) {
       const int w = lane + 32 * slot;
       if (w > blk && w < col_blocks) {
+        // rows of the boxes kept in this block: 8 independent loads in flight per lane, then OR
         unsigned long long acc = 0ull;
         unsigned long long bits = kept_bits;
         while (bits) {
-          const int r = __ffsll((long long)bits) - 1;
-          bits &= bits - 1;
-          acc |= mask[(base + blk * 64 + r) * col_blocks + w];
+          unsigned long long v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            v[u] = 0ull;
+            if (bits) {
+              const int r = __ffsll((long long)bits) - 1;
+              bits &= bits - 1;
+              v[u] = mask[(base + blk * 64 + r) * col_blocks + w];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc |= v[u];
         }
         remv[slot] |= acc;
       }
@@ -609,7 +622,7 @@ int pn_nms(int mode, int n_frames, int segs_per_frame, const float* seg_thr,
     PN_CHECK_LAUNCH();
   }
   dim3 grid(pre_cap / 64, pre_cap / 64, n_segs);
-  k_nms_mask<<<grid, 64, 0, stream>>>(M, sorted_boxes, geom, pre_cap, sorted_count, mask);
+  k_nms_mask<<<grid, kMaskThreads, 0, stream>>>(M, sorted_boxes, geom, pre_cap, sorted_count, mask);
   PN_CHECK_LAUNCH();
   k_nms_sweep<<<n_segs, 32, 0, stream>>>(S, sorted_boxes, pre_cap, sorted_count, mask, keep_idx,
                                          post_cap, keep_count, det_out);
@@ -657,7 +670,7 @@ int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t s
   S.segs_per_frame = 1;
   for (int i = 0; i < 16; ++i) { M.thr[i] = thr; S.post_max[i] = cap; S.use_rect[i] = 0; }
   dim3 grid(cap / 64, cap / 64, 1);
-  k_nms_mask<<<grid, 64, 0, stream>>>(M, rec, geom, cap, cnt, mask);
+  k_nms_mask<<<grid, kMaskThreads, 0, stream>>>(M, rec, geom, cap, cnt, mask);
   PN_CHECK_LAUNCH();
   k_nms_sweep<<<1, 32, 0, stream>>>(S, rec, cap, cnt, mask, keep, cap, num_keep, det);
   PN_CHECK_LAUNCH();
