@@ -84,33 +84,23 @@ __device__ __forceinline__ void run_group(const __nv_bfloat16* __restrict__ in, 
     for (int j = 0; j < COUT; ++j) acc[q][j] = 0.f;
   for (int c0 = 0; c0 < cin; c0 += CHUNK) {
     __syncthreads();
-    // stage halo: half-warp per pixel, lane -> channel pair (64 contiguous bytes per pixel).
-    // Loads are issued in batches of 8 independent requests per thread before the shared-memory
-    // stores, otherwise each of the 77 iterations waits a full L2 round trip.
+    // stage halo: half-warp per pixel, lane -> channel pair (64 contiguous bytes per pixel), written
+    // transposed.  4-byte cp.async with zero-fill keeps the WHOLE halo in flight at once; staging
+    // through registers (8 loads per thread at a time) left the kernel L2-latency bound (measured).
     const int half = tid >> 4, pr = tid & 15;
-    constexpr int kPix = HH_ * HW_, kStep = THREADS / 16, kBatch = 8;
-    for (int px0 = half; px0 < kPix; px0 += kStep * kBatch) {
-      uint32_t u[kBatch];
-      int so[kBatch];
-#pragma unroll
-      for (int i = 0; i < kBatch; ++i) {
-        const int px = px0 + i * kStep;
-        u[i] = 0u;
-        so[i] = -1;
-        if (px < kPix) {
-          const int hy = px / HW_, hx = px - hy * HW_;
-          const int gy = y0 + hy - 1, gx = x0 + hx - 1;
-          so[i] = pr * (HH_ * RS) + hy * RS + hx;
-          if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            const __nv_bfloat16* p =
-                in + ((long long)(b * (H + 2 * pad) + gy + pad) * (W + 2 * pad) + gx + pad) * in_ld + g.in_coff + c0;
-            u[i] = __ldg(reinterpret_cast<const uint32_t*>(p) + pr);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < kBatch; ++i)
-        if (so[i] >= 0) s_in[so[i]] = u[i];
+    constexpr int kPix = HH_ * HW_, kStep = THREADS / 16;
+    const uint32_t s_in_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_in));
+    for (int px = half; px < kPix; px += kStep) {
+      const int hy = px / HW_, hx = px - hy * HW_;
+      const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const __nv_bfloat16* p =
+          in + (ok ? ((long long)(b * (H + 2 * pad) + gy + pad) * (W + 2 * pad) + gx + pad) * in_ld : 0) +
+          g.in_coff + c0;
+      const uint32_t dst = s_in_addr + 4u * (uint32_t)(pr * (HH_ * RS) + hy * RS + hx);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst),
+                   "l"(reinterpret_cast<const uint32_t*>(p) + pr), "r"(ok ? 4u : 0u)
+                   : "memory");
     }
     // stage weights of this channel chunk: s_w[tap][pair][WV] = W[j][tap][c0 + 2*pair + {0,1}], zero padded
     constexpr int WV = WVec<COUT>::value;
@@ -119,6 +109,7 @@ __device__ __forceinline__ void run_group(const __nv_bfloat16* __restrict__ in, 
       const int j = e >> 1;
       s_w[i] = j < COUT ? __ldg(wbuf + g.w_off + (j * 9 + tap) * cin + c0 + 2 * pp + (e & 1)) : 0.f;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     compute_chunk<COUT>(s_in, s_w, ty, tx4, acc);
   }
