@@ -121,9 +121,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major SWIZZLE_128B descriptor; the start address may sit on any 128-byte row of a 1024-byte
-// aligned tile (window shifted by dx rows): `base_offset` (bits 49-51) carries (addr >> 7) & 7 when
-// mode != 0 (see the probe in tests/test_gpu_dense_conv.py; mode selected at run time).
+// K-major SWIZZLE_128B descriptor whose start address may sit on ANY 128-byte row of a 1024-byte
+// aligned tile (window shifted by dx rows).  Measured on B200 (tests/test_gpu_dense_conv.py probe): the
+// 128B swizzle is a function of the absolute shared-memory address, so the shifted window needs NO
+// base_offset (bits 49-51 = 0 gives max-abs error 7e-7; setting (addr >> 7) & 7 there gives garbage).
+// base_offset_mode != 0 exists only for that probe.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, int base_offset_mode) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
@@ -481,8 +483,11 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
     const double waves = (double)PN_DIVUP(tiles, (long long)sms);
     const double bytes = bn * 128.0 + (128.0 * mt + kTailRows) * 128.0 / 3.0;
     const double mma = mt * 4.0 * (bn / 2.0);
-    const double per_tap = bytes / 20.0 > mma ? bytes / 20.0 : mma;
-    const double cost = waves * per_tap;
+    // measured (tools/kbench_dense.py): ~40 B/clk/SM sustained from L2 when all SMs pull; BN=256 without a
+    // second accumulator buffer exposes the epilogue, which matters when K is short (cin = 64)
+    const double per_tap = bytes / 40.0 > mma ? bytes / 40.0 : mma;
+    const double epi = (2 * mt * bn > 512 ? 1.0 : 0.0) * (mt * bn * 6.0) / (9.0 * (cin / 64));
+    const double cost = waves * (per_tap + epi);
     if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
   }
   if (tile_hint >= 1 && tile_hint <= 4) best = tile_hint - 1;

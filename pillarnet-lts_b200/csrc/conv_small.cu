@@ -90,17 +90,23 @@ __device__ __forceinline__ void run_group(const __nv_bfloat16* __restrict__ in, 
     const int half = tid >> 4, pr = tid & 15;
     constexpr int kPix = HH_ * HW_, kStep = THREADS / 16;
     const uint32_t s_in_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_in));
-    for (int px = half; px < kPix; px += kStep) {
-      const int hy = px / HW_, hx = px - hy * HW_;
-      const int gy = y0 + hy - 1, gx = x0 + hx - 1;
-      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-      const __nv_bfloat16* p =
-          in + (ok ? ((long long)(b * (H + 2 * pad) + gy + pad) * (W + 2 * pad) + gx + pad) * in_ld : 0) +
-          g.in_coff + c0;
-      const uint32_t dst = s_in_addr + 4u * (uint32_t)(pr * (HH_ * RS) + hy * RS + hx);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst),
-                   "l"(reinterpret_cast<const uint32_t*>(p) + pr), "r"(ok ? 4u : 0u)
-                   : "memory");
+    {
+      // incremental (hy,hx): kStep = 8 pixels per iteration, no div/mod in the loop
+      int hy = 0, hx = half;
+      const int Wp = W + 2 * pad;
+      const __nv_bfloat16* in_g = in + g.in_coff + c0;
+      const long long frame_base = (long long)b * (H + 2 * pad) * Wp;
+      for (int px = half; px < kPix; px += kStep) {
+        const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        const __nv_bfloat16* p = in_g + (ok ? (frame_base + (long long)(gy + pad) * Wp + gx + pad) * in_ld : 0);
+        const uint32_t dst = s_in_addr + 4u * (uint32_t)(pr * (HH_ * RS) + hy * RS + hx);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst),
+                     "l"(reinterpret_cast<const uint32_t*>(p) + pr), "r"(ok ? 4u : 0u)
+                     : "memory");
+        hx += kStep;
+        if (hx >= HW_) { hx -= HW_; ++hy; }
+      }
     }
     // stage weights of this channel chunk: s_w[tap][pair][WV] = W[j][tap][c0 + 2*pair + {0,1}], zero padded
     constexpr int WV = WVec<COUT>::value;
