@@ -65,6 +65,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();  // protocol bug: trap instead of hanging the box
   }
 }
+// Long waits (epilogue waiting for a whole tile of MMAs): back off so the spinning warps do not steal
+// issue slots from the producer / MMA warps that share their schedulers.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -244,7 +253,16 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
   } else if (warp == 2) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
+      // The issuing thread is a single in-order instruction stream: at BN = 128 an MMA retires every
+      // 64 cycles, so descriptor arithmetic per MMA must be a couple of integer adds.  Stage base
+      // descriptors are built once; window / K-step offsets are compile-time constants added to the
+      // low word (the 14-bit start-address field never carries within a 192 KB tile region).
       constexpr uint32_t idesc = make_idesc<BN>();
+      uint64_t a_base[SA], b_base[SB];
+#pragma unroll
+      for (int i = 0; i < SA; ++i) a_base[i] = make_desc(smem_u32(sm.a[i]), 0);
+#pragma unroll
+      for (int i = 0; i < SB; ++i) b_base[i] = make_desc(smem_u32(sm.b[i]), 0);
       uint32_t ga = 0, gb = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = NACC == 2 ? (tcount & 1u) : 0u;
@@ -253,22 +271,32 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         for (int cc = 0; cc < n_cc; ++cc) {
-          for (int dy = 0; dy < 3; ++dy, ++ga) {
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
             const uint32_t sa = ga % SA, pha = (ga / SA) & 1u;
+            ++ga;
             mbar_wait(&sm.full_a[sa], pha);
-            for (int dx = 0; dx < 3; ++dx, ++gb) {
+            uint64_t a_stage = a_base[0];
+#pragma unroll
+            for (int i = 1; i < SA; ++i) a_stage = (sa == (uint32_t)i) ? a_base[i] : a_stage;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
               const uint32_t sb = gb % SB, phb = (gb / SB) & 1u;
+              ++gb;
               mbar_wait(&sm.full_b[sb], phb);
               tcgen05_fence_after();
-              const uint32_t b_addr = smem_u32(sm.b[sb]);
+              uint64_t b_stage = b_base[0];
+#pragma unroll
+              for (int i = 1; i < SB; ++i) b_stage = (sb == (uint32_t)i) ? b_base[i] : b_stage;
+              const uint32_t first = (dy == 0 && dx == 0) ? (cc != 0 ? 1u : 0u) : 1u;
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
-                const uint32_t a_addr = smem_u32(sm.a[sa]) + (uint32_t)(m * 128 + dx) * 128u;
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / 16; ++k) {
-                  const uint64_t a_desc = make_desc(a_addr + k * 32, P.base_offset_mode);
-                  const uint64_t b_desc = make_desc(b_addr + k * 32, 0);
-                  umma_bf16(d_tmem + m * BN, a_desc, b_desc, idesc, (cc | dy | dx | k) != 0 ? 1u : 0u);
+                  // (m*128 + dx) rows * 128 B + k * 32 B, in 16-byte units
+                  const uint64_t a_desc = a_stage + (uint64_t)((m * 128 + dx) * 8 + k * 2);
+                  const uint64_t b_desc = b_stage + (uint64_t)(k * 2);
+                  umma_bf16(d_tmem + m * BN, a_desc, b_desc, idesc, k == 0 ? first : 1u);
                 }
               }
               umma_commit(&sm.empty_b[sb]);
@@ -298,7 +326,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
         sm.shift[i] = (n < P.cout && P.shift) ? __ldg(P.shift + n) : 0.f;
       }
       named_bar_sync(2, kEpilogueThreads);
-      mbar_wait(&sm.tmem_full[acc], acc_ph);
+      mbar_wait_relaxed(&sm.tmem_full[acc], acc_ph);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {

@@ -76,6 +76,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
+// Long waits (epilogue waiting for a whole tile of MMAs): back off so the spinning warps do not steal
+// issue slots from the producer / MMA warps that share their schedulers.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -368,6 +377,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<BN>();
+      // stage descriptors built once (the issuing thread is one in-order instruction stream)
+      uint64_t a_base[STAGES], b_base[STAGES];
+#pragma unroll
+      for (int i = 0; i < STAGES; ++i) {
+        a_base[i] = make_kmajor_sw128_desc(smem_u32(sm.a[i]));
+        b_base[i] = make_kmajor_sw128_desc(smem_u32(sm.b[i]));
+      }
       uint32_t g = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u, acc_ph = (tcount >> 1) & 1u;
@@ -378,8 +394,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
           const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
           mbar_wait(&sm.full[s], ph);
           tcgen05_fence_after();
-          const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(sm.a[s]));
-          const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(sm.b[s]));
+          uint64_t a_desc = a_base[0], b_desc = b_base[0];
+#pragma unroll
+          for (int i = 1; i < STAGES; ++i) {
+            a_desc = (s == (uint32_t)i) ? a_base[i] : a_desc;
+            b_desc = (s == (uint32_t)i) ? b_base[i] : b_desc;
+          }
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
@@ -407,7 +427,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
         sm.shift[i] = (n < P.cout && P.shift) ? __ldg(P.shift + n) : 0.f;
       }
       named_bar_sync(2, kEpilogueThreads);
-      mbar_wait(&sm.tmem_full[acc], acc_ph);
+      mbar_wait_relaxed(&sm.tmem_full[acc], acc_ph);
       tcgen05_fence_after();
       const int row = m_tile * BLOCK_M + e * 32 + lane;
       const bool row_ok = row < rows;
