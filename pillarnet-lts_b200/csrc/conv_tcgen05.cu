@@ -33,7 +33,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;       // bf16 elements = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * 128;
-constexpr int kProducerThreads = 256;   // 8 warps: the gather is bound by the producers' instruction issue
+constexpr int kProducerThreads = 512;   // 16 warps: in-flight cp.async bytes scale with the number of issuing warps
 constexpr int kEpilogueThreads = 128;
 constexpr int kProducerWarps = kProducerThreads / 32;
 constexpr int kEpilogueWarp0 = kProducerWarps;        // 4 epilogue warps; index % 4 == TMEM lane quarter
@@ -95,7 +95,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
 // Asynchronous arrive: counts as this thread's arrival once all cp.async it issued so far have landed
@@ -275,7 +275,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   if (warp < kProducerWarps) {
     // ===================== A producers (+ weight TMA) =====================
     const int tid = threadIdx.x;
-    const int piece = tid & 7, rg = tid >> 3;          // rg in [0,32): rows rg + 32*i, i < 4
+    const int piece = tid & 7, rg = tid >> 3;          // rg in [0,64): rows rg + 64*i, i < 2
     const int k_total = P.taps * P.cin;
     // swizzled destination of this thread's 16-byte piece inside a stage (row & 7 == rg & 7 for all i)
     const uint32_t dst_off = (uint32_t)rg * 128u + (uint32_t)((piece ^ (rg & 7)) << 4);
@@ -360,11 +360,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
           const int* nb = s_nbr + rg * P.taps + t;
           const uint32_t coff = (uint32_t)c * 2u;
 #pragma unroll
-          for (int i = 0; i < BLOCK_M / 32; ++i) {
-            const int src = k_ok ? nb[i * 32 * P.taps] : -1;
+          for (int i = 0; i < BLOCK_M / (kProducerThreads / 8); ++i) {
+            const int src = k_ok ? nb[i * (kProducerThreads / 8) * P.taps] : -1;
             // 32-bit byte offset (the host checks in_rows*in_ld*2 < 4 GiB); missing neighbour => zero fill
             const uint32_t off = src >= 0 ? (uint32_t)src * in_ld_bytes + coff : 0u;
-            cp_async16(dst + (uint32_t)i * (32u * 128u), in_bytes + off, src >= 0 ? 16u : 0u);
+            cp_async16(dst + (uint32_t)i * ((uint32_t)(kProducerThreads / 8) * 128u), in_bytes + off,
+                       src >= 0 ? 16u : 0u);
           }
             cp_async_mbar_arrive_noinc(&sm.full[s]);
         }
@@ -708,10 +709,13 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
     }
   }
   switch (bn) {
-    case 16: return launch<16, 9, false>(map, map_a, ka, grid, stream);
-    case 32: return launch<32, 9, false>(map, map_a, ka, grid, stream);
-    case 64: return launch<64, 8, false>(map, map_a, ka, grid, stream);
-    case 128: return launch<128, 6, false>(map, map_a, ka, grid, stream);
+    // Few stages on purpose: pipeline depth beyond ~4 chunks bought nothing (measured), while the shared
+    // memory left to L1 lets the .ca gathers hit on the 3x reuse of activation rows between the taps of
+    // horizontally adjacent outputs.
+    case 16: return launch<16, 6, false>(map, map_a, ka, grid, stream);
+    case 32: return launch<32, 6, false>(map, map_a, ka, grid, stream);
+    case 64: return launch<64, 5, false>(map, map_a, ka, grid, stream);
+    case 128: return launch<128, 4, false>(map, map_a, ka, grid, stream);
     default: return launch<256, 4, false>(map, map_a, ka, grid, stream);
   }
 }
