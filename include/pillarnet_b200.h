@@ -89,9 +89,11 @@ int pn_pillarize(const float* points, int point_dim, const int* frame_offsets, i
  *              f = [x-ctr_x, y-ctr_y, p[0..point_dim)]            (2+point_dim values)
  *              h[c] = max(0, dot(weight[c,:], f) * scale[c] + shift[c])
  *   out[m,c] = max over points of pillar m (>= 0 by construction; reference zero-inits out)
- *   weight (c_out, 2+point_dim) f32 row-major (== nn.Linear.weight); scale/shift (c_out) f32.
+ *   weight (c_out, 2+point_dim) f32 row-major (== nn.Linear.weight); scale/shift (c_out) f32 —
+ *   these three are HOST pointers (tiny; they are passed to the kernel as launch parameters).
  *   out_f32 (m_cap, c_out) f32 ; out_bf16 optional (may be NULL) same shape, bf16 copy for the
- *   tensor-core backbone.  arg (m_cap, c_out) i32 optional (NULL for inference): index of a
+ *   tensor-core backbone.  out_f32 may be NULL when out_bf16 is given: bf16-only fast path (vector
+ *   bf16 atomics; bit-identical to rounding the fp32 result because fp32->bf16 rounding is monotone).  arg (m_cap, c_out) i32 optional (NULL for inference): index of a
  *   point attaining the max (lowest point id; the reference's is racy, scatter_ops_gpu.cu:33-35).
  *   c_out must be 32 or 64.  n_points_live: optional device scalar (e.g. frame_offsets + n_frames)
  *   bounding the live points below the host capacity n_points; NULL = all n_points.

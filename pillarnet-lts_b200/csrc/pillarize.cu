@@ -70,10 +70,20 @@ k_mark(const float* __restrict__ pts, int dim, const int* __restrict__ frame_off
   int cell = -1;
   if (cx >= 0 && cx < W && cy >= 0 && cy < H) {
     const int b = frame_of(frame_off, n_frames, p);
-    cell = (b * H + cy) * W + cx;
-    atomicOr(words + (cell >> 5), 1u << (cell & 31));
-  }
+    cell = (b * H + cy) * W + cx;  }
   point_cell[p] = cell;
+  // warp-aggregated marking: lanes that hit the same 32-cell word (scan-order neighbours usually do)
+  // combine their bits and ONE lane issues the atomicOr — and only if the word still lacks a bit
+  // (plain L2 read first; a stale read merely costs a redundant atomic).  Cuts L2 atomics from one per
+  // point to one per distinct word per warp, and removes same-address serialisation on dense cells.
+  const int word = cell >= 0 ? (cell >> 5) : -1;
+  const unsigned peers = __match_any_sync(__activemask(), word);
+  if (word >= 0) {
+    const unsigned bits = __reduce_or_sync(peers, 1u << (cell & 31));
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+      if ((__ldcg(words + word) & bits) != bits) atomicOr(words + word, bits);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kPtThreads)
@@ -98,18 +108,29 @@ k_zero_rows(float* __restrict__ out, int* __restrict__ arg, const int* __restric
   }
 }
 
-// One warp walks 32 staged points; lane = output channel (C/32 channels per lane).  All lanes see
-// the same point, so range checks are warp-uniform and the 128-byte row of out[] is hit by one
-// coalesced RED.MAX per point.  Post-ReLU values are >= 0, so max on the raw int bits is exact and
-// order-independent: the result is deterministic, unlike the reference's CAS loop.
+// PFN + scatter-max.  Phase 1: thread = point computes all C channels (7 FMA per channel, weights read
+// as constant-bank operands of the FFMA, so no load instructions) and parks them in shared memory.
+// Phase 2: each warp walks its 32 points with lane = channel, merges runs of consecutive points of
+// the same pillar in registers (scan-order locality) and issues ONE coalesced 128-byte RED.MAX per run
+// and channel group.  The earlier lane=channel-only version spent ~40 warp instructions per point (all
+// lanes redundantly decoding the same point) and was issue bound at 0.4-0.8 TB/s.
+// Post-ReLU values are >= 0, so max on the raw int bits is exact and order-independent: the result is
+// deterministic, unlike the reference's CAS loop (atomics.cuh:74-86).
+template <int C>
+struct PfnParams {
+  float w[C][kMaxPointDim + 2];
+  float scale[C];
+  float shift[C];
+};
+
 template <int C>
 __global__ void __launch_bounds__(kPtThreads)
-k_pfn_scatter_max(const float* __restrict__ pts, int dim, int n_points, const int* __restrict__ n_live,
-                  const int* __restrict__ point_pillar, float x0, float y0,
-                  float inv, float ps, float xoff, float yoff, const float* __restrict__ weight,
-                  const float* __restrict__ scale, const float* __restrict__ shift,
-                  float* __restrict__ out, int m_cap) {
-  extern __shared__ __align__(16) float s_pts[];
+k_pfn_scatter_max(const __grid_constant__ PfnParams<C> W, const float* __restrict__ pts, int dim, int n_points,
+                  const int* __restrict__ n_live, const int* __restrict__ point_pillar, float x0, float y0,
+                  float inv, float ps, float xoff, float yoff, float* __restrict__ out, int m_cap) {
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_pts = s_dyn;                                   // kPtThreads * dim
+  float* s_h = s_dyn + ((kPtThreads * dim + 3) & ~3);     // kPtThreads * (C + 1)
   __shared__ int s_rank[kPtThreads];
   constexpr int R = C / 32;
   if (n_live) n_points = min(n_points, __ldg(n_live));
@@ -117,56 +138,149 @@ k_pfn_scatter_max(const float* __restrict__ pts, int dim, int n_points, const in
   const int count = min(kPtThreads, n_points - first);
   if (count <= 0) return;
   stage_points(pts, (long long)first * dim, count * dim, s_pts);
-  if ((int)threadIdx.x < count) s_rank[threadIdx.x] = __ldg(point_pillar + first + threadIdx.x);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int fdim = dim + 2;
-  float w[R][kMaxPointDim + 2], sc[R], sh[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int c = lane + 32 * r;
-#pragma unroll
-    for (int k = 0; k < kMaxPointDim + 2; ++k) w[r][k] = k < fdim ? __ldg(weight + c * fdim + k) : 0.f;
-    sc[r] = __ldg(scale + c);
-    sh[r] = __ldg(shift + c);
+  const int t = threadIdx.x;
+  int rank = -1;
+  if (t < count) {
+    rank = __ldg(point_pillar + first + t);
+    if (rank >= m_cap) rank = -1;
   }
+  s_rank[t] = rank;
   __syncthreads();
-  const int j0 = warp * 32;
-  const int j1 = min(j0 + 32, count);
-  for (int j = j0; j < j1; ++j) {
-    const int rank = s_rank[j];
-    if (rank < 0 || rank >= m_cap) continue;
-    const float* p = s_pts + j * dim;
+  if (rank >= 0) {
+    const float* p = s_pts + t * dim;
+    float f[kMaxPointDim + 2];
     const float x = p[0], y = p[1];
     // pillar centre: int->float, *pillar_size, +offset as three separately rounded steps
     // (pillar_utils.py:51-52), then the offset features (pillar_utils.py:54).
-    const float cxf = (float)cell_coord(x, x0, inv);
-    const float cyf = (float)cell_coord(y, y0, inv);
-    const float f0 = __fsub_rn(x, __fadd_rn(__fmul_rn(cxf, ps), xoff));
-    const float f1 = __fsub_rn(y, __fadd_rn(__fmul_rn(cyf, ps), yoff));
+    f[0] = __fsub_rn(x, __fadd_rn(__fmul_rn((float)cell_coord(x, x0, inv), ps), xoff));
+    f[1] = __fsub_rn(y, __fadd_rn(__fmul_rn((float)cell_coord(y, y0, inv), ps), yoff));
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float z = w[r][0] * f0;
-      z = fmaf(w[r][1], f1, z);
+    for (int k = 0; k < kMaxPointDim; ++k) f[k + 2] = k < dim ? p[k] : 0.f;
+    float* hrow = s_h + t * (C + 1);
 #pragma unroll
-      for (int k = 0; k < kMaxPointDim; ++k)
-        if (k < dim) z = fmaf(w[r][k + 2], p[k], z);
-      const float h = fmaf(z, sc[r], sh[r]);
-      if (h > 0.f)
-        atomicMax(reinterpret_cast<int*>(out) + (long long)rank * C + lane + 32 * r,
-                  __float_as_int(h));
+    for (int c = 0; c < C; ++c) {
+      float z = W.w[c][0] * f[0];
+#pragma unroll
+      for (int k = 1; k < kMaxPointDim + 2; ++k) z = fmaf(W.w[c][k], f[k], z);   // zero weights beyond dim+2
+      hrow[c] = fmaxf(fmaf(z, W.scale[c], W.shift[c]), 0.f);
     }
   }
+  __syncthreads();
+  const int lane = t & 31, warp = t >> 5;
+  const int j0 = warp * 32, j1 = min(j0 + 32, count);
+  int cur = -1;
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  for (int j = j0; j <= j1; ++j) {
+    const int rk = j < j1 ? s_rank[j] : -2;   // sentinel flushes the last run
+    if (rk == -1) continue;
+    if (rk != cur) {
+      if (cur >= 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (acc[r] > 0.f)
+            atomicMax(reinterpret_cast<int*>(out) + (long long)cur * C + lane + 32 * r, __float_as_int(acc[r]));
+          acc[r] = 0.f;
+        }
+      }
+      cur = rk;
+    }
+    if (rk >= 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fmaxf(acc[r], s_h[j * (C + 1) + lane + 32 * r]);
+    }
+  }
+}
+
+// bf16-output variant (the tensor-core backbone consumes bf16 rows): max commutes with the monotone
+// fp32->bf16 rounding, so scattering the rounded values gives bit-identical results to rounding the fp32
+// max, and sm_100a has REDG.MAX.BF16x8: one lane-atomic covers 8 channels (16 bytes).  A pillar row of 32
+// channels is 4 lane-atomics instead of 32, which takes the kernel off the per-SM RED issue limit
+// (measured: ~1 lane-atomic per cycle per SM bounded the f32 version at 0.75 TB/s).
+__device__ __forceinline__ void red_max_bf16x8(void* addr, uint4 v) {
+  asm volatile("red.global.v4.bf16x2.max.noftz [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(kPtThreads)
+k_pfn_scatter_max_bf16(const __grid_constant__ PfnParams<C> W, const float* __restrict__ pts, int dim, int n_points,
+                       const int* __restrict__ n_live, const int* __restrict__ point_pillar, float x0, float y0,
+                       float inv, float ps, float xoff, float yoff, __nv_bfloat16* __restrict__ out, int m_cap) {
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_pts = s_dyn;                                                       // kPtThreads * dim
+  constexpr int RW = C / 2 + 4;                                               // u32 per point row (+pad: conflict-free v4)
+  uint32_t* s_h = reinterpret_cast<uint32_t*>(s_dyn + ((kPtThreads * dim + 3) & ~3));  // kPtThreads * RW
+  __shared__ int s_rank[kPtThreads];
+  if (n_live) n_points = min(n_points, __ldg(n_live));
+  const int first = blockIdx.x * kPtThreads;
+  const int count = min(kPtThreads, n_points - first);
+  if (count <= 0) return;
+  stage_points(pts, (long long)first * dim, count * dim, s_pts);
+  const int t = threadIdx.x;
+  int rank = -1;
+  if (t < count) {
+    rank = __ldg(point_pillar + first + t);
+    if (rank >= m_cap) rank = -1;
+  }
+  s_rank[t] = rank;
+  __syncthreads();
+  if (rank >= 0) {
+    const float* p = s_pts + t * dim;
+    float f[kMaxPointDim + 2];
+    const float x = p[0], y = p[1];
+    f[0] = __fsub_rn(x, __fadd_rn(__fmul_rn((float)cell_coord(x, x0, inv), ps), xoff));
+    f[1] = __fsub_rn(y, __fadd_rn(__fmul_rn((float)cell_coord(y, y0, inv), ps), yoff));
+#pragma unroll
+    for (int k = 0; k < kMaxPointDim; ++k) f[k + 2] = k < dim ? p[k] : 0.f;
+    uint32_t* hrow = s_h + t * RW;
+#pragma unroll
+    for (int c = 0; c < C; c += 2) {
+      float h[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float z = W.w[c + e][0] * f[0];
+#pragma unroll
+        for (int k = 1; k < kMaxPointDim + 2; ++k) z = fmaf(W.w[c + e][k], f[k], z);
+        h[e] = fmaxf(fmaf(z, W.scale[c + e], W.shift[c + e]), 0.f);
+      }
+      const __nv_bfloat162 pk = __floats2bfloat162_rn(h[0], h[1]);
+      hrow[c / 2] = *reinterpret_cast<const uint32_t*>(&pk);
+    }
+  }
+  __syncthreads();
+  // lane = (point j8, quad q): one RED instruction flushes 8 points x 4 quads x 8 channels
+  constexpr int QUADS = C / 8;               // lane-atomics per point
+  constexpr int PPI = 32 / QUADS;            // points per RED instruction
+  const int lane = t & 31, warp = t >> 5;
+  const int q = lane % QUADS, jl = lane / QUADS;
+  for (int j = warp * 32 + jl; j < min(warp * 32 + 32, count); j += PPI) {
+    const int rk = s_rank[j];
+    if (rk < 0) continue;
+    const uint4 v = *reinterpret_cast<const uint4*>(s_h + j * RW + q * 4);
+    if ((v.x | v.y | v.z | v.w) != 0u) red_max_bf16x8(out + (long long)rk * C + q * 8, v);
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+k_zero_rows_bf16(__nv_bfloat16* __restrict__ out, const int* __restrict__ num_rows, int m_cap) {
+  const int n = min(*num_rows, m_cap);
+  const long long total8 = (long long)n * C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // Training only: deterministic argmax = lowest point id attaining the max (second pass, like the
 // reference's scatter_arg_max_kernel but exact-compare and tie-broken).
 template <int C>
 __global__ void __launch_bounds__(kPtThreads)
-k_pfn_argmax(const float* __restrict__ pts, int dim, int n_points, const int* __restrict__ n_live,
-             const int* __restrict__ point_pillar, float x0, float y0, float inv, float ps,
-             float xoff, float yoff, const float* __restrict__ weight,
-             const float* __restrict__ scale, const float* __restrict__ shift,
-             const float* __restrict__ out, int* __restrict__ arg, int m_cap) {
+k_pfn_argmax(const __grid_constant__ PfnParams<C> W, const float* __restrict__ pts, int dim, int n_points,
+             const int* __restrict__ n_live, const int* __restrict__ point_pillar, float x0, float y0, float inv,
+             float ps, float xoff, float yoff, const float* __restrict__ out, int* __restrict__ arg, int m_cap) {
   const int p = blockIdx.x * (kPtThreads / 32) + (threadIdx.x >> 5);
   if (p >= n_points || (n_live && p >= __ldg(n_live))) return;
   const int rank = __ldg(point_pillar + p);
@@ -176,14 +290,17 @@ k_pfn_argmax(const float* __restrict__ pts, int dim, int n_points, const int* __
   const float x = __ldg(q), y = __ldg(q + 1);
   const float f0 = __fsub_rn(x, __fadd_rn(__fmul_rn((float)cell_coord(x, x0, inv), ps), xoff));
   const float f1 = __fsub_rn(y, __fadd_rn(__fmul_rn((float)cell_coord(y, y0, inv), ps), yoff));
-  const int fdim = dim + 2;
+  float f[kMaxPointDim + 2];
+  f[0] = f0;
+  f[1] = f1;
+#pragma unroll
+  for (int k = 0; k < kMaxPointDim; ++k) f[k + 2] = k < dim ? __ldg(q + k) : 0.f;
   for (int c = lane; c < C; c += 32) {
-    const float* wr = weight + c * fdim;
-    float z = __ldg(wr) * f0;
-    z = fmaf(__ldg(wr + 1), f1, z);
-    for (int k = 0; k < dim; ++k) z = fmaf(__ldg(wr + k + 2), __ldg(q + k), z);
-    float h = fmaf(z, __ldg(scale + c), __ldg(shift + c));
-    h = fmaxf(h, 0.f);
+    // same operation order as k_pfn_scatter_max, so the recomputed value is bit-identical to the stored max
+    float z = W.w[c][0] * f[0];
+#pragma unroll
+    for (int k = 1; k < kMaxPointDim + 2; ++k) z = fmaf(W.w[c][k], f[k], z);
+    const float h = fmaxf(fmaf(z, W.scale[c], W.shift[c]), 0.f);
     if (h == out[(long long)rank * C + c]) {
       // arg holds -1 (0xFFFFFFFF) initially: unsigned min keeps the lowest flat index
       atomicMin(reinterpret_cast<unsigned*>(arg) + (long long)rank * C + c, (unsigned)(p * C + c));
@@ -264,26 +381,72 @@ int pn_pfn_scatter_max(const float* points, int point_dim, int n_points, const i
   cudaStream_t stream = (cudaStream_t)stream_;
   PN_REQUIRE(point_dim >= 2 && point_dim <= kMaxPointDim);
   PN_REQUIRE(c_out == 32 || c_out == 64);
-  PN_REQUIRE(num_pillars && weight && scale && shift && out_f32 && m_cap >= 0 && n_points >= 0);
+  PN_REQUIRE(num_pillars && weight && scale && shift && (out_f32 || out_bf16) && m_cap >= 0 && n_points >= 0);
+  PN_REQUIRE(out_f32 || !arg);
   if (m_cap == 0) return PN_OK;
   const int sms = pn_detail::sm_count();
   if (sms <= 0) return PN_ERR_CUDA;
   const int zero_blocks = sms * 8;
   const int blocks = PN_DIVUP(n_points, kPtThreads);
-  const size_t smem = kPtThreads * point_dim * sizeof(float);
+  auto smem_pfn = [&](int C) { return (size_t)(((kPtThreads * point_dim + 3) & ~3) + kPtThreads * (C + 1)) * sizeof(float); };
+  // weight/scale/shift are HOST pointers: they travel as kernel parameters (constant bank), so the FFMAs
+  // read them as constant operands instead of issuing loads.
+  static_assert(sizeof(PfnParams<64>) <= 3600, "kernel parameter space");
+  PfnParams<64> hp64;
+  PfnParams<32>& hp32 = *reinterpret_cast<PfnParams<32>*>(&hp64);  // filled below for the C that is used
+  const int fdim = point_dim + 2;
+  auto fill = [&](auto& hp, int C) {
+    for (int c = 0; c < C; ++c) {
+      for (int k = 0; k < kMaxPointDim + 2; ++k) hp.w[c][k] = k < fdim ? weight[c * fdim + k] : 0.f;
+      hp.scale[c] = scale[c];
+      hp.shift[c] = shift[c];
+    }
+  };
+  if (c_out == 32) fill(hp32, 32); else fill(hp64, 64);
+  const void* wparams = c_out == 32 ? (const void*)&hp32 : (const void*)&hp64;
+  if (!out_f32) {
+    // bf16-only fast path: vector bf16 RED straight into the bf16 rows
+    auto smem_bf = [&](int C) { return (size_t)(((kPtThreads * point_dim + 3) & ~3) + kPtThreads * (C / 2 + 4)) * 4; };
+#define PN_PFN_BF16(C)                                                                                \
+    do {                                                                                              \
+      static bool ok##C = false;                                                                      \
+      if (!ok##C) {                                                                                   \
+        PN_CUDA(cudaFuncSetAttribute(k_pfn_scatter_max_bf16<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem_bf(C) + 4096));                                        \
+        ok##C = true;                                                                                 \
+      }                                                                                               \
+      k_zero_rows_bf16<C><<<zero_blocks, 256, 0, stream>>>((__nv_bfloat16*)out_bf16, num_pillars, m_cap); \
+      PN_CHECK_LAUNCH();                                                                              \
+      if (n_points > 0) {                                                                             \
+        k_pfn_scatter_max_bf16<C><<<blocks, kPtThreads, smem_bf(C), stream>>>(                        \
+            *reinterpret_cast<const PfnParams<C>*>(wparams), points, point_dim, n_points, n_points_live, \
+            point_pillar, x0, y0, inv_pillar, pillar_size, x_offset, y_offset, (__nv_bfloat16*)out_bf16, m_cap); \
+        PN_CHECK_LAUNCH();                                                                            \
+      }                                                                                               \
+    } while (0)
+    if (c_out == 32) PN_PFN_BF16(32); else PN_PFN_BF16(64);
+#undef PN_PFN_BF16
+    return PN_OK;
+  }
 #define PN_PFN_LAUNCH(C)                                                                           \
   do {                                                                                             \
+    static bool smem_ok##C = false;                                                                \
+    if (!smem_ok##C) {                                                                             \
+      PN_CUDA(cudaFuncSetAttribute(k_pfn_scatter_max<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,\
+                                   (int)smem_pfn(C) + 4096));                                      \
+      smem_ok##C = true;                                                                           \
+    }                                                                                             \
     k_zero_rows<C><<<zero_blocks, 256, 0, stream>>>(out_f32, arg, num_pillars, m_cap);             \
     PN_CHECK_LAUNCH();                                                                             \
     if (n_points > 0) {                                                                            \
-      k_pfn_scatter_max<C><<<blocks, kPtThreads, smem, stream>>>(                                  \
-          points, point_dim, n_points, n_points_live, point_pillar, x0, y0, inv_pillar,       \
-          pillar_size, x_offset, y_offset, weight, scale, shift, out_f32, m_cap);                               \
+      k_pfn_scatter_max<C><<<blocks, kPtThreads, smem_pfn(C), stream>>>(                                \
+          *reinterpret_cast<const PfnParams<C>*>(wparams), points, point_dim, n_points, n_points_live,     \
+          point_pillar, x0, y0, inv_pillar, pillar_size, x_offset, y_offset, out_f32, m_cap);          \
       PN_CHECK_LAUNCH();                                                                           \
       if (arg) {                                                                                   \
         k_pfn_argmax<C><<<PN_DIVUP(n_points, kPtThreads / 32), kPtThreads, 0, stream>>>(           \
-            points, point_dim, n_points, n_points_live, point_pillar, x0, y0, inv_pillar,         \
-            pillar_size, x_offset, y_offset, weight, scale, shift, out_f32, arg, m_cap);                                  \
+            *reinterpret_cast<const PfnParams<C>*>(wparams), points, point_dim, n_points, n_points_live,   \
+            point_pillar, x0, y0, inv_pillar, pillar_size, x_offset, y_offset, out_f32, arg, m_cap);     \
         PN_CHECK_LAUNCH();                                                                         \
       }                                                                                            \
     }                                                                                              \

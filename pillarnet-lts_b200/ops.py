@@ -83,16 +83,20 @@ def _f32(v):
 
 
 def pfn_scatter_max(points, point_pillar, table, x0, y0, pillar_size, x_offset, y_offset, weight,
-                    scale, shift, want_bf16=False, want_arg=False, n_live=None):
+                    scale, shift, want_bf16=False, want_arg=False, n_live=None, want_f32=True):
     """Fused offset features + Linear + affine(BN) + ReLU + per-pillar max. Returns (f32, bf16|None, arg|None)."""
     lib = _lib.load()
-    require_cuda(points, point_pillar, weight, scale, shift)
+    require_cuda(points, point_pillar)
+    # weight/scale/shift are passed as HOST arrays (they become kernel launch parameters)
+    weight, scale, shift = (t.detach().to("cpu", torch.float32).contiguous() for t in (weight, scale, shift))
     N, D = points.shape
     C = weight.shape[0]
     if weight.shape[1] != D + 2:
         raise RuntimeError(f"PFN weight must be (C,{D + 2})")
     dev = points.device
-    out = torch.empty(table.cap, C, dtype=torch.float32, device=dev)
+    if not want_f32 and not want_bf16:
+        raise RuntimeError("nothing to compute")
+    out = torch.empty(table.cap, C, dtype=torch.float32, device=dev) if want_f32 else None
     out_bf = torch.empty(table.cap, C, dtype=torch.bfloat16, device=dev) if want_bf16 else None
     arg = _i32(table.cap, C, device=dev) if want_arg else None
     inv = (torch.tensor(1.0, dtype=torch.float32) / torch.tensor(pillar_size, dtype=torch.float32)).item()

@@ -53,7 +53,9 @@ class PillarMaxPooling(nn.Module):
         inv = torch.rsqrt(bn.running_var.detach().double() + bn.eps)
         scale = (bn.weight.detach().double() * inv)
         shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
-        val = (lin.weight.detach().float().contiguous(), scale.float().contiguous(), shift.float().contiguous())
+        # host copies: the fused kernel takes these tiny arrays as launch parameters (one sync, at lowering time)
+        val = (lin.weight.detach().float().cpu().contiguous(), scale.float().cpu().contiguous(),
+               shift.float().cpu().contiguous())
         self.__dict__["_pn_folded"] = (key, val)
         return val
 
@@ -67,7 +69,7 @@ class PillarMaxPooling(nn.Module):
         f32, bf16, _ = ops.pfn_scatter_max(points, point_pillar, table, self.point_cloud_range[0],
                                            self.point_cloud_range[1], self.pillar_size, self.x_offset,
                                            self.y_offset, w, scale, shift, want_bf16=want_bf16,
-                                           n_live=frame_offsets[batch_size:])
+                                           want_f32=not want_bf16, n_live=frame_offsets[batch_size:])
         sp = SparseConvTensor(bf16 if want_bf16 else f32, table, (self.height, self.width), batch_size)
         sp.features_f32 = f32
         sp.point_pillar = point_pillar

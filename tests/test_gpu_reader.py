@@ -207,6 +207,25 @@ def test_pfn_scatter_max_vs_oracle_and_reference(kind, cfg, B):
         assert (out[:n] - rout).abs().max().item() <= 1e-4 * scale_ref
 
 
+@pytest.mark.parametrize("kind,cfg,B", [("nuscenes", NUSC, 2), ("waymo", WAYMO, 2)])
+def test_bf16_only_fast_path_is_bit_identical_to_rounded_fp32(kind, cfg, B):
+    """vector bf16 RED path (REDG.MAX.BF16x8) == round_bf16(fp32 scatter-max): rounding is monotone."""
+    from pillarnet_lts_b200 import ops
+    frames = _frames(kind, B, 45)
+    table, pp, pts, ref = _check_vs_oracle(frames, cfg)
+    w, bn = _pfn_params(3)
+    scale, shift = torch.rand(32) + 0.5, torch.randn(32) * 0.1
+    ps, pcr = cfg["ps"], cfg["pcr"]
+    args = (pts, pp, table, pcr[0], pcr[1], ps, ps / 2.0 + pcr[0], ps / 2.0 + pcr[1], w, scale, shift)
+    f32, bf_a, _ = ops.pfn_scatter_max(*args, want_bf16=True)
+    none, bf_b, _ = ops.pfn_scatter_max(*args, want_bf16=True, want_f32=False)
+    torch.cuda.synchronize()
+    n = table.count()
+    assert none is None
+    assert torch.equal(bf_a[:n].view(torch.int16), f32[:n].to(torch.bfloat16).view(torch.int16))
+    assert torch.equal(bf_b[:n].view(torch.int16), bf_a[:n].view(torch.int16))
+
+
 def test_scatter_max_grad_routes_to_argmax():
     from pillarnet_lts_b200 import ops
     frames = _frames("nuscenes", 1, 41)
