@@ -259,19 +259,9 @@ k_pfn_scatter_max_bf16(const __grid_constant__ PfnParams<C> W, const float* __re
   for (int j = warp * 32 + jl; j < min(warp * 32 + 32, count); j += PPI) {
     const int rk = s_rank[j];
     if (rk < 0) continue;
-    // runs of consecutive points of one pillar (scan-order locality): the run head folds its followers
-    // in with packed bf16 max and issues the only atomic of the run
-    if (j > 0 && s_rank[j - 1] == rk) continue;
-    uint4 v = *reinterpret_cast<const uint4*>(s_h + j * RW + q * 4);
-    for (int k = j + 1; k < count && s_rank[k] == rk; ++k) {
-      const uint4 u = *reinterpret_cast<const uint4*>(s_h + k * RW + q * 4);
-      auto mx = [](uint32_t a, uint32_t b) {
-        const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a),
-                                         *reinterpret_cast<const __nv_bfloat162*>(&b));
-        return *reinterpret_cast<const uint32_t*>(&r);
-      };
-      v.x = mx(v.x, u.x); v.y = mx(v.y, u.y); v.z = mx(v.z, u.z); v.w = mx(v.w, u.w);
-    }
+    // (folding runs of same-pillar points before the atomic was measured slower: the serial follower
+    //  loop costs more than the 16-byte vector atomics it saves)
+    const uint4 v = *reinterpret_cast<const uint4*>(s_h + j * RW + q * 4);
     if ((v.x | v.y | v.z | v.w) != 0u) red_max_bf16x8(out + (long long)rk * C + q * 8, v);
   }
 }
