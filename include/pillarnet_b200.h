@@ -197,6 +197,16 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
                      void* out, int out_dtype, int out_ld, int out_coff, int out_compact, int relu,
                      int tile_hint, pn_stream_t stream);
 
+/* Grouped form of pn_conv_dense3x3: n_groups independent 3x3 convs in one launch (the last conv of every
+ * CenterHead branch, center_head.py:34-35).  Group g reads channels [in_coff + g*cin, +cin) of the padded
+ * input, uses weight rows [16g, 16g+16) of the bf16 [n_groups*16][k_pad] matrix (rows >= its cout are
+ * zero) and scale/shift entries [16g, 16g+16), and writes group_tab[g] = {first output column, cout}
+ * (device int32 [n_groups][2]) columns of `out`.  cin % 64 == 0, cout <= 16. */
+int pn_conv_dense3x3_grouped(const void* in, int in_ld, int in_coff, int cin, int n_groups, int n_frames, int H,
+                             int W, const void* weight, int k_pad, const float* scale, const float* shift,
+                             const int* group_tab, void* out, int out_dtype, int out_ld, int out_compact,
+                             int relu, pn_stream_t stream);
+
 /* f32 -> bf16 weight packing with zero padding of K to k_pad (multiple of 64). */
 int pn_conv_pack_weight_bf16(const float* w_f32, int cout, int k, int k_pad, void* w_bf16,
                              pn_stream_t stream);

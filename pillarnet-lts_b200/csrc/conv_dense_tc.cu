@@ -128,6 +128,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B descriptor whose start address may sit on ANY 128-byte row of a 1024-byte
@@ -165,6 +174,10 @@ struct DArgs {
   int out_compact; // 0: padded rows (borders zeroed); 1: compact rows b*H*W + (y-1)*W + (x-1)
   int relu;
   int base_offset_mode;
+  // grouped mode (n_groups > 0): N tile g is an independent conv reading channels
+  // [in_coff + g*cin, +cin), weight rows [g*BN, +BN), writing group_tab[g] = {out_coff, cout} columns
+  int n_groups;
+  const int* group_tab;
 };
 
 template <int MT, int BN, int SA, int SB>
@@ -195,7 +208,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
   constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;     // double-buffer the accumulator when TMEM allows
   constexpr int TCOLS = (NACC * ACC_COLS) < 32 ? 32 : NACC * ACC_COLS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_n_tiles = (P.cout + BN - 1) / BN;
+  const int n_n_tiles = P.n_groups > 0 ? P.n_groups : (P.cout + BN - 1) / BN;
   const int n_tiles = ((P.n_pos + M_TILE - 1) / M_TILE) * n_n_tiles;
   const int n_cc = P.cin / BLOCK_K;
 
@@ -221,13 +234,14 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int m_tile = tile / n_n_tiles;
         const int q0 = m_tile * M_TILE;
+        const int ch0 = P.in_coff + (P.n_groups > 0 ? (tile - m_tile * n_n_tiles) * P.cin : 0);
         for (int cc = 0; cc < n_cc; ++cc) {
           for (int dy = 0; dy < 3; ++dy, ++g) {
             const uint32_t s = g % SA, ph = (g / SA) & 1u;
             mbar_wait(&sm.empty_a[s], ph ^ 1u);
             mbar_arrive_expect_tx(&sm.full_a[s], (uint32_t)(S::kSegRows * 128));
             const int row = q0 + (dy - 1) * P.Wp - 1;   // may be negative / past the end: TMA zero-fills
-            const int ch = P.in_coff + cc * BLOCK_K;
+            const int ch = ch0 + cc * BLOCK_K;
             tma_load_2d(smem_u32(sm.a[s]), &tmap_a_main, ch, row, &sm.full_a[s]);
             tma_load_2d(smem_u32(sm.a[s]) + M_TILE * 128, &tmap_a_tail, ch, row + M_TILE, &sm.full_a[s]);
           }
@@ -316,14 +330,20 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const int m_tile = tile / n_n_tiles, n_tile = tile - m_tile * n_n_tiles;
-      const int n0 = n_tile * BN;
+      const int n0 = n_tile * BN;          // first weight row / scale index of this N tile
+      int cout_t = P.cout, ocol0 = P.out_coff + n0, nbase = n0;
+      if (P.n_groups > 0) {                // grouped: own output columns and channel count
+        ocol0 = __ldg(P.group_tab + 2 * n_tile);
+        cout_t = __ldg(P.group_tab + 2 * n_tile + 1);
+        nbase = 0;
+      }
       const uint32_t acc = NACC == 2 ? (tcount & 1u) : 0u;
       const uint32_t acc_ph = NACC == 2 ? ((tcount >> 1) & 1u) : (tcount & 1u);
       named_bar_sync(2, kEpilogueThreads);
       for (int i = etid; i < BN; i += kEpilogueThreads) {
-        const int n = n0 + i;
-        sm.scale[i] = (n < P.cout && P.scale) ? __ldg(P.scale + n) : 1.f;
-        sm.shift[i] = (n < P.cout && P.shift) ? __ldg(P.shift + n) : 0.f;
+        const bool ok = nbase + i < cout_t;
+        sm.scale[i] = (ok && P.scale) ? __ldg(P.scale + n0 + i) : 1.f;
+        sm.shift[i] = (ok && P.shift) ? __ldg(P.shift + n0 + i) : 0.f;
       }
       named_bar_sync(2, kEpilogueThreads);
       mbar_wait_relaxed(&sm.tmem_full[acc], acc_ph);
@@ -343,37 +363,39 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
           orow = ((long long)b * (P.Hp - 2) + (y - 1)) * (P.Wp - 2) + (x - 1);
         }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          if (n0 + c0 >= P.cout) break;  // warp-uniform
+        constexpr int CH = BN < 32 ? 16 : 32;
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+          if (nbase + c0 >= cout_t) break;  // warp-uniform
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * ACC_COLS + m * BN + c0, v);
+          const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * ACC_COLS + m * BN + c0;
+          if (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
           tmem_wait_ld();
           if (store) {
-            const int nvalid = min(32, P.cout - (n0 + c0));
+            const int nvalid = min(CH, cout_t - (nbase + c0));
             float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < CH; ++j) {
               float t = fmaf(__uint_as_float(v[j]), sm.scale[c0 + j], sm.shift[c0 + j]);
               if (P.relu) t = fmaxf(t, 0.f);
               f[j] = (border && !P.out_compact) ? 0.f : t;
             }
-            const long long ooff = orow * P.out_ld + P.out_coff + n0 + c0;
+            const long long ooff = orow * P.out_ld + ocol0 + c0;
             if (P.out_f32) {
               float* op = reinterpret_cast<float*>(P.out) + ooff;
-              if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+              if (nvalid == CH && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
+                for (int j = 0; j < CH; j += 4)
                   *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
               } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
+                for (int j = 0; j < CH; ++j)
                   if (j < nvalid) op[j] = f[j];
               }
             } else {
               __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + ooff;
-              if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+              if (nvalid == CH && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
+                for (int j = 0; j < CH; j += 8) {
                   uint4 qv;
                   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&qv);
 #pragma unroll
@@ -382,7 +404,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
                 }
               } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
+                for (int j = 0; j < CH; ++j)
                   if (j < nvalid) op[j] = __float2bfloat16_rn(f[j]);
               }
             }
@@ -532,12 +554,51 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
   a.scale = scale; a.shift = shift; a.out = out; a.out_f32 = out_dtype == PN_F32; a.out_ld = out_ld;
   a.out_coff = out_coff; a.out_compact = out_compact; a.relu = relu;
   a.base_offset_mode = (tile_hint & 0x100) ? 1 : 0;
+  a.n_groups = 0;
+  a.group_tab = nullptr;
   const long long tiles = PN_DIVUP(n_pos, (long long)(128 * mt)) * PN_DIVUP(cout, bn);
   const int grid = (int)(tiles < sms ? tiles : sms);
   if (mt == 2 && bn == 256) return launch<2, 256, 2, 4>(ma, mtail, mw, a, grid, stream);
   if (mt == 1 && bn == 256) return launch<1, 256, 3, 5>(ma, mtail, mw, a, grid, stream);
   if (mt == 2 && bn == 128) return launch<2, 128, 3, 6>(ma, mtail, mw, a, grid, stream);
   return launch<1, 128, 4, 8>(ma, mtail, mw, a, grid, stream);
+}
+
+
+// Grouped variant: n_groups independent 3x3 convs (cin channels each, <= 16 outputs each) in one launch —
+// the last conv of every CenterHead branch (center_head.py:34-35) on the tensor cores.  weight: bf16
+// [n_groups*16][k_pad] (rows g*16+j = output j of group g, zero rows above its cout); scale/shift: f32
+// [n_groups*16]; group_tab: device int32 [n_groups][2] = {first output column, cout}.
+int pn_conv_dense3x3_grouped(const void* in, int in_ld, int in_coff, int cin, int n_groups, int n_frames, int H,
+                             int W, const void* weight, int k_pad, const float* scale, const float* shift,
+                             const int* group_tab, void* out, int out_dtype, int out_ld, int out_compact,
+                             int relu, pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(in && weight && out && group_tab && n_groups >= 1 && n_frames >= 1 && H > 0 && W > 0);
+  PN_REQUIRE(cin % BLOCK_K == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && k_pad % BLOCK_K == 0 && k_pad >= 9 * cin);
+  PN_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15u) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15u) == 0);
+  PN_REQUIRE(out_dtype == PN_F32 || out_dtype == PN_BF16);
+  const int Hp = H + 2, Wp = W + 2;
+  const long long n_pos = (long long)n_frames * Hp * Wp;
+  PN_REQUIRE(n_pos < (1ll << 31));
+  const int sms = pn_detail::sm_count();
+  if (sms <= 0) return PN_ERR_CUDA;
+  constexpr int mt = 2, bn = 16;
+  CUtensorMap ma, mtail, mw;
+  int rc = get_map(in, n_pos, in_ld, in_ld, 128 * mt, &ma);
+  if (rc != PN_OK) return rc;
+  rc = get_map(in, n_pos, in_ld, in_ld, kTailRows, &mtail);
+  if (rc != PN_OK) return rc;
+  rc = get_map(weight, (long long)n_groups * bn, k_pad, k_pad, bn, &mw);
+  if (rc != PN_OK) return rc;
+  DArgs a;
+  a.cin = cin; a.in_coff = in_coff; a.cout = bn; a.Hp = Hp; a.Wp = Wp; a.n_pos = (int)n_pos;
+  a.scale = scale; a.shift = shift; a.out = out; a.out_f32 = out_dtype == PN_F32; a.out_ld = out_ld;
+  a.out_coff = 0; a.out_compact = out_compact; a.relu = relu; a.base_offset_mode = 0;
+  a.n_groups = n_groups; a.group_tab = group_tab;
+  const long long tiles = PN_DIVUP(n_pos, (long long)(128 * mt)) * n_groups;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  return launch<2, 16, 3, 8>(ma, mtail, mw, a, grid, stream);
 }
 
 }  // extern "C"

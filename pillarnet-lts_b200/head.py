@@ -131,9 +131,15 @@ class CenterHead(nn.Module):
                            and two_level[0][2][0].out_channels % 32 == 0)
             if fused_final:
                 hc = two_level[0][2][0].out_channels
-                groups, wbuf = self._final_groups(fi, entries, slot, t_off, hc)
-                ops.conv3x3_small_cout(inter.rows, inter.rows.stride(0), hc, feat.B, feat.H, feat.W, groups,
-                                       len(entries), wbuf, all_rows, in_padded=bool(inter.pad))
+                if inter.pad and hc % 64 == 0 and inter.coff == 0:
+                    # tensor-core grouped conv on the padded layout (reads the intermediate 3x, not 9x)
+                    wg, sg, tab = self._final_groups_tc(fi, entries, slot, t_off, hc)
+                    ops.conv_dense3x3_grouped(inter.rows, 0, hc, len(entries), feat.B, feat.H, feat.W, wg, sg, tab,
+                                              all_rows, out_compact=True)
+                else:
+                    groups, wbuf = self._final_groups(fi, entries, slot, t_off, hc)
+                    ops.conv3x3_small_cout(inter.rows, inter.rows.stride(0), hc, feat.B, feat.H, feat.W, groups,
+                                           len(entries), wbuf, all_rows, in_padded=bool(inter.pad))
             for t in tids:
                 th = self.task_heads[t]
                 offsets, c = {}, 0
@@ -166,6 +172,38 @@ class CenterHead(nn.Module):
                 pp.rows, pp.offsets, pp.shape = rows, offsets, (feat.B, feat.H, feat.W)
                 rets[t] = pp
         return rets
+
+    def _final_groups_tc(self, fi, entries, slot, t_off, hc):
+        """bf16 [G*16][k_pad] weights (group = slot order of the fused first-level conv), f32 [G*16] biases and the
+        device {out column, cout} table for pn_conv_dense3x3_grouped (cached on parameter versions)"""
+        finals = [e[2][-1] for e in entries]
+        key = tuple((f.weight.data_ptr(), f.weight._version, f.bias.data_ptr(), f.bias._version) for f in finals)
+        cache = self.__dict__.setdefault("_pn_final_groups_tc", {})
+        hit = cache.get(fi)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2], hit[3]
+        G = len(entries)
+        dev = finals[0].weight.device
+        w = torch.zeros(G * 16, 9 * hc, dtype=torch.float32, device=dev)
+        b = torch.zeros(G * 16, dtype=torch.float32, device=dev)
+        tab = [[0, 0] for _ in range(G)]
+        for t, name, fc in entries:
+            g = slot[id(fc)]
+            f = fc[-1]
+            c = f.out_channels
+            th = self.task_heads[t]
+            col = t_off[t]
+            for nm in th.heads:
+                if nm == name:
+                    break
+                col += th.heads[nm][0]
+            w[g * 16:g * 16 + c] = f.weight.detach().float().permute(0, 2, 3, 1).reshape(c, -1)
+            b[g * 16:g * 16 + c] = f.bias.detach().float()
+            tab[g] = [col, c]
+        wg = ops.pack_weight_bf16(w)
+        tabd = torch.tensor(tab, dtype=torch.int32).to(dev)
+        cache[fi] = (key, wg, b, tabd)
+        return wg, b, tabd
 
     def _final_groups(self, fi, entries, slot, t_off, hc):
         """device descriptors + packed fp32 weights of all final convs on feature `fi` (cached on versions)"""

@@ -123,7 +123,7 @@ def invalidate(module):
     edits through `.data` do not bump (load_state_dict / optimiser steps / copy_ do) — call this after
     such an edit."""
     for m in module.modules():
-        for k in ("_pn_lowered", "_pn_group", "_pn_folded", "_pn_final_groups"):
+        for k in ("_pn_lowered", "_pn_group", "_pn_folded", "_pn_final_groups", "_pn_final_groups_tc"):
             m.__dict__.pop(k, None)
 
 

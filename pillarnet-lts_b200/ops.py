@@ -232,6 +232,17 @@ def conv_dense3x3(inp, in_coff, cin, n_frames, H, W, weight, cout, out, *, scale
     return out
 
 
+def conv_dense3x3_grouped(inp, in_coff, cin, n_groups, n_frames, H, W, weight, shift, group_tab, out, *,
+                          scale=None, out_compact=True, relu=False):
+    """n_groups independent small-Cout 3x3 convs on padded NHWC rows in one tensor-core launch (C header)."""
+    lib = _lib.load()
+    check(lib.pn_conv_dense3x3_grouped(ptr(inp), inp.stride(0), in_coff, cin, n_groups, n_frames, H, W, ptr(weight),
+                                       weight.stride(0), ptr(scale), ptr(shift), ptr(group_tab), ptr(out),
+                                       _DT[out.dtype], out.stride(0), 1 if out_compact else 0, 1 if relu else 0,
+                                       stream_ptr()), "pn_conv_dense3x3_grouped")
+    return out
+
+
 def pack_weight_bf16(w_f32_2d, k_pad=None):
     """(Cout,K) f32 -> (Cout,k_pad) bf16 with K zero-padded to a multiple of 64."""
     lib = _lib.load()

@@ -71,3 +71,39 @@ def test_dense_conv_auto_tile_full_size():
     assert _run(1, 180, 180, 256, 256, 0, False, torch.bfloat16) <= 1e-2
     assert _run(1, 90, 90, 256, 256, 0, False, torch.bfloat16) <= 1e-2
     assert _run(1, 180, 180, 64, 2304, 0, True, torch.bfloat16, relu=True) <= 1e-2
+
+
+def test_grouped_small_cout_dense_conv_vs_torch():
+    """all final head convs in one tensor-core launch vs F.conv2d on the same bf16 operands (2e-3 rel-to-max)."""
+    from pillarnet_lts_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, H, W, hc = 2, 37, 29, 64
+    couts = [2, 1, 3, 2, 2, 1, 4, 16]
+    G = len(couts)
+    x = torch.randn(B, H, W, G * hc, device="cuda", generator=g).to(torch.bfloat16)
+    rows = _pad_rows(x)
+    ws = [torch.randn(c, hc, 3, 3, device="cuda", generator=g) * 0.1 for c in couts]
+    bs = [torch.randn(c, device="cuda", generator=g) for c in couts]
+    wf = torch.zeros(G * 16, 9 * hc, device="cuda")
+    bf = torch.zeros(G * 16, device="cuda")
+    tab, col = [], 3
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        wf[i * 16:i * 16 + w.shape[0]] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+        bf[i * 16:i * 16 + w.shape[0]] = b
+        tab.append([col, w.shape[0]])
+        col += w.shape[0]
+    wg = ops.pack_weight_bf16(wf)
+    tabd = torch.tensor(tab, dtype=torch.int32).cuda()
+    out = torch.full((B * H * W, col + 2), -9.0, device="cuda")
+    ops.conv_dense3x3_grouped(rows, 0, hc, G, B, H, W, wg, bf, tabd, out, out_compact=True)
+    torch.cuda.synchronize()
+    xin = x.float().permute(0, 3, 1, 2)
+    c0 = 3
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        wq = wg[i * 16:i * 16 + w.shape[0], :9 * hc].float().view(w.shape[0], 3, 3, hc).permute(0, 3, 1, 2)
+        want = F.conv2d(xin[:, i * hc:(i + 1) * hc], wq, b, padding=1).permute(0, 2, 3, 1)
+        got = out[:, c0:c0 + w.shape[0]].view(B, H, W, -1)
+        assert (got - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item()), i
+        c0 += w.shape[0]
+    assert bool((out[:, :3] == -9.0).all()) and bool((out[:, col:] == -9.0).all())
