@@ -241,7 +241,17 @@ typedef struct pn_task_args {
   int stride;          /* task stride (tasks[i].stride) */
   int seg_base;        /* first segment (within a frame) owned by this task */
   int per_class;       /* 1 => one segment per class (use_multi_class_nms) */
+  int activated;       /* 1 => maps already hold sigmoid(hm), exp(clamp(dim)), clamped iou (pn_double_flip_merge) */
 } pn_task_args;
+
+/* Double-flip test-time augmentation (center_head.py:233-248,274-304,319-323): frames 4b..4b+3 of
+ * task->maps are the original / y-flipped / x-flipped / xy-flipped views of output frame b.  Each view is
+ * un-flipped, activated (sigmoid hm, exp(clamp(dim)), clamped iou), sign-corrected (reg, rot, vel) and the
+ * four are averaged in torch.mean's order.  out: (n_frames_out*H*W, out_ld) f32 with the same column
+ * offsets; decode it with a copy of `task` that has maps = out, ld = out_ld, activated = 1.
+ * n_cols = number of packed columns of the task. */
+int pn_double_flip_merge(const pn_task_args* task, int n_frames_out, int n_cols, float* out, int out_ld,
+                         pn_stream_t stream);
 
 /* Stage A: per pixel sigmoid/max/threshold/range test; appends (score,pixel) keys to its segment.
  * All `n_tasks` (<= 8) tasks of the head go in one launch.

@@ -37,7 +37,7 @@ class TaskArgs(Structure):
         ("off_reg", c_int), ("off_height", c_int), ("off_dim", c_int), ("off_rot", c_int),
         ("off_vel", c_int), ("off_iou", c_int), ("off_hm", c_int),
         ("num_cls", c_int), ("H", c_int), ("W", c_int), ("stride", c_int),
-        ("seg_base", c_int), ("per_class", c_int),
+        ("seg_base", c_int), ("per_class", c_int), ("activated", c_int),
     ]
 
 
@@ -80,6 +80,7 @@ SIGNATURES = {
     "pn_decode_candidates": (c_int, [POINTER(TaskArgs), c_int, c_int, c_int, c_float, POINTER(c_float),
                                      c_float, c_float, c_float, POINTER(c_float), c_void_p, c_int,
                                      c_void_p, c_void_p]),
+    "pn_double_flip_merge": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pn_select_topk": (c_int, [POINTER(TaskArgs), c_int, c_int, c_int, POINTER(c_int), c_float, c_float,
                                c_float, POINTER(c_float), c_void_p, c_int, c_void_p, c_void_p, c_int,
                                c_void_p, c_void_p]),

@@ -27,7 +27,7 @@ constexpr int kSelSmemKeys = 4096;
 struct TaskDev {
   const float* maps;
   int ld, off_reg, off_height, off_dim, off_rot, off_vel, off_iou, off_hm, num_cls, H, W, stride,
-      seg_base, per_class;
+      seg_base, per_class, activated;
 };
 
 struct Pix {
@@ -44,18 +44,19 @@ __device__ __forceinline__ Pix decode_pixel(const TaskDev& t, const float* __res
                                             int j, float ps, float x0, float y0,
                                             const float* __restrict__ rect_r) {
   Pix p;
-  float best = sigmoid_ref(row[t.off_hm]);
+  // activated maps (output of k_double_flip_merge) already hold probabilities / sizes / clamped iou
+  float best = t.activated ? row[t.off_hm] : sigmoid_ref(row[t.off_hm]);
   int lab = 0;
   for (int k = 1; k < t.num_cls; ++k) {
-    const float s = sigmoid_ref(row[t.off_hm + k]);
+    const float s = t.activated ? row[t.off_hm + k] : sigmoid_ref(row[t.off_hm + k]);
     if (s > best) { best = s; lab = k; }
   }
   p.score = best;
   p.label = lab;
   float iou = 1.0f;
   if (t.off_iou >= 0) {
-    iou = __fmul_rn(__fadd_rn(row[t.off_iou], 1.0f), 0.5f);
-    iou = fminf(fmaxf(iou, 0.0f), 1.0f);
+    iou = row[t.off_iou];
+    if (!t.activated) iou = fminf(fmaxf(__fmul_rn(__fadd_rn(iou, 1.0f), 0.5f), 0.0f), 1.0f);
   }
   const float r = rect_r ? rect_r[lab] : 0.0f;
   if (r == 0.0f) {
@@ -118,6 +119,60 @@ k_decode_candidates(const __grid_constant__ DecodeParams P, unsigned long long* 
       keys[(long long)seg * cand_cap + slot] =
           ((unsigned long long)__float_as_uint(p.rect) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)pix);
     }
+  }
+}
+
+// ---- double-flip test-time augmentation -----------------------------------------------------------
+// center_head.py:233-248 (un-flip the maps of the 4 views), :257-264 (activations are applied per view,
+// before the average), :274-304,319-323 (sign / 1-x corrections, mean over the 4 views).
+// Views of output frame b are input frames 4b..4b+3: original, y-flipped (rows reversed), x-flipped (columns
+// reversed), both.  torch.mean over a strided dim of 4 = ((v0+v1)+v2)+v3 then * 0.25f (ATen reduce kernel:
+// vt0 = 4 accumulators combined left to right).
+__global__ void __launch_bounds__(256)
+k_double_flip_merge(const __grid_constant__ TaskDev t, int n_frames_out, int n_cols, float* __restrict__ out,
+                    int out_ld) {
+  const int hw = t.H * t.W;
+  const long long total = (long long)n_frames_out * hw * n_cols;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(g % n_cols);
+    const long long q = g / n_cols;
+    const int b = (int)(q / hw), pix = (int)(q - (long long)b * hw);
+    const int i = pix / t.W, j = pix - i * t.W;
+    // what this column is
+    int kind = 0;  // 0 plain mean, 1 hm (sigmoid), 2 dim (exp clamp), 3 iou, 4/5 reg x/y, 6/7 rot sin/cos, 8/9 vel x/y
+    if (c >= t.off_hm && c < t.off_hm + t.num_cls) kind = 1;
+    else if (c >= t.off_dim && c < t.off_dim + 3) kind = 2;
+    else if (t.off_iou >= 0 && c == t.off_iou) kind = 3;
+    else if (c == t.off_reg) kind = 4;
+    else if (c == t.off_reg + 1) kind = 5;
+    else if (c == t.off_rot) kind = 6;
+    else if (c == t.off_rot + 1) kind = 7;
+    else if (t.off_vel >= 0 && c == t.off_vel) kind = 8;
+    else if (t.off_vel >= 0 && c == t.off_vel + 1) kind = 9;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ii = (k & 1) ? t.H - 1 - i : i;   // views 1 and 3 are flipped along H
+      const int jj = (k & 2) ? t.W - 1 - j : j;   // views 2 and 3 along W
+      float x = t.maps[((long long)(4 * b + k) * hw + (long long)ii * t.W + jj) * t.ld + c];
+      const bool fy = (k & 1) != 0, fx = (k & 2) != 0;
+      switch (kind) {
+        case 1: x = sigmoid_ref(x); break;
+        case 2: x = expf(fminf(fmaxf(x, -1.2f), 3.2f)); break;
+        case 3: x = fminf(fmaxf(__fmul_rn(__fadd_rn(x, 1.0f), 0.5f), 0.0f), 1.0f); break;
+        case 4: if (fx) x = __fsub_rn(1.0f, x); break;   // x = -x  => reg_x = 1 - reg_x
+        case 5: if (fy) x = __fsub_rn(1.0f, x); break;
+        case 6: if (fx) x = -x; break;                   // sin flips with the x flip (views 2,3)
+        case 7: if (fy) x = -x; break;                   // cos flips with the y flip (views 1,3)
+        case 8: if (fx) x = -x; break;
+        case 9: if (fy) x = -x; break;
+        default: break;
+      }
+      v[k] = x;
+    }
+    const float m = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v[0], v[1]), v[2]), v[3]), 0.25f);
+    out[q * out_ld + c] = m;
   }
 }
 
@@ -242,7 +297,10 @@ k_select_topk(const __grid_constant__ SelectParams P, const unsigned long long* 
     o[2] = p.z;
     // dim = exp(clamp(dim, -1.2, 3.2))  (center_head.py:259)
 #pragma unroll
-    for (int d = 0; d < 3; ++d) o[3 + d] = expf(fminf(fmaxf(row[t.off_dim + d], -1.2f), 3.2f));
+    for (int d = 0; d < 3; ++d) {
+      const float v = row[t.off_dim + d];
+      o[3 + d] = t.activated ? v : expf(fminf(fmaxf(v, -1.2f), 3.2f));
+    }
     o[6] = t.off_vel >= 0 ? row[t.off_vel] : 0.f;
     o[7] = t.off_vel >= 0 ? row[t.off_vel + 1] : 0.f;
     o[8] = atan2f(row[t.off_rot], row[t.off_rot + 1]);  // atan2(rot_sin, rot_cos), :266-267,306
@@ -503,7 +561,7 @@ TaskDev to_dev(const pn_task_args* t) {
   d.maps = t->maps; d.ld = t->ld; d.off_reg = t->off_reg; d.off_height = t->off_height;
   d.off_dim = t->off_dim; d.off_rot = t->off_rot; d.off_vel = t->off_vel; d.off_iou = t->off_iou;
   d.off_hm = t->off_hm; d.num_cls = t->num_cls; d.H = t->H; d.W = t->W; d.stride = t->stride;
-  d.seg_base = t->seg_base; d.per_class = t->per_class;
+  d.seg_base = t->seg_base; d.per_class = t->per_class; d.activated = t->activated;
   return d;
 }
 
@@ -583,6 +641,21 @@ int pn_select_topk(const pn_task_args* tasks, int n_tasks, int n_frames, int seg
   P.ps = pillar_size; P.x0 = x0; P.y0 = y0;
   k_select_topk<<<n_frames * segs_per_frame, kSelThreads, 0, stream>>>(P, cand_keys, cand_cap, cand_count,
                                                                       sorted_boxes, pre_cap, sorted_count);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+int pn_double_flip_merge(const pn_task_args* task, int n_frames_out, int n_cols, float* out, int out_ld,
+                         pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(task && task->maps && out && n_frames_out >= 1 && n_cols >= 1 && n_cols <= task->ld &&
+             out_ld >= n_cols);
+  PN_REQUIRE(task->off_reg >= 0 && task->off_height >= 0 && task->off_dim >= 0 && task->off_rot >= 0 &&
+             task->off_hm >= 0 && task->num_cls >= 1 && task->H > 0 && task->W > 0);
+  PN_REQUIRE((const float*)out != task->maps);
+  const TaskDev t = to_dev(task);
+  const long long total = (long long)n_frames_out * t.H * t.W * n_cols;
+  k_double_flip_merge<<<grid_for(total, 256), 256, 0, stream>>>(t, n_frames_out, n_cols, out, out_ld);
   PN_CHECK_LAUNCH();
   return PN_OK;
 }

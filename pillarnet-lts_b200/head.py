@@ -304,13 +304,21 @@ class CenterHead(nn.Module):
         """Device-only part of predict: returns (det_out (B*S, post_cap, 11) f32, keep_count (B*S) i32, plan).
 
         det_out rows: [x,y,z,w,l,h,vx,vy,rot, score, label-within-task]."""
-        if test_cfg.get("double_flip", False):
-            raise NotImplementedError("double-flip TTA is not on the B200 path yet (SURVEY §8f rank 4)")
         lib = _lib.load()
         plan = self.nms_plan(test_cfg)
         segs = plan["segs"]
         S = len(segs)
         packed = [self._packed(p) for p in preds_dicts]
+        double_flip = bool(test_cfg.get("double_flip", False))
+        if double_flip:
+            # frames come in groups of 4 views (center_head.py:233-248); merge them into one activated map
+            merged = []
+            for t, (rows, offsets, (b4, H, W)) in enumerate(packed):
+                if b4 % 4 != 0:
+                    raise AssertionError(b4)
+                merged.append((ops.double_flip_merge(rows, offsets, self.num_classes[t], b4 // 4, H, W), offsets,
+                               (b4 // 4, H, W)))
+            packed = merged
         B = packed[0][2][0]
         dev = packed[0][0].device
         n_segs = B * S
@@ -332,7 +340,7 @@ class CenterHead(nn.Module):
         for t, (rows, offsets, (b_, H, W)) in enumerate(packed):
             nseg_t = self.num_classes[t] if plan["multi"] else 1
             tasks_arr[t] = ops.make_task_args(rows, offsets, self.num_classes[t], H, W, self.task_strides[t],
-                                              seg_base, plan["multi"])
+                                              seg_base, plan["multi"], activated=double_flip)
             r = list(plan["rects"][t])[:8]
             rect_flat += r + [0.0] * (8 - len(r))
             seg_base += nseg_t
@@ -391,6 +399,8 @@ class CenterHead(nn.Module):
         meta = example.get("metadata", None) if isinstance(example, dict) else None
         if meta is not None and len(meta) == 0:
             meta = None
+        if meta is not None and test_cfg.get("double_flip", False):
+            meta = meta[:4 * plan["B"]:4]   # center_head.py:254-255
         return self.assemble(det_out, keep_count, plan, meta)
 
     def loss(self, example, preds_dicts, train_cfg, **kwargs):

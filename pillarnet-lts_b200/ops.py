@@ -283,7 +283,19 @@ def sparse_to_dense(feat, table, C, out=None, out_coff=0, padded=False):
     return out
 
 
-def make_task_args(maps, offsets, num_cls, H, W, stride, seg_base, per_class):
+def double_flip_merge(rows, offsets, num_cls, n_frames_out, H, W):
+    """center_head.py:233-304: merge the 4 flipped views of every frame into one activated map (same columns)."""
+    lib = _lib.load()
+    require_cuda(rows)
+    n_cols = rows.shape[1]
+    t = make_task_args(rows, offsets, num_cls, H, W, 1, 0, False)
+    out = torch.empty(n_frames_out * H * W, n_cols, dtype=torch.float32, device=rows.device)
+    check(lib.pn_double_flip_merge(byref(t), n_frames_out, n_cols, ptr(out), out.stride(0), stream_ptr()),
+          "pn_double_flip_merge")
+    return out
+
+
+def make_task_args(maps, offsets, num_cls, H, W, stride, seg_base, per_class, activated=False):
     t = TaskArgs()
     t.maps = maps.data_ptr()
     t.ld = maps.stride(0)
@@ -296,6 +308,7 @@ def make_task_args(maps, offsets, num_cls, H, W, stride, seg_base, per_class):
     t.off_hm = offsets.get("hm", -1)
     t.num_cls, t.H, t.W, t.stride = num_cls, H, W, stride
     t.seg_base, t.per_class = seg_base, 1 if per_class else 0
+    t.activated = 1 if activated else 0
     return t
 
 

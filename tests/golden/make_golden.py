@@ -6,6 +6,7 @@ Fixtures (all small .npz):
   iou_pairs.npz          det3d/ops/iou3d_nms/src/iou3d_cpu.cpp:232-250 boxes_iou_bev_cpu on seeded boxes
   circle_nms.npz         det3d/core/utils/circle_nms_jit.py:4-28 (numba) keep lists
   head_predict_circle.npz det3d/models/bbox_heads/center_head.py:216-413 CenterHead.predict (circular_nms)
+  head_predict_double_flip.npz center_head.py:233-304 double-flip test-time augmentation branch of predict
   neck_head_forward.npz  det3d/models/necks/rpn.py:137-207 RPNV1 + center_head.py:116-127 forward (torch CPU)
   set_by_task_cfg.json   det3d/core/utils/center_utils.py:229-274 on the Waymo FPN test_cfg
 """
@@ -101,6 +102,49 @@ def gen_predict():
     np.savez_compressed(os.path.join(HERE, "head_predict_circle.npz"), **save)
 
 
+def gen_predict_double_flip():
+    """center_head.py:233-304,319-323: 4 flipped views per frame (2 output frames), circular NMS.
+    The maps carry an 'iou' head: without one the reference's own double-flip branch raises IndexError
+    (its stand-in torch.ones((B,4,H)) loses the W axis at :265-266, then `ious[mask]` fails at :376)."""
+    rng = np.random.default_rng(15)
+    tasks = [dict(stride=8, class_names=["car"]), dict(stride=8, class_names=["ped", "cone"])]
+    ps, pcr = 0.075, [-54, -54, -5.0, 54, 54, 3.0]
+    head = CenterHead(tasks=[Config(t) for t in tasks], in_channels=[16], code_weights=[1.0] * 10,
+                      common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2)},
+                      share_channel=8, pillar_size=ps, point_cloud_range=pcr, logger=logging.getLogger("g"))
+    Bo, H, W = 2, 36, 44
+    test_cfg = Config(dict(circular_nms=True, min_radius=[4.0, 0.85], double_flip=True,
+                           nms=dict(nms_pre_max_size=[1000, 1000], nms_post_max_size=[83, 83], nms_iou_threshold=0.2),
+                           score_threshold=0.1, post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]))
+    preds, save = [], {}
+    for t, task in enumerate(tasks):
+        K = len(task["class_names"])
+        d = {}
+        for name, c in (("reg", 2), ("height", 1), ("dim", 3), ("rot", 2), ("vel", 2), ("iou", 1), ("hm", K)):
+            v = rng.normal(0, 0.7, (Bo, 4, c, H, W)).astype(np.float32)
+            if name == "hm":
+                base = rng.normal(-3.5, 1.8, (Bo, 1, c, H, W)).astype(np.float32)
+                v = np.repeat(base, 4, 1) + rng.normal(0, 0.3, (Bo, 4, c, H, W)).astype(np.float32)
+                v[:, 1] = v[:, 1, :, ::-1]          # the network sees the flipped scene
+                v[:, 2] = v[:, 2, :, :, ::-1]
+                v[:, 3] = v[:, 3, :, ::-1, ::-1]
+            if name == "reg":
+                v = rng.uniform(0, 1, (Bo, 4, c, H, W)).astype(np.float32)
+            v = np.ascontiguousarray(v.reshape(Bo * 4, c, H, W))
+            d[name] = torch.from_numpy(v)
+            save[f"t{t}_{name}"] = v
+        preds.append(d)
+    rets = head.predict({"metadata": [None] * (4 * Bo)}, [dict((k, v.clone()) for k, v in p.items()) for p in preds],
+                        test_cfg)
+    assert len(rets) == Bo
+    for b, r in enumerate(rets):
+        save[f"out{b}_boxes"] = r["box3d_lidar"].numpy()
+        save[f"out{b}_scores"] = r["scores"].numpy()
+        save[f"out{b}_labels"] = r["label_preds"].numpy()
+        assert r["scores"].numel() > 5
+    np.savez_compressed(os.path.join(HERE, "head_predict_double_flip.npz"), **save)
+
+
 def gen_neck_head():
     torch.manual_seed(14)
     tasks = [dict(stride=8, class_names=["car"]), dict(stride=8, class_names=["ped", "cone"])]
@@ -144,6 +188,7 @@ if __name__ == "__main__":
     gen_iou()
     gen_circle()
     gen_predict()
+    gen_predict_double_flip()
     gen_neck_head()
     gen_cfg()
     print("golden fixtures written to", HERE)

@@ -77,6 +77,68 @@ def test_predict_circle_vs_reference_golden(golden_dir):
         np.testing.assert_allclose(r["box3d_lidar"].cpu().numpy(), g[f"out{b}_boxes"], rtol=1e-5, atol=1e-5)
 
 
+HEADS_IOU = dict(HEADS, iou=(1, 2))
+
+
+def test_predict_double_flip_vs_reference_golden(golden_dir):
+    """double-flip TTA (center_head.py:233-304): 8 input frames -> 2 output frames, vs the reference's predict."""
+    from pillarnet_lts_b200.head import CenterHead
+    from pillarnet_lts_b200.registry import ConfigDict
+    g = np.load(os.path.join(golden_dir, "head_predict_double_flip.npz"))
+    head = CenterHead(tasks=TASKS, in_channels=[16], code_weights=[1.0] * 10, common_heads=HEADS_IOU,
+                      share_channel=8, pillar_size=PS, point_cloud_range=PCR).cuda()
+    cfg = ConfigDict.wrap(dict(circular_nms=True, min_radius=[4.0, 0.85], double_flip=True,
+                               nms=dict(nms_pre_max_size=[1000, 1000], nms_post_max_size=[83, 83],
+                                        nms_iou_threshold=0.2),
+                               score_threshold=0.1, post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]))
+    preds = [{n: torch.from_numpy(g[f"t{t}_{n}"]).cuda() for n in ["reg", "height", "dim", "rot", "vel", "iou", "hm"]}
+             for t in range(2)]
+    rets = head.predict({"metadata": list(range(8))}, preds, cfg)
+    assert len(rets) == 2 and [r["metadata"] for r in rets] == [0, 4]
+    for b, r in enumerate(rets):
+        assert np.array_equal(r["label_preds"].cpu().numpy(), g[f"out{b}_labels"])
+        np.testing.assert_allclose(r["scores"].cpu().numpy(), g[f"out{b}_scores"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(r["box3d_lidar"].cpu().numpy(), g[f"out{b}_boxes"], rtol=1e-5, atol=1e-5)
+
+
+def test_double_flip_merge_bit_exact_vs_torch():
+    """pn_double_flip_merge vs the torch-CUDA op sequence of center_head.py:233-304 on the same maps: bit-exact."""
+    from pillarnet_lts_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Bo, H, W, K = 3, 33, 47, 2
+    offs = {"reg": 0, "height": 2, "dim": 3, "rot": 6, "vel": 8, "iou": 10, "hm": 11}
+    C = 11 + K
+    maps = torch.randn(Bo * 4, H, W, C, device="cuda", generator=g) * 1.5
+    wide = torch.full((Bo * 4 * H * W, C + 5), 7.0, device="cuda")
+    wide[:, 2:2 + C] = maps.view(-1, C)
+    got = ops.double_flip_merge(wide[:, 2:2 + C], offs, K, Bo, H, W).view(Bo, H, W, C)
+    v = maps.clone().view(Bo, 4, H, W, C)
+    v[:, 1] = torch.flip(v[:, 1], dims=[1])
+    v[:, 2] = torch.flip(v[:, 2], dims=[2])
+    v[:, 3] = torch.flip(v[:, 3], dims=[1, 2])
+    hm = torch.sigmoid(v[..., 11:]).mean(dim=1)
+    dim = torch.exp(v[..., 3:6].clamp(min=-1.2, max=3.2)).mean(dim=1)
+    iou = torch.clamp((v[..., 10] + 1) * 0.5, min=0, max=1.).mean(dim=1)
+    reg, rots, rotc, vel = v[..., 0:2], v[..., 6:7], v[..., 7:8], v[..., 8:10]
+    reg[:, 1, ..., 1] = 1 - reg[:, 1, ..., 1]
+    reg[:, 2, ..., 0] = 1 - reg[:, 2, ..., 0]
+    reg[:, 3, ..., 0] = 1 - reg[:, 3, ..., 0]
+    reg[:, 3, ..., 1] = 1 - reg[:, 3, ..., 1]
+    rotc[:, 1] *= -1
+    rots[:, 2] *= -1
+    rots[:, 3] *= -1
+    rotc[:, 3] *= -1
+    vel[:, 1, ..., 1] *= -1
+    vel[:, 2, ..., 0] *= -1
+    vel[:, 3] *= -1
+    want = torch.cat([reg.mean(dim=1), v[..., 2:3].mean(dim=1), dim, rots.mean(dim=1), rotc.mean(dim=1),
+                      vel.mean(dim=1), iou.unsqueeze(-1), hm], dim=-1)
+    torch.cuda.synchronize()
+    for name, lo, hi in (("reg", 0, 2), ("height", 2, 3), ("dim", 3, 6), ("rot", 6, 8), ("vel", 8, 10),
+                         ("iou", 10, 11), ("hm", 11, C)):
+        assert torch.equal(got[..., lo:hi], want[..., lo:hi]), name
+
+
 def _torch_predict_rotate(preds, strides, num_classes, cfg, nms_gpu):
     """center_head.py:216-413 + box_torch_ops.py:296-322 restated with torch CUDA ops (stable sort)."""
     outs = None

@@ -58,6 +58,39 @@ def test_predict_oracle_vs_reference_centerhead(golden_dir):
         np.testing.assert_allclose(bx, g[f"out{b}_boxes"], rtol=1e-5, atol=1e-5)
 
 
+def test_predict_double_flip_oracle_vs_reference_centerhead(golden_dir):
+    """double-flip branch of predict (center_head.py:233-304) vs the reference executed from /root/reference."""
+    g = np.load(os.path.join(golden_dir, "head_predict_double_flip.npz"))
+    ps, pcr = 0.075, [-54, -54, -5.0, 54, 54, 3.0]
+    names = ["reg", "height", "dim", "rot", "vel", "iou", "hm"]
+    ncls = [1, 2]
+    min_radius = [4.0, 0.85]
+    B = g["t0_hm"].shape[0] // 4
+    per_frame = [[] for _ in range(B)]
+    for t in range(2):
+        offs, parts, c = {}, [], 0
+        for n in names:
+            v = g[f"t{t}_{n}"].transpose(0, 2, 3, 1)
+            offs[n] = c
+            c += v.shape[-1]
+            parts.append(v)
+        boxes, hm, iou = O.decode_task(np.concatenate(parts, -1), offs, ncls[t], 8, ps, pcr, double_flip=True)
+        assert boxes.shape[0] == B
+        for b in range(B):
+            cfg = dict(mode="circle", min_radius=min_radius[t], post_max=83, score_threshold=0.1,
+                       post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0])
+            bx, sc, lb = O.post_process_frame(boxes[b], hm[b], iou[b], cfg)
+            per_frame[b].append((bx, sc, lb + sum(ncls[:t])))
+    for b in range(B):
+        bx = np.concatenate([p[0] for p in per_frame[b]])
+        sc = np.concatenate([p[1] for p in per_frame[b]])
+        lb = np.concatenate([p[2] for p in per_frame[b]])
+        assert len(bx) == len(g[f"out{b}_boxes"]) > 10
+        assert np.array_equal(lb, g[f"out{b}_labels"])
+        np.testing.assert_allclose(sc, g[f"out{b}_scores"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(bx, g[f"out{b}_boxes"], rtol=1e-5, atol=1e-5)
+
+
 def test_set_by_task_cfg_vs_reference(golden_dir):
     import pillarnet_lts_b200  # noqa: F401
     from pillarnet_lts_b200.detector import set_by_task_cfg
