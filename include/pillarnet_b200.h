@@ -108,6 +108,18 @@ int pn_pfn_scatter_max(const float* points, int point_dim, int n_points, const i
 int pn_scatter_max_grad(const float* grad_out, const int* arg, const int* num_pillars, int m_cap,
                         int c_out, float* grad_src, pn_stream_t stream);
 
+/* Training-path reader ops.
+ * pn_point_features: out (n_points, 2+point_dim) f32 = [x-ctr_x, y-ctr_y, p[0..point_dim)] with the pillar
+ *   centre recomputed from the point's own cell (pillar_utils.py:51-56 without the gather).
+ * pn_scatter_max: drop-in for pillar_cuda.scatter_max_wrapper (scatter_ops.cpp:7-24): out (n_pillars,c) f32 =
+ *   max(0, max over points with index==m of src) — written in full (zero-init inside), arg (n_pillars,c) i32 =
+ *   LOWEST flat index p*c+ch attaining the max, -1 if none (the reference: any point within 1e-5, racy).
+ *   index values outside [0,n_pillars) are ignored.  n_points*c must fit int32. */
+int pn_point_features(const float* points, int point_dim, int n_points, float x0, float y0, float inv_pillar,
+                      float pillar_size, float x_offset, float y_offset, float* out, pn_stream_t stream);
+int pn_scatter_max(const float* src, const int* index, int n_points, int n_pillars, int c, float* out, int* arg,
+                   pn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (3) Rulebooks (replace spconv's indice-pair generation).
  * Output-stationary neighbour tables: nbr[o*9 + ky*3+kx] = input row or -1.
@@ -207,6 +219,19 @@ int pn_conv_dense3x3_grouped(const void* in, int in_ld, int in_coff, int cin, in
                              const int* group_tab, void* out, int out_dtype, int out_ld, int out_compact,
                              int relu, pn_stream_t stream);
 
+/* Backward of pn_conv_gather (spconv's autograd for SubMConv2d / SparseConv2d, external in the reference).
+ * pn_rulebook_transpose: nbr_t[i*taps + t] = o  <=>  nbr[o*taps + t] = i  (else -1): the input-stationary
+ *   table; the data gradient is then a forward gather conv  dx = pn_conv_gather(dy, nbr_t, W^T)  with
+ *   W^T[ci][t*cout + co] = W[co][t*cin + ci].  num_out: device count of live output rows (NULL = out_cap).
+ * pn_conv_wgrad: dw[co*dw_ld + t*cin + ci] = sum_o dy[o][co] * x[nbr[o,t]][ci]   (f32, overwritten).
+ *   nbr NULL = identity (1x1 / linear).  impl PN_IMPL_TCGEN05: bf16 operands, MN-major UMMA over the rows,
+ *   fp32 accumulation in TMEM, split-K fp32 RED (summation order not fixed); PN_IMPL_SIMT: f32 or bf16. */
+int pn_rulebook_transpose(const int* nbr, const int* num_out, int out_cap, int taps, int in_cap, int* nbr_t,
+                          pn_stream_t stream);
+int pn_conv_wgrad(const void* x, int x_dtype, int x_ld, const void* dy, int dy_dtype, int dy_ld, const int* nbr,
+                  int taps, const int* num_rows, int rows_cap, int cin, int cout, float* dw, int dw_ld, int impl,
+                  pn_stream_t stream);
+
 /* f32 -> bf16 weight packing with zero padding of K to k_pad (multiple of 64). */
 int pn_conv_pack_weight_bf16(const float* w_f32, int cout, int k, int k_pad, void* w_bf16,
                              pn_stream_t stream);
@@ -295,6 +320,10 @@ int pn_nms(int mode, int n_frames, int segs_per_frame, const float* seg_thr /*ho
 /* Standalone drop-ins for iou3d_nms_cuda (boxes (n,7) f32 [x,y,z,dx,dy,dz,heading], device). */
 int pn_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* iou,
                      pn_stream_t stream);
+/* drop-in for iou3d_nms_cuda.boxes_aligned_overlap_bev_gpu (iou3d_nms.cpp, kernel iou3d_nms_kernel.cu:251-262):
+ * overlap[i] = BEV intersection area of boxes_a[i] and boxes_b[i] (training: IouLoss target). */
+int pn_boxes_aligned_overlap_bev(const float* boxes_a, const float* boxes_b, int n, float* overlap,
+                                 pn_stream_t stream);
 /* keep (n) i32 device, num_keep (1) i32 device; boxes must already be score-sorted (as nms_gpu). */
 int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t scratch_bytes,
                    int* keep, int* num_keep, pn_stream_t stream);

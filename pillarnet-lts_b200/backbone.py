@@ -9,7 +9,7 @@ rulebook of a stage is built once (spconv's `indice_key` cache) and shared by it
 import torch
 from torch import nn
 
-from . import config, ops
+from . import config, ops, train
 from .layers import (DenseMap, SparseConv2d, SparseReLU, SparseSequential, SubMConv2d,
                      build_norm_layer, dense_conv3x3, lower, new_dense_rows, run_conv, use_padded_layout)
 from .registry import BACKBONES
@@ -36,6 +36,8 @@ def _rows_hint(table):
 def _subm(sp, seq, relu, residual=None):
     """SparseSequential(SubMConv2d, BN[, SparseReLU]) as one launch."""
     conv, bn = seq[0], seq[1]
+    if bn.training:
+        return train.subm_block(sp, seq, relu, residual)
     t = sp.table
     lw = lower(conv, bn)
     out = run_conv(sp.feat, lw, t.subm_nbr(), 9, conv.in_channels, conv.out_channels, t.cap, num=t.num,
@@ -90,6 +92,11 @@ def _run_stage(sp, stage):
     i = 0
     if isinstance(mods[0], SparseConv2d):
         conv, bn = mods[0], mods[1]
+        if bn.training:
+            sp = train.down_block(sp, conv, bn)
+            for m in mods[3:]:
+                sp = m(sp)
+            return sp
         out_table, nbr = ops.rulebook_down3x3s2(sp.table)
         lw = lower(conv, bn)
         feat = run_conv(sp.feat, lw, nbr, 9, conv.in_channels, conv.out_channels, out_table.cap,
@@ -153,6 +160,14 @@ class _PillarResNet(nn.Module):
         x3 = _run_stage(x2, self.conv3)
         x4 = _run_stage(x3, self.conv4)
         feats = {"conv1": x1, "conv2": x2, "conv3": x3, "conv4": x4}
+        if self.training:
+            if self.DENSE:
+                # training: dense conv5 runs in PyTorch (cuDNN) under autograd
+                with train.autocast_ctx():
+                    d4 = train.dense_from_sparse(x4)
+                    feats["conv4"] = d4
+                    feats["conv5"] = self.conv5(d4)
+            return feats
         if self.DENSE:
             # x_conv4.dense() lands in the left half of a 2C-wide buffer so the neck's channel concat
             # (necks/rpn.py:201-205) needs no copy: the up-sampled branch writes the right half.

@@ -532,6 +532,17 @@ k_boxes_iou(const float* __restrict__ A, int na, const float* __restrict__ B, in
   }
 }
 
+// iou3d_nms_kernel.cu:251-262 boxes_aligned_overlap_kernel: overlap area of pair i <-> i
+__global__ void __launch_bounds__(256)
+k_boxes_aligned_overlap(const float* __restrict__ A, const float* __restrict__ B, int n, float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    BoxGeom a, b;
+    pn_iou::make_geom(A[i * 7], A[i * 7 + 1], A[i * 7 + 3], A[i * 7 + 4], A[i * 7 + 6], a);
+    pn_iou::make_geom(B[i * 7], B[i * 7 + 1], B[i * 7 + 3], B[i * 7 + 4], B[i * 7 + 6], b);
+    out[i] = pn_iou::overlap_area(a, b);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_boxes7_to_records(const float* __restrict__ boxes, int n, float* __restrict__ rec,
                     float* __restrict__ geom, int* __restrict__ count) {
@@ -709,6 +720,17 @@ int pn_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb,
   PN_REQUIRE(boxes_a && boxes_b && iou && na >= 0 && nb >= 0);
   if (na == 0 || nb == 0) return PN_OK;
   k_boxes_iou<<<grid_for((long long)na * nb, 256), 256, 0, stream>>>(boxes_a, na, boxes_b, nb, iou);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+int pn_boxes_aligned_overlap_bev(const float* boxes_a, const float* boxes_b, int n, float* overlap,
+                                 pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(n >= 0);
+  if (n == 0) return PN_OK;
+  PN_REQUIRE(boxes_a && boxes_b && overlap);
+  k_boxes_aligned_overlap<<<grid_for(n, 256), 256, 0, stream>>>(boxes_a, boxes_b, n, overlap);
   PN_CHECK_LAUNCH();
   return PN_OK;
 }

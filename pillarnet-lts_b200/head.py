@@ -18,7 +18,7 @@ from ctypes import byref, c_float, c_size_t
 import torch
 from torch import nn
 
-from . import _lib, config, ops
+from . import _lib, config, losses, ops, train
 from ._lib import check, farr, iarr, ptr, stream_ptr
 from .layers import DenseMap, Sequential, dense_conv3x3, lower, lower_group, run_conv
 from .registry import HEADS
@@ -93,10 +93,30 @@ class CenterHead(nn.Module):
             heads.update(dict(hm=(num_cls, 2)))
             self.task_heads.append(SepHead(share_channel, heads))
         self.share_channel = share_channel
+        self.reg_iou = reg_iou
+        # center_head.py:81-89
+        self.crit = losses.FastFocalLoss()
+        self.crit_reg = losses.RegLoss()
+        if self.use_iou:
+            self.crit_iou = losses.IouLoss()
+        if self.use_reg_iou:
+            self.crit_reg_iou = losses.IouRegLoss(reg_iou)
 
     # ------------------------------------------------------------------------------------------
+    def _forward_train(self, x):
+        """center_head.py:116-127 with the torch modules themselves (training: cuDNN + autograd)"""
+        rets = []
+        with train.autocast_ctx():
+            share = [sc(x[k]) for k, sc in enumerate(self.share_convs)]
+            for idx, task in enumerate(self.task_heads):
+                feat = share[self.task_idx[idx]]
+                rets.append({name: getattr(task, name)(feat) for name in task.heads})
+        return rets
+
     def forward(self, x):
         assert len(x) == len(self.share_convs)
+        if self.training:
+            return self._forward_train(x)
         share = []
         for k, sc in enumerate(self.share_convs):
             share.append(dense_conv3x3(DenseMap.from_nchw(x[k]), sc[0], sc[1], relu=True))
@@ -403,6 +423,49 @@ class CenterHead(nn.Module):
             meta = meta[:4 * plan["B"]:4]   # center_head.py:254-255
         return self.assemble(det_out, keep_count, plan, meta)
 
+    @staticmethod
+    def _sigmoid(x):
+        return torch.clamp(torch.sigmoid(x), min=1e-4, max=1 - 1e-4)
+
     def loss(self, example, preds_dicts, train_cfg, **kwargs):
-        raise NotImplementedError("CenterHead.loss stays in PyTorch in the reference (SURVEY §8f rank 1); "
-                                  "the B200 path covers inference in this round")
+        """center_head.py:133-214.  example: hm / ind / mask / cat / anno_box (/ gt_box) lists per task."""
+        rets = {}
+        for task_id, preds in enumerate(preds_dicts):
+            p = {k: v.permute(0, 2, 3, 1).contiguous().float() for k, v in preds.items()}
+            hm = self._sigmoid(p["hm"])
+            mask, ind = example["mask"][task_id], example["ind"][task_id]
+            hm_loss = self.crit(hm, example["hm"][task_id], ind, mask, example["cat"][task_id])
+            target_box = example["anno_box"][task_id]
+            if "vel" in p:
+                anno = torch.cat((p["reg"], p["height"], p["dim"], p["vel"], p["rot"]), dim=-1)
+            else:
+                anno = torch.cat((p["reg"], p["height"], p["dim"], p["rot"]), dim=-1)
+                target_box = target_box[..., [0, 1, 2, 3, 4, 5, -2, -1]]
+            box_loss = self.crit_reg(anno, mask, ind, target_box)
+            loc_loss = (box_loss * box_loss.new_tensor(self.code_weights)).sum()
+            loss = hm_loss * train_cfg["hm_weight"] + loc_loss * train_cfg["bbox_weight"]
+            ret = {"hm_loss": hm_loss.detach(), "loc_loss": loc_loss, "loc_loss_elem": box_loss.detach(),
+                   "num_positive": mask.float().sum()}
+            if self.use_iou or self.use_reg_iou:
+                dim = torch.exp(p["dim"].clamp(min=-1.2, max=3.2))
+                rot = torch.atan2(p["rot"][..., 0:1], p["rot"][..., 1:2])
+                B, H, W, _ = dim.shape
+                ys, xs = torch.meshgrid(torch.arange(0, H, device=dim.device), torch.arange(0, W, device=dim.device),
+                                        indexing="ij")
+                xs = xs.view(1, H, W, 1).to(dim) + p["reg"][..., 0:1]
+                ys = ys.view(1, H, W, 1).to(dim) + p["reg"][..., 1:2]
+                xs = xs * self.task_strides[task_id] * self.pillar_size + self.point_cloud_range[0]
+                ys = ys * self.task_strides[task_id] * self.pillar_size + self.point_cloud_range[1]
+                box_preds = torch.cat([xs, ys, p["height"], dim, rot], dim=-1)
+            if self.use_iou:
+                iou_loss = self.crit_iou(p["iou"], mask, ind, box_preds.detach(), example["gt_box"][task_id])
+                loss = loss + iou_loss * train_cfg["iou_weight"]
+                ret["iou_loss"] = iou_loss.detach()
+            if self.use_reg_iou:
+                reg_iou_loss = self.crit_reg_iou(box_preds, mask, ind, example["gt_box"][task_id])
+                loss = loss + reg_iou_loss * train_cfg["reg_iou_weight"]
+                ret["reg_iou_loss"] = reg_iou_loss.detach()
+            ret["loss"] = loss
+            for k, v in ret.items():
+                rets.setdefault(k, []).append(v)
+        return rets

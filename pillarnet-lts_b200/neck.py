@@ -11,7 +11,7 @@ import logging
 import torch
 from torch import nn
 
-from . import config
+from . import config, train
 from .layers import (DenseMap, Sequential, build_norm_layer, dense_conv3x3, dense_deconv2x2, new_dense_rows,
                      use_padded_layout)
 from .registry import NECKS
@@ -88,7 +88,16 @@ class RPNV1(_RPNBase):
         self.block_4 = self._build_layer(in_channels[1] * 2, num_filters, layer_nums[1], stride=1)
         (logger or logging.getLogger("RPN")).info("Finish RPN Initialization")
 
+    def _forward_train(self, f):
+        """necks/rpn.py:196-207 with the torch modules themselves (training: cuDNN + autograd)"""
+        with train.autocast_ctx():
+            x4, x5 = train.to_dense(f["conv4"]), train.to_dense(f["conv5"])
+            up = self.deblock_5(self.block_5(x5))
+            return tuple([self.block_4(torch.cat([x4, up], dim=1))])
+
     def forward(self, pillar_features, **kwargs):
+        if self.training:
+            return self._forward_train(pillar_features)
         x4 = _to_dense_map(pillar_features["conv4"], cat_room=True)
         x5 = _to_dense_map(pillar_features["conv5"])
         x = self._run_block(x5, self.block_5)
@@ -113,7 +122,16 @@ class RPNV2(_RPNBase):
         self.block_3 = self._build_layer(in_channels[1] * 2, num_filters, layer_nums[1], stride=1)
         (logger or logging.getLogger("RPN")).info("Finish RPN Initialization")
 
+    def _forward_train(self, f):
+        """necks/rpn.py:262-272"""
+        with train.autocast_ctx():
+            x3, x4 = train.to_dense(f["conv3"]), train.to_dense(f["conv4"])
+            up = self.deblock_4(self.block_4(x4))
+            return tuple([self.block_3(torch.cat([x3, up], dim=1))])
+
     def forward(self, pillar_features, **kwargs):
+        if self.training:
+            return self._forward_train(pillar_features)
         x3 = _to_dense_map(pillar_features["conv3"], cat_room=True)
         x4 = _to_dense_map(pillar_features["conv4"])
         x = self._run_block(x4, self.block_4)
@@ -143,7 +161,18 @@ class RPNG(_RPNBase):
         self.block_3 = self._build_layer(in_channels[2] * 2, num_filters[1], layer_nums[1])
         (logger or logging.getLogger("RPN")).info("Finish RPN Initialization")
 
+    def _forward_train(self, f):
+        """necks/rpn.py:336-355"""
+        with train.autocast_ctx():
+            x3, x4, x5 = (train.to_dense(f[k]) for k in ("conv3", "conv4", "conv5"))
+            x5 = self.block_5(x5)
+            x4 = self.block_4(torch.cat([x4, self.top_down_54(x5)], dim=1))
+            x3 = self.block_3(torch.cat([x3, self.top_down_43(x4)], dim=1))
+            return tuple([x4, x3])
+
     def forward(self, pillar_features, **kwargs):
+        if self.training:
+            return self._forward_train(pillar_features)
         x3 = _to_dense_map(pillar_features["conv3"], cat_room=True)
         x4 = _to_dense_map(pillar_features["conv4"], cat_room=True)
         x5 = _to_dense_map(pillar_features["conv5"])
@@ -187,7 +216,18 @@ class RPNGV2(_RPNBase):
         self.block_3 = self._build_layer(num_filters[1], num_filters[1], layer_nums[1])
         (logger or logging.getLogger("RPN")).info("Finish RPN Initialization")
 
+    def _forward_train(self, f):
+        """necks/rpn.py:428-450"""
+        with train.autocast_ctx():
+            x3, x4, x5 = (train.to_dense(f[k]) for k in ("conv3", "conv4", "conv5"))
+            x5 = self.block_5(x5)
+            x4 = self.block_4(torch.cat([self.reduce_4(x4), self.top_down_54(x5)], dim=1))
+            x3 = self.block_3(torch.cat([self.reduce_3(x3), self.top_down_43(x4)], dim=1))
+            return tuple([x4, x3])
+
     def forward(self, pillar_features, **kwargs):
+        if self.training:
+            return self._forward_train(pillar_features)
         x3 = _to_dense_map(pillar_features["conv3"])
         x4 = _to_dense_map(pillar_features["conv4"])
         x5 = _to_dense_map(pillar_features["conv5"])

@@ -27,12 +27,13 @@ class RankTable:
     coords (cap,3) int32 [b,y,x] in ascending cell order; num: device int32 scalar (1,) ; cap: host.
     """
 
-    __slots__ = ("words", "prefix", "coords", "num", "cap", "B", "H", "W", "_nbr_subm")
+    __slots__ = ("words", "prefix", "coords", "num", "cap", "B", "H", "W", "_nbr_subm", "_train")
 
     def __init__(self, words, prefix, coords, num, cap, B, H, W):
         self.words, self.prefix, self.coords, self.num = words, prefix, coords, num
         self.cap, self.B, self.H, self.W = cap, B, H, W
         self._nbr_subm = None
+        self._train = None   # training-path caches (exact-size view, rulebooks): train.py
 
     def count(self):
         """host sync: number of active rows"""
@@ -337,3 +338,80 @@ def nms_rotated(boxes, thr):
     check(lib.pn_nms_rotated(ptr(boxes), n, c_float(thr), ptr(scratch), c_size_t(sb), ptr(keep), ptr(num),
                              stream_ptr()), "pn_nms_rotated")
     return keep, num
+
+
+# ---- training-path operators ------------------------------------------------------
+
+def point_features(points, x0, y0, pillar_size, x_offset, y_offset):
+    """(n, 2+D) f32 [x-ctr_x, y-ctr_y, p...] (pillar_utils.py:51-56); points must be in range."""
+    lib = _lib.load()
+    require_cuda(points)
+    n, D = points.shape
+    out = torch.empty(n, D + 2, dtype=torch.float32, device=points.device)
+    inv = (torch.tensor(1.0, dtype=torch.float32) / torch.tensor(pillar_size, dtype=torch.float32)).item()
+    check(lib.pn_point_features(ptr(points), D, n, c_float(_f32(x0)), c_float(_f32(y0)), c_float(inv),
+                                c_float(_f32(pillar_size)), c_float(_f32(x_offset)), c_float(_f32(y_offset)),
+                                ptr(out), stream_ptr()), "pn_point_features")
+    return out
+
+
+def scatter_max(src, index, n_pillars, want_arg=True):
+    """drop-in for pillar_cuda.scatter_max_wrapper: returns (out (M,C) f32, arg (M,C) i32 | None)."""
+    lib = _lib.load()
+    require_cuda(src, index)
+    if src.dtype != torch.float32 or index.dtype != torch.int32 or not src.is_contiguous() or not index.is_contiguous():
+        raise RuntimeError("scatter_max: src must be contiguous f32 (L,C), index contiguous int32 (L)")
+    L, C = src.shape
+    out = torch.empty(n_pillars, C, dtype=torch.float32, device=src.device)
+    arg = _i32(n_pillars, C, device=src.device) if want_arg else None
+    check(lib.pn_scatter_max(ptr(src), ptr(index), L, n_pillars, C, ptr(out), ptr(arg), stream_ptr()),
+          "pn_scatter_max")
+    return out, arg
+
+
+def scatter_max_grad_flat(grad_out, arg, n_points):
+    """drop-in for pillar_cuda.scatter_max_grad_wrapper with an exact pillar count (M = arg.shape[0])."""
+    lib = _lib.load()
+    require_cuda(grad_out, arg)
+    M, C = arg.shape
+    grad_out = grad_out.float().contiguous()
+    grad_src = torch.zeros(n_points, C, dtype=torch.float32, device=grad_out.device)
+    num = torch.tensor([M], dtype=torch.int32).to(grad_out.device)
+    check(lib.pn_scatter_max_grad(ptr(grad_out), ptr(arg), ptr(num), M, C, ptr(grad_src), stream_ptr()),
+          "pn_scatter_max_grad")
+    return grad_src
+
+
+def rulebook_transpose(nbr, n_in, num_out=None):
+    """(n_in, taps) int32 input-stationary table of an output-stationary rulebook (see the C header)."""
+    lib = _lib.load()
+    require_cuda(nbr)
+    n_out, taps = nbr.shape
+    nbr_t = _i32(n_in, taps, device=nbr.device)
+    check(lib.pn_rulebook_transpose(ptr(nbr), ptr(num_out), n_out, taps, n_in, ptr(nbr_t), stream_ptr()),
+          "pn_rulebook_transpose")
+    return nbr_t
+
+
+def conv_wgrad(x, dy, nbr, taps, cin, cout, *, num=None, rows=None, impl=PN_IMPL_SIMT):
+    """dW (cout, taps*cin) f32 = sum_o dy[o]^T x[nbr[o,t]]  (see pn_conv_wgrad)."""
+    lib = _lib.load()
+    require_cuda(x, dy)
+    if x.dtype != dy.dtype:
+        raise RuntimeError("conv_wgrad: x and dy must have the same dtype")
+    rows = dy.shape[0] if rows is None else rows
+    dw = torch.empty(cout, taps * cin, dtype=torch.float32, device=x.device)
+    check(lib.pn_conv_wgrad(ptr(x), _DT[x.dtype], x.stride(0), ptr(dy), _DT[dy.dtype], dy.stride(0), ptr(nbr), taps,
+                            ptr(num), rows, cin, cout, ptr(dw), dw.stride(0), impl, stream_ptr()), "pn_conv_wgrad")
+    return dw
+
+
+def boxes_aligned_overlap_bev(boxes_a, boxes_b):
+    """drop-in for iou3d_nms_cuda.boxes_aligned_overlap_bev_gpu: (n,) BEV intersection areas (pcdet boxes)."""
+    lib = _lib.load()
+    require_cuda(boxes_a, boxes_b)
+    n = boxes_a.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=boxes_a.device)
+    check(lib.pn_boxes_aligned_overlap_bev(ptr(boxes_a.contiguous()), ptr(boxes_b.contiguous()), n, ptr(out),
+                                           stream_ptr()), "pn_boxes_aligned_overlap_bev")
+    return out

@@ -61,6 +61,9 @@ class PillarMaxPooling(nn.Module):
 
     def forward(self, points, frame_offsets, batch_size):
         """points (N,D) f32 concatenated frames; frame_offsets (B+1,) int32 device."""
+        if self.training:
+            from . import train
+            return train.reader_forward(self, points, frame_offsets, batch_size)
         table, point_pillar = ops.pillarize(points, frame_offsets, batch_size, self.height, self.width,
                                             self.point_cloud_range[0], self.point_cloud_range[1],
                                             self.pillar_size)

@@ -7,6 +7,7 @@ Fixtures (all small .npz):
   circle_nms.npz         det3d/core/utils/circle_nms_jit.py:4-28 (numba) keep lists
   head_predict_circle.npz det3d/models/bbox_heads/center_head.py:216-413 CenterHead.predict (circular_nms)
   head_predict_double_flip.npz center_head.py:233-304 double-flip test-time augmentation branch of predict
+  head_loss.npz          center_head.py:133-214 + losses/centernet_loss.py CenterHead.loss (focal + L1 + GIoU)
   neck_head_forward.npz  det3d/models/necks/rpn.py:137-207 RPNV1 + center_head.py:116-127 forward (torch CPU)
   set_by_task_cfg.json   det3d/core/utils/center_utils.py:229-274 on the Waymo FPN test_cfg
 """
@@ -145,6 +146,54 @@ def gen_predict_double_flip():
     np.savez_compressed(os.path.join(HERE, "head_predict_double_flip.npz"), **save)
 
 
+def gen_loss():
+    """center_head.py:133-214 CenterHead.loss (FastFocalLoss + RegLoss + GIoU IouRegLoss, nuScenes head set) on CPU."""
+    rng = np.random.default_rng(16)
+    tasks = [dict(stride=8, class_names=["car"]), dict(stride=8, class_names=["ped", "cone"])]
+    ps, pcr = 0.075, [-54, -54, -5.0, 54, 54, 3.0]
+    cw = [1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.2, 0.2, 1.0, 1.0]
+    head = CenterHead(tasks=[Config(t) for t in tasks], in_channels=[16], code_weights=cw,
+                      common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2)},
+                      share_channel=8, reg_iou="GIoU", pillar_size=ps, point_cloud_range=pcr,
+                      logger=logging.getLogger("g"))
+    B, H, W, M = 2, 16, 20, 12
+    train_cfg = Config(dict(hm_weight=1, bbox_weight=0.25, iou_weight=1, reg_iou_weight=0.25))
+    preds, example, save = [], {k: [] for k in ("hm", "ind", "mask", "cat", "anno_box", "gt_box")}, {}
+    for t, task in enumerate(tasks):
+        K = len(task["class_names"])
+        d = {}
+        for name, c in (("reg", 2), ("height", 1), ("dim", 3), ("rot", 2), ("vel", 2), ("hm", K)):
+            v = rng.normal(0, 0.7, (B, c, H, W)).astype(np.float32)
+            if name == "hm":
+                v = rng.normal(-2.0, 1.5, (B, c, H, W)).astype(np.float32)
+            d[name] = torch.from_numpy(v)
+            save[f"t{t}_{name}"] = v
+        preds.append(d)
+        hm = rng.uniform(0, 1, (B, H, W, K)).astype(np.float32) ** 4   # (B,H,W,C): preprocess.py:317
+        ind = np.stack([rng.choice(H * W, M, replace=False) for _ in range(B)]).astype(np.int64)
+        mask = (rng.uniform(0, 1, (B, M)) < 0.7).astype(np.uint8)
+        mask[1, :] = mask[1, :] if t == 0 else 0              # one frame without objects in task 1
+        cat = rng.integers(0, K, (B, M)).astype(np.int64)
+        for b in range(B):
+            for m in range(M):
+                if mask[b, m]:
+                    hm[b, ind[b, m] // W, ind[b, m] % W, cat[b, m]] = 1.0
+        anno = rng.normal(0, 0.5, (B, M, 10)).astype(np.float32)
+        gt = np.zeros((B, M, 7), np.float32)
+        gt[..., 0:2] = rng.uniform(-50, 50, (B, M, 2))
+        gt[..., 2] = rng.uniform(-2, 1, (B, M))
+        gt[..., 3:6] = rng.uniform(0.5, 5, (B, M, 3))
+        gt[..., 6] = rng.uniform(-3, 3, (B, M))
+        for k, v in (("hm", hm), ("ind", ind), ("mask", mask), ("cat", cat), ("anno_box", anno), ("gt_box", gt)):
+            example[k].append(torch.from_numpy(v))
+            save[f"ex{t}_{k}"] = v
+    out = head.loss(example, [dict((k, v.clone()) for k, v in p.items()) for p in preds], train_cfg)
+    for t in range(2):
+        for k in ("loss", "hm_loss", "loc_loss", "loc_loss_elem", "reg_iou_loss", "num_positive"):
+            save[f"out{t}_{k}"] = np.asarray(out[k][t].detach().numpy(), np.float32).reshape(-1)
+    np.savez_compressed(os.path.join(HERE, "head_loss.npz"), **save)
+
+
 def gen_neck_head():
     torch.manual_seed(14)
     tasks = [dict(stride=8, class_names=["car"]), dict(stride=8, class_names=["ped", "cone"])]
@@ -189,6 +238,7 @@ if __name__ == "__main__":
     gen_circle()
     gen_predict()
     gen_predict_double_flip()
+    gen_loss()
     gen_neck_head()
     gen_cfg()
     print("golden fixtures written to", HERE)

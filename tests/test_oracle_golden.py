@@ -102,3 +102,25 @@ def test_set_by_task_cfg_vs_reference(golden_dir):
                post_center_limit_range=[-80, -80, -10.0, 80, 80, 10.0])
     got = set_by_task_cfg(cfg, [1, 2])
     assert json.loads(json.dumps(got)) == want
+
+
+def test_centerhead_loss_vs_reference(golden_dir):
+    """CenterHead.loss (PyTorch restatement, losses.py) vs the reference's loss executed from /root/reference."""
+    import torch
+    from pillarnet_lts_b200.head import CenterHead
+    g = np.load(os.path.join(golden_dir, "head_loss.npz"))
+    tasks = [dict(stride=8, class_names=["car"]), dict(stride=8, class_names=["ped", "cone"])]
+    head = CenterHead(tasks=tasks, in_channels=[16], code_weights=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.2, 0.2, 1.0, 1.0],
+                      common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "vel": (2, 2)},
+                      share_channel=8, reg_iou="GIoU", pillar_size=0.075, point_cloud_range=[-54, -54, -5.0, 54, 54, 3.0])
+    preds = [{n: torch.from_numpy(g[f"t{t}_{n}"]).requires_grad_(True) for n in ["reg", "height", "dim", "rot", "vel", "hm"]}
+             for t in range(2)]
+    example = {k: [torch.from_numpy(g[f"ex{t}_{k}"]) for t in range(2)]
+               for k in ("hm", "ind", "mask", "cat", "anno_box", "gt_box")}
+    out = head.loss(example, preds, dict(hm_weight=1, bbox_weight=0.25, iou_weight=1, reg_iou_weight=0.25))
+    for t in range(2):
+        for k in ("loss", "hm_loss", "loc_loss", "loc_loss_elem", "reg_iou_loss", "num_positive"):
+            np.testing.assert_allclose(out[k][t].detach().numpy().reshape(-1), g[f"out{t}_{k}"], rtol=1e-5, atol=1e-6,
+                                       err_msg=f"{t} {k}")
+    sum(out["loss"]).sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for d in preds for p in d.values())
