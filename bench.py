@@ -347,6 +347,89 @@ def run_gpu(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+def run_train(args):
+    """BASELINE config 4: one data-parallel training step (reader + sparse backbone forward/backward on the
+    library's kernels, dense neck/head + loss in PyTorch, overlapped NCCL gradient all-reduce)."""
+    import torch.distributed as dist
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200 import _lib, configs, train
+    from pillarnet_lts_b200.dist import GradientAverager
+    from pillarnet_lts_b200.registry import ConfigDict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P.set_precision(args.precision)
+    lib = _lib.load()
+    B = args.frames_per_step
+    cfg = configs.get(args.workload)
+    torch.manual_seed(0)
+    model = P.build_detector(ConfigDict.wrap(cfg["model"]), cfg["train_cfg"], ConfigDict.wrap(cfg["test_cfg"]))
+    model = model.to(dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+    avg = GradientAverager(list(model.parameters()), bucket_mb=25) if world > 1 else None
+    pool = 4
+    rng = np.random.default_rng(7 + rank)
+    H, W = model.reader.height, model.reader.width
+    batches = []
+    for i in range(pool):
+        fs = [make_frames(cfg["synth"], 1, seed0=2000 + ((i * B + j) * world + rank))[0] for j in range(B)]
+        offs = np.cumsum([0] + [len(f) for f in fs]).astype(np.int32)
+        ex = {"points_batched": (torch.from_numpy(np.concatenate(fs)).to(dev), torch.from_numpy(offs).to(dev)),
+              "points": None, "metadata": [None] * B}
+        ex.update(train.synthetic_targets(model.bbox_head, B, H, W, rng, max_objs=500, device=dev))
+        batches.append(ex)
+    n_pts = int(np.mean([b["points_batched"][0].shape[0] for b in batches]) / B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        loss = train.train_step(model, batches[i % pool], opt, avg)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.pn_launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(args.steps):
+        loss = train.train_step(model, batches[i % pool], opt, avg)
+    e.record()
+    barrier()
+    gpu_ms = s.elapsed_time(e)
+    launches = lib.pn_launch_count() - l0
+    clocks = sampler.stop()
+    t = torch.tensor([gpu_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gpu_ms = t.item()
+    if rank == 0:
+        value = args.steps * B * world / (gpu_ms / 1e3)
+        line = {
+            "metric": "frames/s (training step: reader + sparse backbone fwd/bwd, dense neck/head + loss, grad all-reduce)",
+            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": gpu_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}-train: {B} frames/GPU (~{n_pts} pts/frame), AdamW, synthetic targets, "
+                                   f"random-init weights; inputs larger than L2 (activations ~GBs per step)",
+                       "frames_per_step_per_gpu": B, "precision": args.precision,
+                       "host_syncs": "one per rulebook (exact row counts), as the reference"},
+            "clocks": clocks, "gpu_launches": int(launches), "loss_last": float(loss),
+            "e2e": None, "roofline": None, "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
 def cpu_run(model, frames, steps, warmup):
     """the oracle port of the whole path on the host cores; returns (seconds per step list, timings)"""
     import copy
@@ -415,6 +498,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="nusc18", choices=["nusc18", "nusc34", "waymo34"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train: BASELINE config 4 (training step); not the headline metric")
     ap.add_argument("--frames-per-step", type=int, default=1)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--hm-cells", type=int, default=1500)
@@ -427,6 +512,9 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; see --impl reference)")
+    if args.mode == "train":
+        run_train(args)
+        return
     run_gpu(args)
 
 

@@ -18,7 +18,6 @@ class ScatterMaxFunction(Function):
         """src (L,C) f32, index (L,) int32 -> out (M,C) f32: max(0, max over the pillar's points)."""
         out, arg = ops.scatter_max(src.contiguous(), index.contiguous(), int(M), want_arg=True)
         ctx.for_backwards = (src.shape[0], src.shape[1], arg)
-        ctx.mark_non_differentiable(arg)
         return out
 
     @staticmethod

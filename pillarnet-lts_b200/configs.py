@@ -36,7 +36,9 @@ def _nusc(backbone):
         rectifier=0, score_threshold=0.1, double_flip=False,
         post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0],
     )
-    return dict(model=model, test_cfg=test_cfg, train_cfg=None, synth="nuscenes", pillar_size=ps, pc_range=pcr)
+    # pillarnet_centerhead_nusc.py:61-66
+    train_cfg = dict(hm_weight=1, bbox_weight=0.25, iou_weight=1, reg_iou_weight=0.25)
+    return dict(model=model, test_cfg=test_cfg, train_cfg=train_cfg, synth="nuscenes", pillar_size=ps, pc_range=pcr)
 
 
 def _waymo34():
@@ -59,7 +61,9 @@ def _waymo34():
         rectifier=[0., 0., 0.], score_threshold=0.1,
         post_center_limit_range=[-80, -80, -10.0, 80, 80, 10.0],
     )
-    return dict(model=model, test_cfg=test_cfg, train_cfg=None, synth="waymo", pillar_size=ps, pc_range=pcr)
+    # pillarnet34_fpn_centerhead_waymo.py:56-61
+    train_cfg = dict(hm_weight=1, bbox_weight=2, iou_weight=1, reg_iou_weight=2)
+    return dict(model=model, test_cfg=test_cfg, train_cfg=train_cfg, synth="waymo", pillar_size=ps, pc_range=pcr)
 
 
 WORKLOADS = {

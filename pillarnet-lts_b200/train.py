@@ -114,3 +114,63 @@ def dense_from_sparse(sp):
 
 def to_dense(x):
     return dense_from_sparse(x) if isinstance(x, SparseConvTensor) else x
+
+
+# ---- synthetic supervision + one optimisation step ---------------------------------------------------
+
+def synthetic_targets(head, n_frames, bev_h, bev_w, rng, max_objs=500, device="cuda"):
+    """Random CenterPoint-style targets with the shapes AssignLabel produces (datasets/pipelines/preprocess.py:
+    249-345): per task hm (B,H,W,K) with unit peaks at the object centres, ind/mask/cat (B,M), anno_box (B,M,10)
+    [reg2, height, log-dim3, vel2, sin, cos], gt_box (B,M,7).  Benchmark / test input only."""
+    import numpy as np
+    out = {k: [] for k in ("hm", "ind", "mask", "cat", "anno_box", "gt_box")}
+    for t, K in enumerate(head.num_classes):
+        s = head.task_strides[t]
+        H, W = bev_h // s, bev_w // s
+        M = max_objs
+        hm = np.zeros((n_frames, H, W, K), np.float32)
+        ind = np.zeros((n_frames, M), np.int64)
+        mask = np.zeros((n_frames, M), np.uint8)
+        cat = np.zeros((n_frames, M), np.int64)
+        anno = np.zeros((n_frames, M, 10), np.float32)
+        gt = np.zeros((n_frames, M, 7), np.float32)
+        for b in range(n_frames):
+            n = int(rng.integers(max(1, M // 8), max(2, M // 2)))
+            pix = rng.choice(H * W, n, replace=False)
+            ind[b, :n], mask[b, :n] = pix, 1
+            cat[b, :n] = rng.integers(0, K, n)
+            ys, xs = pix // W, pix % W
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    yy, xx = np.clip(ys + dy, 0, H - 1), np.clip(xs + dx, 0, W - 1)
+                    v = 1.0 if (dy == 0 and dx == 0) else 0.4
+                    np.maximum.at(hm, (b, yy, xx, cat[b, :n]), v)
+            reg = rng.uniform(0, 1, (n, 2)).astype(np.float32)
+            dim = rng.uniform(0.5, 5.0, (n, 3)).astype(np.float32)
+            rot = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+            z = rng.uniform(-2, 1, n).astype(np.float32)
+            anno[b, :n, 0:2], anno[b, :n, 2], anno[b, :n, 3:6] = reg, z, np.log(dim)
+            anno[b, :n, 6:8] = rng.normal(0, 1, (n, 2))
+            anno[b, :n, 8], anno[b, :n, 9] = np.sin(rot), np.cos(rot)
+            gt[b, :n, 0] = (xs + reg[:, 0]) * s * head.pillar_size + head.point_cloud_range[0]
+            gt[b, :n, 1] = (ys + reg[:, 1]) * s * head.pillar_size + head.point_cloud_range[1]
+            gt[b, :n, 2], gt[b, :n, 3:6], gt[b, :n, 6] = z, dim, rot
+        for k, v in (("hm", hm), ("ind", ind), ("mask", mask), ("cat", cat), ("anno_box", anno), ("gt_box", gt)):
+            out[k].append(torch.from_numpy(v).to(device))
+    return out
+
+
+def train_step(model, example, optimizer, averager=None):
+    """forward + loss + backward (+ overlapped gradient all-reduce, dist.GradientAverager) + optimiser step;
+    returns the summed loss (device scalar)."""
+    if averager is not None:
+        averager.zero_grad()
+    else:
+        optimizer.zero_grad(set_to_none=True)
+    losses = model(example, return_loss=True)
+    loss = sum(l.sum() for l in losses["loss"])
+    loss.backward()
+    if averager is not None:
+        averager.finish()
+    optimizer.step()
+    return loss.detach()

@@ -57,3 +57,57 @@ def test_shard_indices_are_a_partition():
             assert flat == list(range(n))
             order = pd.unshard_order(n, world)
             assert sorted(order) == list(range(n))
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import pillarnet_lts_b200  # noqa: F401
+    from pillarnet_lts_b200 import dist as pd
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                       # same init on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                              torch.nn.Linear(16, 3))
+    unused = torch.nn.Parameter(torch.ones(5))           # never receives a gradient
+    params = list(net.parameters()) + [unused]
+    g = torch.Generator().manual_seed(100)
+    data = torch.randn(world, 8, 6, generator=g)          # rank r trains on data[r]
+    # reference result: mean over ranks of the per-rank gradients
+    want = []
+    for r in range(world):
+        net.zero_grad()
+        net(data[r]).pow(2).mean().backward()
+        want.append([p.grad.clone() for p in net.parameters()])
+    want = [sum(gs) / world for gs in zip(*want)]
+    ok = True
+    # (1) overlapped bucketed averager (tiny buckets: several all-reduces launched from backward hooks)
+    avg = pd.GradientAverager(params, bucket_mb=0.0002)
+    assert len(avg.buckets) > 2
+    for _ in range(2):                                    # two steps: counters re-arm, buffers are reused
+        avg.zero_grad()
+        net(data[rank]).pow(2).mean().backward()
+        avg.finish()
+        ok = ok and all(torch.allclose(p.grad, w, atol=1e-6) for p, w in zip(net.parameters(), want))
+        ok = ok and bool((unused.grad == 0).all())
+    avg.remove()
+    # (2) the reference's after-backward helper, coalesced and bucketed
+    for kw in (dict(coalesce=True, bucket_size_mb=-1), dict(coalesce=True, bucket_size_mb=1), dict(coalesce=False)):
+        for p in params:
+            p.grad = None
+        net(data[rank]).pow(2).mean().backward()
+        pd.allreduce_grads(params, **kw)
+        ok = ok and all(torch.allclose(p.grad, w, atol=1e-6) for p, w in zip(net.parameters(), want))
+    ret[rank] = ok
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_averaging_world2():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}

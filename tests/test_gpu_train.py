@@ -1,0 +1,179 @@
+"""GPU parity of the training path: scatter-max forward/backward vs the reference's own
+pillar_cuda extension, point features vs the torch expression of pillar_utils.py:51-56, sparse-conv forward /
+data gradient / weight gradient vs torch autograd on the dense-equivalent convolution, aligned BEV overlap vs
+the reference's iou3d_nms_cuda, and one whole training step of the detector.
+
+Tolerances: fp32 (SIMT) 1e-4 relative to max|ref|; bf16 tensor-core kernels against the fp32 kernels fed the
+same bf16-rounded operands: 5e-3 rel-to-max for dW (fp32 accumulation over thousands of rows, split-K order),
+1e-2 for activations / data gradients (one bf16 rounding of the result)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.gpu_util import batch_points, rand_boxes, rand_points, ref_ext
+from tests.test_gpu_rulebook_conv import _random_sites, _table_from_sites
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return (a.float() - b.float()).abs().max().item() / max(1e-12, b.float().abs().max().item())
+
+
+def test_point_features_vs_torch_expression():
+    from pillarnet_lts_b200 import ops
+    rng = np.random.default_rng(3)
+    pts = torch.from_numpy(rand_points(rng, 5000, -53.9, 53.9)).cuda()
+    ps, x0, y0 = 0.075, -54.0, -54.0
+    xoff, yoff = ps / 2.0 + x0, ps / 2.0 + y0
+    got = ops.point_features(pts, x0, y0, ps, xoff, yoff)
+    # dynamic_pillar_encoder.py:34-35 + pillar_utils.py:51-56 with torch CUDA ops
+    cx = torch.floor((pts[:, 0] - x0) / ps).int()
+    cy = torch.floor((pts[:, 1] - y0) / ps).int()
+    ctr = torch.stack([cx, cy], 1).float() * ps + torch.tensor([xoff, yoff], device="cuda")
+    want = torch.cat([pts[:, :2] - ctr, pts], 1)
+    assert torch.equal(got, want)
+
+
+def test_scatter_max_forward_backward_vs_reference_extension():
+    pillar = ref_ext("pillar_cuda")
+    if pillar is None:
+        pytest.skip("oracle/_ref/pillar_cuda not built")
+    from pillarnet_lts_b200.autograd import scatter_max
+    g = torch.Generator(device="cuda").manual_seed(9)
+    L, C, M = 20000, 32, 1500
+    src = torch.randn(L, C, device="cuda", generator=g)           # negatives too: floor at 0
+    index = torch.randint(0, M - 7, (L,), device="cuda", generator=g, dtype=torch.int32)   # 7 empty pillars
+    arg_ref = torch.full((M, C), -1, dtype=torch.int32, device="cuda")
+    out_ref = torch.zeros(M, C, device="cuda")
+    pillar.scatter_max_wrapper(index, src, arg_ref, out_ref)
+    s = src.clone().requires_grad_(True)
+    out = scatter_max(s, index, M)
+    assert torch.equal(out, out_ref)                               # bit-exact forward
+    go = torch.randn(M, C, device="cuda", generator=g)
+    out.backward(go)
+    grad_ref = torch.zeros(L, C, device="cuda")
+    pillar.scatter_max_grad_wrapper(go, arg_ref, grad_ref)
+    # The reference routes to ANY point within 1e-5 of the max (last writer wins); ours to the exact, lowest-index
+    # argmax.  With continuous random values the two differ only at near-ties: allow a handful of entries.
+    assert (s.grad != grad_ref).sum().item() <= 40
+    assert torch.equal(s.grad.sum(0), grad_ref.sum(0)) or _rel(s.grad.sum(0), grad_ref.sum(0)) < 1e-5
+    # own invariants: every positive pillar max is routed to a point of that pillar holding exactly that value
+    routed = s.grad != 0
+    p_idx = torch.nonzero(routed)
+    assert torch.equal(out[index[p_idx[:, 0]].long(), p_idx[:, 1]], src[p_idx[:, 0], p_idx[:, 1]])
+
+
+def _dense_equiv(x_rows, coords, B, H, W, weight, bias, stride, out_coords):
+    """torch reference of a sparse conv: densify, F.conv2d, gather the active output sites"""
+    c = coords.long()
+    dense = x_rows.new_zeros(B, H, W, x_rows.shape[1])
+    dense = dense.index_put((c[:, 0], c[:, 1], c[:, 2]), x_rows).permute(0, 3, 1, 2)
+    y = F.conv2d(dense, weight.permute(0, 3, 1, 2), bias, stride=stride, padding=1)
+    oc = out_coords.long()
+    return y.permute(0, 2, 3, 1)[oc[:, 0], oc[:, 1], oc[:, 2]]
+
+
+@pytest.mark.parametrize("precision,cin,cout,strided", [
+    ("fp32", 32, 32, False), ("fp32", 16, 48, True), ("fp32", 64, 128, True),
+    ("bf16", 32, 32, False), ("bf16", 64, 64, False), ("bf16", 64, 128, True), ("bf16", 128, 128, False),
+    ("bf16", 128, 256, True), ("bf16", 256, 256, False)])
+def test_sparse_conv_autograd_vs_torch_dense_equivalent(precision, cin, cout, strided):
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200 import train
+    from pillarnet_lts_b200.autograd import sparse_conv
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    P.set_precision(precision)
+    try:
+        rng = np.random.default_rng(cin + cout)
+        B, H, W, n = 2, 48, 40, 1500
+        table = train._exact(_table_from_sites(_random_sites(rng, B, H, W, n), B, H, W))
+        g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout)
+        x = torch.randn(n, cin, device="cuda", generator=g)
+        w = torch.randn(cout, 3, 3, cin, device="cuda", generator=g) * (1.0 / (3.0 * cin ** 0.5))
+        b = torch.randn(cout, device="cuda", generator=g)
+        if precision == "bf16":                                      # identical operands on both sides
+            x, w = x.bfloat16().float(), w.bfloat16().float()
+        if strided:
+            out_table, rb = train.down_rulebook(table)
+        else:
+            out_table, rb = table, train.subm_rulebook(table)
+        dy = torch.randn(out_table.cap, cout, device="cuda", generator=g)
+        if precision == "bf16":
+            dy = dy.bfloat16().float()
+        xa, wa, ba = (t.clone().requires_grad_(True) for t in (x, w, b))
+        y = sparse_conv(xa.to(P.config.act_dtype()), wa, ba, rb)
+        y.backward(dy.to(y.dtype))
+        xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+        yr = _dense_equiv(xr, table.coords, B, H, W, wr, br, 2 if strided else 1, out_table.coords)
+        yr.backward(dy)
+        torch.cuda.synchronize()
+        tol_act, tol_w = (1e-4, 1e-4) if precision == "fp32" else (1e-2, 5e-3)
+        assert _rel(y, yr) <= tol_act
+        assert _rel(xa.grad, xr.grad) <= tol_act
+        assert _rel(wa.grad, wr.grad) <= tol_w
+        assert _rel(ba.grad, br.grad) <= tol_w
+    finally:
+        P.set_precision("bf16")
+
+
+def test_rulebook_transpose_is_the_inverse_relation():
+    from pillarnet_lts_b200 import ops, train
+    rng = np.random.default_rng(5)
+    B, H, W, n = 2, 33, 31, 700
+    table = train._exact(_table_from_sites(_random_sites(rng, B, H, W, n), B, H, W))
+    out_table, rb = train.down_rulebook(table)
+    nbr, nbr_t = rb.nbr.cpu().numpy(), rb.nbr_t.cpu().numpy()
+    want = np.full((n, 9), -1, np.int32)
+    for o in range(nbr.shape[0]):
+        for t in range(9):
+            if nbr[o, t] >= 0:
+                assert want[nbr[o, t], t] == -1          # (input, tap) pairs are unique
+                want[nbr[o, t], t] = o
+    assert np.array_equal(nbr_t, want)
+    sub = train.subm_rulebook(table)
+    assert np.array_equal(sub.nbr_t.cpu().numpy(), ops.rulebook_transpose(sub.nbr, n).cpu().numpy())
+
+
+def test_aligned_overlap_bit_exact_vs_reference_extension():
+    iou3d = ref_ext("iou3d_nms_cuda")
+    if iou3d is None:
+        pytest.skip("oracle/_ref/iou3d_nms_cuda not built")
+    from pillarnet_lts_b200 import ops
+    rng = np.random.default_rng(8)
+    a = rand_boxes(rng, 4000, spread=5.0)
+    b = a + rng.normal(0, 0.3, a.shape).astype(np.float32)
+    b[:500] = rand_boxes(rng, 500, spread=5.0)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    want = torch.zeros(len(a), 1, device="cuda")
+    iou3d.boxes_aligned_overlap_bev_gpu(ta, tb, want)
+    got = ops.boxes_aligned_overlap_bev(ta, tb)
+    assert torch.equal(got, want.view(-1))
+    assert (got > 0).sum().item() > 2000
+
+
+def test_detector_training_step_runs_and_reaches_every_parameter():
+    """PillarNet-18 (small grid) forward + loss + backward in bf16: finite loss, finite gradients everywhere."""
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200 import configs, synth, train
+    torch.manual_seed(0)
+    cfg = configs.get("nusc18")
+    cfg["model"]["reader"]["pc_range"] = [-24.0, -24.0, -5.0, 24.0, 24.0, 3.0]
+    cfg["model"]["bbox_head"]["point_cloud_range"] = [-24.0, -24.0, -5.0, 24.0, 24.0, 3.0]
+    model = P.build_detector(cfg["model"], train_cfg=cfg["train_cfg"], test_cfg=cfg["test_cfg"]).cuda().train()
+    rng = np.random.default_rng(1)
+    frames = [rand_points(rng, 30000, -23.9, 23.9) for _ in range(2)]
+    pts, off = batch_points(frames)
+    example = {"points_batched": (pts, off), "points": None, "metadata": [None, None]}
+    example.update(train.synthetic_targets(model.bbox_head, 2, 640, 640, rng, max_objs=50))
+    losses = model(example, return_loss=True)
+    loss = sum(l.sum() for l in losses["loss"])
+    assert torch.isfinite(loss)
+    loss.backward()
+    missing = [n for n, p in model.named_parameters() if p.grad is None]
+    assert not missing, missing
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters())
+    # the gradient reaches the reader's Linear through the scatter-max backward and the sparse-conv dgrads
+    assert model.reader.pfn_layers.shared_mlps[0].weight.grad.abs().max().item() > 0
