@@ -287,7 +287,8 @@ def sparse_to_dense(feat, table, C, out=None, out_coff=0, padded=False):
 def double_flip_merge(rows, offsets, num_cls, n_frames_out, H, W):
     """center_head.py:233-304: merge the 4 flipped views of every frame into one activated map (same columns)."""
     lib = _lib.load()
-    require_cuda(rows)
+    if not rows.is_cuda or rows.dtype != torch.float32 or rows.stride(1) != 1:
+        raise RuntimeError("double_flip_merge: rows must be a CUDA f32 (n, cols) view with unit column stride")
     n_cols = rows.shape[1]
     t = make_task_args(rows, offsets, num_cls, H, W, 1, 0, False)
     out = torch.empty(n_frames_out * H * W, n_cols, dtype=torch.float32, device=rows.device)

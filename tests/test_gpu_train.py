@@ -137,7 +137,10 @@ def test_rulebook_transpose_is_the_inverse_relation():
     assert np.array_equal(sub.nbr_t.cpu().numpy(), ops.rulebook_transpose(sub.nbr, n).cpu().numpy())
 
 
-def test_aligned_overlap_bit_exact_vs_reference_extension():
+def test_aligned_overlap_vs_reference_extension():
+    """IouLoss target (training only).  Tolerance 1e-5 rel-to-max: nvcc's FMA contraction of the polygon-area
+    arithmetic differs by instantiation context (measured: 25 % of pairs differ in the last bit, max 1.9e-6), unlike
+    the thresholded NMS / IoU kernels, which are bit-exact (tests/test_gpu_nms.py)."""
     iou3d = ref_ext("iou3d_nms_cuda")
     if iou3d is None:
         pytest.skip("oracle/_ref/iou3d_nms_cuda not built")
@@ -150,7 +153,11 @@ def test_aligned_overlap_bit_exact_vs_reference_extension():
     want = torch.zeros(len(a), 1, device="cuda")
     iou3d.boxes_aligned_overlap_bev_gpu(ta, tb, want)
     got = ops.boxes_aligned_overlap_bev(ta, tb)
-    assert torch.equal(got, want.view(-1))
+    want = want.view(-1)
+    # degenerate pairs (parallel edges, D == 0 in the line-intersection fallback) give NaN in both
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    g, w = torch.nan_to_num(got), torch.nan_to_num(want)
+    assert (g - w).abs().max().item() <= 1e-5 * w.abs().max().item()
     assert (got > 0).sum().item() > 2000
 
 
