@@ -20,6 +20,8 @@
 // un-padded NHWC).
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -86,6 +88,35 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// multicast: the box lands at the same CTA-relative offset of every CTA in `mask`, and each destination
+// CTA's barrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PN_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -115,6 +146,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// arrive on the same-offset barrier of every CTA in `mask` once this CTA's prior MMAs have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -178,7 +216,19 @@ struct DArgs {
   // [in_coff + g*cin, +cin), weight rows [g*BN, +BN), writing group_tab[g] = {out_coff, cout} columns
   int n_groups;
   const int* group_tab;
+  // development aid (PN_DENSE_TIMELINE=1): CTA 0 records %globaltimer at its pipeline milestones
+  unsigned long long* dbg;
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PN_DBG(slot)                                                        \
+  do {                                                                      \
+    if (P.dbg) P.dbg[blockIdx.x * 8 + slot] = gtime_ns();                   \
+  } while (0)
 
 template <int MT, int BN, int SA, int SB>
 struct DSmem {
@@ -196,7 +246,11 @@ struct DSmem {
   float shift[BN];
 };
 
-template <int MT, int BN, int SA, int SB>
+// CL > 1: thread-block cluster of CL CTAs that work on CL consecutive row tiles of the SAME N tile; every
+// weight tile is fetched once per cluster — each CTA loads BN/CL rows and TMA-multicasts them into all CL
+// shared memories — so weight bytes per CTA drop CL-fold (the kernel is L2->SM bound and weights are ~75 % of
+// its traffic at BN = 256).  A weight stage is recycled only after all CL consumers released it (multicast commit).
+template <int MT, int BN, int SA, int SB, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_constant__ CUtensorMap tmap_a_tail,
              const __grid_constant__ CUtensorMap tmap_w, const DArgs P) {
@@ -208,14 +262,25 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
   constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;     // double-buffer the accumulator when TMEM allows
   constexpr int TCOLS = (NACC * ACC_COLS) < 32 ? 32 : NACC * ACC_COLS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) PN_DBG(0);
+  // Programmatic dependent launch: this grid may start during its predecessor's tail.  Weights, scale/shift and
+  // the group table are constants, so the weight producer runs ahead unconditionally; the activation producer
+  // and the epilogue (reads nothing, but overwrites `out`) wait for the predecessor first.
+  pdl_launch_dependents();
   const int n_n_tiles = P.n_groups > 0 ? P.n_groups : (P.cout + BN - 1) / BN;
-  const int n_tiles = ((P.n_pos + M_TILE - 1) / M_TILE) * n_n_tiles;
+  const int n_m_tiles = (P.n_pos + M_TILE - 1) / M_TILE;
+  // work unit = (N tile, group of CL consecutive row tiles); CTA `rank` of the cluster takes row tile
+  // m_group*CL + rank (past the end for the last group: its loads are zero-filled, its stores masked)
+  const int n_tiles = ((n_m_tiles + CL - 1) / CL) * n_n_tiles;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
   const int n_cc = P.cin / BLOCK_K;
 
   if (warp == 2) {
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) { mbar_init(&sm.full_a[s], 1); mbar_init(&sm.empty_a[s], 1); }
-      for (int s = 0; s < SB; ++s) { mbar_init(&sm.full_b[s], 1); mbar_init(&sm.empty_b[s], 1); }
+      for (int s = 0; s < SB; ++s) { mbar_init(&sm.full_b[s], 1); mbar_init(&sm.empty_b[s], CL); }
       for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], kEpilogueThreads); }
       fence_barrier_init();
     }
@@ -223,18 +288,20 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
     tmem_alloc<TCOLS>(&sm.tmem_base);
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // barriers of every CTA initialised before any remote signal
   tcgen05_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
+  if (threadIdx.x == 0) PN_DBG(1);
 
   if (warp == 0) {
     // ===================== activation segments (TMA) =====================
     if (lane == 0) {
+      pdl_wait();
       uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m_tile = tile / n_n_tiles;
+      for (int tile = unit0; tile < n_tiles; tile += unit_step) {
+        const int m_tile = (tile / n_n_tiles) * CL + crank;
         const int q0 = m_tile * M_TILE;
-        const int ch0 = P.in_coff + (P.n_groups > 0 ? (tile - m_tile * n_n_tiles) * P.cin : 0);
+        const int ch0 = P.in_coff + (P.n_groups > 0 ? (tile % n_n_tiles) * P.cin : 0);
         for (int cc = 0; cc < n_cc; ++cc) {
           for (int dy = 0; dy < 3; ++dy, ++g) {
             const uint32_t s = g % SA, ph = (g / SA) & 1u;
@@ -252,14 +319,20 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
     // ===================== weight tiles (TMA) =====================
     if (lane == 0) {
       uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < n_tiles; tile += unit_step) {
         const int n_tile = tile % n_n_tiles;
         for (int cc = 0; cc < n_cc; ++cc) {
           for (int tap = 0; tap < 9; ++tap, ++g) {
             const uint32_t s = g % SB, ph = (g / SB) & 1u;
             mbar_wait(&sm.empty_b[s], ph ^ 1u);
             mbar_arrive_expect_tx(&sm.full_b[s], (uint32_t)(BN * 128));
-            tma_load_2d(smem_u32(sm.b[s]), &tmap_w, tap * P.cin + cc * BLOCK_K, n_tile * BN, &sm.full_b[s]);
+            if (CL == 1) {
+              tma_load_2d(smem_u32(sm.b[s]), &tmap_w, tap * P.cin + cc * BLOCK_K, n_tile * BN, &sm.full_b[s]);
+            } else {
+              constexpr int kSlice = BN / CL;   // rows of the tile this CTA fetches for the whole cluster
+              tma_load_2d_mc(smem_u32(sm.b[s]) + crank * kSlice * 128, &tmap_w, tap * P.cin + cc * BLOCK_K,
+                             n_tile * BN + crank * kSlice, &sm.full_b[s], kMask);
+            }
           }
         }
       }
@@ -278,7 +351,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
 #pragma unroll
       for (int i = 0; i < SB; ++i) b_base[i] = make_desc(smem_u32(sm.b[i]), 0);
       uint32_t ga = 0, gb = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      for (int tile = unit0; tile < n_tiles; tile += unit_step, ++tcount) {
         const uint32_t acc = NACC == 2 ? (tcount & 1u) : 0u;
         const uint32_t acc_ph = NACC == 2 ? ((tcount >> 1) & 1u) : (tcount & 1u);
         mbar_wait(&sm.tmem_empty[acc], acc_ph ^ 1u);
@@ -299,6 +372,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
               ++gb;
               mbar_wait(&sm.full_b[sb], phb);
               tcgen05_fence_after();
+              if (gb == 1) PN_DBG(2);
               uint64_t b_stage = b_base[0];
 #pragma unroll
               for (int i = 1; i < SB; ++i) b_stage = (sb == (uint32_t)i) ? b_base[i] : b_stage;
@@ -313,12 +387,13 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
                   umma_bf16(d_tmem + m * BN, a_desc, b_desc, idesc, k == 0 ? first : 1u);
                 }
               }
-              umma_commit(&sm.empty_b[sb]);
+              if (CL == 1) umma_commit(&sm.empty_b[sb]); else umma_commit_mc(&sm.empty_b[sb], kMask);
             }
             umma_commit(&sm.empty_a[sa]);
           }
         }
         umma_commit(&sm.tmem_full[acc]);
+        PN_DBG(3);
       }
     }
     __syncwarp();
@@ -328,8 +403,9 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
     const int etid = threadIdx.x - 4 * 32;
     const int hw_p = P.Hp * P.Wp;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-      const int m_tile = tile / n_n_tiles, n_tile = tile - m_tile * n_n_tiles;
+    pdl_wait();
+    for (int tile = unit0; tile < n_tiles; tile += unit_step, ++tcount) {
+      const int n_tile = tile % n_n_tiles, m_tile = (tile / n_n_tiles) * CL + crank;
       const int n0 = n_tile * BN;          // first weight row / scale index of this N tile
       int cout_t = P.cout, ocol0 = P.out_coff + n0, nbase = n0;
       if (P.n_groups > 0) {                // grouped: own output columns and channel count
@@ -348,6 +424,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       named_bar_sync(2, kEpilogueThreads);
       mbar_wait_relaxed(&sm.tmem_full[acc], acc_ph);
       tcgen05_fence_after();
+      if (etid == 0) PN_DBG(4);
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
         const int q = m_tile * M_TILE + m * 128 + e * 32 + lane;
@@ -413,14 +490,16 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       }
       tcgen05_fence_before();
       mbar_arrive(&sm.tmem_empty[acc]);
+      if (etid == 0) PN_DBG(5);
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA may exit while peers still signal its barriers
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc<TCOLS>(tmem_base);
   }
+  if (threadIdx.x == 0) PN_DBG(6);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -487,19 +566,93 @@ int get_map(const void* base, long long rows, int cols, int ld, int box_rows, CU
   return PN_OK;
 }
 
-template <int MT, int BN, int SA, int SB>
-int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, const DArgs& a, int grid,
+// `units` = work units (see the kernel); the grid is CL x min(units, co-resident clusters).
+template <int MT, int BN, int SA, int SB, int CL = 1>
+int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, const DArgs& a, long long units,
            cudaStream_t stream) {
   constexpr size_t smem = sizeof(DSmem<MT, BN, SA, SB>) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    PN_CUDA(cudaFuncSetAttribute(k_conv_dense<MT, BN, SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    configured = true;
+  static_assert(CL == 1 || (BN / CL) % 8 == 0, "a weight slice must keep the 8-row swizzle period");
+  static int max_clusters = 0;
+  auto kern = k_conv_dense<MT, BN, SA, SB, CL>;
+  if (max_clusters == 0) {
+    PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sms = pn_detail::sm_count();
+    if (CL == 1) {
+      max_clusters = sms;
+    } else {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(sms / CL * CL);
+      q.blockDim = dim3(kThreads);
+      q.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      q.attrs = at; q.numAttrs = 1;
+      int n = 0;
+      PN_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &q));
+      if (n <= 0) return PN_ERR_UNSUPPORTED;
+      max_clusters = n;
+    }
   }
-  k_conv_dense<MT, BN, SA, SB><<<grid, kThreads, smem, stream>>>(ma, mt, mw, a);
+  const int clusters = (int)(units < max_clusters ? units : max_clusters);
+  static const bool timeline = [] { const char* e = getenv("PN_DENSE_TIMELINE"); return e && e[0] == '1'; }();
+  static unsigned long long* dbg_buf = nullptr;
+  DArgs a_dbg = a;
+  if (timeline) {
+    if (!dbg_buf) PN_CUDA(cudaMalloc(&dbg_buf, 8 * 1024 * sizeof(unsigned long long)));   // device memory: no page faults
+    PN_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * 1024 * sizeof(unsigned long long), stream));
+    PN_CUDA(cudaStreamSynchronize(stream));
+    a_dbg.dbg = dbg_buf;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int n_at = 0;
+  if (CL > 1) {
+    at[n_at].id = cudaLaunchAttributeClusterDimension;
+    at[n_at].val.clusterDim.x = CL; at[n_at].val.clusterDim.y = 1; at[n_at].val.clusterDim.z = 1;
+    ++n_at;
+  }
+  if (pdl_enabled()) {
+    at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n_at].val.programmaticStreamSerializationAllowed = 1;
+    ++n_at;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n_at;
+  PN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mt, mw, a_dbg));
   PN_CHECK_LAUNCH();
+  if (timeline) {
+    PN_CUDA(cudaStreamSynchronize(stream));
+    static unsigned long long t[8 * 1024];
+    PN_CUDA(cudaMemcpy(t, dbg_buf, sizeof(t), cudaMemcpyDeviceToHost));
+    const int n = clusters * CL;
+    unsigned long long t_min = ~0ull, t_max = 0;
+    for (int c = 0; c < n; ++c) {
+      if (t[c * 8] < t_min) t_min = t[c * 8];
+      if (t[c * 8 + 6] > t_max) t_max = t[c * 8 + 6];
+    }
+    double s_start = 0, s_first = 0, s_mma = 0, s_epi = 0, s_tot = 0, m_start = 0, m_mma = 0, m_tot = 0, m_epi = 0;
+    for (int c = 0; c < n; ++c) {
+      const unsigned long long* q = t + c * 8;
+      const double st = (double)(q[0] - t_min), fi = (double)(q[2] - q[1]), mm = (double)(q[3] - q[2]),
+                   ep = (double)(q[5] - q[4]), to = (double)(q[6] - q[0]);
+      s_start += st; s_first += fi; s_mma += mm; s_epi += ep; s_tot += to;
+      if (st > m_start) m_start = st;
+      if (mm > m_mma) m_mma = mm;
+      if (to > m_tot) m_tot = to;
+      if (ep > m_epi) m_epi = ep;
+    }
+    fprintf(stderr, "[dense<%d,%d,%d,%d,cl%d> grid %d units %lld] span %.1f us | CTA start skew avg %.1f max %.1f | first "
+                    "operands avg %.1f | mma phase avg %.1f max %.1f | last epilogue avg %.1f max %.1f | CTA total avg %.1f "
+                    "max %.1f\n",
+            MT, BN, SA, SB, CL, n, units, (t_max - t_min) / 1e3, s_start / n / 1e3, m_start / 1e3, s_first / n / 1e3,
+            s_mma / n / 1e3, m_mma / 1e3, s_epi / n / 1e3, m_epi / 1e3, s_tot / n / 1e3, m_tot / 1e3);
+  }
   return PN_OK;
 }
 
@@ -540,14 +693,21 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
     const double cost = waves * (per_tap + epi);
     if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
   }
-  if (tile_hint >= 1 && tile_hint <= 4) best = tile_hint - 1;
+  if ((tile_hint & 0xF) >= 1 && (tile_hint & 0xF) <= 4) best = (tile_hint & 0xF) - 1;
   const int mt = cands[best].mt, bn = cands[best].bn;
+  // cluster size for the weight multicast: tile_hint bits 9/10 force 2 / 4, bit 11 forces 1
+  int cl = 1;   // measured on B200: multicast of the weight tiles buys nothing here (the kernel is MMA/latency bound)
+  if (tile_hint & 0x200) cl = 2;
+  if (tile_hint & 0x400) cl = 4;
+  if (tile_hint & 0x800) cl = 1;
+  const long long m_tiles = PN_DIVUP(n_pos, (long long)(128 * mt));
+  if (m_tiles < cl) cl = 1;
   CUtensorMap ma, mtail, mw;
   int rc = get_map(in, n_pos, in_ld, in_ld, 128 * mt, &ma);
   if (rc != PN_OK) return rc;
   rc = get_map(in, n_pos, in_ld, in_ld, kTailRows, &mtail);
   if (rc != PN_OK) return rc;
-  rc = get_map(weight, cout, k_pad, k_pad, bn, &mw);
+  rc = get_map(weight, cout, k_pad, k_pad, bn / cl, &mw);
   if (rc != PN_OK) return rc;
   DArgs a;
   a.cin = cin; a.in_coff = in_coff; a.cout = cout; a.Hp = Hp; a.Wp = Wp; a.n_pos = (int)n_pos;
@@ -556,12 +716,19 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
   a.base_offset_mode = (tile_hint & 0x100) ? 1 : 0;
   a.n_groups = 0;
   a.group_tab = nullptr;
-  const long long tiles = PN_DIVUP(n_pos, (long long)(128 * mt)) * PN_DIVUP(cout, bn);
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  if (mt == 2 && bn == 256) return launch<2, 256, 2, 4>(ma, mtail, mw, a, grid, stream);
-  if (mt == 1 && bn == 256) return launch<1, 256, 3, 5>(ma, mtail, mw, a, grid, stream);
-  if (mt == 2 && bn == 128) return launch<2, 128, 3, 6>(ma, mtail, mw, a, grid, stream);
-  return launch<1, 128, 4, 8>(ma, mtail, mw, a, grid, stream);
+  a.dbg = nullptr;
+  const long long units = PN_DIVUP(m_tiles, (long long)cl) * PN_DIVUP(cout, bn);
+#define PN_DENSE_LAUNCH(MT_, BN_, SA_, SB_)                                                       \
+  do {                                                                                            \
+    if (cl == 4) return launch<MT_, BN_, SA_, SB_, 4>(ma, mtail, mw, a, units, stream);           \
+    if (cl == 2) return launch<MT_, BN_, SA_, SB_, 2>(ma, mtail, mw, a, units, stream);           \
+    return launch<MT_, BN_, SA_, SB_, 1>(ma, mtail, mw, a, units, stream);                        \
+  } while (0)
+  if (mt == 2 && bn == 256) PN_DENSE_LAUNCH(2, 256, 2, 4);
+  if (mt == 1 && bn == 256) PN_DENSE_LAUNCH(1, 256, 3, 5);
+  if (mt == 2 && bn == 128) PN_DENSE_LAUNCH(2, 128, 3, 6);
+  PN_DENSE_LAUNCH(1, 128, 4, 8);
+#undef PN_DENSE_LAUNCH
 }
 
 
@@ -595,10 +762,9 @@ int pn_conv_dense3x3_grouped(const void* in, int in_ld, int in_coff, int cin, in
   a.cin = cin; a.in_coff = in_coff; a.cout = bn; a.Hp = Hp; a.Wp = Wp; a.n_pos = (int)n_pos;
   a.scale = scale; a.shift = shift; a.out = out; a.out_f32 = out_dtype == PN_F32; a.out_ld = out_ld;
   a.out_coff = 0; a.out_compact = out_compact; a.relu = relu; a.base_offset_mode = 0;
-  a.n_groups = n_groups; a.group_tab = group_tab;
+  a.n_groups = n_groups; a.group_tab = group_tab; a.dbg = nullptr;
   const long long tiles = PN_DIVUP(n_pos, (long long)(128 * mt)) * n_groups;
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  return launch<2, 16, 3, 8>(ma, mtail, mw, a, grid, stream);
+  return launch<2, 16, 3, 8, 1>(ma, mtail, mw, a, tiles, stream);
 }
 
 }  // extern "C"

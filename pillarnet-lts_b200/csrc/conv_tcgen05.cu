@@ -22,6 +22,7 @@
 // (cin = 32) — each 16-byte piece belongs to exactly one tap because cin % 8 == 0.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -72,7 +73,18 @@ struct KArgs {
   int out_hp, out_wp;  // != 0: zero the border rows of a padded output map
   int in_rows;         // allocated rows of `in` (TMA gather path: index >= in_rows reads zeros)
   int cin_shift;       // log2(cin) when cin is a power of two, else -1
+  unsigned long long* dbg;   // development aid (PN_CONV_TIMELINE=1): per-CTA %globaltimer milestones
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PN_DBG(slot)                                                        \
+  do {                                                                      \
+    if (P.dbg) P.dbg[blockIdx.x * 8 + slot] = gtime_ns();                   \
+  } while (0)
 
 template <int BN, int STAGES>
 struct Smem {
@@ -100,10 +112,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   using S = Smem<BN, STAGES>;
   S& sm = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows = P.num_rows ? min(*P.num_rows, P.rows_cap) : P.rows_cap;
-  const int n_n_tiles = (P.cout + BN - 1) / BN;
-  const int n_tiles = ((rows + BLOCK_M - 1) / BLOCK_M) * n_n_tiles;
   constexpr int TCOLS = tmem_cols<BN>();
+  if (threadIdx.x == 0) PN_DBG(0);
+  pdl_launch_dependents();   // our successor may be scheduled; it waits for this grid's completion itself
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -124,6 +135,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
+  // barrier init / TMEM allocation above overlap the predecessor's tail; everything below reads its results
+  // (the live row count, the rulebook, activations) or overwrites buffers it may still read
+  pdl_wait();
+  const int rows = P.num_rows ? min(*P.num_rows, P.rows_cap) : P.rows_cap;
+  const int n_n_tiles = (P.cout + BN - 1) / BN;
+  const int n_tiles = ((rows + BLOCK_M - 1) / BLOCK_M) * n_n_tiles;
+  if (threadIdx.x == 0) PN_DBG(1);
 
   if (warp < kProducerWarps) {
     // ===================== A producers (+ weight TMA) =====================
@@ -248,6 +266,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
           const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
           mbar_wait(&sm.full[s], ph);
           tcgen05_fence_after();
+          if (g == 0) PN_DBG(2);
           uint64_t a_desc = a_base[0], b_desc = b_base[0];
 #pragma unroll
           for (int i = 1; i < STAGES; ++i) {
@@ -262,6 +281,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
           umma_commit(&sm.empty[s]);
         }
         umma_commit(&sm.tmem_full[acc]);
+        PN_DBG(3);
       }
     }
     __syncwarp();
@@ -283,6 +303,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
       named_bar_sync(2, kEpilogueThreads);
       mbar_wait_relaxed(&sm.tmem_full[acc], acc_ph);
       tcgen05_fence_after();
+      if (etid == 0) PN_DBG(4);
       const int row = m_tile * BLOCK_M + e * 32 + lane;
       const bool row_ok = row < rows;
       bool border = false;
@@ -380,6 +401,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
       }
       tcgen05_fence_before();
       mbar_arrive(&sm.tmem_empty[acc]);
+      if (etid == 0) PN_DBG(5);
     }
   }
   tcgen05_fence_before();
@@ -388,6 +410,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
     tcgen05_fence_after();
     tmem_dealloc<TCOLS>(tmem_base);
   }
+  if (threadIdx.x == 0) PN_DBG(6);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -469,8 +492,55 @@ int launch(const CUtensorMap& map_w, const CUtensorMap& map_a, const KArgs& ka, 
                                  (int)smem));
     configured = true;
   }
-  k_conv_tc<BN, STAGES, TMA_A><<<grid, kThreads, smem, stream>>>(map_w, map_a, ka);
+  static const bool timeline = [] { const char* e = getenv("PN_CONV_TIMELINE"); return e && e[0] == '1'; }();
+  static unsigned long long* dbg_buf = nullptr;
+  KArgs ka_dbg = ka;
+  if (timeline) {
+    if (!dbg_buf) PN_CUDA(cudaMalloc(&dbg_buf, 8 * 1024 * sizeof(unsigned long long)));
+    PN_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * 1024 * sizeof(unsigned long long), stream));
+    PN_CUDA(cudaStreamSynchronize(stream));
+    ka_dbg.dbg = dbg_buf;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  PN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<BN, STAGES, TMA_A>, map_w, map_a, ka_dbg));
   PN_CHECK_LAUNCH();
+  if (timeline) {
+    PN_CUDA(cudaStreamSynchronize(stream));
+    static unsigned long long t[8 * 1024];
+    PN_CUDA(cudaMemcpy(t, dbg_buf, sizeof(t), cudaMemcpyDeviceToHost));
+    unsigned long long t_min = ~0ull, t_max = 0;
+    int n = 0;
+    for (int c = 0; c < grid; ++c) {
+      if (t[c * 8 + 3] == 0) continue;   // CTA without tiles
+      ++n;
+      if (t[c * 8] < t_min) t_min = t[c * 8];
+      if (t[c * 8 + 6] > t_max) t_max = t[c * 8 + 6];
+    }
+    double s_first = 0, s_mma = 0, s_epi = 0, s_tot = 0, m_mma = 0, m_tot = 0, s_setup = 0;
+    for (int c = 0; c < grid; ++c) {
+      const unsigned long long* q = t + c * 8;
+      if (q[3] == 0) continue;
+      const double fi = (double)(q[2] - q[1]), mm = (double)(q[3] - q[2]), ep = (double)(q[5] - q[4]),
+                   to = (double)(q[6] - q[0]);
+      s_setup += (double)(q[1] - q[0]); s_first += fi; s_mma += mm; s_epi += ep; s_tot += to;
+      if (mm > m_mma) m_mma = mm;
+      if (to > m_tot) m_tot = to;
+    }
+    if (n > 0)
+      fprintf(stderr, "[conv_tc<%d,%d> cin %d cout %d taps %d rows_cap %d grid %d busy %d] span %.1f us | setup avg %.1f | "
+                      "first operands avg %.1f | mma phase avg %.1f max %.1f | last epilogue avg %.1f | CTA total avg %.1f max %.1f\n",
+              BN, STAGES, ka.cin, ka.cout, ka.taps, ka.rows_cap, grid, n, (t_max - t_min) / 1e3, s_setup / n / 1e3,
+              s_first / n / 1e3, s_mma / n / 1e3, m_mma / 1e3, s_epi / n / 1e3, s_tot / n / 1e3, m_tot / 1e3);
+  }
   return PN_OK;
 }
 
@@ -545,6 +615,7 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
   ka.out_wp = a->out_wp;
   ka.in_rows = a->in_rows;
   ka.cin_shift = -1;
+  ka.dbg = nullptr;
   for (int sft = 3; sft < 16; ++sft)
     if ((1 << sft) == a->cin) ka.cin_shift = sft;
   if (a->in_rows > 0 && (long long)a->in_rows * a->in_ld * 2 >= (1ll << 32)) return PN_ERR_UNSUPPORTED;

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pn_tc {
@@ -156,4 +158,21 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Programmatic dependent launch (PDL): a kernel launched with programmaticStreamSerialization may start while
+// its stream predecessor is still running; it must execute griddepcontrol.wait before touching anything the
+// predecessor (transitively: any earlier kernel) produced or still reads.  launch_dependents lets OUR
+// successor be scheduled early.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PN_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 }  // namespace pn_tc

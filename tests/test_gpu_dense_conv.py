@@ -58,13 +58,15 @@ def test_descriptor_window_mode_probe():
     assert min(errs.values()) <= 2e-3
 
 
+@pytest.mark.parametrize("cluster", [0x800, 0x200, 0x400])   # weight-tile multicast over 1 / 2 / 4 CTAs
 @pytest.mark.parametrize("tile", [1, 2, 3, 4])
-@pytest.mark.parametrize("B,H,W,cin,cout", [(1, 20, 24, 64, 64), (2, 33, 17, 128, 256), (1, 45, 45, 256, 160)])
-def test_dense_conv_vs_torch(tile, B, H, W, cin, cout):
+@pytest.mark.parametrize("B,H,W,cin,cout", [(1, 20, 24, 64, 64), (2, 33, 17, 128, 256), (1, 45, 45, 256, 160),
+                                            (3, 61, 50, 64, 320)])
+def test_dense_conv_vs_torch(cluster, tile, B, H, W, cin, cout):
     if tile in (1, 2) and cout <= 128:
         pytest.skip("BN=256 tiles are not offered for cout <= 128")
-    assert _run(B, H, W, cin, cout, tile, False, torch.float32) <= 2e-3
-    assert _run(B, H, W, cin, cout, tile, True, torch.bfloat16, in_extra=64) <= 1e-2
+    assert _run(B, H, W, cin, cout, tile | cluster, False, torch.float32) <= 2e-3
+    assert _run(B, H, W, cin, cout, tile | cluster, True, torch.bfloat16, in_extra=64) <= 1e-2
 
 
 def test_dense_conv_auto_tile_full_size():

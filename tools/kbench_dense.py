@@ -19,16 +19,21 @@ def timeit(fn, iters=20, warm=3):
     return ts[len(ts) // 2]
 
 
-res = []
-for (H, cin, cout) in [(180, 256, 256), (90, 256, 256), (180, 64, 2304), (180, 512, 256), (180, 256, 64)]:
-    rows = torch.randn((H + 2) * (H + 2), cin, device="cuda").to(torch.bfloat16)
-    w = ops.pack_weight_bf16(torch.randn(cout, 9 * cin, device="cuda") * 0.02)
-    out = torch.empty((H + 2) * (H + 2), cout, device="cuda", dtype=torch.bfloat16)
-    for hint in (0, 1, 2, 3, 4):
-        if hint in (1, 2) and cout <= 128:
-            continue
-        us = timeit(lambda: ops.conv_dense3x3(rows, 0, cin, 1, H, H, w, cout, out, relu=True, tile_hint=hint))
-        res.append(dict(H=H, cin=cin, cout=cout, hint=hint, us=round(us, 1),
-                        tflops=round(2.0 * H * H * 9 * cin * cout / us / 1e6, 1)))
-        print(res[-1], flush=True)
-json.dump(res, open("gpurun_out/kbench_dense.json", "w"))
+def main():
+    res = []
+    for (H, cin, cout) in [(180, 256, 256), (90, 256, 256), (180, 64, 2304), (180, 512, 256), (180, 256, 64)]:
+        rows = torch.randn((H + 2) * (H + 2), cin, device="cuda").to(torch.bfloat16)
+        w = ops.pack_weight_bf16(torch.randn(cout, 9 * cin, device="cuda") * 0.02)
+        out = torch.empty((H + 2) * (H + 2), cout, device="cuda", dtype=torch.bfloat16)
+        for hint in (0, 1, 2, 3, 4, 0x801, 0x802, 0x803, 0x804, 0x401, 0x402, 0x403, 0x404):   # 0x8xx: no cluster, 0x4xx: cluster 4
+            if (hint & 0xF) in (1, 2) and cout <= 128:
+                continue
+            us = timeit(lambda: ops.conv_dense3x3(rows, 0, cin, 1, H, H, w, cout, out, relu=True, tile_hint=hint))
+            res.append(dict(H=H, cin=cin, cout=cout, hint=hex(hint), us=round(us, 1),
+                            tflops=round(2.0 * H * H * 9 * cin * cout / us / 1e6, 1)))
+            print(res[-1], flush=True)
+    json.dump(res, open("gpurun_out/kbench_dense.json", "w"))
+
+
+if __name__ == "__main__":
+    main()
