@@ -203,21 +203,26 @@ int pn_conv3x3_small_cout(const void* in, int in_ld, int cin, int n_frames, int 
  * weight: bf16 [cout][k_pad] (tap-major, k_pad >= 9*cin, multiple of 64) as pn_conv_pack_weight_bf16 makes
  * out: padded rows again (borders written as zeros; out_compact = 0) or compact rows
  *      b*H*W + y*W + x (out_compact = 1); bf16 or f32; columns [out_coff, out_coff+cout).
+ * out_group_cols = gc > 0: planar output for a following grouped conv — output channels [g*gc, (g+1)*gc) go to
+ *      their own contiguous padded map; the maps are stacked as one (cout/gc * n_rows, gc) matrix (out_ld = gc,
+ *      out_coff = 0, out_compact = 0).  Each group's activations are then contiguous in memory.
  * cin % 64 == 0.  tile_hint: 0 = automatic tile shape (1..4 force one; testing only). */
 int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_frames, int H, int W,
                      const void* weight, int k_pad, int cout, const float* scale, const float* shift,
-                     void* out, int out_dtype, int out_ld, int out_coff, int out_compact, int relu,
-                     int tile_hint, pn_stream_t stream);
+                     void* out, int out_dtype, int out_ld, int out_coff, int out_compact, int out_group_cols,
+                     int relu, int tile_hint, pn_stream_t stream);
 
 /* Grouped form of pn_conv_dense3x3: n_groups independent 3x3 convs in one launch (the last conv of every
  * CenterHead branch, center_head.py:34-35).  Group g reads channels [in_coff + g*cin, +cin) of the padded
  * input, uses weight rows [16g, 16g+16) of the bf16 [n_groups*16][k_pad] matrix (rows >= its cout are
  * zero) and scale/shift entries [16g, 16g+16), and writes group_tab[g] = {first output column, cout}
- * (device int32 [n_groups][2]) columns of `out`.  cin % 64 == 0, cout <= 16. */
+ * (device int32 [n_groups][2]) columns of `out`.  cin % 64 == 0, cout <= 16.
+ * in_planar != 0: `in` is the planar layout pn_conv_dense3x3 writes with out_group_cols = cin (in_ld = cin,
+ * in_coff = 0): group g reads its own contiguous map. */
 int pn_conv_dense3x3_grouped(const void* in, int in_ld, int in_coff, int cin, int n_groups, int n_frames, int H,
                              int W, const void* weight, int k_pad, const float* scale, const float* shift,
                              const int* group_tab, void* out, int out_dtype, int out_ld, int out_compact,
-                             int relu, pn_stream_t stream);
+                             int relu, int in_planar, pn_stream_t stream);
 
 /* Backward of pn_conv_gather (spconv's autograd for SubMConv2d / SparseConv2d, external in the reference).
  * pn_rulebook_transpose: nbr_t[i*taps + t] = o  <=>  nbr[o*taps + t] = i  (else -1): the input-stationary

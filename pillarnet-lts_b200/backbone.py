@@ -86,8 +86,37 @@ class Sparse2DBasicBlock(nn.Module):
         return _subm(out, self.conv2, relu=True, residual=x.feat)
 
 
-def _run_stage(sp, stage):
-    """Runs one `convN` SparseSequential: optional [SparseConv2d, BN, SparseReLU] head then blocks."""
+_side_streams = {}
+
+
+def _prefetch_rulebooks(table, n_levels):
+    """Rulebooks depend only on the active-site sets, not on features: all strided levels (and their submanifold
+    tables) are built on a side stream while the main stream runs the first stage's convs.  Returns
+    [(out_table, nbr_down, ready_event)] per level.  Fork/join is by events, so it is CUDA-graph capturable."""
+    main = torch.cuda.current_stream()
+    dev = table.coords.device
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(main)                  # the level-0 table was produced on the main stream
+    out = []
+    with torch.cuda.stream(side):
+        t = table
+        for _ in range(n_levels):
+            ot, nbr = ops.rulebook_down3x3s2(t)
+            sub = ot.subm_nbr()
+            ev = torch.cuda.Event()
+            ev.record(side)
+            for x in (ot.words, ot.prefix, ot.coords, ot.num, nbr, sub):
+                x.record_stream(main)       # allocated on the side stream, consumed on the main stream
+            out.append((ot, nbr, ev))
+            t = ot
+    return out
+
+
+def _run_stage(sp, stage, pre=None):
+    """Runs one `convN` SparseSequential: optional [SparseConv2d, BN, SparseReLU] head then blocks.
+    pre = (out_table, nbr, event) when the level's rulebook was prefetched on the side stream."""
     mods = list(stage)
     i = 0
     if isinstance(mods[0], SparseConv2d):
@@ -97,7 +126,11 @@ def _run_stage(sp, stage):
             for m in mods[3:]:
                 sp = m(sp)
             return sp
-        out_table, nbr = ops.rulebook_down3x3s2(sp.table)
+        if pre is not None:
+            out_table, nbr, ev = pre
+            torch.cuda.current_stream().wait_event(ev)
+        else:
+            out_table, nbr = ops.rulebook_down3x3s2(sp.table)
         lw = lower(conv, bn)
         feat = run_conv(sp.feat, lw, nbr, 9, conv.in_channels, conv.out_channels, out_table.cap,
                         num=out_table.num, relu=True, rows_hint=_rows_hint(out_table))
@@ -155,10 +188,14 @@ class _PillarResNet(nn.Module):
             self.backbone_strides["conv5"] = 16
 
     def forward(self, sp_tensor):
+        pre = [None, None, None]
+        if not self.training and config.overlap_rulebooks():
+            sp_tensor.table.subm_nbr()                      # needed at once by conv1: main stream
+            pre = _prefetch_rulebooks(sp_tensor.table, 3)
         x1 = _run_stage(sp_tensor, self.conv1)
-        x2 = _run_stage(x1, self.conv2)
-        x3 = _run_stage(x2, self.conv3)
-        x4 = _run_stage(x3, self.conv4)
+        x2 = _run_stage(x1, self.conv2, pre[0])
+        x3 = _run_stage(x2, self.conv3, pre[1])
+        x4 = _run_stage(x3, self.conv4, pre[2])
         feats = {"conv1": x1, "conv2": x2, "conv3": x3, "conv4": x4}
         if self.training:
             if self.DENSE:

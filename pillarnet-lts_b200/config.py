@@ -3,6 +3,7 @@
 "fp32": fp32 activations/weights, fp32 FMA kernels (PN_IMPL_SIMT) — the 1e-3 parity mode.
 "bf16": bf16 activations/weights, fp32 accumulation in TMEM on tcgen05 (PN_IMPL_TCGEN05) — the fast mode.
 """
+import os
 import torch
 
 from ._lib import PN_IMPL_SIMT, PN_IMPL_TCGEN05
@@ -27,3 +28,11 @@ def act_dtype():
 
 def conv_impl():
     return PN_IMPL_SIMT if _precision == "fp32" else PN_IMPL_TCGEN05
+
+
+_overlap_rulebooks = os.environ.get("PN_OVERLAP_RULEBOOKS", "1") != "0"
+
+
+def overlap_rulebooks():
+    """build the strided-level rulebooks on a side stream, concurrently with the first stage's convs"""
+    return _overlap_rulebooks

@@ -216,6 +216,11 @@ struct DArgs {
   // [in_coff + g*cin, +cin), weight rows [g*BN, +BN), writing group_tab[g] = {out_coff, cout} columns
   int n_groups;
   const int* group_tab;
+  // group-major ("planar") intermediate: channels [g*gc, (g+1)*gc) of a logical (rows, C) matrix live in
+  // their own contiguous (n_pos, gc) map, map g at row offset g*n_pos of one tall (G*n_pos, gc) matrix.
+  // out_group_cols > 0: this conv WRITES that layout (out_ld = gc); in_planar != 0: the grouped conv READS it.
+  int out_group_cols;
+  int in_planar;
   // development aid (PN_DENSE_TIMELINE=1): CTA 0 records %globaltimer at its pipeline milestones
   unsigned long long* dbg;
 };
@@ -227,7 +232,7 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 }
 #define PN_DBG(slot)                                                        \
   do {                                                                      \
-    if (P.dbg) P.dbg[blockIdx.x * 8 + slot] = gtime_ns();                   \
+    if (P.dbg) P.dbg[blockIdx.x * 16 + slot] = gtime_ns();                   \
   } while (0)
 
 template <int MT, int BN, int SA, int SB>
@@ -250,7 +255,10 @@ struct DSmem {
 // weight tile is fetched once per cluster — each CTA loads BN/CL rows and TMA-multicasts them into all CL
 // shared memories — so weight bytes per CTA drop CL-fold (the kernel is L2->SM bound and weights are ~75 % of
 // its traffic at BN = 256).  A weight stage is recycled only after all CL consumers released it (multicast commit).
-template <int MT, int BN, int SA, int SB, int CL>
+// BS ("B stationary", grouped mode only): the CTA works on ONE group (g = blockIdx.x % n_groups) for all its row
+// tiles, so the group's nine weight tiles are loaded once into the SB (>= 9) weight slots and never recycled —
+// no per-tap weight TMA, barrier wait or commit in the steady state.
+template <int MT, int BN, int SA, int SB, int CL, bool BS = false>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_constant__ CUtensorMap tmap_a_tail,
              const __grid_constant__ CUtensorMap tmap_w, const DArgs P) {
@@ -271,9 +279,14 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
   const int n_m_tiles = (P.n_pos + M_TILE - 1) / M_TILE;
   // work unit = (N tile, group of CL consecutive row tiles); CTA `rank` of the cluster takes row tile
   // m_group*CL + rank (past the end for the last group: its loads are zero-filled, its stores masked)
-  const int n_tiles = ((n_m_tiles + CL - 1) / CL) * n_n_tiles;
+  static_assert(!BS || (CL == 1 && SB >= 9), "B-stationary mode: no cluster, one slot per tap");
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+  // BS: the loop variable is the row tile itself; CTAs sharing a group interleave over its row tiles
+  const int g_fixed = BS ? (int)(blockIdx.x % n_n_tiles) : 0;
+  const int ctas_of_g = BS ? ((int)gridDim.x - 1 - g_fixed) / n_n_tiles + 1 : 1;
+  const int n_tiles = BS ? n_m_tiles : ((n_m_tiles + CL - 1) / CL) * n_n_tiles;
+  const int unit0 = BS ? (int)(blockIdx.x / n_n_tiles) : (int)(blockIdx.x / CL);
+  const int unit_step = BS ? ctas_of_g : (int)(gridDim.x / CL);
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
   const int n_cc = P.cin / BLOCK_K;
 
@@ -299,15 +312,19 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       pdl_wait();
       uint32_t g = 0;
       for (int tile = unit0; tile < n_tiles; tile += unit_step) {
-        const int m_tile = (tile / n_n_tiles) * CL + crank;
+        const int m_tile = BS ? tile : (tile / n_n_tiles) * CL + crank;
         const int q0 = m_tile * M_TILE;
-        const int ch0 = P.in_coff + (P.n_groups > 0 ? (tile % n_n_tiles) * P.cin : 0);
+        const int grp = BS ? g_fixed : (P.n_groups > 0 ? tile % n_n_tiles : 0);
+        const int ch0 = P.in_coff + (P.in_planar ? 0 : grp * P.cin);
+        // planar input: group g's map starts g*n_pos rows further down; rows that fall outside a map land in the
+        // zero border rows of the neighbouring map (or outside the matrix: TMA zero fill) — zeros either way
+        const int row_base = P.in_planar ? grp * P.n_pos : 0;
         for (int cc = 0; cc < n_cc; ++cc) {
           for (int dy = 0; dy < 3; ++dy, ++g) {
             const uint32_t s = g % SA, ph = (g / SA) & 1u;
             mbar_wait(&sm.empty_a[s], ph ^ 1u);
             mbar_arrive_expect_tx(&sm.full_a[s], (uint32_t)(S::kSegRows * 128));
-            const int row = q0 + (dy - 1) * P.Wp - 1;   // may be negative / past the end: TMA zero-fills
+            const int row = row_base + q0 + (dy - 1) * P.Wp - 1;   // may be negative / past the end: TMA zero-fills
             const int ch = ch0 + cc * BLOCK_K;
             tma_load_2d(smem_u32(sm.a[s]), &tmap_a_main, ch, row, &sm.full_a[s]);
             tma_load_2d(smem_u32(sm.a[s]) + M_TILE * 128, &tmap_a_tail, ch, row + M_TILE, &sm.full_a[s]);
@@ -317,7 +334,13 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== weight tiles (TMA) =====================
-    if (lane == 0) {
+    if (lane == 0 && BS) {
+      if (unit0 < n_tiles) {   // a CTA without row tiles must not leave a TMA in flight
+        mbar_arrive_expect_tx(&sm.full_b[0], (uint32_t)(9 * BN * 128));
+        for (int tap = 0; tap < 9; ++tap)
+          tma_load_2d(smem_u32(sm.b[tap]), &tmap_w, tap * P.cin, g_fixed * BN, &sm.full_b[0]);
+      }
+    } else if (lane == 0) {
       uint32_t g = 0;
       for (int tile = unit0; tile < n_tiles; tile += unit_step) {
         const int n_tile = tile % n_n_tiles;
@@ -351,10 +374,18 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
 #pragma unroll
       for (int i = 0; i < SB; ++i) b_base[i] = make_desc(smem_u32(sm.b[i]), 0);
       uint32_t ga = 0, gb = 0, tcount = 0;
+      long long w_acc = 0, w_a = 0, w_b = 0, c0 = 0;
+      if (BS && unit0 < n_tiles) {
+        mbar_wait(&sm.full_b[0], 0);
+        tcgen05_fence_after();
+        PN_DBG(2);
+      }
       for (int tile = unit0; tile < n_tiles; tile += unit_step, ++tcount) {
         const uint32_t acc = NACC == 2 ? (tcount & 1u) : 0u;
         const uint32_t acc_ph = NACC == 2 ? ((tcount >> 1) & 1u) : (tcount & 1u);
+        if (P.dbg) c0 = clock64();
         mbar_wait(&sm.tmem_empty[acc], acc_ph ^ 1u);
+        if (P.dbg) w_acc += clock64() - c0;
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         for (int cc = 0; cc < n_cc; ++cc) {
@@ -362,20 +393,32 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
           for (int dy = 0; dy < 3; ++dy) {
             const uint32_t sa = ga % SA, pha = (ga / SA) & 1u;
             ++ga;
+            if (P.dbg) c0 = clock64();
             mbar_wait(&sm.full_a[sa], pha);
+            if (P.dbg) w_a += clock64() - c0;
             uint64_t a_stage = a_base[0];
 #pragma unroll
             for (int i = 1; i < SA; ++i) a_stage = (sa == (uint32_t)i) ? a_base[i] : a_stage;
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-              const uint32_t sb = gb % SB, phb = (gb / SB) & 1u;
-              ++gb;
-              mbar_wait(&sm.full_b[sb], phb);
-              tcgen05_fence_after();
-              if (gb == 1) PN_DBG(2);
-              uint64_t b_stage = b_base[0];
+              uint32_t sb = 0;
+              uint64_t b_stage;
+              if constexpr (BS) {
+                b_stage = b_base[dy * 3 + dx];     // compile-time slot: dy, dx are unrolled
+                if (dx == 0) tcgen05_fence_after();
+              } else {
+                sb = gb % SB;
+                const uint32_t phb = (gb / SB) & 1u;
+                ++gb;
+                if (P.dbg) c0 = clock64();
+                mbar_wait(&sm.full_b[sb], phb);
+                if (P.dbg) w_b += clock64() - c0;
+                tcgen05_fence_after();
+                if (gb == 1) PN_DBG(2);
+                b_stage = b_base[0];
 #pragma unroll
-              for (int i = 1; i < SB; ++i) b_stage = (sb == (uint32_t)i) ? b_base[i] : b_stage;
+                for (int i = 1; i < SB; ++i) b_stage = (sb == (uint32_t)i) ? b_base[i] : b_stage;
+              }
               const uint32_t first = (dy == 0 && dx == 0) ? (cc != 0 ? 1u : 0u) : 1u;
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
@@ -387,13 +430,21 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
                   umma_bf16(d_tmem + m * BN, a_desc, b_desc, idesc, k == 0 ? first : 1u);
                 }
               }
-              if (CL == 1) umma_commit(&sm.empty_b[sb]); else umma_commit_mc(&sm.empty_b[sb], kMask);
+              if constexpr (!BS) {
+                if (CL == 1) umma_commit(&sm.empty_b[sb]); else umma_commit_mc(&sm.empty_b[sb], kMask);
+              }
             }
             umma_commit(&sm.empty_a[sa]);
           }
         }
         umma_commit(&sm.tmem_full[acc]);
         PN_DBG(3);
+      }
+      if (P.dbg) {
+        P.dbg[blockIdx.x * 16 + 8] = (unsigned long long)w_acc;
+        P.dbg[blockIdx.x * 16 + 9] = (unsigned long long)w_a;
+        P.dbg[blockIdx.x * 16 + 10] = (unsigned long long)w_b;
+        P.dbg[blockIdx.x * 16 + 11] = tcount;
       }
     }
     __syncwarp();
@@ -405,7 +456,8 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
     uint32_t tcount = 0;
     pdl_wait();
     for (int tile = unit0; tile < n_tiles; tile += unit_step, ++tcount) {
-      const int n_tile = tile % n_n_tiles, m_tile = (tile / n_n_tiles) * CL + crank;
+      const int n_tile = BS ? g_fixed : tile % n_n_tiles;
+      const int m_tile = BS ? tile : (tile / n_n_tiles) * CL + crank;
       const int n0 = n_tile * BN;          // first weight row / scale index of this N tile
       int cout_t = P.cout, ocol0 = P.out_coff + n0, nbase = n0;
       if (P.n_groups > 0) {                // grouped: own output columns and channel count
@@ -439,24 +491,39 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
           store = valid && !border;
           orow = ((long long)b * (P.Hp - 2) + (y - 1)) * (P.Wp - 2) + (x - 1);
         }
-#pragma unroll 1
+        // software-pipelined over column chunks: the TMEM load of chunk c+1 is in flight while chunk c is
+        // converted and stored (tcgen05.wait::ld only covers loads issued before it)
         constexpr int CH = BN < 32 ? 16 : 32;
-        for (int c0 = 0; c0 < BN; c0 += CH) {
-          if (nbase + c0 >= cout_t) break;  // warp-uniform
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * ACC_COLS + m * BN + c0;
-          if (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+        const int n_ch = min(BN, cout_t - nbase + CH - 1) / CH;   // warp-uniform number of live chunks
+        const uint32_t tbase = tmem_base + ((uint32_t)(e * 32) << 16) + acc * ACC_COLS + m * BN;
+        uint32_t v[32], w[32];
+        if (n_ch > 0) {
+          if (CH == 32) tmem_ld32(tbase, v); else tmem_ld16(tbase, v);
+        }
+#pragma unroll 1
+        for (int ci = 0; ci < n_ch; ++ci) {
+          const int c0 = ci * CH;
           tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < CH; ++j) w[j] = v[j];
+          if (ci + 1 < n_ch) {
+            if (CH == 32) tmem_ld32(tbase + c0 + CH, v); else tmem_ld16(tbase + c0 + CH, v);
+          }
           if (store) {
             const int nvalid = min(CH, cout_t - (nbase + c0));
             float f[32];
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
-              float t = fmaf(__uint_as_float(v[j]), sm.scale[c0 + j], sm.shift[c0 + j]);
+              float t = fmaf(__uint_as_float(w[j]), sm.scale[c0 + j], sm.shift[c0 + j]);
               if (P.relu) t = fmaxf(t, 0.f);
               f[j] = (border && !P.out_compact) ? 0.f : t;
             }
-            const long long ooff = orow * P.out_ld + ocol0 + c0;
+            long long ooff = orow * P.out_ld + ocol0 + c0;
+            if (P.out_group_cols > 0) {   // planar output: a CH-wide chunk never straddles two maps (gc % CH == 0)
+              const int col = ocol0 + c0;
+              const int g = col / P.out_group_cols;
+              ooff = ((long long)g * P.n_pos + orow) * P.out_ld + (col - g * P.out_group_cols);
+            }
             if (P.out_f32) {
               float* op = reinterpret_cast<float*>(P.out) + ooff;
               if (nvalid == CH && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
@@ -567,14 +634,14 @@ int get_map(const void* base, long long rows, int cols, int ld, int box_rows, CU
 }
 
 // `units` = work units (see the kernel); the grid is CL x min(units, co-resident clusters).
-template <int MT, int BN, int SA, int SB, int CL = 1>
+template <int MT, int BN, int SA, int SB, int CL = 1, bool BS = false>
 int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, const DArgs& a, long long units,
            cudaStream_t stream) {
   constexpr size_t smem = sizeof(DSmem<MT, BN, SA, SB>) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static_assert(CL == 1 || (BN / CL) % 8 == 0, "a weight slice must keep the 8-row swizzle period");
   static int max_clusters = 0;
-  auto kern = k_conv_dense<MT, BN, SA, SB, CL>;
+  auto kern = k_conv_dense<MT, BN, SA, SB, CL, BS>;
   if (max_clusters == 0) {
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int sms = pn_detail::sm_count();
@@ -600,8 +667,8 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, 
   static unsigned long long* dbg_buf = nullptr;
   DArgs a_dbg = a;
   if (timeline) {
-    if (!dbg_buf) PN_CUDA(cudaMalloc(&dbg_buf, 8 * 1024 * sizeof(unsigned long long)));   // device memory: no page faults
-    PN_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * 1024 * sizeof(unsigned long long), stream));
+    if (!dbg_buf) PN_CUDA(cudaMalloc(&dbg_buf, 16 * 1024 * sizeof(unsigned long long)));   // device memory: no page faults
+    PN_CUDA(cudaMemsetAsync(dbg_buf, 0, 16 * 1024 * sizeof(unsigned long long), stream));
     PN_CUDA(cudaStreamSynchronize(stream));
     a_dbg.dbg = dbg_buf;
   }
@@ -628,17 +695,17 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, 
   PN_CHECK_LAUNCH();
   if (timeline) {
     PN_CUDA(cudaStreamSynchronize(stream));
-    static unsigned long long t[8 * 1024];
+    static unsigned long long t[16 * 1024];
     PN_CUDA(cudaMemcpy(t, dbg_buf, sizeof(t), cudaMemcpyDeviceToHost));
     const int n = clusters * CL;
     unsigned long long t_min = ~0ull, t_max = 0;
     for (int c = 0; c < n; ++c) {
-      if (t[c * 8] < t_min) t_min = t[c * 8];
-      if (t[c * 8 + 6] > t_max) t_max = t[c * 8 + 6];
+      if (t[c * 16] < t_min) t_min = t[c * 16];
+      if (t[c * 16 + 6] > t_max) t_max = t[c * 16 + 6];
     }
     double s_start = 0, s_first = 0, s_mma = 0, s_epi = 0, s_tot = 0, m_start = 0, m_mma = 0, m_tot = 0, m_epi = 0;
     for (int c = 0; c < n; ++c) {
-      const unsigned long long* q = t + c * 8;
+      const unsigned long long* q = t + c * 16;
       const double st = (double)(q[0] - t_min), fi = (double)(q[2] - q[1]), mm = (double)(q[3] - q[2]),
                    ep = (double)(q[5] - q[4]), to = (double)(q[6] - q[0]);
       s_start += st; s_first += fi; s_mma += mm; s_epi += ep; s_tot += to;
@@ -646,6 +713,12 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, 
       if (mm > m_mma) m_mma = mm;
       if (to > m_tot) m_tot = to;
       if (ep > m_epi) m_epi = ep;
+    }
+    {
+      double wa = 0, wb = 0, wc = 0, tl = 0;
+      for (int c = 0; c < n; ++c) { wc += (double)t[c * 16 + 8]; wa += (double)t[c * 16 + 9]; wb += (double)t[c * 16 + 10]; tl += (double)t[c * 16 + 11]; }
+      fprintf(stderr, "   MMA warp waits (avg kclk per CTA): accumulator %.1f | A operands %.1f | B operands %.1f | tiles/CTA %.1f\n",
+              wc / n / 1e3, wa / n / 1e3, wb / n / 1e3, tl / n);
     }
     fprintf(stderr, "[dense<%d,%d,%d,%d,cl%d> grid %d units %lld] span %.1f us | CTA start skew avg %.1f max %.1f | first "
                     "operands avg %.1f | mma phase avg %.1f max %.1f | last epilogue avg %.1f max %.1f | CTA total avg %.1f "
@@ -662,13 +735,16 @@ extern "C" {
 
 int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_frames, int H, int W,
                      const void* weight, int k_pad, int cout, const float* scale, const float* shift,
-                     void* out, int out_dtype, int out_ld, int out_coff, int out_compact, int relu,
-                     int tile_hint, pn_stream_t stream_) {
+                     void* out, int out_dtype, int out_ld, int out_coff, int out_compact, int out_group_cols,
+                     int relu, int tile_hint, pn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   PN_REQUIRE(in && weight && out && n_frames >= 1 && H > 0 && W > 0 && cout >= 1);
   PN_REQUIRE(cin % BLOCK_K == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && k_pad % BLOCK_K == 0 && k_pad >= 9 * cin);
   PN_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15u) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15u) == 0);
   PN_REQUIRE(out_dtype == PN_F32 || out_dtype == PN_BF16);
+  // planar output: padded rows only, whole maps, 32-column chunks must not straddle maps
+  PN_REQUIRE(out_group_cols == 0 || (out_group_cols % 32 == 0 && !out_compact && out_coff == 0 &&
+                                     cout % out_group_cols == 0 && out_ld == out_group_cols));
   const int Hp = H + 2, Wp = W + 2;
   const long long n_pos = (long long)n_frames * Hp * Wp;
   PN_REQUIRE(n_pos < (1ll << 31));
@@ -717,6 +793,8 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
   a.n_groups = 0;
   a.group_tab = nullptr;
   a.dbg = nullptr;
+  a.out_group_cols = out_group_cols;
+  a.in_planar = 0;
   const long long units = PN_DIVUP(m_tiles, (long long)cl) * PN_DIVUP(cout, bn);
 #define PN_DENSE_LAUNCH(MT_, BN_, SA_, SB_)                                                       \
   do {                                                                                            \
@@ -739,7 +817,7 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
 int pn_conv_dense3x3_grouped(const void* in, int in_ld, int in_coff, int cin, int n_groups, int n_frames, int H,
                              int W, const void* weight, int k_pad, const float* scale, const float* shift,
                              const int* group_tab, void* out, int out_dtype, int out_ld, int out_compact,
-                             int relu, pn_stream_t stream_) {
+                             int relu, int in_planar, pn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   PN_REQUIRE(in && weight && out && group_tab && n_groups >= 1 && n_frames >= 1 && H > 0 && W > 0);
   PN_REQUIRE(cin % BLOCK_K == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && k_pad % BLOCK_K == 0 && k_pad >= 9 * cin);
@@ -751,10 +829,12 @@ int pn_conv_dense3x3_grouped(const void* in, int in_ld, int in_coff, int cin, in
   const int sms = pn_detail::sm_count();
   if (sms <= 0) return PN_ERR_CUDA;
   constexpr int mt = 2, bn = 16;
+  PN_REQUIRE(!in_planar || (in_ld == cin && in_coff == 0 && n_pos * n_groups < (1ll << 31)));
+  const long long in_rows = in_planar ? n_pos * n_groups : n_pos;
   CUtensorMap ma, mtail, mw;
-  int rc = get_map(in, n_pos, in_ld, in_ld, 128 * mt, &ma);
+  int rc = get_map(in, in_rows, in_ld, in_ld, 128 * mt, &ma);
   if (rc != PN_OK) return rc;
-  rc = get_map(in, n_pos, in_ld, in_ld, kTailRows, &mtail);
+  rc = get_map(in, in_rows, in_ld, in_ld, kTailRows, &mtail);
   if (rc != PN_OK) return rc;
   rc = get_map(weight, (long long)n_groups * bn, k_pad, k_pad, bn, &mw);
   if (rc != PN_OK) return rc;
@@ -763,8 +843,10 @@ int pn_conv_dense3x3_grouped(const void* in, int in_ld, int in_coff, int cin, in
   a.scale = scale; a.shift = shift; a.out = out; a.out_f32 = out_dtype == PN_F32; a.out_ld = out_ld;
   a.out_coff = 0; a.out_compact = out_compact; a.relu = relu; a.base_offset_mode = 0;
   a.n_groups = n_groups; a.group_tab = group_tab; a.dbg = nullptr;
+  a.out_group_cols = 0; a.in_planar = in_planar;
   const long long tiles = PN_DIVUP(n_pos, (long long)(128 * mt)) * n_groups;
-  return launch<2, 16, 3, 8, 1>(ma, mtail, mw, a, tiles, stream);
+  if (cin == BLOCK_K && n_groups <= sms) return launch<2, 16, 6, 9, 1, true>(ma, mtail, mw, a, tiles, stream);   // weights stay resident
+  return launch<2, 16, 6, 8, 1>(ma, mtail, mw, a, tiles, stream);
 }
 
 }  // extern "C"

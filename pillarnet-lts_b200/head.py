@@ -132,11 +132,19 @@ class CenterHead(nn.Module):
             inter = None
             pad = feat.pad
             n_pix = feat.B * feat.H * feat.W
+            planar = False
             if two_level:
                 lw = lower_group([e[2][0] for e in two_level], [e[2][1] for e in two_level])
                 hc = two_level[0][2][0].out_channels
+                # every branch is a 2-conv stack with a tiny last conv: the tensor-core grouped conv follows, and
+                # it wants each branch's hc intermediate channels as one contiguous map (planar layout) — in the
+                # interleaved (pixel, n_heads*hc) layout a branch reads 128 B out of every 4.6 KB row
+                planar = (feat.pad and feat.rows.dtype == torch.bfloat16 and feat.C % 64 == 0 and feat.coff % 8 == 0
+                          and hc % 64 == 0 and len(two_level) == len(entries)
+                          and all(e[2][-1].out_channels <= 4 for e in entries))
                 # all first-level head convs of all tasks on this feature: one conv, Cout = n_heads*hc
-                inter = dense_conv3x3(feat, _GroupConv(hc * len(two_level)), None, relu=True, lowered=lw)
+                inter = dense_conv3x3(feat, _GroupConv(hc * len(two_level)), None, relu=True, lowered=lw,
+                                      planar_cols=hc if planar else 0)
             slot = {id(e[2]): i for i, e in enumerate(two_level)}
             # gather table of the final convs: reads the (possibly padded) intermediate, writes compact rows
             nbr = ops.dense_nbr_table(0, feat.B, feat.H, feat.W, 1, feat.rows.device, in_pad=bool(pad), out_pad=False)
@@ -155,7 +163,7 @@ class CenterHead(nn.Module):
                     # tensor-core grouped conv on the padded layout (reads the intermediate 3x, not 9x)
                     wg, sg, tab = self._final_groups_tc(fi, entries, slot, t_off, hc)
                     ops.conv_dense3x3_grouped(inter.rows, 0, hc, len(entries), feat.B, feat.H, feat.W, wg, sg, tab,
-                                              all_rows, out_compact=True)
+                                              all_rows, out_compact=True, in_planar=planar)
                 else:
                     groups, wbuf = self._final_groups(fi, entries, slot, t_off, hc)
                     ops.conv3x3_small_cout(inter.rows, inter.rows.stride(0), hc, feat.B, feat.H, feat.W, groups,

@@ -236,16 +236,27 @@ def new_dense_rows(B, H, W, width, dtype, device, pad):
 
 
 def dense_conv3x3(x, conv, bn, relu=True, stride=1, out=None, out_coff=0, out_dtype=None, out_compact=False,
-                  lowered=None):
+                  lowered=None, planar_cols=0):
     """3x3 pad-1 dense conv (also ZeroPad2d(1)+valid conv, necks/rpn.py:172-176) on a DenseMap.
     Padded maps + stride 1 run on the TMA-fed dense tensor-core kernel; everything else on the gather conv."""
     Ho, Wo = (x.H + 2 - 3) // stride + 1, (x.W + 2 - 3) // stride + 1
     lw = lowered if lowered is not None else lower(conv, bn)
     cout = conv.out_channels
     opad = 0 if out_compact else x.pad
+    tc_dense = x.pad and stride == 1 and x.C % 64 == 0 and x.coff % 8 == 0
+    if planar_cols:
+        # planar output (one contiguous padded map per `planar_cols` channels) for a following grouped conv
+        if not (tc_dense and opad and out is None and cout % planar_cols == 0):
+            raise RuntimeError("planar output needs the padded tensor-core path")
+        n_rows = x.B * (Ho + 2) * (Wo + 2)
+        out = torch.empty(cout // planar_cols * n_rows, planar_cols, dtype=out_dtype or x.rows.dtype,
+                          device=x.rows.device)
+        ops.conv_dense3x3(x.rows, x.coff, x.C, x.B, x.H, x.W, lw.weight, cout, out, scale=lw.scale, shift=lw.shift,
+                          relu=relu, out_group_cols=planar_cols)
+        return DenseMap(out, x.B, Ho, Wo, planar_cols, 0, opad)
     if out is None:
         out = new_dense_rows(x.B, Ho, Wo, cout, out_dtype or x.rows.dtype, x.rows.device, opad)
-    if x.pad and stride == 1 and x.C % 64 == 0 and x.coff % 8 == 0:
+    if tc_dense:
         ops.conv_dense3x3(x.rows, x.coff, x.C, x.B, x.H, x.W, lw.weight, cout, out, scale=lw.scale, shift=lw.shift,
                           out_coff=out_coff, out_compact=out_compact, relu=relu)
     else:

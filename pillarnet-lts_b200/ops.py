@@ -223,24 +223,25 @@ def conv3x3_small_cout(inp, in_ld, cin, n_frames, H, W, groups, n_groups, wbuf, 
 
 
 def conv_dense3x3(inp, in_coff, cin, n_frames, H, W, weight, cout, out, *, scale=None, shift=None, out_coff=0,
-                  out_compact=False, relu=False, tile_hint=0):
-    """3x3/s1/p1 conv on zero-padded NHWC rows (B*(H+2)*(W+2), ld) -> padded (or compact) rows; see the C header."""
+                  out_compact=False, relu=False, tile_hint=0, out_group_cols=0):
+    """3x3/s1/p1 conv on zero-padded NHWC rows (B*(H+2)*(W+2), ld) -> padded (or compact) rows; see the C header.
+    out_group_cols = gc: `out` is the planar (cout/gc * rows, gc) matrix (one contiguous map per channel group)."""
     lib = _lib.load()
     check(lib.pn_conv_dense3x3(ptr(inp), inp.stride(0), in_coff, cin, n_frames, H, W, ptr(weight), weight.stride(0),
                                cout, ptr(scale), ptr(shift), ptr(out), _DT[out.dtype], out.stride(0), out_coff,
-                               1 if out_compact else 0, 1 if relu else 0, tile_hint, stream_ptr()),
+                               1 if out_compact else 0, out_group_cols, 1 if relu else 0, tile_hint, stream_ptr()),
           "pn_conv_dense3x3")
     return out
 
 
 def conv_dense3x3_grouped(inp, in_coff, cin, n_groups, n_frames, H, W, weight, shift, group_tab, out, *,
-                          scale=None, out_compact=True, relu=False):
+                          scale=None, out_compact=True, relu=False, in_planar=False):
     """n_groups independent small-Cout 3x3 convs on padded NHWC rows in one tensor-core launch (C header)."""
     lib = _lib.load()
     check(lib.pn_conv_dense3x3_grouped(ptr(inp), inp.stride(0), in_coff, cin, n_groups, n_frames, H, W, ptr(weight),
                                        weight.stride(0), ptr(scale), ptr(shift), ptr(group_tab), ptr(out),
                                        _DT[out.dtype], out.stride(0), 1 if out_compact else 0, 1 if relu else 0,
-                                       stream_ptr()), "pn_conv_dense3x3_grouped")
+                                       1 if in_planar else 0, stream_ptr()), "pn_conv_dense3x3_grouped")
     return out
 
 

@@ -109,3 +109,41 @@ def test_grouped_small_cout_dense_conv_vs_torch():
         assert (got - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item()), i
         c0 += w.shape[0]
     assert bool((out[:, :3] == -9.0).all()) and bool((out[:, col:] == -9.0).all())
+
+
+def test_planar_intermediate_layout_matches_interleaved():
+    """pn_conv_dense3x3(out_group_cols=64) writes one contiguous padded map per 64 output channels, and
+    pn_conv_dense3x3_grouped(in_planar=1) reads it: both must equal the interleaved-layout results bit for bit."""
+    from pillarnet_lts_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, H, W, cin, G, hc = 2, 23, 31, 64, 5, 64
+    x = torch.randn(B, H, W, cin, device="cuda", generator=g).to(torch.bfloat16)
+    rows = _pad_rows(x)
+    n_rows = rows.shape[0]
+    w1 = ops.pack_weight_bf16(torch.randn(G * hc, 9 * cin, device="cuda", generator=g) * 0.05)
+    sc = torch.rand(G * hc, device="cuda", generator=g) + 0.5
+    sh = torch.randn(G * hc, device="cuda", generator=g) * 0.1
+    inter = torch.empty(n_rows, G * hc, device="cuda", dtype=torch.bfloat16)
+    ops.conv_dense3x3(rows, 0, cin, B, H, W, w1, G * hc, inter, scale=sc, shift=sh, relu=True)
+    planar = torch.full((G * n_rows, hc), 3.0, device="cuda", dtype=torch.bfloat16)
+    ops.conv_dense3x3(rows, 0, cin, B, H, W, w1, G * hc, planar, scale=sc, shift=sh, relu=True, out_group_cols=hc)
+    torch.cuda.synchronize()
+    assert torch.equal(planar.view(G, n_rows, hc).permute(1, 0, 2).reshape(n_rows, G * hc), inter)
+    couts = [2, 1, 3, 2, 4]
+    wf = torch.zeros(G * 16, 9 * hc, device="cuda")
+    bf = torch.zeros(G * 16, device="cuda")
+    tab, col = [], 0
+    for i, c in enumerate(couts):
+        wf[i * 16:i * 16 + c] = torch.randn(c, 9 * hc, device="cuda", generator=g) * 0.1
+        bf[i * 16:i * 16 + c] = torch.randn(c, device="cuda", generator=g)
+        tab.append([col, c])
+        col += c
+    wg = ops.pack_weight_bf16(wf)
+    tabd = torch.tensor(tab, dtype=torch.int32).cuda()
+    out_a = torch.full((B * H * W, col), -9.0, device="cuda")
+    out_b = torch.full((B * H * W, col), -9.0, device="cuda")
+    ops.conv_dense3x3_grouped(inter, 0, hc, G, B, H, W, wg, bf, tabd, out_a, out_compact=True)
+    ops.conv_dense3x3_grouped(planar, 0, hc, G, B, H, W, wg, bf, tabd, out_b, out_compact=True, in_planar=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out_a, out_b)
+    assert float(out_a.abs().max()) > 0.1

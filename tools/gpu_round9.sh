@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --profile-pass"
+PN_PDL=0 timeout 600 $CMD > /dev/null 2>&1 && PN_PDL=0 timeout 1500 ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:"k_conv_dense|k_conv_tc" -o gpurun_out/prof_convs_r1 -f $CMD > gpurun_out/ncu_convs.log 2>&1
+echo "ncu rc=$?"; tail -2 gpurun_out/ncu_convs.log

@@ -76,7 +76,7 @@ void run(int iters) {
 
 int main() {
   const int it = 2000;
-  run<64, 1, 0>(it); run<128, 1, 0>(it); run<256, 1, 0>(it);
+  run<16, 1, 0>(it); run<16, 2, 0>(it); run<32, 1, 0>(it); run<32, 2, 0>(it); run<64, 1, 0>(it); run<64, 2, 0>(it); run<128, 1, 0>(it); run<256, 1, 0>(it);
   run<128, 2, 0>(it); run<256, 2, 0>(it);
   run<128, 2, 4>(it); run<256, 2, 4>(it);
   run<128, 2, 16>(it); run<256, 2, 16>(it);
