@@ -14,8 +14,8 @@
 // 3x instead of 9x per tile and needs no rulebook; with MT = 2 the 256-row CTA also reuses every weight
 // tile for two MMAs, halving weight bytes per FLOP (the kernel is L2->SM-bandwidth bound).
 //
-// Warp roles (256 threads, persistent): warp 0 lane 0 = activation TMA producer, warp 1 lane 0 = weight
-// TMA producer, warp 2 = TMEM owner + MMA issuer, warps 4-7 = epilogue (folded BN/bias, ReLU, zeroed
+// Warp roles (384 threads, persistent): warp 0 lane 0 = activation TMA producer, warp 1 lane 0 = weight
+// TMA producer, warp 2 = TMEM owner + MMA issuer, warps 4-11 = epilogue (folded BN/bias, ReLU, zeroed
 // border rows so the output is again a valid padded map — or compact rows for consumers that want
 // un-padded NHWC).
 #include <cuda.h>
@@ -30,8 +30,8 @@
 namespace {
 
 constexpr int BLOCK_K = 64;
-constexpr int kThreads = 256;
-constexpr int kEpilogueThreads = 128;
+constexpr int kThreads = 384;            // warps 0-2: producers + MMA, 3: idle, 4-11: epilogue
+constexpr int kEpilogueThreads = 256;    // 8 warps: two per TMEM lane quarter, each takes every other column chunk
 constexpr int kTailRows = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -223,6 +223,7 @@ struct DArgs {
   int in_planar;
   // development aid (PN_DENSE_TIMELINE=1): CTA 0 records %globaltimer at its pipeline milestones
   unsigned long long* dbg;
+  int dbg_mode;   // development only: bit 0 = skip the global stores, bit 1 = skip the TMEM loads
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -450,7 +451,8 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
     __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int e = warp - 4;
+    const int e = (warp - 4) & 3;          // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = (warp - 4) >> 2;      // which of the two interleaved column-chunk sets
     const int etid = threadIdx.x - 4 * 32;
     const int hw_p = P.Hp * P.Wp;
     uint32_t tcount = 0;
@@ -497,19 +499,19 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
         const int n_ch = min(BN, cout_t - nbase + CH - 1) / CH;   // warp-uniform number of live chunks
         const uint32_t tbase = tmem_base + ((uint32_t)(e * 32) << 16) + acc * ACC_COLS + m * BN;
         uint32_t v[32], w[32];
-        if (n_ch > 0) {
-          if (CH == 32) tmem_ld32(tbase, v); else tmem_ld16(tbase, v);
+        if (half < n_ch && !(P.dbg_mode & 2)) {
+          if (CH == 32) tmem_ld32(tbase + half * CH, v); else tmem_ld16(tbase + half * CH, v);
         }
 #pragma unroll 1
-        for (int ci = 0; ci < n_ch; ++ci) {
+        for (int ci = half; ci < n_ch; ci += 2) {
           const int c0 = ci * CH;
-          tmem_wait_ld();
+          if (!(P.dbg_mode & 2)) tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < CH; ++j) w[j] = v[j];
-          if (ci + 1 < n_ch) {
-            if (CH == 32) tmem_ld32(tbase + c0 + CH, v); else tmem_ld16(tbase + c0 + CH, v);
+          if (ci + 2 < n_ch && !(P.dbg_mode & 2)) {
+            if (CH == 32) tmem_ld32(tbase + c0 + 2 * CH, v); else tmem_ld16(tbase + c0 + 2 * CH, v);
           }
-          if (store) {
+          if (store && !(P.dbg_mode & 1)) {
             const int nvalid = min(CH, cout_t - (nbase + c0));
             float f[32];
 #pragma unroll
@@ -662,10 +664,14 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, 
       max_clusters = n;
     }
   }
-  const int clusters = (int)(units < max_clusters ? units : max_clusters);
+  // balanced persistent grid: every CTA (cluster) gets the same number of work units (260 units on 148 SMs run
+  // as 130 x 2, not 148 with a ragged second wave)
+  const long long per_cta = PN_DIVUP(units, (long long)max_clusters);
+  const int clusters = (int)PN_DIVUP(units, per_cta);
   static const bool timeline = [] { const char* e = getenv("PN_DENSE_TIMELINE"); return e && e[0] == '1'; }();
   static unsigned long long* dbg_buf = nullptr;
   DArgs a_dbg = a;
+  { const char* e = getenv("PN_DENSE_DBGMODE"); a_dbg.dbg_mode = e ? atoi(e) : 0; }
   if (timeline) {
     if (!dbg_buf) PN_CUDA(cudaMalloc(&dbg_buf, 16 * 1024 * sizeof(unsigned long long)));   // device memory: no page faults
     PN_CUDA(cudaMemsetAsync(dbg_buf, 0, 16 * 1024 * sizeof(unsigned long long), stream));
@@ -762,11 +768,14 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
     const double waves = (double)PN_DIVUP(tiles, (long long)sms);
     const double bytes = bn * 128.0 + (128.0 * mt + kTailRows) * 128.0 / 3.0;
     const double mma = mt * 4.0 * (bn / 2.0);
-    // measured (tools/kbench_dense.py): ~40 B/clk/SM sustained from L2 when all SMs pull; BN=256 without a
-    // second accumulator buffer exposes the epilogue, which matters when K is short (cin = 64)
+    // measured (tools/kbench_dense.py, PN_DENSE_TIMELINE): ~40 B/clk/SM sustained from L2 when all SMs pull; the
+    // epilogue of a tile costs ~27 clk per (128-row block x column) — it is bound by the burst of global stores —
+    // and is hidden behind the next tile's MMAs only when TMEM holds two accumulators; the last one never is
     const double per_tap = bytes / 40.0 > mma ? bytes / 40.0 : mma;
-    const double epi = (2 * mt * bn > 512 ? 1.0 : 0.0) * (mt * bn * 6.0) / (9.0 * (cin / 64));
-    const double cost = waves * (per_tap + epi);
+    const double tile_clk = 9.0 * (cin / 64) * per_tap;
+    const double epi_clk = mt * bn * 27.0;
+    const bool two_acc = 2 * mt * bn <= 512;
+    const double cost = waves * tile_clk + (two_acc ? 1.0 : waves) * epi_clk;
     if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
   }
   if ((tile_hint & 0xF) >= 1 && (tile_hint & 0xF) <= 4) best = (tile_hint & 0xF) - 1;
