@@ -290,6 +290,11 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
   const int unit_step = BS ? ctas_of_g : (int)(gridDim.x / CL);
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
   const int n_cc = P.cin / BLOCK_K;
+  // K-loop rotation: CTA (cluster) c starts its (channel chunk, kernel row) walk at step c mod (3*n_cc).  With one
+  // tile per CTA every CTA would otherwise request the very same weight tile at the very same moment (130 SMs
+  // hitting one L2 line set); the accumulation order is free, so the walk is staggered instead.
+  const int n_u = 3 * n_cc;
+  const int rot = (BS || P.dbg_mode & 4) ? 0 : (int)((blockIdx.x / CL) % n_u);
 
   if (warp == 2) {
     if (lane == 0) {
@@ -320,8 +325,11 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
         // planar input: group g's map starts g*n_pos rows further down; rows that fall outside a map land in the
         // zero border rows of the neighbouring map (or outside the matrix: TMA zero fill) — zeros either way
         const int row_base = P.in_planar ? grp * P.n_pos : 0;
-        for (int cc = 0; cc < n_cc; ++cc) {
-          for (int dy = 0; dy < 3; ++dy, ++g) {
+        for (int u = 0; u < n_u; ++u, ++g) {
+          {
+            int u2 = u + rot;
+            if (u2 >= n_u) u2 -= n_u;
+            const int cc = u2 / 3, dy = u2 - cc * 3;
             const uint32_t s = g % SA, ph = (g / SA) & 1u;
             mbar_wait(&sm.empty_a[s], ph ^ 1u);
             mbar_arrive_expect_tx(&sm.full_a[s], (uint32_t)(S::kSegRows * 128));
@@ -345,8 +353,12 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       uint32_t g = 0;
       for (int tile = unit0; tile < n_tiles; tile += unit_step) {
         const int n_tile = tile % n_n_tiles;
-        for (int cc = 0; cc < n_cc; ++cc) {
-          for (int tap = 0; tap < 9; ++tap, ++g) {
+        for (int u = 0; u < n_u; ++u) {
+          int u2 = u + rot;
+          if (u2 >= n_u) u2 -= n_u;
+          const int cc = u2 / 3, dy = u2 - cc * 3;
+          for (int dx = 0; dx < 3; ++dx, ++g) {
+            const int tap = dy * 3 + dx;
             const uint32_t s = g % SB, ph = (g / SB) & 1u;
             mbar_wait(&sm.empty_b[s], ph ^ 1u);
             mbar_arrive_expect_tx(&sm.full_b[s], (uint32_t)(BN * 128));
@@ -389,9 +401,11 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
         if (P.dbg) w_acc += clock64() - c0;
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-        for (int cc = 0; cc < n_cc; ++cc) {
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
+        for (int u = 0; u < n_u; ++u) {
+          {
+            int u2 = u + rot;
+            if (u2 >= n_u) u2 -= n_u;
+            const int dy = u2 - (u2 / 3) * 3;
             const uint32_t sa = ga % SA, pha = (ga / SA) & 1u;
             ++ga;
             if (P.dbg) c0 = clock64();
@@ -405,7 +419,10 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
               uint32_t sb = 0;
               uint64_t b_stage;
               if constexpr (BS) {
-                b_stage = b_base[dy * 3 + dx];     // compile-time slot: dy, dx are unrolled
+                const uint32_t slot = (uint32_t)(dy * 3 + dx);   // resident weight slot of this tap
+                b_stage = b_base[0];
+#pragma unroll
+                for (int i = 1; i < 9; ++i) b_stage = (slot == (uint32_t)i) ? b_base[i] : b_stage;
                 if (dx == 0) tcgen05_fence_after();
               } else {
                 sb = gb % SB;
@@ -420,7 +437,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
 #pragma unroll
                 for (int i = 1; i < SB; ++i) b_stage = (sb == (uint32_t)i) ? b_base[i] : b_stage;
               }
-              const uint32_t first = (dy == 0 && dx == 0) ? (cc != 0 ? 1u : 0u) : 1u;
+              const uint32_t first = (u == 0 && dx == 0) ? 0u : 1u;
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
 #pragma unroll
