@@ -292,3 +292,10 @@ def test_engine_graph_replay_equals_eager_and_serves_smaller_frames():
             assert torch.equal(torch.as_tensor(dets[0]["label_preds"]).cpu(), e[0]["label_preds"].cpu()), tag
         outs[tag] = dets[0]["scores"].shape[0]
     assert outs["big"] > 0
+    # the double-buffered throughput API returns the same detections, in order
+    seq = [[big.cpu()], [small.cpu()], [big.cpu()], [small.cpu()], [small.cpu()]]
+    res, h2d, d2h = eng.run_pipelined(seq)
+    assert len(res) == 5 and h2d > 0 and d2h > 0
+    for frames, r in zip(seq, res):
+        want = eng.infer(frames)
+        assert torch.equal(r[0]["scores"], want[0]["scores"]) and torch.equal(r[0]["box3d_lidar"], want[0]["box3d_lidar"])
