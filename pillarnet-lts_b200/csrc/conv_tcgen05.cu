@@ -140,7 +140,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   pdl_wait();
   const int rows = P.num_rows ? min(*P.num_rows, P.rows_cap) : P.rows_cap;
   const int n_n_tiles = (P.cout + BN - 1) / BN;
-  const int n_tiles = ((rows + BLOCK_M - 1) / BLOCK_M) * n_n_tiles;
+  // Balanced schedule: every CTA owns an equal, contiguous share of the rows and walks it in 128-row tiles (the
+  // last one partial).  The kernel is bound by the gathers, whose cost is proportional to live rows, not by the
+  // MMAs: with round-robin 128-row tiles, 235 tiles on 148 SMs made 87 CTAs work twice as long as the rest.
+  // Only when one N tile covers cout: with several, a CTA would gather its rows and stream ALL the weights once per
+  // N tile (measured: 30 -> 36 us on the 256->256 stage), so those layers keep round-robin (row tile, N tile) units.
+  const bool balanced = n_n_tiles == 1;
+  const int share = max(64, (((rows + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7);
+  const int row_begin = balanced ? min(rows, (int)blockIdx.x * share) : 0;
+  const int row_end = balanced ? min(rows, row_begin + share) : rows;
+  const int tiles_all = ((rows + BLOCK_M - 1) / BLOCK_M) * n_n_tiles;
+  // this CTA's k-th unit is global tile tile0 + k*tstep; n_tiles = number of units it owns
+  const int tile0 = balanced ? 0 : (int)blockIdx.x, tstep = balanced ? 1 : (int)gridDim.x;
+  const int n_tiles = balanced ? (row_end - row_begin + BLOCK_M - 1) / BLOCK_M
+                               : (tiles_all > tile0 ? (tiles_all - tile0 + tstep - 1) / tstep : 0);
   if (threadIdx.x == 0) PN_DBG(1);
 
   if (warp < kProducerWarps) {
@@ -158,8 +171,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
     constexpr int kNbrPerThread = (BLOCK_M * kMaxTaps + kProducerThreads - 1) / kProducerThreads;
     const int nbr_elems = BLOCK_M * P.taps;
     auto fetch_nbr = [&](int tile, int (&regs)[kNbrPerThread]) {
-      const int m_tile = tile / n_n_tiles;
-      const int row0 = m_tile * BLOCK_M;
+      const int m_tile = (tile0 + tile * tstep) / n_n_tiles;   // `tile` = local unit index
+      const int row0 = row_begin + m_tile * BLOCK_M;
 #pragma unroll
       for (int q = 0; q < kNbrPerThread; ++q) {
         const int i = tid + q * kProducerThreads;
@@ -167,7 +180,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
         if (i < nbr_elems && tile < n_tiles) {
           const int r = i / P.taps, t = i - r * P.taps;
           const int row = row0 + r;
-          if (row < rows) src = P.nbr ? __ldg(P.nbr + (long long)row * P.taps + t) : row;
+          if (row < row_end) src = P.nbr ? __ldg(P.nbr + (long long)row * P.taps + t) : row;
         }
         regs[q] = src;
       }
@@ -180,14 +193,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
       }
     };
     int nbr_regs[kNbrPerThread];
-    fetch_nbr(blockIdx.x, nbr_regs);
+    fetch_nbr(0, nbr_regs);
     park_nbr(0, nbr_regs);
     named_bar_sync(1, kProducerThreads);
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-      const int m_tile = tile / n_n_tiles, n_tile = tile - m_tile * n_n_tiles;
+    for (int tile = 0; tile < n_tiles; ++tile, ++tl) {
+      const int gt = tile0 + tile * tstep;
+      const int m_tile = gt / n_n_tiles, n_tile = gt - m_tile * n_n_tiles;
       const int* s_nbr = sm.nbr[tl & 1u];
-      fetch_nbr(tile + gridDim.x, nbr_regs);  // next tile's rows: loads in flight during this tile
+      fetch_nbr(tile + 1, nbr_regs);  // next tile's rows: loads in flight during this tile
       if constexpr (TMA_A) {
         // one warp feeds the tile: lane l gathers rows 4l..4l+3 of the chunk with one TMA gather4
         // (cin % 64 == 0, so a 64-channel chunk lies inside one tap); lane 0 also loads the weights.
@@ -257,7 +271,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
         b_base[i] = make_kmajor_sw128_desc(smem_u32(sm.b[i]));
       }
       uint32_t g = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      for (int tile = 0; tile < n_tiles; ++tile, ++tcount) {
         const uint32_t acc = tcount & 1u, acc_ph = (tcount >> 1) & 1u;
         mbar_wait(&sm.tmem_empty[acc], acc_ph ^ 1u);
         tcgen05_fence_after();
@@ -290,8 +304,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
     const int e = warp - kEpilogueWarp0;
     const int etid = threadIdx.x - kEpilogueWarp0 * 32;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-      const int m_tile = tile / n_n_tiles, n_tile = tile - m_tile * n_n_tiles;
+    for (int tile = 0; tile < n_tiles; ++tile, ++tcount) {
+      const int gt = tile0 + tile * tstep;
+      const int m_tile = gt / n_n_tiles, n_tile = gt - m_tile * n_n_tiles;
       const int n0 = n_tile * BN;
       const uint32_t acc = tcount & 1u, acc_ph = (tcount >> 1) & 1u;
       named_bar_sync(2, kEpilogueThreads);
@@ -304,8 +319,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
       mbar_wait_relaxed(&sm.tmem_full[acc], acc_ph);
       tcgen05_fence_after();
       if (etid == 0) PN_DBG(4);
-      const int row = m_tile * BLOCK_M + e * 32 + lane;
-      const bool row_ok = row < rows;
+      const int row = row_begin + m_tile * BLOCK_M + e * 32 + lane;
+      const bool row_ok = row < row_end;
       bool border = false;
       if (P.out_wp > 0) {
         const int q = row % (P.out_hp * P.out_wp);
@@ -621,8 +636,11 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
   if (a->in_rows > 0 && (long long)a->in_rows * a->in_ld * 2 >= (1ll << 32)) return PN_ERR_UNSUPPORTED;
   const int sms = sm_count();
   if (sms <= 0) return PN_ERR_CUDA;
-  const long long tiles_cap = (long long)PN_DIVUP(a->rows_cap, BLOCK_M) * PN_DIVUP(a->cout, bn);
-  const int grid = (int)(tiles_cap < sms ? tiles_cap : sms);
+  // every CTA handles all N tiles of its row share (>= 64 rows), so the grid depends on the rows only
+  const long long shares_cap = PN_DIVUP(a->cout, bn) == 1
+                                   ? PN_DIVUP((long long)a->rows_cap, 64ll)
+                                   : (long long)PN_DIVUP(a->rows_cap, BLOCK_M) * PN_DIVUP(a->cout, bn);
+  const int grid = (int)(shares_cap < sms ? (shares_cap < 1 ? 1 : shares_cap) : sms);
   if (tma_a) {
     switch (bn) {
       case 16: return launch<16, 8, true>(map, map_a, ka, grid, stream);
