@@ -224,6 +224,20 @@ int pn_conv_dense3x3_grouped(const void* in, int in_ld, int in_coff, int cin, in
                              const int* group_tab, void* out, int out_dtype, int out_ld, int out_compact,
                              int relu, int in_planar, pn_stream_t stream);
 
+/* Training targets on the GPU (SURVEY §8 f rank 1): AssignLabel of the reference's data pipeline
+ * (det3d/datasets/pipelines/preprocess.py:248-317) for ONE task: per object the Gaussian radius
+ * (center_utils.py:16-38), the heat-map patch (draw_umich_gaussian, :48-64) and the regression targets.
+ *   gt_boxes (n_frames, max_objs, box_dim) f32, box_dim 9 [x,y,z,w,l,h,vx,vy,rot] or 7 [x,y,z,w,l,h,rot];
+ *   gt_cls   (n_frames, max_objs) i32: class id WITHIN the task, 1-based, 0 = empty slot (slot k = object k);
+ *   H, W = task grid (BEV grid // stride); cell = pillar_size*stride as fp32; min_radius: HOST ints, 1 or per class.
+ * Outputs (all written in full): hm (n_frames,H,W,num_cls) f32, ind/cat (n_frames,max_objs) i64,
+ * mask (n_frames,max_objs) u8, anno_box (n_frames,max_objs,10) f32 [dx,dy,z,log w,log l,log h,vx,vy,sin,cos],
+ * gt_box (n_frames,max_objs,7) f32. */
+int pn_assign_labels(const float* gt_boxes, int box_dim, const int* gt_cls, int n_frames, int max_objs, int num_cls,
+                     int H, int W, float x0, float y0, float cell, float gaussian_overlap, const int* min_radius,
+                     int n_min_radius, float* hm, long long* ind, unsigned char* mask, long long* cat,
+                     float* anno_box, float* gt_box, pn_stream_t stream);
+
 /* Backward of pn_conv_gather (spconv's autograd for SubMConv2d / SparseConv2d, external in the reference).
  * pn_rulebook_transpose: nbr_t[i*taps + t] = o  <=>  nbr[o*taps + t] = i  (else -1): the input-stationary
  *   table; the data gradient is then a forward gather conv  dx = pn_conv_gather(dy, nbr_t, W^T)  with

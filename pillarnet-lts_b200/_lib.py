@@ -89,6 +89,9 @@ SIGNATURES = {
     "pn_conv_wgrad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
                               c_int, c_void_p, c_int, c_int, c_void_p]),
     "pn_boxes_aligned_overlap_bev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "pn_assign_labels": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
+                                 c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
     "pn_select_topk": (c_int, [POINTER(TaskArgs), c_int, c_int, c_int, POINTER(c_int), c_float, c_float,
                                c_float, POINTER(c_float), c_void_p, c_int, c_void_p, c_void_p, c_int,
                                c_void_p, c_void_p]),

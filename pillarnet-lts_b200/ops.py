@@ -417,3 +417,26 @@ def boxes_aligned_overlap_bev(boxes_a, boxes_b):
     check(lib.pn_boxes_aligned_overlap_bev(ptr(boxes_a.contiguous()), ptr(boxes_b.contiguous()), n, ptr(out),
                                            stream_ptr()), "pn_boxes_aligned_overlap_bev")
     return out
+
+
+def assign_labels_task(gt_boxes, gt_cls, num_cls, H, W, x0, y0, cell, gaussian_overlap, min_radius):
+    """pn_assign_labels for one task.  gt_boxes (B,M,9|7) f32, gt_cls (B,M) int32 (1-based, 0 = empty).
+    Returns dict(hm (B,H,W,K) f32, ind/cat (B,M) i64, mask (B,M) u8, anno_box (B,M,10), gt_box (B,M,7))."""
+    lib = _lib.load()
+    require_cuda(gt_boxes, gt_cls)
+    if gt_boxes.dtype != torch.float32 or gt_cls.dtype != torch.int32:
+        raise RuntimeError("assign_labels: gt_boxes float32, gt_cls int32")
+    B, M, D = gt_boxes.shape
+    dev = gt_boxes.device
+    out = dict(hm=torch.empty(B, H, W, num_cls, dtype=torch.float32, device=dev),
+               ind=torch.empty(B, M, dtype=torch.int64, device=dev),
+               mask=torch.empty(B, M, dtype=torch.uint8, device=dev),
+               cat=torch.empty(B, M, dtype=torch.int64, device=dev),
+               anno_box=torch.empty(B, M, 10, dtype=torch.float32, device=dev),
+               gt_box=torch.empty(B, M, 7, dtype=torch.float32, device=dev))
+    mr = list(min_radius) if isinstance(min_radius, (list, tuple)) else [int(min_radius)]
+    check(lib.pn_assign_labels(ptr(gt_boxes), D, ptr(gt_cls), B, M, num_cls, H, W, c_float(_f32(x0)), c_float(_f32(y0)),
+                               c_float(cell), c_float(_f32(gaussian_overlap)), iarr(mr), len(mr), ptr(out["hm"]),
+                               ptr(out["ind"]), ptr(out["mask"]), ptr(out["cat"]), ptr(out["anno_box"]),
+                               ptr(out["gt_box"]), stream_ptr()), "pn_assign_labels")
+    return out

@@ -8,6 +8,7 @@ Fixtures (all small .npz):
   head_predict_circle.npz det3d/models/bbox_heads/center_head.py:216-413 CenterHead.predict (circular_nms)
   head_predict_double_flip.npz center_head.py:233-304 double-flip test-time augmentation branch of predict
   head_loss.npz          center_head.py:133-214 + losses/centernet_loss.py CenterHead.loss (focal + L1 + GIoU)
+  assign_label.npz       datasets/pipelines/preprocess.py:177-350 AssignLabel (heat-maps, ind/mask/cat, anno_box, gt_box)
   neck_head_forward.npz  det3d/models/necks/rpn.py:137-207 RPNV1 + center_head.py:116-127 forward (torch CPU)
   set_by_task_cfg.json   det3d/core/utils/center_utils.py:229-274 on the Waymo FPN test_cfg
 """
@@ -194,6 +195,69 @@ def gen_loss():
     np.savez_compressed(os.path.join(HERE, "head_loss.npz"), **save)
 
 
+def _load_reference_preprocess():
+    """det3d/datasets/pipelines/preprocess.py loaded as a stand-alone module: the package __init__ chain pulls in
+    dataset code that needs pyquaternion / Python < 3.10, so its few imports are stubbed."""
+    import importlib.util
+    import types
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class _Reg:
+        def register_module(self, cls):
+            return cls
+
+    stub("det3d.builder", build_dbsampler=lambda *a, **k: None)
+    stub("det3d.datasets").__path__ = []
+    stub("det3d.datasets.registry", PIPELINES=_Reg())
+    stub("det3d.datasets.pipelines").__path__ = []
+    import det3d.core.bbox.box_np_ops  # noqa: F401
+    stub("det3d.core.sampler").__path__ = []
+    stub("det3d.core.sampler.preprocess")
+    spec = importlib.util.spec_from_file_location("det3d.datasets.pipelines.preprocess",
+                                                  "/root/reference/det3d/datasets/pipelines/preprocess.py")
+    mod = importlib.util.module_from_spec(spec)
+    mod.__package__ = "det3d.datasets.pipelines"
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def gen_assign_label():
+    """datasets/pipelines/preprocess.py:177-350 AssignLabel on seeded nuScenes-style annotations (3 frames, 2 tasks
+    with strides 8 and 4, objects on the border and outside the range; the reference asserts total objects <= max_objs)."""
+    mod = _load_reference_preprocess()
+    rng = np.random.default_rng(17)
+    tasks = [dict(stride=8, class_names=["car"]), dict(stride=4, class_names=["ped", "cone"])]
+    cfg = Config(dict(target_assigner=dict(tasks=tasks), gaussian_overlap=0.1, max_objs=80, min_radius=2,
+                      pc_range=[-24.0, -24.0, -5.0, 24.0, 24.0, 3.0], pillar_size=0.075))
+    al = mod.AssignLabel(cfg=cfg)
+    save = {}
+    for f, n in enumerate([25, 70, 3]):
+        boxes = np.zeros((n, 9), np.float32)
+        boxes[:, 0:2] = rng.uniform(-26, 26, (n, 2))              # some outside the range
+        boxes[:3, 0] = [-24.0, 23.99, -24.04][:min(3, n)]         # on / just outside the border
+        boxes[:, 2] = rng.uniform(-2, 1, n)
+        boxes[:, 3:6] = rng.uniform(0.3, 6.0, (n, 3))
+        boxes[:, 6:8] = rng.normal(0, 2, (n, 2))
+        boxes[:, 8] = rng.uniform(-7, 7, n)                       # headings beyond +-pi: limit_period
+        cls = rng.integers(1, 4, n).astype(np.int32)
+        names = np.array([["car", "ped", "cone"][c - 1] for c in cls])
+        res = {"type": "NuScenesDataset",
+               "lidar": {"annotations": {"gt_boxes": boxes.copy(), "gt_classes": cls.copy(), "gt_names": names}}}
+        res, _ = al(res, {})
+        tg = res["lidar"]["targets"]
+        save[f"f{f}_boxes"], save[f"f{f}_cls"] = boxes, cls
+        for t in range(2):
+            for k in ("hm", "anno_box", "ind", "mask", "cat", "gt_box"):
+                save[f"f{f}_t{t}_{k}"] = np.ascontiguousarray(tg[k][t])
+    np.savez_compressed(os.path.join(HERE, "assign_label.npz"), **save)
+
+
 def gen_neck_head():
     torch.manual_seed(14)
     tasks = [dict(stride=8, class_names=["car"]), dict(stride=8, class_names=["ped", "cone"])]
@@ -239,6 +303,7 @@ if __name__ == "__main__":
     gen_predict()
     gen_predict_double_flip()
     gen_loss()
+    gen_assign_label()
     gen_neck_head()
     gen_cfg()
     print("golden fixtures written to", HERE)

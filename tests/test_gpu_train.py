@@ -203,3 +203,30 @@ def test_training_reduces_the_loss_on_a_fixed_batch():
     losses = [float(train.train_step(model, example, opt)) for _ in range(6)]
     assert all(np.isfinite(losses))
     assert losses[-1] < 0.9 * losses[0], losses
+
+
+def test_assign_label_gpu_vs_reference_golden(golden_dir):
+    """labels.AssignLabel (pn_assign_labels) on a 3-frame batch vs the reference's AssignLabel pipeline stage:
+    ind / mask / cat / gt_box exact, heat-map within one fp32 ulp (double exp, rounded once), anno_box 1e-6."""
+    import os
+    from pillarnet_lts_b200.labels import AssignLabel
+    g = np.load(os.path.join(golden_dir, "assign_label.npz"))
+    tasks = [dict(stride=8, class_names=["car"]), dict(stride=4, class_names=["ped", "cone"])]
+    al = AssignLabel(dict(target_assigner=dict(tasks=tasks), gaussian_overlap=0.1, max_objs=80, min_radius=2,
+                          pc_range=[-24.0, -24.0, -5.0, 24.0, 24.0, 3.0], pillar_size=0.075))
+    boxes = [torch.from_numpy(g[f"f{f}_boxes"]).cuda() for f in range(3)]
+    cls = [torch.from_numpy(g[f"f{f}_cls"]).cuda() for f in range(3)]
+    out = al(boxes, cls)
+    torch.cuda.synchronize()
+    for t in range(2):
+        for f in range(3):
+            for k in ("ind", "mask", "cat"):
+                assert np.array_equal(out[k][t][f].cpu().numpy(), g[f"f{f}_t{t}_{k}"]), (f, t, k)
+            assert np.array_equal(out["gt_box"][t][f].cpu().numpy(), g[f"f{f}_t{t}_gt_box"])
+            hm, want = out["hm"][t][f].cpu().numpy(), g[f"f{f}_t{t}_hm"]
+            assert hm.shape == want.shape
+            assert np.array_equal(hm > 0, want > 0)
+            np.testing.assert_allclose(hm, want, rtol=1.2e-7, atol=0)
+            np.testing.assert_allclose(out["anno_box"][t][f].cpu().numpy(), g[f"f{f}_t{t}_anno_box"], rtol=2e-6, atol=2e-7)
+    # the targets plug into the loss
+    assert out["hm"][1].shape == (3, 160, 160, 2) and out["ind"][0].dtype == torch.int64

@@ -124,3 +124,37 @@ def test_centerhead_loss_vs_reference(golden_dir):
                                        err_msg=f"{t} {k}")
     sum(out["loss"]).sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for d in preds for p in d.values())
+
+
+def _assign_cases(g):
+    """(frame, task) -> per-task boxes / 1-based class ids in the reference's order (preprocess.py:203-237)"""
+    tasks = [dict(stride=8, names=[1]), dict(stride=4, names=[2, 3])]
+    for f in range(3):
+        boxes, cls = g[f"f{f}_boxes"], g[f"f{f}_cls"]
+        for t, task in enumerate(tasks):
+            sel = np.concatenate([np.where(cls == c)[0] for c in task["names"]])
+            tb = boxes[sel].copy()
+            tb[:, -1] = tb[:, -1] - np.floor(tb[:, -1] / (np.pi * 2) + 0.5) * (np.pi * 2)   # limit_period
+            tc = np.concatenate([np.full((cls == c).sum(), j + 1) for j, c in enumerate(task["names"])])
+            yield f, t, task, tb.astype(np.float32), tc.astype(np.int32)
+
+
+def test_assign_label_oracle_vs_reference(golden_dir):
+    """numpy restatement of AssignLabel (one task, one frame) vs the reference pipeline stage run from /root/reference"""
+    g = np.load(os.path.join(golden_dir, "assign_label.npz"))
+    M, ps = 80, np.float32(0.075)
+    positives = 0
+    for f, t, task, tb, tc in _assign_cases(g):
+        boxes = np.zeros((M, 9), np.float32)
+        cls = np.zeros(M, np.int32)
+        boxes[:len(tb)], cls[:len(tc)] = tb, tc
+        grid = 640 // task["stride"]
+        r = O.assign_labels_task(boxes, cls, len(task["names"]), grid, grid, -24.0, -24.0, np.float32(ps * task["stride"]),
+                                 0.1, 2)
+        for k in ("ind", "mask", "cat"):
+            assert np.array_equal(r[k], g[f"f{f}_t{t}_{k}"]), (f, t, k)
+        assert np.array_equal(r["hm"], g[f"f{f}_t{t}_hm"]), (f, t)                 # bit-exact heat-map
+        assert np.array_equal(r["gt_box"], g[f"f{f}_t{t}_gt_box"])
+        np.testing.assert_allclose(r["anno_box"], g[f"f{f}_t{t}_anno_box"], rtol=1e-6, atol=1e-7)
+        positives += int(r["mask"].sum())
+    assert positives > 50
