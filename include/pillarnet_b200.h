@@ -78,6 +78,21 @@ int pn_pillarize(const float* points, int point_dim, const int* frame_offsets, i
                  int* point_pillar, int* num_pillars, void* scratch, size_t scratch_bytes,
                  pn_stream_t stream);
 
+/* Multi-sweep accumulation in front of pn_pillarize (SURVEY §8 f rank 2; det3d/datasets/pipelines/loading.py:
+ * 37-61,118-141): sweep 0 (the key frame) is kept whole; every other sweep drops the points with |x| < min_distance
+ * and |y| < min_distance (sensor frame), is transformed by its 3x4 float64 matrix (rounded once to fp32) and gets
+ * its time lag as the extra last column.  Order preserving.
+ *   raw (n_raw, in_dim) f32 device, sweeps concatenated; the first n_feat columns are kept (x,y,z,features...)
+ *   sweep_offsets (n_sweeps+1) HOST ints, [0] = 0, [n_sweeps] = n_raw; n_sweeps <= 16
+ *   transforms (n_sweeps,12) HOST doubles row-major 3x4, a row of NaNs = no transform; time_lag (n_sweeps) HOST
+ *   out (out_cap, n_feat+1) f32; rows are written from *out_base (device scalar, NULL = 0) on;
+ *   n_total (1) i32 device = *out_base + points kept (clamped to out_cap): chain frames by passing it as the next
+ *   call's out_base; the vector of bases/totals is pn_pillarize's frame_offsets. */
+size_t pn_merge_sweeps_scratch_bytes(int n_raw);
+int pn_merge_sweeps(const float* raw, int in_dim, int n_feat, const int* sweep_offsets, int n_sweeps,
+                    const double* transforms, const float* time_lag, float min_distance, const int* out_base,
+                    float* out, int out_cap, int* n_total, void* scratch, size_t scratch_bytes, pn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (2) PFN (Linear -> BatchNorm1d(eval, folded to scale/shift) -> ReLU) fused with scatter-max.
  * Replaces PillarQueryAndGroup's centre/offset features (pillar_utils.py:51-56, gather_feature

@@ -92,6 +92,9 @@ SIGNATURES = {
     "pn_assign_labels": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
                                  c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
+    "pn_merge_sweeps_scratch_bytes": (c_size_t, [c_int]),
+    "pn_merge_sweeps": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pn_select_topk": (c_int, [POINTER(TaskArgs), c_int, c_int, c_int, POINTER(c_int), c_float, c_float,
                                c_float, POINTER(c_float), c_void_p, c_int, c_void_p, c_void_p, c_int,
                                c_void_p, c_void_p]),

@@ -440,3 +440,29 @@ def assign_labels_task(gt_boxes, gt_cls, num_cls, H, W, x0, y0, cell, gaussian_o
                                ptr(out["ind"]), ptr(out["mask"]), ptr(out["cat"]), ptr(out["anno_box"]),
                                ptr(out["gt_box"]), stream_ptr()), "pn_assign_labels")
     return out
+
+
+def merge_sweeps(raw, sweep_offsets, transforms, time_lags, min_distance=1.0, n_feat=4, out=None, out_base=None):
+    """pn_merge_sweeps: raw (n_raw, in_dim) f32 CUDA (key frame + sweeps concatenated), sweep_offsets host ints,
+    transforms list of 4x4 / 3x4 arrays or None per sweep, time_lags host floats.
+    Returns (out (cap, n_feat+1) f32, n_total (1,) int32 device)."""
+    import numpy as np
+    lib = _lib.load()
+    require_cuda(raw)
+    n_sweeps = len(sweep_offsets) - 1
+    n_raw = int(sweep_offsets[-1])
+    T = np.full((n_sweeps, 12), np.nan, np.float64)
+    for k, m in enumerate(transforms):
+        if m is not None:
+            T[k] = np.asarray(m, np.float64)[:3, :4].reshape(12)
+    lag = np.asarray(time_lags, np.float32)
+    if out is None:
+        out = torch.empty(max(n_raw, 1), n_feat + 1, dtype=torch.float32, device=raw.device)
+    n_total = _i32(1, device=raw.device)
+    sb = lib.pn_merge_sweeps_scratch_bytes(n_raw)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=raw.device)
+    check(lib.pn_merge_sweeps(ptr(raw), raw.shape[1], n_feat, iarr([int(v) for v in sweep_offsets]), n_sweeps,
+                              T.ctypes.data_as(c_void_p), lag.ctypes.data_as(c_void_p), c_float(_f32(min_distance)),
+                              ptr(out_base), ptr(out), out.shape[0], ptr(n_total), ptr(scratch), c_size_t(sb),
+                              stream_ptr()), "pn_merge_sweeps")
+    return out, n_total

@@ -9,6 +9,7 @@ Fixtures (all small .npz):
   head_predict_double_flip.npz center_head.py:233-304 double-flip test-time augmentation branch of predict
   head_loss.npz          center_head.py:133-214 + losses/centernet_loss.py CenterHead.loss (focal + L1 + GIoU)
   assign_label.npz       datasets/pipelines/preprocess.py:177-350 AssignLabel (heat-maps, ind/mask/cat, anno_box, gt_box)
+  sweeps.npz             datasets/pipelines/loading.py:102-141 key frame + sweeps (remove_close, transform, time lag)
   neck_head_forward.npz  det3d/models/necks/rpn.py:137-207 RPNV1 + center_head.py:116-127 forward (torch CPU)
   set_by_task_cfg.json   det3d/core/utils/center_utils.py:229-274 on the Waymo FPN test_cfg
 """
@@ -258,6 +259,69 @@ def gen_assign_label():
     np.savez_compressed(os.path.join(HERE, "assign_label.npz"), **save)
 
 
+def gen_sweeps():
+    """datasets/pipelines/loading.py:102-141 LoadPointCloudFromFile (nuScenes branch) on seeded .bin files: a key
+    frame + 4 sweeps with rigid transforms and time lags, points close to the sensor in every sweep."""
+    import importlib.util
+    import tempfile
+    import types
+
+    class _Reg:
+        def register_module(self, cls):
+            return cls
+
+    if "det3d.datasets" not in sys.modules:
+        m = types.ModuleType("det3d.datasets")
+        m.__path__ = []
+        sys.modules["det3d.datasets"] = m
+        r = types.ModuleType("det3d.datasets.registry")
+        r.PIPELINES = _Reg()
+        sys.modules["det3d.datasets.registry"] = r
+        pm = types.ModuleType("det3d.datasets.pipelines")
+        pm.__path__ = []
+        sys.modules["det3d.datasets.pipelines"] = pm
+    spec = importlib.util.spec_from_file_location("det3d.datasets.pipelines.loading",
+                                                  "/root/reference/det3d/datasets/pipelines/loading.py")
+    mod = importlib.util.module_from_spec(spec)
+    mod.__package__ = "det3d.datasets.pipelines"
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(18)
+    tmp = tempfile.mkdtemp(prefix="pn_sweeps_")
+    save, files = {}, []
+    for k, n in enumerate([3000, 2500, 2800, 100, 2600]):
+        p = np.zeros((n, 5), np.float32)
+        p[:, :2] = rng.normal(0, 12, (n, 2))
+        p[: n // 10, :2] = rng.uniform(-1.5, 1.5, (n // 10, 2))      # many inside / on the 1 m box
+        p[:, 2] = rng.uniform(-3, 1, n)
+        p[:, 3] = rng.uniform(0, 255, n)
+        p[:, 4] = rng.integers(0, 32, n)
+        path = os.path.join(tmp, f"s{k}.bin")
+        p.tofile(path)
+        files.append(path)
+        save[f"raw{k}"] = p
+    sweeps = []
+    for k in range(1, 5):
+        a = rng.uniform(-0.2, 0.2)
+        T = np.eye(4)
+        T[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+        T[:3, 3] = rng.normal(0, 1.5, 3)
+        if k == 3:
+            T = None                                                   # a sweep without a transform
+        sweeps.append(dict(lidar_path=files[k], transform_matrix=T, time_lag=0.05 * k))
+        save[f"T{k}"] = np.full((4, 4), np.nan) if T is None else T
+        save[f"lag{k}"] = np.float64(0.05 * k)
+    loader = mod.LoadPointCloudFromFile(dataset="NuScenesDataset")
+    np.random.seed(3)                                                  # the stage draws the sweep order at random
+    res = {"lidar": {"nsweeps": 5}, "virtual": False}
+    res, _ = loader(res, {"lidar_path": files[0], "sweeps": sweeps})
+    np.random.seed(3)
+    save["order"] = np.random.choice(4, 4, replace=False)
+    save["combined"] = res["lidar"]["combined"].astype(np.float32)
+    assert res["lidar"]["combined"].dtype == np.float32
+    np.savez_compressed(os.path.join(HERE, "sweeps.npz"), **save)
+
+
 def gen_neck_head():
     torch.manual_seed(14)
     tasks = [dict(stride=8, class_names=["car"]), dict(stride=8, class_names=["ped", "cone"])]
@@ -304,6 +368,7 @@ if __name__ == "__main__":
     gen_predict_double_flip()
     gen_loss()
     gen_assign_label()
+    gen_sweeps()
     gen_neck_head()
     gen_cfg()
     print("golden fixtures written to", HERE)

@@ -243,3 +243,31 @@ def test_scatter_max_grad_routes_to_argmax():
     want = torch.zeros(pts.shape[0] * 32, device="cuda")
     want[arg[:n].reshape(-1).long()] = g[:n].reshape(-1)
     assert torch.equal(gs.view(-1), want)
+
+
+def test_merge_sweeps_vs_reference_golden_and_feeds_pillarize(golden_dir):
+    """pn_merge_sweeps vs the reference's multi-sweep loader: same points in the same order (coordinates within one
+    fp32 ulp: float64 product rounded once), and a two-frame batch chains on the device into pn_pillarize."""
+    import os
+    from pillarnet_lts_b200 import ops, sweeps as S
+    g = np.load(os.path.join(golden_dir, "sweeps.npz"))
+    key = torch.from_numpy(g["raw0"]).cuda()
+    sw = []
+    for i in g["order"]:
+        k = int(i) + 1
+        T = g[f"T{k}"]
+        sw.append(dict(points=torch.from_numpy(g[f"raw{k}"]).cuda(), transform_matrix=None if np.isnan(T[0, 0]) else T,
+                       time_lag=float(g[f"lag{k}"])))
+    out, total = S.merge_frame(key, sw)
+    n = int(total.item())
+    want = g["combined"]
+    assert n == len(want)
+    got = out[:n].cpu().numpy()
+    assert np.array_equal(got[:, 3:], want[:, 3:])                      # intensity and time lag: exact
+    np.testing.assert_allclose(got[:, :3], want[:, :3], rtol=1.2e-7, atol=1e-7)
+    assert (got[:, :3] != want[:, :3]).mean() < 1e-3                     # and all but a few coordinates bit-equal
+    # batch of two frames (the second: key frame only), offsets stay on the device
+    pts, offs = S.merge_batch([(key, sw), (key[:500], [])])
+    assert offs.dtype == torch.int32 and offs.cpu().tolist() == [0, n, n + 500]
+    table, pp = ops.pillarize(pts, offs, 2, 1440, 1440, -54.0, -54.0, 0.075)
+    assert table.count() > 1000 and int((pp[:n + 500] >= 0).sum()) > 0

@@ -158,3 +158,22 @@ def test_assign_label_oracle_vs_reference(golden_dir):
         np.testing.assert_allclose(r["anno_box"], g[f"f{f}_t{t}_anno_box"], rtol=1e-6, atol=1e-7)
         positives += int(r["mask"].sum())
     assert positives > 50
+
+
+def _sweep_case(g):
+    key = g["raw0"]
+    sweeps = []
+    for i in g["order"]:                                # the order the reference drew (np.random.choice, seed 3)
+        k = int(i) + 1
+        T = g[f"T{k}"]
+        sweeps.append((g[f"raw{k}"], None if np.isnan(T[0, 0]) else T, float(g[f"lag{k}"])))
+    return key, sweeps
+
+
+def test_merge_sweeps_oracle_vs_reference(golden_dir):
+    """numpy restatement of the multi-sweep loader vs the reference's LoadPointCloudFromFile run on seeded files"""
+    g = np.load(os.path.join(golden_dir, "sweeps.npz"))
+    key, sweeps = _sweep_case(g)
+    got = O.merge_sweeps(key, sweeps)
+    assert got.dtype == np.float32 and np.array_equal(got, g["combined"])
+    assert len(got) < sum(len(g[f"raw{k}"]) for k in range(5))        # remove_close dropped points
