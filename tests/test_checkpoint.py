@@ -1,0 +1,46 @@
+"""CPU: checkpoint loading rules of det3d/torchie/trainer/checkpoint.py:67-137,166-218 (module. prefix, state_dict
+wrapper, spconv 1.x -> 2.x weight layout, reporting instead of raising)."""
+import logging
+import os
+
+import pytest
+import torch
+
+
+def _backbone():
+    import pillarnet_lts_b200  # noqa: F401
+    from pillarnet_lts_b200.backbone import PillarResNet18S
+    torch.manual_seed(0)
+    return PillarResNet18S(in_channels=32)
+
+
+def test_roundtrip_with_module_prefix_and_spconv1_layout(tmp_path):
+    from pillarnet_lts_b200.checkpoint import load_checkpoint
+    src, dst = _backbone(), _backbone()
+    for p in src.parameters():
+        torch.nn.init.normal_(p)
+    sd = {}
+    for k, v in src.state_dict().items():
+        if v.dim() == 4 and "conv" in k and k.endswith(".weight"):      # sparse conv: save it the spconv-1.x way
+            v = v.permute(1, 2, 3, 0).contiguous()                      # (Cout,kH,kW,Cin) -> (kH,kW,Cin,Cout)
+        sd["module." + k] = v
+    sd["module.not_in_the_model"] = torch.zeros(3)
+    path = os.path.join(tmp_path, "ckpt.pth")
+    torch.save({"state_dict": sd, "meta": {"epoch": 20}}, path)
+    ck = load_checkpoint(dst, path, map_location="cpu", logger=logging.getLogger("t"))
+    assert ck["meta"]["epoch"] == 20
+    for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_strict_raises_and_missing_files_are_errors(tmp_path):
+    from pillarnet_lts_b200.checkpoint import load_checkpoint, load_state_dict
+    m = _backbone()
+    sd = dict(m.state_dict())
+    sd.pop(next(k for k in sd if k.endswith("bias")))
+    with pytest.raises(RuntimeError):
+        load_state_dict(m, sd, strict=True)
+    rep = load_state_dict(m, sd, strict=False, logger=logging.getLogger("t"))
+    assert len(rep["missing"]) == 1 and not rep["unexpected"]
+    with pytest.raises(IOError):
+        load_checkpoint(m, os.path.join(tmp_path, "nope.pth"))
