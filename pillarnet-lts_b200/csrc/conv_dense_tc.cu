@@ -109,6 +109,11 @@ inline bool pdl_enabled() {
   }();
   return on;
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -153,6 +158,51 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(smem_u32(bar)), "h"(mask)
       : "memory");
+}
+// ---- cta_group::2 (one UMMA across the two SMs of a CTA pair) ----
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the issuing CTA's prior MMAs retired) on the same-offset barrier of both CTAs of the pair
+__device__ __forceinline__ void umma_commit2_mc(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+// shared::cluster address of `p` in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+// TMA load into OUR shared memory whose completion bytes are credited to a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                                uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -236,11 +286,11 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
     if (P.dbg) P.dbg[blockIdx.x * 16 + slot] = gtime_ns();                   \
   } while (0)
 
-template <int MT, int BN, int SA, int SB>
+template <int MT, int BN, int SA, int SB, int BROWS = BN>
 struct DSmem {
   static constexpr int kSegRows = 128 * MT + kTailRows;
   alignas(1024) uint8_t a[SA][kSegRows * 128];
-  alignas(1024) uint8_t b[SB][BN * 128];
+  alignas(1024) uint8_t b[SB][BROWS * 128];   // BROWS = BN, or BN/2 when a CTA pair shares every weight tile
   alignas(8) uint64_t full_a[SA];
   uint64_t empty_a[SA];
   uint64_t full_b[SB];
@@ -259,12 +309,19 @@ struct DSmem {
 // BS ("B stationary", grouped mode only): the CTA works on ONE group (g = blockIdx.x % n_groups) for all its row
 // tiles, so the group's nine weight tiles are loaded once into the SB (>= 9) weight slots and never recycled —
 // no per-tap weight TMA, barrier wait or commit in the steady state.
-template <int MT, int BN, int SA, int SB, int CL, bool BS = false>
+// TWO (requires CL == 2): the pair of CTAs runs ONE tcgen05.mma.cta_group::2 per K step — M = 256 (128 rows from
+// each CTA's activation segment, accumulated in each CTA's own TMEM), N = BN with each CTA holding half of the
+// weight tile.  Every SM then ingests half of the weight bytes.  Rank 0 issues all MMAs; both CTAs' TMA loads
+// credit rank 0's full barriers, its commits are multicast to both CTAs' empty / tmem_full barriers, and both
+// epilogues release the accumulator on rank 0's tmem_empty barrier.
+template <int MT, int BN, int SA, int SB, int CL, bool BS = false, bool TWO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_constant__ CUtensorMap tmap_a_tail,
              const __grid_constant__ CUtensorMap tmap_w, const DArgs P) {
   extern __shared__ uint8_t smem_raw[];
-  using S = DSmem<MT, BN, SA, SB>;
+  static_assert(!TWO || (CL == 2 && !BS), "2-SM mode needs a cluster of exactly two CTAs");
+  constexpr int BROWS = TWO ? BN / 2 : BN;
+  using S = DSmem<MT, BN, SA, SB, BROWS>;
   S& sm = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int M_TILE = 128 * MT;
   constexpr int ACC_COLS = MT * BN;                       // fp32 columns per tile
@@ -299,12 +356,15 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
   if (warp == 2) {
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) { mbar_init(&sm.full_a[s], 1); mbar_init(&sm.empty_a[s], 1); }
-      for (int s = 0; s < SB; ++s) { mbar_init(&sm.full_b[s], 1); mbar_init(&sm.empty_b[s], CL); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], kEpilogueThreads); }
+      for (int s = 0; s < SB; ++s) { mbar_init(&sm.full_b[s], 1); mbar_init(&sm.empty_b[s], TWO ? 1 : CL); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&sm.tmem_full[i], 1);
+        mbar_init(&sm.tmem_empty[i], TWO ? 2 * kEpilogueThreads : kEpilogueThreads);
+      }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<TCOLS>(&sm.tmem_base);
+    if constexpr (TWO) tmem_alloc2<TCOLS>(&sm.tmem_base); else tmem_alloc<TCOLS>(&sm.tmem_base);
   }
   tcgen05_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();   // barriers of every CTA initialised before any remote signal
@@ -332,11 +392,19 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
             const int cc = u2 / 3, dy = u2 - cc * 3;
             const uint32_t s = g % SA, ph = (g / SA) & 1u;
             mbar_wait(&sm.empty_a[s], ph ^ 1u);
-            mbar_arrive_expect_tx(&sm.full_a[s], (uint32_t)(S::kSegRows * 128));
             const int row = row_base + q0 + (dy - 1) * P.Wp - 1;   // may be negative / past the end: TMA zero-fills
             const int ch = ch0 + cc * BLOCK_K;
-            tma_load_2d(smem_u32(sm.a[s]), &tmap_a_main, ch, row, &sm.full_a[s]);
-            tma_load_2d(smem_u32(sm.a[s]) + M_TILE * 128, &tmap_a_tail, ch, row + M_TILE, &sm.full_a[s]);
+            if constexpr (TWO) {
+              // the leader's barrier counts both CTAs' segments
+              if (crank == 0) mbar_arrive_expect_tx(&sm.full_a[s], (uint32_t)(2 * S::kSegRows * 128));
+              const uint32_t lb = map_to_cta(&sm.full_a[s], 0);
+              tma_load_2d_2sm(smem_u32(sm.a[s]), &tmap_a_main, ch, row, lb);
+              tma_load_2d_2sm(smem_u32(sm.a[s]) + M_TILE * 128, &tmap_a_tail, ch, row + M_TILE, lb);
+            } else {
+              mbar_arrive_expect_tx(&sm.full_a[s], (uint32_t)(S::kSegRows * 128));
+              tma_load_2d(smem_u32(sm.a[s]), &tmap_a_main, ch, row, &sm.full_a[s]);
+              tma_load_2d(smem_u32(sm.a[s]) + M_TILE * 128, &tmap_a_tail, ch, row + M_TILE, &sm.full_a[s]);
+            }
           }
         }
       }
@@ -361,6 +429,13 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
             const int tap = dy * 3 + dx;
             const uint32_t s = g % SB, ph = (g / SB) & 1u;
             mbar_wait(&sm.empty_b[s], ph ^ 1u);
+            if constexpr (TWO) {
+              // this CTA's half of the weight tile, into its own shared memory; bytes credited to the leader
+              if (crank == 0) mbar_arrive_expect_tx(&sm.full_b[s], (uint32_t)(BN * 128));
+              tma_load_2d_2sm(smem_u32(sm.b[s]), &tmap_w, tap * P.cin + cc * BLOCK_K, n_tile * BN + crank * BROWS,
+                              map_to_cta(&sm.full_b[s], 0));
+              continue;
+            }
             mbar_arrive_expect_tx(&sm.full_b[s], (uint32_t)(BN * 128));
             if (CL == 1) {
               tma_load_2d(smem_u32(sm.b[s]), &tmap_w, tap * P.cin + cc * BLOCK_K, n_tile * BN, &sm.full_b[s]);
@@ -375,94 +450,89 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
     }
   } else if (warp == 2) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop converged (barrier waits, stage counters and descriptors are warp-uniform, so
+    // they live in uniform registers); one elected lane issues the tcgen05 instructions.  Entering the loop with a
+    // single active lane instead made the compiler wrap every UTCHMMA in an ELECT / broadcast / retry sequence.
+    const bool issuer = elect_one();
+    if (!TWO || crank == 0) {
       // The issuing thread is a single in-order instruction stream: at BN = 128 an MMA retires every
       // 64 cycles, so descriptor arithmetic per MMA must be a couple of integer adds.  Stage base
       // descriptors are built once; window / K-step offsets are compile-time constants added to the
       // low word (the 14-bit start-address field never carries within a 192 KB tile region).
-      constexpr uint32_t idesc = make_idesc<BN>();
-      uint64_t a_base[SA], b_base[SB];
-#pragma unroll
-      for (int i = 0; i < SA; ++i) a_base[i] = make_desc(smem_u32(sm.a[i]), 0);
-#pragma unroll
-      for (int i = 0; i < SB; ++i) b_base[i] = make_desc(smem_u32(sm.b[i]), 0);
-      uint32_t ga = 0, gb = 0, tcount = 0;
-      long long w_acc = 0, w_a = 0, w_b = 0, c0 = 0;
+      // cta_group::2: M = 256 in the instruction descriptor (bits 24-28 hold M >> 4)
+      constexpr uint32_t idesc = TWO ? (make_idesc<BN>() + ((uint32_t)(128 >> 4) << 24)) : make_idesc<BN>();
+      // Lean issue loop (SASS-checked): the first version spent ~90 instructions per tap on stage select chains,
+      // modulo/divide stage counters and timing reads — ~450 clk of one thread's dependent issue against the 256 clk
+      // four N=128 MMAs take, which made every small-tile layer issue bound.  Stage descriptors are now
+      // base + stage * stride (stages are contiguous arrays), stage/phase counters are incremental.
+      const uint64_t a_desc0 = make_desc(smem_u32(sm.a[0]), 0);
+      const uint64_t b_desc0 = make_desc(smem_u32(sm.b[0]), 0);
+      constexpr uint32_t kAStep = (uint32_t)(S::kSegRows * 128) >> 4;   // descriptor units (16 B) between A stages
+      constexpr uint32_t kBStep = (uint32_t)(BROWS * 128) >> 4;
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tcount = 0;
+      bool first_tap = true;
       if (BS && unit0 < n_tiles) {
         mbar_wait(&sm.full_b[0], 0);
         tcgen05_fence_after();
-        PN_DBG(2);
       }
       for (int tile = unit0; tile < n_tiles; tile += unit_step, ++tcount) {
         const uint32_t acc = NACC == 2 ? (tcount & 1u) : 0u;
         const uint32_t acc_ph = NACC == 2 ? ((tcount >> 1) & 1u) : (tcount & 1u);
-        if (P.dbg) c0 = clock64();
         mbar_wait(&sm.tmem_empty[acc], acc_ph ^ 1u);
-        if (P.dbg) w_acc += clock64() - c0;
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        int dy = rot % 3;                       // kernel row of this step (the walk is rotated per CTA)
         for (int u = 0; u < n_u; ++u) {
-          {
-            int u2 = u + rot;
-            if (u2 >= n_u) u2 -= n_u;
-            const int dy = u2 - (u2 / 3) * 3;
-            const uint32_t sa = ga % SA, pha = (ga / SA) & 1u;
-            ++ga;
-            if (P.dbg) c0 = clock64();
-            mbar_wait(&sm.full_a[sa], pha);
-            if (P.dbg) w_a += clock64() - c0;
-            uint64_t a_stage = a_base[0];
+          mbar_wait(&sm.full_a[sa], pha);
+          const uint64_t a_stage = a_desc0 + (uint64_t)(sa * kAStep);
 #pragma unroll
-            for (int i = 1; i < SA; ++i) a_stage = (sa == (uint32_t)i) ? a_base[i] : a_stage;
+          for (int dx = 0; dx < 3; ++dx) {
+            uint64_t b_stage;
+            if constexpr (BS) {
+              b_stage = b_desc0 + (uint64_t)((uint32_t)(dy * 3 + dx) * kBStep);   // resident weight slot of this tap
+              if (dx == 0) tcgen05_fence_after();
+            } else {
+              mbar_wait(&sm.full_b[sb], phb);
+              tcgen05_fence_after();
+              b_stage = b_desc0 + (uint64_t)(sb * kBStep);
+            }
+            if (first_tap) { if (issuer) PN_DBG(2); first_tap = false; }
+            const uint32_t first = (u == 0 && dx == 0) ? 0u : 1u;
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              uint32_t sb = 0;
-              uint64_t b_stage;
-              if constexpr (BS) {
-                const uint32_t slot = (uint32_t)(dy * 3 + dx);   // resident weight slot of this tap
-                b_stage = b_base[0];
+            for (int m = 0; m < MT; ++m) {
 #pragma unroll
-                for (int i = 1; i < 9; ++i) b_stage = (slot == (uint32_t)i) ? b_base[i] : b_stage;
-                if (dx == 0) tcgen05_fence_after();
-              } else {
-                sb = gb % SB;
-                const uint32_t phb = (gb / SB) & 1u;
-                ++gb;
-                if (P.dbg) c0 = clock64();
-                mbar_wait(&sm.full_b[sb], phb);
-                if (P.dbg) w_b += clock64() - c0;
-                tcgen05_fence_after();
-                if (gb == 1) PN_DBG(2);
-                b_stage = b_base[0];
-#pragma unroll
-                for (int i = 1; i < SB; ++i) b_stage = (sb == (uint32_t)i) ? b_base[i] : b_stage;
-              }
-              const uint32_t first = (u == 0 && dx == 0) ? 0u : 1u;
-#pragma unroll
-              for (int m = 0; m < MT; ++m) {
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / 16; ++k) {
-                  // (m*128 + dx) rows * 128 B + k * 32 B, in 16-byte units
-                  const uint64_t a_desc = a_stage + (uint64_t)((m * 128 + dx) * 8 + k * 2);
-                  const uint64_t b_desc = b_stage + (uint64_t)(k * 2);
-                  umma_bf16(d_tmem + m * BN, a_desc, b_desc, idesc, k == 0 ? first : 1u);
+              for (int k = 0; k < BLOCK_K / 16; ++k) {
+                // (m*128 + dx) rows * 128 B + k * 32 B, in 16-byte units
+                const uint64_t a_desc = a_stage + (uint64_t)((m * 128 + dx) * 8 + k * 2);
+                const uint64_t b_desc = b_stage + (uint64_t)(k * 2);
+                if (issuer) {
+                  if constexpr (TWO) umma_bf16_2(d_tmem + m * BN, a_desc, b_desc, idesc, k == 0 ? first : 1u);
+                  else umma_bf16(d_tmem + m * BN, a_desc, b_desc, idesc, k == 0 ? first : 1u);
                 }
               }
-              if constexpr (!BS) {
+            }
+            if (issuer) {
+              if constexpr (TWO) {
+                umma_commit2_mc(&sm.empty_b[sb]);
+              } else if constexpr (!BS) {
                 if (CL == 1) umma_commit(&sm.empty_b[sb]); else umma_commit_mc(&sm.empty_b[sb], kMask);
               }
             }
-            umma_commit(&sm.empty_a[sa]);
+            if constexpr (!BS) {
+              if (++sb == SB) { sb = 0; phb ^= 1u; }
+            }
           }
+          if (issuer) {
+            if constexpr (TWO) umma_commit2_mc(&sm.empty_a[sa]); else umma_commit(&sm.empty_a[sa]);
+          }
+          if (++sa == SA) { sa = 0; pha ^= 1u; }
+          if (++dy == 3) dy = 0;
         }
-        umma_commit(&sm.tmem_full[acc]);
-        PN_DBG(3);
-      }
-      if (P.dbg) {
-        P.dbg[blockIdx.x * 16 + 8] = (unsigned long long)w_acc;
-        P.dbg[blockIdx.x * 16 + 9] = (unsigned long long)w_a;
-        P.dbg[blockIdx.x * 16 + 10] = (unsigned long long)w_b;
-        P.dbg[blockIdx.x * 16 + 11] = tcount;
+        if (issuer) {
+          if constexpr (TWO) umma_commit2_mc(&sm.tmem_full[acc]); else umma_commit(&sm.tmem_full[acc]);
+          PN_DBG(3);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -575,7 +645,8 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
         }
       }
       tcgen05_fence_before();
-      mbar_arrive(&sm.tmem_empty[acc]);
+      if constexpr (TWO) mbar_arrive_cluster(map_to_cta(&sm.tmem_empty[acc], 0));   // the leader's MMA thread waits
+      else mbar_arrive(&sm.tmem_empty[acc]);
       if (etid == 0) PN_DBG(5);
     }
   }
@@ -583,7 +654,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
   if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA may exit while peers still signal its barriers
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc<TCOLS>(tmem_base);
+    if constexpr (TWO) tmem_dealloc2<TCOLS>(tmem_base); else tmem_dealloc<TCOLS>(tmem_base);
   }
   if (threadIdx.x == 0) PN_DBG(6);
 }
@@ -653,14 +724,14 @@ int get_map(const void* base, long long rows, int cols, int ld, int box_rows, CU
 }
 
 // `units` = work units (see the kernel); the grid is CL x min(units, co-resident clusters).
-template <int MT, int BN, int SA, int SB, int CL = 1, bool BS = false>
+template <int MT, int BN, int SA, int SB, int CL = 1, bool BS = false, bool TWO = false>
 int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, const DArgs& a, long long units,
            cudaStream_t stream) {
-  constexpr size_t smem = sizeof(DSmem<MT, BN, SA, SB>) + 1024;
+  constexpr size_t smem = sizeof(DSmem<MT, BN, SA, SB, TWO ? BN / 2 : BN>) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static_assert(CL == 1 || (BN / CL) % 8 == 0, "a weight slice must keep the 8-row swizzle period");
   static int max_clusters = 0;
-  auto kern = k_conv_dense<MT, BN, SA, SB, CL, BS>;
+  auto kern = k_conv_dense<MT, BN, SA, SB, CL, BS, TWO>;
   if (max_clusters == 0) {
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int sms = pn_detail::sm_count();
@@ -737,12 +808,6 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, 
       if (to > m_tot) m_tot = to;
       if (ep > m_epi) m_epi = ep;
     }
-    {
-      double wa = 0, wb = 0, wc = 0, tl = 0;
-      for (int c = 0; c < n; ++c) { wc += (double)t[c * 16 + 8]; wa += (double)t[c * 16 + 9]; wb += (double)t[c * 16 + 10]; tl += (double)t[c * 16 + 11]; }
-      fprintf(stderr, "   MMA warp waits (avg kclk per CTA): accumulator %.1f | A operands %.1f | B operands %.1f | tiles/CTA %.1f\n",
-              wc / n / 1e3, wa / n / 1e3, wb / n / 1e3, tl / n);
-    }
     fprintf(stderr, "[dense<%d,%d,%d,%d,cl%d> grid %d units %lld] span %.1f us | CTA start skew avg %.1f max %.1f | first "
                     "operands avg %.1f | mma phase avg %.1f max %.1f | last epilogue avg %.1f max %.1f | CTA total avg %.1f "
                     "max %.1f\n",
@@ -785,10 +850,11 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
     const double waves = (double)PN_DIVUP(tiles, (long long)sms);
     const double bytes = bn * 128.0 + (128.0 * mt + kTailRows) * 128.0 / 3.0;
     const double mma = mt * 4.0 * (bn / 2.0);
-    // measured (tools/kbench_dense.py, PN_DENSE_TIMELINE): ~40 B/clk/SM sustained from L2 when all SMs pull; the
-    // epilogue of a tile costs ~27 clk per (128-row block x column) — it is bound by the burst of global stores —
-    // and is hidden behind the next tile's MMAs only when TMEM holds two accumulators; the last one never is
-    const double per_tap = bytes / 40.0 > mma ? bytes / 40.0 : mma;
+    // measured with PN_DENSE_TIMELINE after the issue loop was made lean: a tap costs its MMAs plus ~150 clk of
+    // barrier hand-shakes, or its bytes at ~56 B/clk/SM, whichever is larger; the epilogue of a tile costs ~27 clk
+    // per (128-row block x column) — a burst of global stores — and is hidden behind the next tile's MMAs only
+    // when TMEM holds two accumulators; the last one never is
+    const double per_tap = bytes / 56.0 > mma + 150.0 ? bytes / 56.0 : mma + 150.0;
     const double tile_clk = 9.0 * (cin / 64) * per_tap;
     const double epi_clk = mt * bn * 27.0;
     const bool two_acc = 2 * mt * bn <= 512;
@@ -802,6 +868,8 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
   if (tile_hint & 0x200) cl = 2;
   if (tile_hint & 0x400) cl = 4;
   if (tile_hint & 0x800) cl = 1;
+  const bool two_sm = (tile_hint & 0x1000) != 0;      // cta_group::2 pair kernel
+  if (two_sm) cl = 2;
   const long long m_tiles = PN_DIVUP(n_pos, (long long)(128 * mt));
   if (m_tiles < cl) cl = 1;
   CUtensorMap ma, mtail, mw;
@@ -809,7 +877,7 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
   if (rc != PN_OK) return rc;
   rc = get_map(in, n_pos, in_ld, in_ld, kTailRows, &mtail);
   if (rc != PN_OK) return rc;
-  rc = get_map(weight, cout, k_pad, k_pad, bn / cl, &mw);
+  rc = get_map(weight, cout, k_pad, k_pad, bn / cl, &mw);   // multicast slice or the pair's half tile: bn/2 rows
   if (rc != PN_OK) return rc;
   DArgs a;
   a.cin = cin; a.in_coff = in_coff; a.cout = cout; a.Hp = Hp; a.Wp = Wp; a.n_pos = (int)n_pos;
@@ -822,6 +890,13 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
   a.out_group_cols = out_group_cols;
   a.in_planar = 0;
   const long long units = PN_DIVUP(m_tiles, (long long)cl) * PN_DIVUP(cout, bn);
+  if (two_sm && m_tiles >= 2) {
+    // half-size weight stages: the freed shared memory buys deeper pipelines
+    if (mt == 2 && bn == 256) return launch<2, 256, 3, 6, 2, false, true>(ma, mtail, mw, a, units, stream);
+    if (mt == 1 && bn == 256) return launch<1, 256, 4, 8, 2, false, true>(ma, mtail, mw, a, units, stream);
+    if (mt == 2 && bn == 128) return launch<2, 128, 4, 8, 2, false, true>(ma, mtail, mw, a, units, stream);
+    return launch<1, 128, 6, 12, 2, false, true>(ma, mtail, mw, a, units, stream);
+  }
 #define PN_DENSE_LAUNCH(MT_, BN_, SA_, SB_)                                                       \
   do {                                                                                            \
     if (cl == 4) return launch<MT_, BN_, SA_, SB_, 4>(ma, mtail, mw, a, units, stream);           \

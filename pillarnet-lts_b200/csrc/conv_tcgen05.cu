@@ -261,44 +261,45 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
     if constexpr (!TMA_A) cp_async_wait_all();   // nothing of this CTA's may still be in flight at exit
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop converged (waits, stage counters and descriptors are warp-uniform and live in
+    // uniform registers) and one elected lane issues the tcgen05 instructions: entering with a single active lane
+    // made the compiler wrap every UTCHMMA in an ELECT / broadcast / retry sequence, ~90 dependent instructions
+    // per 64-channel chunk against the 180-256 clk its four MMAs take (see conv_dense_tc.cu).
+    {
+      const bool issuer = elect_one();
       constexpr uint32_t idesc = make_idesc<BN>();
-      // stage descriptors built once (the issuing thread is one in-order instruction stream)
-      uint64_t a_base[STAGES], b_base[STAGES];
-#pragma unroll
-      for (int i = 0; i < STAGES; ++i) {
-        a_base[i] = make_kmajor_sw128_desc(smem_u32(sm.a[i]));
-        b_base[i] = make_kmajor_sw128_desc(smem_u32(sm.b[i]));
-      }
-      uint32_t g = 0, tcount = 0;
+      const uint64_t a_desc0 = make_kmajor_sw128_desc(smem_u32(sm.a[0]));
+      const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_u32(sm.b[0]));
+      constexpr uint32_t kAStep = (uint32_t)A_STAGE_BYTES >> 4, kBStep = (uint32_t)(BN * 128) >> 4;
+      uint32_t s = 0, ph = 0, tcount = 0;
+      bool first_chunk = true;
       for (int tile = 0; tile < n_tiles; ++tile, ++tcount) {
         const uint32_t acc = tcount & 1u, acc_ph = (tcount >> 1) & 1u;
         mbar_wait(&sm.tmem_empty[acc], acc_ph ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kc = 0; kc < P.n_chunks; ++kc, ++g) {
-          const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+        for (int kc = 0; kc < P.n_chunks; ++kc) {
           mbar_wait(&sm.full[s], ph);
           tcgen05_fence_after();
-          if (g == 0) PN_DBG(2);
-          uint64_t a_desc = a_base[0], b_desc = b_base[0];
+          if (first_chunk) { if (issuer) PN_DBG(2); first_chunk = false; }
+          const uint64_t a_desc = a_desc0 + (uint64_t)(s * kAStep), b_desc = b_desc0 + (uint64_t)(s * kBStep);
+          if (issuer) {
 #pragma unroll
-          for (int i = 1; i < STAGES; ++i) {
-            a_desc = (s == (uint32_t)i) ? a_base[i] : a_desc;
-            b_desc = (s == (uint32_t)i) ? b_base[i] : b_desc;
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+              umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&sm.empty[s]);
           }
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&sm.empty[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        umma_commit(&sm.tmem_full[acc]);
-        PN_DBG(3);
+        if (issuer) {
+          umma_commit(&sm.tmem_full[acc]);
+          PN_DBG(3);
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ===================== epilogue =====================
     const int e = warp - kEpilogueWarp0;

@@ -58,7 +58,7 @@ def test_descriptor_window_mode_probe():
     assert min(errs.values()) <= 2e-3
 
 
-@pytest.mark.parametrize("cluster", [0x800, 0x200, 0x400])   # weight-tile multicast over 1 / 2 / 4 CTAs
+@pytest.mark.parametrize("cluster", [0x800, 0x200, 0x400, 0x1000])   # no cluster / multicast over 2, 4 CTAs / cta_group::2 pair
 @pytest.mark.parametrize("tile", [1, 2, 3, 4])
 @pytest.mark.parametrize("B,H,W,cin,cout", [(1, 20, 24, 64, 64), (2, 33, 17, 128, 256), (1, 45, 45, 256, 160),
                                             (3, 61, 50, 64, 320)])
