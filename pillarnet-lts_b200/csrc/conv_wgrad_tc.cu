@@ -157,25 +157,32 @@ k_wgrad_tc(const WArgs P) {
     cp_async_wait_all();
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp converged, one elected lane issues (see conv_tcgen05.cu)
+    {
+      const bool issuer = elect_one();
       constexpr uint32_t idesc = make_idesc_mn<BN>();
+      const uint64_t a_desc0 = make_mnmajor_sw128_desc(smem_u32(sm.a[0]), ATOM_BYTES);
+      const uint64_t b_desc0 = make_mnmajor_sw128_desc(smem_u32(sm.b[0]), ATOM_BYTES);
+      constexpr uint32_t kAStep = (uint32_t)(2 * ATOM_BYTES) >> 4, kBStep = (uint32_t)((BN / 64) * ATOM_BYTES) >> 4;
+      uint32_t s = 0, ph = 0;
       for (int kc = 0; kc < n_chunks; ++kc) {
-        const uint32_t s = kc % STAGES, ph = (kc / STAGES) & 1u;
         mbar_wait(&sm.full[s], ph);
         fence_proxy_async_smem();   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
         tcgen05_fence_after();
-        const uint64_t a_desc = make_mnmajor_sw128_desc(smem_u32(sm.a[s]), ATOM_BYTES);
-        const uint64_t b_desc = make_mnmajor_sw128_desc(smem_u32(sm.b[s]), ATOM_BYTES);
+        const uint64_t a_desc = a_desc0 + (uint64_t)(s * kAStep), b_desc = b_desc0 + (uint64_t)(s * kBStep);
+        if (issuer) {
 #pragma unroll
-        for (int k = 0; k < BK_ROWS / 16; ++k) {
-          // 16 rows (K) further = 2048 bytes = +128 in the (>>4) start-address field
-          umma_bf16(tmem_base, a_desc + 128 * k, b_desc + 128 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK_ROWS / 16; ++k) {
+            // 16 rows (K) further = 2048 bytes = +128 in the (>>4) start-address field
+            umma_bf16(tmem_base, a_desc + 128 * k, b_desc + 128 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&sm.empty[s]);
         }
-        umma_commit(&sm.empty[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
-      umma_commit(&sm.tmem_full);
+      if (issuer) umma_commit(&sm.tmem_full);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================== epilogue: split-K reduction into dW =====================
     const int e = warp - kEpilogueWarp0;
