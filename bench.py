@@ -370,7 +370,7 @@ def run_gpu(args):
         breakdown, stages, n_conv = conv_breakdown(eng)
         top = breakdown[0]
         flop_total = sum(2.0 * r["rows"] * r["taps"] * r["cin"] * r["cout"] * r["launches_per_pass"] for r in breakdown)
-        traffic, traffic_src = _ncu_traffic(top)
+        traffic, traffic_src = _ncu_traffic(top) if (args.workload == "nusc18" and B == 1) else (None, None)
         roof = {"bound": "tensor", "kernel": top["kernel"] + " (tcgen05 implicit-GEMM conv)",
                 "shape": {k: top[k] for k in ("taps", "cin", "cout", "rows")},
                 "achieved": top["tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
