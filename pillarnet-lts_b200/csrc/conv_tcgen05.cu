@@ -95,7 +95,7 @@ struct Smem {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
-  int nbr[2][BLOCK_M * kMaxTaps];
+  int nbr[3][BLOCK_M * kMaxTaps];   // rulebook rows of the current tile and the next two (ring)
   float scale[BN];
   float shift[BN];
 };
@@ -115,6 +115,52 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   constexpr int TCOLS = tmem_cols<BN>();
   if (threadIdx.x == 0) PN_DBG(0);
   pdl_launch_dependents();   // our successor may be scheduled; it waits for this grid's completion itself
+  // Everything below reads the predecessor's results (live row count, rulebook, activations) or overwrites buffers
+  // it may still read.  Waiting first lets the producers fetch their first rulebook rows while the MMA warp sets
+  // up barriers and TMEM (programmatic launch itself is worth < 1 % here: the graph replay hides launch latency).
+  pdl_wait();
+  const int rows = P.num_rows ? min(*P.num_rows, P.rows_cap) : P.rows_cap;
+  const int n_n_tiles = (P.cout + BN - 1) / BN;
+  // Balanced schedule: every CTA owns an equal, contiguous share of the rows and walks it in 128-row tiles (the
+  // last one partial).  The kernel is bound by the gathers, whose cost is proportional to live rows, not by the
+  // MMAs: with round-robin 128-row tiles, 235 tiles on 148 SMs made 87 CTAs work twice as long as the rest.
+  // Only when one N tile covers cout: with several, a CTA would gather its rows and stream ALL the weights once per
+  // N tile (measured: 30 -> 36 us on the 256->256 stage), so those layers keep round-robin (row tile, N tile) units.
+  const bool balanced = n_n_tiles == 1;
+  const int share = max(64, (((rows + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7);
+  const int row_begin = balanced ? min(rows, (int)blockIdx.x * share) : 0;
+  const int row_end = balanced ? min(rows, row_begin + share) : rows;
+  const int tiles_all = ((rows + BLOCK_M - 1) / BLOCK_M) * n_n_tiles;
+  // this CTA's k-th unit is global tile tile0 + k*tstep; n_tiles = number of units it owns
+  const int tile0 = balanced ? 0 : (int)blockIdx.x, tstep = balanced ? 1 : (int)gridDim.x;
+  const int n_tiles = balanced ? (row_end - row_begin + BLOCK_M - 1) / BLOCK_M
+                               : (tiles_all > tile0 ? (tiles_all - tile0 + tstep - 1) / tstep : 0);
+
+  // Rulebook rows travel global -> registers -> shared two tiles ahead of their use (two register sets, three
+  // shared buffers): short-K layers (32/64 channels, < 1 us per tile) would otherwise expose the load latency per tile.
+  constexpr int kNbrPerThread = (BLOCK_M * kMaxTaps + kProducerThreads - 1) / kProducerThreads;
+  const int tid = threadIdx.x;
+  const int nbr_elems = BLOCK_M * P.taps;
+  auto fetch_nbr = [&](int tile, int (&regs)[kNbrPerThread]) {
+    const int m_tile = (tile0 + tile * tstep) / n_n_tiles;   // `tile` = local unit index
+    const int row0 = row_begin + m_tile * BLOCK_M;
+#pragma unroll
+    for (int q = 0; q < kNbrPerThread; ++q) {
+      const int i = tid + q * kProducerThreads;
+      int src = -1;
+      if (i < nbr_elems && tile < n_tiles) {
+        const int r = i / P.taps, t = i - r * P.taps;
+        const int row = row0 + r;
+        if (row < row_end) src = P.nbr ? __ldg(P.nbr + (long long)row * P.taps + t) : row;
+      }
+      regs[q] = src;
+    }
+  };
+  int nbr_r0[kNbrPerThread], nbr_r1[kNbrPerThread];
+  if (warp < kProducerWarps) {
+    fetch_nbr(0, nbr_r0);      // in flight while the MMA warp initialises barriers and allocates TMEM
+    fetch_nbr(1, nbr_r1);
+  }
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -135,30 +181,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
-  // barrier init / TMEM allocation above overlap the predecessor's tail; everything below reads its results
-  // (the live row count, the rulebook, activations) or overwrites buffers it may still read
-  pdl_wait();
-  const int rows = P.num_rows ? min(*P.num_rows, P.rows_cap) : P.rows_cap;
-  const int n_n_tiles = (P.cout + BN - 1) / BN;
-  // Balanced schedule: every CTA owns an equal, contiguous share of the rows and walks it in 128-row tiles (the
-  // last one partial).  The kernel is bound by the gathers, whose cost is proportional to live rows, not by the
-  // MMAs: with round-robin 128-row tiles, 235 tiles on 148 SMs made 87 CTAs work twice as long as the rest.
-  // Only when one N tile covers cout: with several, a CTA would gather its rows and stream ALL the weights once per
-  // N tile (measured: 30 -> 36 us on the 256->256 stage), so those layers keep round-robin (row tile, N tile) units.
-  const bool balanced = n_n_tiles == 1;
-  const int share = max(64, (((rows + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7);
-  const int row_begin = balanced ? min(rows, (int)blockIdx.x * share) : 0;
-  const int row_end = balanced ? min(rows, row_begin + share) : rows;
-  const int tiles_all = ((rows + BLOCK_M - 1) / BLOCK_M) * n_n_tiles;
-  // this CTA's k-th unit is global tile tile0 + k*tstep; n_tiles = number of units it owns
-  const int tile0 = balanced ? 0 : (int)blockIdx.x, tstep = balanced ? 1 : (int)gridDim.x;
-  const int n_tiles = balanced ? (row_end - row_begin + BLOCK_M - 1) / BLOCK_M
-                               : (tiles_all > tile0 ? (tiles_all - tile0 + tstep - 1) / tstep : 0);
   if (threadIdx.x == 0) PN_DBG(1);
 
   if (warp < kProducerWarps) {
     // ===================== A producers (+ weight TMA) =====================
-    const int tid = threadIdx.x;
     const int piece = tid & 7, rg = tid >> 3;          // rg in [0,64): rows rg + 64*i, i < 2
     const int k_total = P.taps * P.cin;
     // swizzled destination of this thread's 16-byte piece inside a stage (row & 7 == rg & 7 for all i)
@@ -166,25 +192,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
     const uint32_t in_ld_bytes = (uint32_t)P.in_ld * 2u;
     const char* in_bytes = reinterpret_cast<const char*>(P.in);
     uint32_t g = 0;
-    // The rulebook rows of a tile are fetched one tile ahead into registers and parked in the other
-    // half of sm.nbr, so a tile never starts with an exposed global-memory round trip.
-    constexpr int kNbrPerThread = (BLOCK_M * kMaxTaps + kProducerThreads - 1) / kProducerThreads;
-    const int nbr_elems = BLOCK_M * P.taps;
-    auto fetch_nbr = [&](int tile, int (&regs)[kNbrPerThread]) {
-      const int m_tile = (tile0 + tile * tstep) / n_n_tiles;   // `tile` = local unit index
-      const int row0 = row_begin + m_tile * BLOCK_M;
-#pragma unroll
-      for (int q = 0; q < kNbrPerThread; ++q) {
-        const int i = tid + q * kProducerThreads;
-        int src = -1;
-        if (i < nbr_elems && tile < n_tiles) {
-          const int r = i / P.taps, t = i - r * P.taps;
-          const int row = row0 + r;
-          if (row < row_end) src = P.nbr ? __ldg(P.nbr + (long long)row * P.taps + t) : row;
-        }
-        regs[q] = src;
-      }
-    };
     auto park_nbr = [&](int buf, const int (&regs)[kNbrPerThread]) {
 #pragma unroll
       for (int q = 0; q < kNbrPerThread; ++q) {
@@ -192,16 +199,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
         if (i < nbr_elems) sm.nbr[buf][i] = regs[q];
       }
     };
-    int nbr_regs[kNbrPerThread];
-    fetch_nbr(0, nbr_regs);
-    park_nbr(0, nbr_regs);
+    park_nbr(0, nbr_r0);
     named_bar_sync(1, kProducerThreads);
-    uint32_t tl = 0;
-    for (int tile = 0; tile < n_tiles; ++tile, ++tl) {
+    // one tile: rows of tile+2 start travelling into `rf`; at the end `rp` (tile+1, fetched a tile ago) is parked
+    auto run_tile = [&](int tile, int (&rf)[kNbrPerThread], const int (&rp)[kNbrPerThread]) {
       const int gt = tile0 + tile * tstep;
       const int m_tile = gt / n_n_tiles, n_tile = gt - m_tile * n_n_tiles;
-      const int* s_nbr = sm.nbr[tl & 1u];
-      fetch_nbr(tile + 1, nbr_regs);  // next tile's rows: loads in flight during this tile
+      (void)m_tile;
+      const int* s_nbr = sm.nbr[tile % 3];
+      fetch_nbr(tile + 2, rf);
       if constexpr (TMA_A) {
         // one warp feeds the tile: lane l gathers rows 4l..4l+3 of the chunk with one TMA gather4
         // (cin % 64 == 0, so a 64-channel chunk lies inside one tap); lane 0 also loads the weights.
@@ -255,8 +261,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
             cp_async_mbar_arrive_noinc(&sm.full[s]);
         }
       }
-      park_nbr((tl + 1u) & 1u, nbr_regs);   // the other buffer: nobody reads it during this tile
+      park_nbr((tile + 1) % 3, rp);          // read from the tile after this barrier on; its old content (tile-2) is dead
       named_bar_sync(1, kProducerThreads);
+    };
+    for (int tile = 0; tile < n_tiles; tile += 2) {
+      run_tile(tile, nbr_r0, nbr_r1);
+      if (tile + 1 < n_tiles) run_tile(tile + 1, nbr_r1, nbr_r0);
     }
     if constexpr (!TMA_A) cp_async_wait_all();   // nothing of this CTA's may still be in flight at exit
   } else if (warp == kMmaWarp) {
