@@ -60,8 +60,9 @@ constexpr int kMarkPerThread = 4;   // points per thread (strided by the block s
 __global__ void __launch_bounds__(kPtThreads)
 k_mark(const float* __restrict__ pts, int dim, const int* __restrict__ frame_off, int n_points,
        int n_frames, int H, int W, float x0, float y0, float inv, uint32_t* __restrict__ words,
-       int* __restrict__ point_cell) {
+       int* __restrict__ point_cell, int* __restrict__ scan_state, int n_state) {
   __shared__ int s_frame[2];
+  pn_detail::zero_scan_state(scan_state, n_state);   // for the single-pass scan launched next (mask_scan.cu)
   n_points = min(n_points, __ldg(frame_off + n_frames));  // live count on the device, capacity on the host
   const int first = blockIdx.x * (kPtThreads * kMarkPerThread);
   if (first >= n_points) return;
@@ -371,16 +372,17 @@ int pn_pillarize(const float* points, int point_dim, const int* frame_offsets, i
   PN_REQUIRE(occ_words && word_prefix && num_pillars && scratch);
   PN_REQUIRE(n_points == 0 || (points && frame_offsets && point_pillar));
   const long long nw = pn_detail::n_words((long long)n_frames * H * W);
+  if (scratch_bytes < pn_detail::scan_scratch_bytes(nw)) return PN_ERR_WORKSPACE;
   PN_CUDA(cudaMemsetAsync(occ_words, 0, nw * sizeof(uint32_t), stream));
   const int blocks = PN_DIVUP(n_points, kPtThreads);
   if (n_points > 0) {
     k_mark<<<PN_DIVUP(n_points, kPtThreads * kMarkPerThread), kPtThreads, 0, stream>>>(
         points, point_dim, frame_offsets, n_points, n_frames, H, W, x0, y0, inv_pillar, occ_words,
-        point_pillar);
+        point_pillar, reinterpret_cast<int*>(scratch), pn_detail::scan_state_words(nw));
     PN_CHECK_LAUNCH();
   }
   int rc = pn_detail::mask_scan_emit(occ_words, word_prefix, nw, H * W, W, pillar_coords, m_cap,
-                                     num_pillars, scratch, scratch_bytes, stream);
+                                     num_pillars, scratch, scratch_bytes, stream, /*state_is_zero=*/n_points > 0);
   if (rc != PN_OK) return rc;
   if (n_points > 0) {
     k_rank<<<blocks, kPtThreads, 0, stream>>>(occ_words, word_prefix, n_points, frame_offsets + n_frames,

@@ -27,30 +27,39 @@ k_subm_nbr(const uint32_t* __restrict__ words, const int* __restrict__ prefix,
   }
 }
 
-// Each active input marks the (up to 4) outputs whose 3x3/s2/p1 window contains it:
-// input y is tap ky of output oy iff 2*oy - 1 + ky == y.
+// Occupancy of the strided level, computed densely from the input bitmask: output (oy,ox) of a 3x3/s2/p1 conv is
+// active iff any input cell of rows 2oy-1..2oy+1, columns 2ox-1..2ox+1 is.  One thread per output cell, the warp's
+// ballot is the output word — no memset, no atomics, work independent of the number of active sites (the first
+// version had every active input atomicOr its <= 4 outputs into a cleared mask: two launches).  Also clears the
+// state of the scan that follows.
 __global__ void __launch_bounds__(256)
-k_down_mark(const int* __restrict__ coords, const int* __restrict__ num_rows, int m_cap, int Ho,
-            int Wo, uint32_t* __restrict__ out_words) {
-  const int n = min(*num_rows, m_cap);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int b = __ldg(coords + 3 * i), y = __ldg(coords + 3 * i + 1), x = __ldg(coords + 3 * i + 2);
+k_down_mask(const uint32_t* __restrict__ in_words, int n_frames, int H, int W, int Ho, int Wo,
+            uint32_t* __restrict__ out_words, long long n_out_words, int* __restrict__ scan_state, int n_state) {
+  pn_detail::zero_scan_state(scan_state, n_state);
+  const long long cells = (long long)n_frames * Ho * Wo;
+  const long long padded = n_out_words * 32;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < padded;
+       c += (long long)gridDim.x * blockDim.x) {
+    bool on = false;
+    if (c < cells) {
+      const int b = (int)(c / ((long long)Ho * Wo));
+      const int r = (int)(c - (long long)b * Ho * Wo);
+      const int oy = r / Wo, ox = r - oy * Wo;
+      const int xa = max(2 * ox - 1, 0), xb = min(2 * ox + 1, W - 1);
+      const int n = xb - xa + 1;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int ty = y + 1 - ky;
-      if (ty < 0 || (ty & 1)) continue;
-      const int oy = ty >> 1;
-      if (oy >= Ho) continue;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int tx = x + 1 - kx;
-        if (tx < 0 || (tx & 1)) continue;
-        const int ox = tx >> 1;
-        if (ox >= Wo) continue;
-        const int cell = (b * Ho + oy) * Wo + ox;
-        atomicOr(out_words + (cell >> 5), 1u << (cell & 31));
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = 2 * oy - 1 + ky;
+        if (yy < 0 || yy >= H) continue;
+        const long long lo = ((long long)b * H + yy) * W + xa;
+        const int sh = (int)(lo & 31);
+        uint32_t v = __ldg(in_words + (lo >> 5)) >> sh;
+        if (sh + n > 32) v |= __ldg(in_words + (lo >> 5) + 1) << (32 - sh);
+        on |= (v & ((1u << n) - 1u)) != 0u;
       }
     }
+    const uint32_t word = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0) out_words[c >> 5] = word;
   }
 }
 
@@ -120,7 +129,10 @@ k_dense_nbr_deconv2(int n_frames, int H, int W, int pi, int po, int* __restrict_
 inline int grid_for(long long work, int threads) {
   const int sms = pn_detail::sm_count();
   long long g = PN_DIVUP(work, (long long)threads);
-  const long long cap = (long long)(sms > 0 ? sms : 148) * 16;
+  // Grids are sized from capacities (the live row count is on the device) and the kernels are grid-stride loops:
+  // 4 blocks per SM are enough to saturate them, and a rulebook built on the side stream has to find room beside
+  // the persistent conv CTAs of the main stream — thousands of empty blocks queued for 49 us there.
+  const long long cap = (long long)(sms > 0 ? sms : 148) * 4;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
@@ -157,14 +169,14 @@ int pn_rulebook_down3x3s2(const uint32_t* in_words, const int* in_prefix, const 
   PN_REQUIRE(n_frames >= 1 && H_in > 0 && W_in > 0 && in_m_cap >= 0 && out_m_cap >= 0);
   const int Ho = (H_in + 2 - 3) / 2 + 1, Wo = (W_in + 2 - 3) / 2 + 1;
   const long long nw = pn_detail::n_words((long long)n_frames * Ho * Wo);
-  PN_CUDA(cudaMemsetAsync(out_words, 0, nw * sizeof(uint32_t), stream));
-  if (in_m_cap > 0) {
-    k_down_mark<<<grid_for(in_m_cap, 256), 256, 0, stream>>>(in_coords, in_num_rows, in_m_cap, Ho,
-                                                            Wo, out_words);
-    PN_CHECK_LAUNCH();
-  }
+  (void)in_coords; (void)in_num_rows; (void)in_m_cap;   // the occupancy comes from the input bitmask alone
+  if (scratch_bytes < pn_detail::scan_scratch_bytes(nw)) return PN_ERR_WORKSPACE;
+  k_down_mask<<<grid_for(nw * 32, 256), 256, 0, stream>>>(in_words, n_frames, H_in, W_in, Ho, Wo, out_words, nw,
+                                                         reinterpret_cast<int*>(scratch),
+                                                         pn_detail::scan_state_words(nw));
+  PN_CHECK_LAUNCH();
   int rc = pn_detail::mask_scan_emit(out_words, out_prefix, nw, Ho * Wo, Wo, out_coords, out_m_cap,
-                                     out_num_rows, scratch, scratch_bytes, stream);
+                                     out_num_rows, scratch, scratch_bytes, stream, /*state_is_zero=*/true);
   if (rc != PN_OK) return rc;
   if (out_m_cap > 0) {
     k_down_nbr<<<grid_for((long long)out_m_cap * 9, 256), 256, 0, stream>>>(

@@ -60,10 +60,17 @@ class InferenceEngine:
         return self.model.forward_device(self.points, self.offsets)
 
     def prepare(self, warmup=2):
-        """eager warm-up (fills lowering caches, static tables) then capture"""
+        """eager warm-up (fills lowering caches, static tables; the first pass also measures the active-row
+        counts of the sparse stages on whatever batch is staged, which steer the conv tile shapes) then capture"""
+        from . import backbone
         with torch.cuda.stream(self.stream), torch.no_grad():
-            for _ in range(warmup):
+            for i in range(max(1, warmup)):
+                if i == 0:
+                    backbone.observe_rows_begin()
                 out = self._forward()
+                if i == 0:
+                    self.stream.synchronize()
+                    self.rows_seen = backbone.observe_rows_end()
             self.stream.synchronize()
             if self.use_graph:
                 self.graph = torch.cuda.CUDAGraph()
@@ -91,10 +98,10 @@ class InferenceEngine:
 
     # -- public API ------------------------------------------------------------------------------
     def infer(self, frames, metadata=None):
-        if self.det_out is None:
-            self.prepare()
         n = self.stage_host(frames)
         self.upload(n)
+        if self.det_out is None:
+            self.prepare()       # after the upload: the warm-up passes see a real batch
         self.launch()
         self.download()
         self.stream.synchronize()
@@ -142,7 +149,10 @@ class InferenceEngine:
         """Runs a sequence of batches (each a list of B frames) with the next batch's host packing and H2D
         overlapped with the current batch's graph replay.  `consume(i, detections)` is called per batch (default:
         collect and return).  Returns (results, h2d_bytes_per_batch, d2h_bytes_per_batch)."""
-        if self.det_out is None:
+        if self.det_out is None and len(batches) > 0:
+            self.upload(self.stage_host(batches[0]))    # the warm-up passes see a real batch
+            self.prepare()
+        elif self.det_out is None:
             self.prepare()
         if not hasattr(self, "_p_host"):
             self._init_pipeline()

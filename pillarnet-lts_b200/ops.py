@@ -27,13 +27,14 @@ class RankTable:
     coords (cap,3) int32 [b,y,x] in ascending cell order; num: device int32 scalar (1,) ; cap: host.
     """
 
-    __slots__ = ("words", "prefix", "coords", "num", "cap", "B", "H", "W", "_nbr_subm", "_train")
+    __slots__ = ("words", "prefix", "coords", "num", "cap", "B", "H", "W", "_nbr_subm", "_train", "ready")
 
     def __init__(self, words, prefix, coords, num, cap, B, H, W):
         self.words, self.prefix, self.coords, self.num = words, prefix, coords, num
         self.cap, self.B, self.H, self.W = cap, B, H, W
         self._nbr_subm = None
         self._train = None   # training-path caches (exact-size view, rulebooks): train.py
+        self.ready = None    # event recorded when the table was complete (lets a side stream fork right there)
 
     def count(self):
         """host sync: number of active rows"""
@@ -75,7 +76,10 @@ def pillarize(points, frame_offsets, n_frames, H, W, x0, y0, pillar_size, m_cap=
                            c_float(_f32(x0)), c_float(_f32(y0)), c_float(inv), ptr(words), ptr(prefix),
                            ptr(coords), m_cap, ptr(point_pillar), ptr(num), ptr(scratch), c_size_t(sb),
                            stream_ptr()), "pn_pillarize")
-    return RankTable(words, prefix, coords, num, m_cap, n_frames, H, W), point_pillar[:N]
+    table = RankTable(words, prefix, coords, num, m_cap, n_frames, H, W)
+    table.ready = torch.cuda.Event()
+    table.ready.record()
+    return table, point_pillar[:N]
 
 
 def _f32(v):

@@ -62,3 +62,17 @@ for name, us, n in rows:
     print(f"{us:9.1f} us {100 * us / tot:5.1f}%  n={n:5.1f} avg={us / n:7.1f}  {short}")
     out.append(dict(kernel=short, us_per_step=us, launches=n))
 json.dump(out, open(os.path.join(ROOT, args.out), "w"), indent=1)
+
+# --- timeline of the last profiled step: start offset, duration and stream of every kernel (what overlaps what) ---
+if os.environ.get("PN_PROF_TIMELINE", "0") == "1":
+    per = len(evs) // args.steps
+    last = evs[-per:]
+    t0 = last[0].time_range.start
+    end_prev = {}
+    print(f"--- timeline of one replay ({per} records) ---")
+    crit = t0
+    for e in last:
+        st, en = e.time_range.start - t0, e.time_range.end - t0
+        sid = getattr(e, "device_resource_id", None)
+        short = e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:48]
+        print(f"{st:8.1f} -> {en:8.1f}  ({en - st:6.1f} us) stream {sid}  {short}")
