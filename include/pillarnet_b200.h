@@ -152,6 +152,27 @@ int pn_rulebook_down3x3s2(const uint32_t* in_words, const int* in_prefix, const 
                           int out_m_cap, int* nbr, void* scratch, size_t scratch_bytes,
                           pn_stream_t stream);
 
+/* All strided levels of the backbone at once (PillarResNet.py:87,95,103 applied in sequence, plus the submanifold
+ * table of each new level, backbones/base.py:38-52 with indice_key res2..res4).  Same results as n_levels calls of
+ * pn_rulebook_down3x3s2 + pn_rulebook_subm3x3, in n_levels + 2 launches instead of 5 per level: the occupancy
+ * masks are chained first (each depends only on the previous mask), then one launch scans every level and one
+ * launch writes every level's two neighbour tables.  Level l (0-based) has H_l = (H_{l-1}+2-3)/2+1.
+ * `levels` is a host array; every pointer in it is device memory owned by the caller. */
+typedef struct pn_rulebook_level {
+  uint32_t* words;      /* out: occupancy words, pn_mask_words(n_frames, H_l, W_l) */
+  int* prefix;          /* out: exclusive popcount prefix per word */
+  int* coords;          /* out: (m_cap,3) [b,y,x] */
+  int* num_rows;        /* out: device scalar, active rows of this level */
+  int m_cap;
+  int* nbr_down;        /* out: (m_cap,9) rows of the previous level (the strided conv's rulebook) */
+  int* nbr_subm;        /* out: (m_cap,9) rows of this level (its submanifold rulebook) */
+} pn_rulebook_level;
+#define PN_MAX_RULEBOOK_LEVELS 4
+size_t pn_rulebook_pyramid_scratch_bytes(int n_frames, int H0, int W0, int n_levels);
+int pn_rulebook_pyramid3x3s2(const uint32_t* words0, const int* prefix0, int n_frames, int H0, int W0,
+                             int n_levels, const pn_rulebook_level* levels, void* scratch,
+                             size_t scratch_bytes, pn_stream_t stream);
+
 /* Static gather tables for the dense BEV convs (NHWC rows = b*H*W + y*W + x), computed once per shape:
  *   mode 0: 3x3 stride s pad 1 (Conv2d / ZeroPad2d+valid conv), taps 9
  *   mode 1: ConvTranspose2d(k=2,s=2): taps 4, exactly one valid tap (dy*2+dx) per output pixel.

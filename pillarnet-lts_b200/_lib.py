@@ -31,6 +31,14 @@ class ConvArgs(Structure):
     ]
 
 
+class RulebookLevel(Structure):
+    """pn_rulebook_level"""
+    _fields_ = [
+        ("words", c_void_p), ("prefix", c_void_p), ("coords", c_void_p), ("num_rows", c_void_p),
+        ("m_cap", c_int), ("nbr_down", c_void_p), ("nbr_subm", c_void_p),
+    ]
+
+
 class TaskArgs(Structure):
     _fields_ = [
         ("maps", c_void_p), ("ld", c_int),
@@ -59,6 +67,9 @@ SIGNATURES = {
     "pn_rulebook_subm3x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
     "pn_rulebook_down_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pn_rulebook_pyramid_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "pn_rulebook_pyramid3x3s2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                         c_size_t, c_void_p]),
     "pn_rulebook_down3x3s2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                       c_void_p, c_size_t, c_void_p]),

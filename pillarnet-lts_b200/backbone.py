@@ -136,16 +136,13 @@ def _prefetch_rulebooks(table, n_levels):
         side.wait_stream(main)
     out = []
     with torch.cuda.stream(side):
-        t = table
-        for _ in range(n_levels):
-            ot, nbr = ops.rulebook_down3x3s2(t)
-            sub = ot.subm_nbr()
-            ev = torch.cuda.Event()
-            ev.record(side)
-            for x in (ot.words, ot.prefix, ot.coords, ot.num, nbr, sub):
+        levels = ops.rulebook_pyramid(table, n_levels)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        for ot, nbr in levels:
+            for x in (ot.words, ot.prefix, ot.coords, ot.num, nbr, ot._nbr_subm):
                 x.record_stream(main)       # allocated on the side stream, consumed on the main stream
             out.append((ot, nbr, ev))
-            t = ot
     return out
 
 

@@ -71,10 +71,10 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_emit(const uint32_t* __restrict__ words, long long n_words, int n_tiles, uint32_t* __restrict__ state,
-            int cells_per_frame, int W, int* __restrict__ prefix, int* __restrict__ coords, int m_cap,
-            int* __restrict__ num_out) {
+__device__ __forceinline__ void scan_emit_tile(const uint32_t* __restrict__ words, long long n_words, int n_tiles,
+                                               uint32_t* __restrict__ state, int cells_per_frame, int W,
+                                               int* __restrict__ prefix, int* __restrict__ coords, int m_cap,
+                                               int* __restrict__ num_out) {
   __shared__ int s_tile, s_excl;
   if (threadIdx.x == 0) s_tile = (int)atomicAdd(state, 1u);
   __syncthreads();
@@ -137,6 +137,31 @@ k_scan_emit(const uint32_t* __restrict__ words, long long n_words, int n_tiles, 
     }
     ++run;
   }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_emit(const uint32_t* __restrict__ words, long long n_words, int n_tiles, uint32_t* __restrict__ state,
+            int cells_per_frame, int W, int* __restrict__ prefix, int* __restrict__ coords, int m_cap,
+            int* __restrict__ num_out) {
+  scan_emit_tile(words, n_words, n_tiles, state, cells_per_frame, W, prefix, coords, m_cap, num_out);
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_emit_multi(const __grid_constant__ ScanJobs J) {
+  int j = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxScanJobs; ++i)
+    if (i < J.n_jobs && (int)blockIdx.x >= J.block_begin[i]) j = i;
+  const ScanJob& q = J.job[j];
+  scan_emit_tile(q.words, q.n_words, q.n_tiles, q.state, q.cells_per_frame, q.W, q.prefix, q.coords, q.m_cap,
+                 q.num_out);
+}
+
+int mask_scan_emit_multi(const ScanJobs& jobs, cudaStream_t stream) {
+  if (jobs.n_jobs < 1 || jobs.n_jobs > kMaxScanJobs) return PN_ERR_INVALID_ARG;
+  k_scan_emit_multi<<<jobs.block_begin[jobs.n_jobs], kScanThreads, 0, stream>>>(jobs);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
 }
 
 int mask_scan_emit(const uint32_t* words, int* prefix, long long n_words, int cells_per_frame,

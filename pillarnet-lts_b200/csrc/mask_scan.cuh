@@ -30,6 +30,27 @@ int mask_scan_emit(const uint32_t* words, int* prefix, long long n_words, int ce
                    int W, int* coords, int m_cap, int* num_out, void* scratch,
                    size_t scratch_bytes, cudaStream_t stream, bool state_is_zero = false);
 
+// Several independent masks in one launch (the strided rulebook levels): block b works on job j with
+// block_begin[j] <= b < block_begin[j+1].  Every job's state must be zero.
+struct ScanJob {
+  const uint32_t* words;
+  long long n_words;
+  int n_tiles;
+  uint32_t* state;
+  int cells_per_frame, W;
+  int* prefix;
+  int* coords;
+  int m_cap;
+  int* num_out;
+};
+constexpr int kMaxScanJobs = 4;
+struct ScanJobs {
+  ScanJob job[kMaxScanJobs];
+  int block_begin[kMaxScanJobs + 1];
+  int n_jobs;
+};
+int mask_scan_emit_multi(const ScanJobs& jobs, cudaStream_t stream);
+
 // for the kernel that runs right before the scan: all threads of the grid call it
 __device__ __forceinline__ void zero_scan_state(int* state, int n_state) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_state; i += gridDim.x * blockDim.x) state[i] = 0;

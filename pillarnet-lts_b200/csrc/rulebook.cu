@@ -82,6 +82,43 @@ k_down_nbr(const uint32_t* __restrict__ in_words, const int* __restrict__ in_pre
   }
 }
 
+// Both neighbour tables of every strided level in one launch: for output row o of level l, tap k reads
+// (2oy-1+ky, 2ox-1+kx) of level l-1 (strided conv) and (oy+ky-1, ox+kx-1) of level l (submanifold convs).
+struct NbrLevel {
+  const uint32_t* in_words;  const int* in_prefix;  int H_in, W_in;
+  const uint32_t* words;     const int* prefix;     int H, W;
+  const int* coords;         const int* num_rows;   int m_cap;
+  int* nbr_down;             int* nbr_subm;
+};
+struct NbrLevels {
+  NbrLevel lv[PN_MAX_RULEBOOK_LEVELS];
+  int n_levels;
+};
+
+__global__ void __launch_bounds__(256)
+k_pyramid_nbr(const __grid_constant__ NbrLevels L) {
+  for (int l = 0; l < L.n_levels; ++l) {
+    const NbrLevel& q = L.lv[l];
+    const int n = min(*q.num_rows, q.m_cap);
+    const long long total = (long long)n * 9;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+      const int o = (int)(t / 9), k = (int)(t - (long long)o * 9);
+      const int b = __ldg(q.coords + 3 * o), oy = __ldg(q.coords + 3 * o + 1), ox = __ldg(q.coords + 3 * o + 2);
+      const int ky = k / 3, kx = k - ky * 3;
+      int yy = 2 * oy - 1 + ky, xx = 2 * ox - 1 + kx;
+      int r = -1;
+      if (yy >= 0 && yy < q.H_in && xx >= 0 && xx < q.W_in)
+        r = pn_rank_of(q.in_words, q.in_prefix, (b * q.H_in + yy) * q.W_in + xx);
+      q.nbr_down[t] = r;
+      yy = oy + ky - 1, xx = ox + kx - 1;
+      r = -1;
+      if (yy >= 0 && yy < q.H && xx >= 0 && xx < q.W) r = pn_rank_of(q.words, q.prefix, (b * q.H + yy) * q.W + xx);
+      q.nbr_subm[t] = r;
+    }
+  }
+}
+
 // Dense NHWC gather tables (static per shape).  pi/po = 1 when the input/output rows index a
 // zero-padded (H+2, W+2) map.
 __global__ void __launch_bounds__(256)
@@ -183,6 +220,74 @@ int pn_rulebook_down3x3s2(const uint32_t* in_words, const int* in_prefix, const 
         in_words, in_prefix, H_in, W_in, out_coords, out_num_rows, out_m_cap, nbr);
     PN_CHECK_LAUNCH();
   }
+  return PN_OK;
+}
+
+size_t pn_rulebook_pyramid_scratch_bytes(int n_frames, int H0, int W0, int n_levels) {
+  size_t bytes = 0;
+  int H = H0, W = W0;
+  for (int l = 0; l < n_levels; ++l) {
+    H = (H + 2 - 3) / 2 + 1;
+    W = (W + 2 - 3) / 2 + 1;
+    bytes += pn_detail::scan_scratch_bytes(pn_detail::n_words((long long)n_frames * H * W));
+  }
+  return bytes;
+}
+
+int pn_rulebook_pyramid3x3s2(const uint32_t* words0, const int* prefix0, int n_frames, int H0, int W0,
+                             int n_levels, const pn_rulebook_level* levels, void* scratch,
+                             size_t scratch_bytes, pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(words0 && prefix0 && levels && scratch && n_frames >= 1 && H0 > 0 && W0 > 0);
+  PN_REQUIRE(n_levels >= 1 && n_levels <= PN_MAX_RULEBOOK_LEVELS);
+  if (scratch_bytes < pn_rulebook_pyramid_scratch_bytes(n_frames, H0, W0, n_levels)) return PN_ERR_WORKSPACE;
+  pn_detail::ScanJobs jobs = {};
+  NbrLevels nl = {};
+  jobs.n_jobs = nl.n_levels = n_levels;
+  int state_words = 0;
+  {
+    int H = H0, W = W0;
+    for (int l = 0; l < n_levels; ++l) {
+      H = (H + 2 - 3) / 2 + 1;
+      W = (W + 2 - 3) / 2 + 1;
+      state_words += (int)(pn_detail::scan_scratch_bytes(pn_detail::n_words((long long)n_frames * H * W)) / sizeof(int));
+    }
+  }
+  int* state = reinterpret_cast<int*>(scratch);
+  const uint32_t* in_words = words0;
+  const int* in_prefix = prefix0;
+  int H = H0, W = W0, blocks = 0;
+  long long nbr_items = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const pn_rulebook_level& lv = levels[l];
+    PN_REQUIRE(lv.words && lv.prefix && lv.coords && lv.num_rows && lv.nbr_down && lv.nbr_subm && lv.m_cap >= 1);
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long nw = pn_detail::n_words((long long)n_frames * Ho * Wo);
+    // the first mask kernel clears the scan state of every level
+    k_down_mask<<<grid_for(nw * 32, 256), 256, 0, stream>>>(in_words, n_frames, H, W, Ho, Wo, lv.words, nw,
+                                                           reinterpret_cast<int*>(scratch), l == 0 ? state_words : 0);
+    PN_CHECK_LAUNCH();
+    pn_detail::ScanJob& j = jobs.job[l];
+    j.words = lv.words;  j.n_words = nw;  j.n_tiles = pn_detail::scan_tiles(nw);
+    j.state = reinterpret_cast<uint32_t*>(state);
+    j.cells_per_frame = Ho * Wo;  j.W = Wo;  j.prefix = lv.prefix;  j.coords = lv.coords;  j.m_cap = lv.m_cap;
+    j.num_out = lv.num_rows;
+    jobs.block_begin[l] = blocks;
+    blocks += j.n_tiles;
+    state += pn_detail::scan_scratch_bytes(nw) / sizeof(int);
+    NbrLevel& q = nl.lv[l];
+    q.in_words = in_words;  q.in_prefix = in_prefix;  q.H_in = H;  q.W_in = W;
+    q.words = lv.words;  q.prefix = lv.prefix;  q.H = Ho;  q.W = Wo;
+    q.coords = lv.coords;  q.num_rows = lv.num_rows;  q.m_cap = lv.m_cap;
+    q.nbr_down = lv.nbr_down;  q.nbr_subm = lv.nbr_subm;
+    nbr_items += (long long)lv.m_cap * 9;
+    in_words = lv.words;  in_prefix = lv.prefix;  H = Ho;  W = Wo;
+  }
+  jobs.block_begin[n_levels] = blocks;
+  int rc = pn_detail::mask_scan_emit_multi(jobs, stream);
+  if (rc != PN_OK) return rc;
+  k_pyramid_nbr<<<grid_for(nbr_items, 256), 256, 0, stream>>>(nl);
+  PN_CHECK_LAUNCH();
   return PN_OK;
 }
 

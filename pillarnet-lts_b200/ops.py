@@ -154,6 +154,36 @@ def rulebook_down3x3s2(table, out_cap=None):
     return RankTable(words, prefix, coords, num, out_cap, table.B, Ho, Wo), nbr
 
 
+def rulebook_pyramid(table, n_levels):
+    """All strided levels below `table` in n_levels + 2 launches (pn_rulebook_pyramid3x3s2).
+    Returns [(out RankTable with its submanifold table attached, nbr_down (cap,9))] per level — the same
+    tensors as rulebook_down3x3s2 + RankTable.subm_nbr() level by level."""
+    lib = _lib.load()
+    dev = table.coords.device
+    B, H, W, cap = table.B, table.H, table.W, table.cap
+    levels = (_lib.RulebookLevel * n_levels)()
+    out = []
+    for l in range(n_levels):
+        H, W = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+        cap = max(1, min(4 * cap, B * H * W))      # every active input can activate up to 4 outputs
+        nw = lib.pn_mask_words(B, H, W)
+        words, prefix = _i32(nw, device=dev), _i32(nw, device=dev)
+        coords, num = _i32(cap, 3, device=dev), _i32(1, device=dev)
+        nbr_down, nbr_subm = _i32(cap, 9, device=dev), _i32(cap, 9, device=dev)
+        lv = levels[l]
+        lv.words, lv.prefix, lv.coords, lv.num_rows = ptr(words), ptr(prefix), ptr(coords), ptr(num)
+        lv.m_cap, lv.nbr_down, lv.nbr_subm = cap, ptr(nbr_down), ptr(nbr_subm)
+        t = RankTable(words, prefix, coords, num, cap, B, H, W)
+        t._nbr_subm = nbr_subm
+        out.append((t, nbr_down))
+    sb = lib.pn_rulebook_pyramid_scratch_bytes(B, table.H, table.W, n_levels)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
+    check(lib.pn_rulebook_pyramid3x3s2(ptr(table.words), ptr(table.prefix), B, table.H, table.W, n_levels,
+                                       ctypes.byref(levels), ptr(scratch), c_size_t(sb), stream_ptr()),
+          "pn_rulebook_pyramid3x3s2")
+    return out
+
+
 _dense_nbr_cache = {}
 
 

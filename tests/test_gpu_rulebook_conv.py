@@ -60,6 +60,32 @@ def test_rulebooks_bit_exact_vs_oracle(B, H, W, n):
     assert np.array_equal(t3.coords[:m3].cpu().numpy(), o3) and np.array_equal(nbr3[:m3].cpu().numpy(), n3)
 
 
+@pytest.mark.parametrize("B,H,W,n,levels", [(1, 16, 16, 40, 3), (3, 37, 29, 500, 3), (2, 128, 128, 6000, 3),
+                                             (1, 7, 5, 35, 2), (2, 300, 212, 9000, 4), (1, 64, 64, 1, 3)])
+def test_rulebook_pyramid_bit_exact_vs_oracle(B, H, W, n, levels):
+    """pn_rulebook_pyramid3x3s2 (all strided levels + their submanifold tables in n_levels + 2 launches):
+    coordinates, counts and both neighbour tables of every level equal the brute-force oracle's, and the
+    occupancy words / prefixes equal the level-by-level entry point's."""
+    from pillarnet_lts_b200 import ops
+    rng = np.random.default_rng(B * 977 + n)
+    idx = _random_sites(rng, B, H, W, n)
+    table = _table_from_sites(idx, B, H, W)
+    out = ops.rulebook_pyramid(table, levels)
+    assert len(out) == levels
+    prev_idx, prev_table, h, w = idx, table, H, W
+    for t, nbr_down in out:
+        oidx, onbr, (Ho, Wo) = O.rulebook_down3x3s2(prev_idx, h, w)
+        m = t.count()
+        assert (t.H, t.W, t.B) == (Ho, Wo, B) and m == len(oidx)
+        assert np.array_equal(t.coords[:m].cpu().numpy(), oidx)
+        assert np.array_equal(nbr_down[:m].cpu().numpy(), onbr)
+        assert np.array_equal(t.subm_nbr()[:m].cpu().numpy(), O.rulebook_subm3x3(oidx, Ho, Wo))
+        ref_t, ref_nbr = ops.rulebook_down3x3s2(prev_table)
+        assert torch.equal(ref_t.words, t.words) and torch.equal(ref_t.prefix, t.prefix)
+        assert torch.equal(ref_t.num, t.num) and torch.equal(ref_nbr[:m], nbr_down[:m])
+        prev_idx, prev_table, h, w = oidx, t, Ho, Wo
+
+
 def test_rulebook_properties_at_full_nuscenes_size():
     """size-independent properties at BASELINE size: centre tap is the identity, the table is symmetric
     (k <-> 8-k), strided outputs equal max_pool2d of the occupancy."""
