@@ -217,6 +217,13 @@ typedef struct pn_conv_args {
   int rows_hint;         /* expected live rows (tile-shape heuristic only); 0 => rows_cap */
   int out_hp, out_wp;    /* != 0: output rows are a zero-padded (B,out_hp,out_wp) map; border rows are written as 0 */
   int in_rows;           /* allocated rows of `in` (enables the TMA gather4 activation path); 0 = unknown */
+  /* ConvTranspose2d(k=2,s=2) as ONE GEMM (necks/rpn.py:150-154,184-189): deconv_cout != 0 selects it.  `in` rows
+   * index the zero-padded (B, deconv_hp_in, deconv_wp_in) input map, taps == 1, nbr == NULL, cout == 4*deconv_cout
+   * with weight row (dy*2+dx)*deconv_cout + o, scale/shift repeated per tap; the result of input pixel (py,px)
+   * and tap (dy,dx) goes to row (2py-1+dy, 2px-1+dx) of the padded (B,out_hp,out_wp) output map, columns
+   * [out_coff, out_coff+deconv_cout).  A quarter of the MMAs and gathers of the 4-tap gather formulation (each
+   * output pixel has exactly one valid tap).  PN_IMPL_TCGEN05 only. */
+  int deconv_cout, deconv_hp_in, deconv_wp_in;
 } pn_conv_args;
 
 int pn_conv_gather(const pn_conv_args* args, int impl, pn_stream_t stream);

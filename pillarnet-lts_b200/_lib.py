@@ -28,6 +28,7 @@ class ConvArgs(Structure):
         ("relu", c_int),
         ("num_rows", c_void_p), ("rows_cap", c_int),
         ("cin", c_int), ("cout", c_int), ("rows_hint", c_int), ("out_hp", c_int), ("out_wp", c_int), ("in_rows", c_int),
+        ("deconv_cout", c_int), ("deconv_hp_in", c_int), ("deconv_wp_in", c_int),
     ]
 
 

@@ -36,3 +36,17 @@ _overlap_rulebooks = os.environ.get("PN_OVERLAP_RULEBOOKS", "1") != "0"
 def overlap_rulebooks():
     """build the strided-level rulebooks on a side stream, concurrently with the first stage's convs"""
     return _overlap_rulebooks
+
+
+_deconv_gemm = os.environ.get("PN_DECONV_GEMM", "1") != "0"
+
+
+def deconv_gemm():
+    """ConvTranspose2d(k=2,s=2) as one GEMM with a scattering epilogue (layers.dense_deconv2x2) instead of a 4-tap
+    gather conv; PN_DECONV_GEMM=0 restores the latter (A/B measurements, parity tests)."""
+    return _deconv_gemm
+
+
+def set_deconv_gemm(on):
+    global _deconv_gemm
+    _deconv_gemm = bool(on)

@@ -199,6 +199,7 @@ int pn_conv_gather(const pn_conv_args* a, int impl, pn_stream_t stream_) {
   if (a->rows_cap == 0) return PN_OK;
   if (impl == PN_IMPL_TCGEN05) return pn_detail::conv_tcgen05(a, stream);
   if (impl != PN_IMPL_SIMT) return PN_ERR_INVALID_ARG;
+  if (a->deconv_cout != 0) return PN_ERR_UNSUPPORTED;   // the GEMM form of the transposed conv is tensor-core only
   if (a->in_dtype == PN_F32 && a->out_dtype == PN_F32) return launch_simt<float, float>(a, stream);
   if (a->in_dtype == PN_BF16 && a->out_dtype == PN_BF16)
     return launch_simt<__nv_bfloat16, __nv_bfloat16>(a, stream);

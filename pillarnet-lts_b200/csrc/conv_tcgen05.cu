@@ -73,6 +73,7 @@ struct KArgs {
   int out_hp, out_wp;  // != 0: zero the border rows of a padded output map
   int in_rows;         // allocated rows of `in` (TMA gather path: index >= in_rows reads zeros)
   int cin_shift;       // log2(cin) when cin is a power of two, else -1
+  int dc_cout, dc_hp_in, dc_wp_in;   // transposed 2x2/s2 conv as one GEMM (pn_conv_args.deconv_*): 0 = off
   unsigned long long* dbg;   // development aid (PN_CONV_TIMELINE=1): per-CTA %globaltimer milestones
 };
 
@@ -375,10 +376,24 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
       tcgen05_fence_after();
       const long long _e2 = P.dbg ? clock64() : 0;
       if (etid == 0) PN_DBG(4);
-      const int row = row_begin + m_tile * BLOCK_M + e * 32 + lane;
-      const bool row_ok = row < row_end;
+      int row = row_begin + m_tile * BLOCK_M + e * 32 + lane;
+      bool row_ok = row < row_end;
       bool border = false;
-      if (P.out_wp > 0) {
+      int dc_col = 0;   // deconv mode: first output column of this N tile within its tap
+      if (P.dc_cout > 0) {
+        // `row` is an input pixel of the padded map, the N tile lies inside one tap (BN divides dc_cout): the result
+        // belongs to output pixel (2py-1+dy, 2px-1+dx) — every pixel of the padded output map, its zero border
+        // included, is produced exactly once; positions that fall outside it are dropped
+        const int tap = n0 / P.dc_cout;
+        dc_col = tap * P.dc_cout;
+        const int per = P.dc_hp_in * P.dc_wp_in;
+        const int b = row / per, q = row - b * per;
+        const int py = q / P.dc_wp_in, px = q - py * P.dc_wp_in;
+        const int oy = 2 * py - 1 + (tap >> 1), ox = 2 * px - 1 + (tap & 1);
+        row_ok = row_ok && oy >= 0 && oy < P.out_hp && ox >= 0 && ox < P.out_wp;
+        border = ox == 0 || ox == P.out_wp - 1 || oy == 0 || oy == P.out_hp - 1;
+        row = (b * P.out_hp + oy) * P.out_wp + ox;
+      } else if (P.out_wp > 0) {
         const int q = row % (P.out_hp * P.out_wp);
         const int y = q / P.out_wp, x = q - y * P.out_wp;
         border = x == 0 || x == P.out_wp - 1 || y == 0 || y == P.out_hp - 1;
@@ -396,7 +411,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
           float f[CH];
 #pragma unroll
           for (int j = 0; j < CH; ++j) f[j] = fmaf(__uint_as_float(v[j]), sm.scale[c0 + j], sm.shift[c0 + j]);
-          const long long ooff = (long long)row * P.out_ld + P.out_coff + n0 + c0;
+          const long long ooff = (long long)row * P.out_ld + P.out_coff + (n0 - dc_col) + c0;
           if (P.out_f32) {
             float* op = reinterpret_cast<float*>(P.out) + ooff;
             if (P.residual) {
@@ -634,6 +649,13 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
     return PN_ERR_UNSUPPORTED;
   if (a->k_pad % BLOCK_K != 0 || (reinterpret_cast<uintptr_t>(a->weight) & 15u) != 0) return PN_ERR_UNSUPPORTED;
   int bn = a->cout <= 16 ? 16 : a->cout <= 32 ? 32 : a->cout <= 64 ? 64 : a->cout <= 128 ? 128 : 256;
+  const bool deconv = a->deconv_cout != 0;
+  if (deconv) {
+    if (a->taps != 1 || a->nbr != nullptr || a->cout != 4 * a->deconv_cout || a->residual != nullptr ||
+        a->deconv_cout % 16 != 0 || a->deconv_hp_in <= 0 || a->deconv_wp_in <= 0 || a->out_hp <= 0 || a->out_wp <= 0)
+      return PN_ERR_INVALID_ARG;
+    while (a->deconv_cout % bn != 0) bn >>= 1;   // an N tile must lie inside one tap
+  }
   {
     // Tile-shape choice.  The kernel is bound by L2->SM bytes (A tile 128 rows + B tile bn rows per
     // K chunk), so pick the bn that minimises waves x bytes-per-tile; with few row tiles (deep,
@@ -646,6 +668,7 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
       long long best_cost = -1;
       int best = bn;
       for (int cand = bn; cand >= 64; cand >>= 1) {
+        if (deconv && a->deconv_cout % cand != 0) continue;
         const int n_n = PN_DIVUP(a->cout, cand);
         long long units;   // 128-row tiles the busiest CTA walks
         if (n_n == 1) {
@@ -706,6 +729,9 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
   ka.out_wp = a->out_wp;
   ka.in_rows = a->in_rows;
   ka.cin_shift = -1;
+  ka.dc_cout = a->deconv_cout;
+  ka.dc_hp_in = a->deconv_hp_in;
+  ka.dc_wp_in = a->deconv_wp_in;
   ka.dbg = nullptr;
   for (int sft = 3; sft < 16; ++sft)
     if ((1 << sft) == a->cin) ka.cin_shift = sft;

@@ -123,7 +123,8 @@ def invalidate(module):
     edits through `.data` do not bump (load_state_dict / optimiser steps / copy_ do) — call this after
     such an edit."""
     for m in module.modules():
-        for k in ("_pn_lowered", "_pn_group", "_pn_folded", "_pn_final_groups", "_pn_final_groups_tc"):
+        for k in ("_pn_lowered", "_pn_group", "_pn_folded", "_pn_final_groups", "_pn_final_groups_tc",
+                  "_pn_deconv_gemm"):
             m.__dict__.pop(k, None)
 
 
@@ -177,14 +178,14 @@ def lower_group(convs, bns, precision=None):
 
 
 def run_conv(x2d, lw, nbr, taps, cin, cout, rows_cap, *, num=None, relu=False, residual=None, out=None,
-             out_coff=0, out_dtype=None, in_ld=None, in_ptr_offset=0, rows_hint=0, out_hw_pad=None):
+             out_coff=0, out_dtype=None, in_ld=None, in_ptr_offset=0, rows_hint=0, out_hw_pad=None, deconv=None):
     """One fused conv launch on channels-last rows."""
     if out is None:
         out = torch.empty(rows_cap, cout, dtype=out_dtype or x2d.dtype, device=x2d.device)
     ops.conv_gather(x2d, lw.weight, nbr, taps, cin, cout, out, in_ld=in_ld, k_pad=lw.k_pad, scale=lw.scale,
                     shift=lw.shift, residual=residual, out_coff=out_coff, relu=relu, num=num,
                     rows_cap=rows_cap, impl=config.conv_impl(), in_ptr_offset=in_ptr_offset, rows_hint=rows_hint,
-                    out_hw_pad=out_hw_pad)
+                    out_hw_pad=out_hw_pad, deconv=deconv)
     return out
 
 
@@ -268,14 +269,42 @@ def dense_conv3x3(x, conv, bn, relu=True, stride=1, out=None, out_coff=0, out_dt
     return DenseMap(out, x.B, Ho, Wo, cout, out_coff, opad)
 
 
+def lower_deconv_gemm(conv, bn):
+    """ConvTranspose2d(k=2,s=2) as one GEMM: weight rows (dy*2+dx)*Cout + o over K = Cin, affine repeated per tap."""
+    base = lower(conv, bn)
+    cache = conv.__dict__.setdefault("_pn_deconv_gemm", {})
+    hit = cache.get("bf16")
+    if hit is not None and hit.key == base.key:
+        return hit
+    cout, cin = conv.out_channels, conv.in_channels
+    w = weight_matrix(conv).float().reshape(cout, 4, cin).permute(1, 0, 2).reshape(4 * cout, cin).contiguous()
+    lw = Lowered()
+    lw.weight = ops.pack_weight_bf16(w)
+    lw.k_pad = lw.weight.shape[1]
+    lw.scale, lw.shift = base.scale.repeat(4).contiguous(), base.shift.repeat(4).contiguous()
+    lw.key = base.key
+    cache["bf16"] = lw
+    return lw
+
+
 def dense_deconv2x2(x, conv, bn, relu=True, out=None, out_coff=0):
-    """ConvTranspose2d(k=2,s=2)+BN+ReLU (necks/rpn.py:150-154) as a 4-tap gather conv."""
-    nbr = ops.dense_nbr_table(1, x.B, x.H, x.W, 2, x.rows.device, in_pad=bool(x.pad), out_pad=bool(x.pad))
-    lw = lower(conv, bn)
+    """ConvTranspose2d(k=2,s=2)+BN+ReLU (necks/rpn.py:150-154).  On padded bf16 maps: one GEMM over the input
+    pixels whose epilogue scatters each tap's 2x-upsampled position (pn_conv_args.deconv_*); otherwise a 4-tap
+    gather conv over the output pixels (three of the four taps of every output pixel are empty)."""
     cout = conv.out_channels
     Ho, Wo = 2 * x.H, 2 * x.W
     if out is None:
         out = new_dense_rows(x.B, Ho, Wo, cout, x.rows.dtype, x.rows.device, x.pad)
+    if (x.pad and config.get_precision() == "bf16" and config.deconv_gemm() and x.C % 64 == 0 and cout % 16 == 0
+            and x.coff % 8 == 0):
+        lw = lower_deconv_gemm(conv, bn)
+        rows_in = x.B * (x.H + 2) * (x.W + 2)
+        run_conv(x.rows, lw, None, 1, x.C, 4 * cout, rows_in, relu=relu, out=out, out_coff=out_coff,
+                 in_ld=x.rows.stride(0), in_ptr_offset=x.coff, out_hw_pad=(Ho + 2, Wo + 2),
+                 deconv=(cout, x.H + 2, x.W + 2))
+        return DenseMap(out, x.B, Ho, Wo, cout, out_coff, x.pad)
+    nbr = ops.dense_nbr_table(1, x.B, x.H, x.W, 2, x.rows.device, in_pad=bool(x.pad), out_pad=bool(x.pad))
+    lw = lower(conv, bn)
     rows_cap = x.B * (Ho + 2 * x.pad) * (Wo + 2 * x.pad)
     run_conv(x.rows, lw, nbr, 4, x.C, cout, rows_cap, relu=relu, out=out, out_coff=out_coff,
              in_ld=x.rows.stride(0), in_ptr_offset=x.coff, out_hw_pad=(Ho + 2, Wo + 2) if x.pad else None)

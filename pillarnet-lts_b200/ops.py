@@ -209,8 +209,9 @@ def dense_nbr_table(mode, n_frames, H, W, stride, device, in_pad=False, out_pad=
 
 def conv_gather(inp, weight, nbr, taps, cin, cout, out, *, in_ld=None, k_pad=None, scale=None,
                 shift=None, residual=None, res_ld=None, out_ld=None, out_coff=0, relu=False, num=None,
-                rows_cap=None, impl=PN_IMPL_SIMT, in_ptr_offset=0, rows_hint=0, out_hw_pad=None):
+                rows_cap=None, impl=PN_IMPL_SIMT, in_ptr_offset=0, rows_hint=0, out_hw_pad=None, deconv=None):
     """out[o, coff:coff+cout] = act((sum_t W_t . in[nbr[o,t]]) * scale + shift + residual).
+    deconv = (cout_per_tap, Hp_in, Wp_in): the 2x2/s2 transposed conv as one GEMM (pn_conv_args.deconv_*).
 
     `inp`/`out` are 2-D channels-last tensors (possibly wider than cin/cout: in_ld/out_ld are the
     row strides in elements; in_ptr_offset selects a channel slice of the input)."""
@@ -241,6 +242,7 @@ def conv_gather(inp, weight, nbr, taps, cin, cout, out, *, in_ld=None, k_pad=Non
     a.rows_hint = int(rows_hint)
     a.out_hp, a.out_wp = (out_hw_pad if out_hw_pad is not None else (0, 0))
     a.in_rows = inp.shape[0]
+    a.deconv_cout, a.deconv_hp_in, a.deconv_wp_in = deconv if deconv is not None else (0, 0, 0)
     if residual is not None and residual.dtype != out.dtype:
         raise RuntimeError("residual dtype must match the output dtype")
     check(lib.pn_conv_gather(byref(a), impl, stream_ptr()), "pn_conv_gather")

@@ -147,3 +147,52 @@ def test_planar_intermediate_layout_matches_interleaved():
     torch.cuda.synchronize()
     assert torch.equal(out_a, out_b)
     assert float(out_a.abs().max()) > 0.1
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,coff,width", [(1, 12, 9, 64, 64, 0, 64), (2, 45, 45, 256, 256, 256, 512),
+                                                        (1, 90, 90, 256, 128, 8, 136), (1, 5, 7, 128, 48, 0, 48)])
+def test_deconv2x2_gemm_form_vs_torch_and_gather_form(B, H, W, cin, cout, coff, width):
+    """ConvTranspose2d(k=2,s=2)+BN+ReLU (necks/rpn.py:150-154) as one GEMM with a scattering epilogue
+    (pn_conv_args.deconv_*): equals torch on the same bf16-rounded operands within one bf16 ulp (1e-2 rel-to-max),
+    equals the 4-tap gather formulation bit for bit (same products, same fp32 accumulation order over Cin),
+    keeps the zero border of the padded output map and leaves the neighbouring columns untouched."""
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200 import config
+    from pillarnet_lts_b200.layers import DenseMap, dense_deconv2x2
+    P.set_precision("bf16")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(H * 100 + cin + cout)
+    conv = torch.nn.ConvTranspose2d(cin, cout, 2, stride=2, bias=False).cuda()
+    bn = torch.nn.BatchNorm2d(cout, eps=1e-3).cuda().eval()
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.1)
+        bn.running_var.uniform_(0.5, 1.5)
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.1)
+    x = torch.randn(B, H, W, cin, device="cuda").to(torch.bfloat16)
+    xm = DenseMap(_pad_rows(x), B, H, W, cin, 0, 1)
+    outs = []
+    for gemm in (True, False):
+        config.set_deconv_gemm(gemm)
+        rows = torch.full((B * (2 * H + 2) * (2 * W + 2), width), 3.0, device="cuda", dtype=torch.bfloat16)
+        try:
+            dense_deconv2x2(xm, conv, bn, relu=True, out=rows, out_coff=coff)
+        finally:
+            config.set_deconv_gemm(True)
+        torch.cuda.synchronize()
+        outs.append(rows)
+    got, ref_gather = outs
+    assert torch.equal(got, ref_gather)
+    full = got.view(B, 2 * H + 2, 2 * W + 2, width)
+    if coff:
+        assert bool((full[..., :coff] == 3.0).all())
+    assert bool((full[..., coff + cout:] == 3.0).all())
+    y = full[..., coff:coff + cout].float()
+    assert float(y[:, 0].abs().max()) == 0 and float(y[:, -1].abs().max()) == 0
+    assert float(y[:, :, 0].abs().max()) == 0 and float(y[:, :, -1].abs().max()) == 0
+    with torch.no_grad():
+        w = conv.weight.to(torch.bfloat16).float()
+        want = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), w, stride=2)
+        want = bn(want).relu().permute(0, 2, 3, 1)
+    err = (y[:, 1:-1, 1:-1] - want).abs().max().item() / max(1.0, want.abs().max().item())
+    assert err < 1e-2, err
