@@ -470,7 +470,8 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       constexpr uint32_t kAStep = (uint32_t)(S::kSegRows * 128) >> 4;   // descriptor units (16 B) between A stages
       constexpr uint32_t kBStep = (uint32_t)(BROWS * 128) >> 4;
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tcount = 0;
-      bool first_tap = true;
+      bool first_tap = true, a_ahead = false, b_ahead = false;
+      const bool look_ahead = (P.dbg_mode & 8) == 0;   // PN_DENSE_DBGMODE=8 disables it (A/B measurements)
       if (BS && unit0 < n_tiles) {
         mbar_wait(&sm.full_b[0], 0);
         tcgen05_fence_after();
@@ -482,8 +483,10 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         int dy = rot % 3;                       // kernel row of this step (the walk is rotated per CTA)
+        const bool more_tiles = tile + unit_step < n_tiles;
         for (int u = 0; u < n_u; ++u) {
-          mbar_wait(&sm.full_a[sa], pha);
+          if (!a_ahead) mbar_wait(&sm.full_a[sa], pha);
+          a_ahead = false;
           const uint64_t a_stage = a_desc0 + (uint64_t)(sa * kAStep);
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
@@ -492,7 +495,8 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
               b_stage = b_desc0 + (uint64_t)((uint32_t)(dy * 3 + dx) * kBStep);   // resident weight slot of this tap
               if (dx == 0) tcgen05_fence_after();
             } else {
-              mbar_wait(&sm.full_b[sb], phb);
+              if (!b_ahead) mbar_wait(&sm.full_b[sb], phb);
+              b_ahead = false;
               tcgen05_fence_after();
               b_stage = b_desc0 + (uint64_t)(sb * kBStep);
             }
@@ -502,6 +506,24 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
             for (int m = 0; m < MT; ++m) {
 #pragma unroll
               for (int k = 0; k < BLOCK_K / 16; ++k) {
+                if (m == MT - 1 && k == BLOCK_K / 16 - 1) {
+                  // Look ahead before the tap's LAST MMA: the barrier poll of the next tap's operands (~90 clk even
+                  // when they have landed) then runs while the MMAs issued so far execute, instead of after them with
+                  // the tensor pipe drained (measured before: a tap cost its MMAs + ~150 clk).  No deadlock: the
+                  // stage waited for was released by a commit issued SA / SB taps ago, never by the pending one.
+                  if (look_ahead && !(u == n_u - 1 && dx == 2 && !more_tiles)) {
+                    if constexpr (!BS) {
+                      const uint32_t sbn = sb + 1 == SB ? 0u : sb + 1, phbn = sb + 1 == SB ? phb ^ 1u : phb;
+                      mbar_wait(&sm.full_b[sbn], phbn);
+                      b_ahead = true;
+                    }
+                    if (dx == 2) {
+                      const uint32_t san = sa + 1 == SA ? 0u : sa + 1, phan = sa + 1 == SA ? pha ^ 1u : pha;
+                      mbar_wait(&sm.full_a[san], phan);
+                      a_ahead = true;
+                    }
+                  }
+                }
                 // (m*128 + dx) rows * 128 B + k * 32 B, in 16-byte units
                 const uint64_t a_desc = a_stage + (uint64_t)((m * 128 + dx) * 8 + k * 2);
                 const uint64_t b_desc = b_stage + (uint64_t)(k * 2);
