@@ -60,6 +60,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
 // aggregate, then its inclusive prefix once warp 0 has looked back over its predecessors 32 at a time
 // (status word = flag << 30 | value; value < 2^30 cells).  Replaces three launches (tile sums, scan of the sums,
 // emission): beside the persistent conv CTAs every extra dependent launch of the rulebook chain cost 5-15 us.
+constexpr int kSinglePassMaxTiles = 1024;
 constexpr uint32_t kFlagAgg = 1u << 30, kFlagPre = 2u << 30, kFlagMask = 3u << 30, kValMask = (1u << 30) - 1u;
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
@@ -71,19 +72,25 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+template <bool LOOKBACK>
 __device__ __forceinline__ void scan_emit_tile(const uint32_t* __restrict__ words, long long n_words, int n_tiles,
                                                uint32_t* __restrict__ state, int cells_per_frame, int W,
                                                int* __restrict__ prefix, int* __restrict__ coords, int m_cap,
                                                int* __restrict__ num_out) {
   __shared__ int s_tile, s_excl;
-  if (threadIdx.x == 0) s_tile = (int)atomicAdd(state, 1u);
-  __syncthreads();
-  const int tile = s_tile;
+  if (LOOKBACK) {
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(state, 1u);
+    __syncthreads();
+  }
+  // !LOOKBACK: `state` holds the exclusive offsets of the tiles (large masks, see mask_scan_emit)
+  const int tile = LOOKBACK ? s_tile : (int)blockIdx.x;
   const long long w = (long long)tile * kScanTile + threadIdx.x;
   uint32_t bits = w < n_words ? __ldg(words + w) : 0u;
   int tot;
   const int ex = block_exclusive_scan(__popc(bits), &tot);
-  if (threadIdx.x < 32) {
+  if (!LOOKBACK) {
+    if (threadIdx.x == 0) s_excl = (int)state[tile];
+  } else if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     uint32_t* st = state + 1;
     int excl = 0;
@@ -143,7 +150,41 @@ __global__ void __launch_bounds__(kScanThreads)
 k_scan_emit(const uint32_t* __restrict__ words, long long n_words, int n_tiles, uint32_t* __restrict__ state,
             int cells_per_frame, int W, int* __restrict__ prefix, int* __restrict__ coords, int m_cap,
             int* __restrict__ num_out) {
-  scan_emit_tile(words, n_words, n_tiles, state, cells_per_frame, W, prefix, coords, m_cap, num_out);
+  scan_emit_tile<true>(words, n_words, n_tiles, state, cells_per_frame, W, prefix, coords, m_cap, num_out);
+}
+
+// Large masks (thousands of tiles: batches of 8+ frames): with 1 KB tiles the look-back chain's hop latency adds up
+// (measured at 4050 tiles: pillarize 137 -> 160 us), so they keep the three-launch form: per-tile sums, one CTA
+// scanning the sums, emission from the precomputed offsets.
+__global__ void __launch_bounds__(kScanThreads)
+k_tile_sums(const uint32_t* __restrict__ words, long long n_words, int* __restrict__ tile_sums) {
+  const long long w = (long long)blockIdx.x * kScanTile + threadIdx.x;
+  const int c = w < n_words ? __popc(__ldg(words + w)) : 0;
+  int tot;
+  (void)block_exclusive_scan(c, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_tile_offsets(const int* __restrict__ tile_sums, int n_tiles, int* __restrict__ tile_offsets,
+               int* __restrict__ num_out) {
+  int carry = 0;
+  for (int base = 0; base < n_tiles; base += kScanThreads) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_tiles ? tile_sums[i] : 0;
+    int tot;
+    const int ex = block_exclusive_scan(v, &tot);
+    if (i < n_tiles) tile_offsets[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) *num_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_emit(const uint32_t* __restrict__ words, long long n_words, int n_tiles, const int* __restrict__ tile_offsets,
+       int cells_per_frame, int W, int* __restrict__ prefix, int* __restrict__ coords, int m_cap) {
+  scan_emit_tile<false>(words, n_words, n_tiles, reinterpret_cast<uint32_t*>(const_cast<int*>(tile_offsets)),
+                        cells_per_frame, W, prefix, coords, m_cap, nullptr);
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -153,8 +194,8 @@ k_scan_emit_multi(const __grid_constant__ ScanJobs J) {
   for (int i = 1; i < kMaxScanJobs; ++i)
     if (i < J.n_jobs && (int)blockIdx.x >= J.block_begin[i]) j = i;
   const ScanJob& q = J.job[j];
-  scan_emit_tile(q.words, q.n_words, q.n_tiles, q.state, q.cells_per_frame, q.W, q.prefix, q.coords, q.m_cap,
-                 q.num_out);
+  scan_emit_tile<true>(q.words, q.n_words, q.n_tiles, q.state, q.cells_per_frame, q.W, q.prefix, q.coords, q.m_cap,
+                       q.num_out);
 }
 
 int mask_scan_emit_multi(const ScanJobs& jobs, cudaStream_t stream) {
@@ -170,6 +211,18 @@ int mask_scan_emit(const uint32_t* words, int* prefix, long long n_words, int ce
   if (n_words <= 0) return PN_ERR_INVALID_ARG;
   if (scratch_bytes < scan_scratch_bytes(n_words)) return PN_ERR_WORKSPACE;
   const int n_tiles = scan_tiles(n_words);
+  if (n_tiles > kSinglePassMaxTiles) {
+    int* tile_sums = reinterpret_cast<int*>(scratch);
+    int* tile_offsets = tile_sums + (n_tiles + 1);
+    k_tile_sums<<<n_tiles, kScanThreads, 0, stream>>>(words, n_words, tile_sums);
+    PN_CHECK_LAUNCH();
+    k_tile_offsets<<<1, kScanThreads, 0, stream>>>(tile_sums, n_tiles, tile_offsets, num_out);
+    PN_CHECK_LAUNCH();
+    k_emit<<<n_tiles, kScanThreads, 0, stream>>>(words, n_words, n_tiles, tile_offsets, cells_per_frame, W, prefix,
+                                                 coords, m_cap);
+    PN_CHECK_LAUNCH();
+    return PN_OK;
+  }
   if (!state_is_zero) {
     PN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int) * (size_t)scan_state_words(n_words), stream));
   }

@@ -28,38 +28,73 @@ k_subm_nbr(const uint32_t* __restrict__ words, const int* __restrict__ prefix,
 }
 
 // Occupancy of the strided level, computed densely from the input bitmask: output (oy,ox) of a 3x3/s2/p1 conv is
-// active iff any input cell of rows 2oy-1..2oy+1, columns 2ox-1..2ox+1 is.  One thread per output cell, the warp's
-// ballot is the output word — no memset, no atomics, work independent of the number of active sites (the first
-// version had every active input atomicOr its <= 4 outputs into a cleared mask: two launches).  Also clears the
-// state of the scan that follows.
+// active iff any input cell of rows 2oy-1..2oy+1, columns 2ox-1..2ox+1 is.  No memset, no atomics, work independent
+// of the number of active sites (the first version had every active input atomicOr its <= 4 outputs into a cleared
+// mask: two launches), and it needs only the previous level's *mask*, so the masks of all levels can be chained.
+// One thread per output WORD: for each run of its cells that lies in one output row it pulls the 2*len input bits of
+// the three input rows (unaligned 64-bit extracts), ORs the rows, smears each bit onto its neighbours and keeps the
+// even positions — ~100 integer instructions per 32 cells (the per-cell version cost 15x that at batch 8).
+// Also clears the state of the scan that follows.
+__device__ __forceinline__ unsigned long long extract_bits64(const uint32_t* __restrict__ words, long long n_words,
+                                                             long long bit, int n) {
+  // n (1..64) bits starting at linear bit offset `bit`; bits past the array read as 0
+  const long long wi = bit >> 5;
+  const int sh = (int)(bit & 31);
+  const unsigned long long w0 = wi < n_words ? __ldg(words + wi) : 0u;
+  const unsigned long long w1 = wi + 1 < n_words ? __ldg(words + wi + 1) : 0u;
+  unsigned long long v = (w0 | (w1 << 32)) >> sh;
+  if (sh > 0 && sh + n > 64) {
+    const unsigned long long w2 = wi + 2 < n_words ? __ldg(words + wi + 2) : 0u;
+    v |= w2 << (64 - sh);
+  }
+  return n >= 64 ? v : (v & ((1ull << n) - 1ull));
+}
+
+__device__ __forceinline__ uint32_t even_bits(unsigned long long x) {
+  x &= 0x5555555555555555ull;
+  x = (x | (x >> 1)) & 0x3333333333333333ull;
+  x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+  x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+  x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+  x = (x | (x >> 16)) & 0x00000000FFFFFFFFull;
+  return (uint32_t)x;
+}
+
 __global__ void __launch_bounds__(256)
-k_down_mask(const uint32_t* __restrict__ in_words, int n_frames, int H, int W, int Ho, int Wo,
+k_down_mask(const uint32_t* __restrict__ in_words, long long n_in_words, int n_frames, int H, int W, int Ho, int Wo,
             uint32_t* __restrict__ out_words, long long n_out_words, int* __restrict__ scan_state, int n_state) {
   pn_detail::zero_scan_state(scan_state, n_state);
   const long long cells = (long long)n_frames * Ho * Wo;
-  const long long padded = n_out_words * 32;
-  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < padded;
-       c += (long long)gridDim.x * blockDim.x) {
-    bool on = false;
-    if (c < cells) {
+  for (long long ow = (long long)blockIdx.x * blockDim.x + threadIdx.x; ow < n_out_words;
+       ow += (long long)gridDim.x * blockDim.x) {
+    long long c = ow * 32;
+    const long long c_end = min(c + 32, cells);
+    uint32_t word = 0u;
+    while (c < c_end) {
       const int b = (int)(c / ((long long)Ho * Wo));
       const int r = (int)(c - (long long)b * Ho * Wo);
-      const int oy = r / Wo, ox = r - oy * Wo;
-      const int xa = max(2 * ox - 1, 0), xb = min(2 * ox + 1, W - 1);
-      const int n = xb - xa + 1;
+      const int oy = r / Wo, xa = r - oy * Wo;
+      const int len = (int)min((long long)(Wo - xa), c_end - c);      // cells of this run (one output row)
+      const int n = min(2 * len, W - 2 * xa);                          // input columns 2xa .. 2xa+n-1 exist
+      unsigned long long main_bits = 0ull, left = 0ull;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int yy = 2 * oy - 1 + ky;
         if (yy < 0 || yy >= H) continue;
-        const long long lo = ((long long)b * H + yy) * W + xa;
-        const int sh = (int)(lo & 31);
-        uint32_t v = __ldg(in_words + (lo >> 5)) >> sh;
-        if (sh + n > 32) v |= __ldg(in_words + (lo >> 5) + 1) << (32 - sh);
-        on |= (v & ((1u << n) - 1u)) != 0u;
+        const long long row0 = ((long long)b * H + yy) * W;
+        main_bits |= extract_bits64(in_words, n_in_words, row0 + 2 * xa, n);
+        if (xa > 0) {
+          const long long lb = row0 + 2 * xa - 1;
+          left |= (__ldg(in_words + (lb >> 5)) >> (lb & 31)) & 1u;
+        }
       }
+      const unsigned long long t = main_bits | (main_bits >> 1) | (main_bits << 1) | left;
+      uint32_t seg = even_bits(t);
+      if (len < 32) seg &= (1u << len) - 1u;
+      word |= seg << (int)(c - ow * 32);
+      c += len;
     }
-    const uint32_t word = __ballot_sync(0xffffffffu, on);
-    if ((threadIdx.x & 31) == 0) out_words[c >> 5] = word;
+    out_words[ow] = word;
   }
 }
 
@@ -167,9 +202,9 @@ inline int grid_for(long long work, int threads) {
   const int sms = pn_detail::sm_count();
   long long g = PN_DIVUP(work, (long long)threads);
   // Grids are sized from capacities (the live row count is on the device) and the kernels are grid-stride loops:
-  // 4 blocks per SM are enough to saturate them, and a rulebook built on the side stream has to find room beside
+  // 8 blocks of 256 threads fill every thread slot of an SM, and a rulebook built on the side stream has to find room beside
   // the persistent conv CTAs of the main stream — thousands of empty blocks queued for 49 us there.
-  const long long cap = (long long)(sms > 0 ? sms : 148) * 4;
+  const long long cap = (long long)(sms > 0 ? sms : 148) * 8;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
@@ -208,9 +243,9 @@ int pn_rulebook_down3x3s2(const uint32_t* in_words, const int* in_prefix, const 
   const long long nw = pn_detail::n_words((long long)n_frames * Ho * Wo);
   (void)in_coords; (void)in_num_rows; (void)in_m_cap;   // the occupancy comes from the input bitmask alone
   if (scratch_bytes < pn_detail::scan_scratch_bytes(nw)) return PN_ERR_WORKSPACE;
-  k_down_mask<<<grid_for(nw * 32, 256), 256, 0, stream>>>(in_words, n_frames, H_in, W_in, Ho, Wo, out_words, nw,
-                                                         reinterpret_cast<int*>(scratch),
-                                                         pn_detail::scan_state_words(nw));
+  k_down_mask<<<grid_for(nw, 256), 256, 0, stream>>>(in_words, pn_detail::n_words((long long)n_frames * H_in * W_in),
+                                                    n_frames, H_in, W_in, Ho, Wo, out_words, nw,
+                                                    reinterpret_cast<int*>(scratch), pn_detail::scan_state_words(nw));
   PN_CHECK_LAUNCH();
   int rc = pn_detail::mask_scan_emit(out_words, out_prefix, nw, Ho * Wo, Wo, out_coords, out_m_cap,
                                      out_num_rows, scratch, scratch_bytes, stream, /*state_is_zero=*/true);
@@ -264,8 +299,9 @@ int pn_rulebook_pyramid3x3s2(const uint32_t* words0, const int* prefix0, int n_f
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long nw = pn_detail::n_words((long long)n_frames * Ho * Wo);
     // the first mask kernel clears the scan state of every level
-    k_down_mask<<<grid_for(nw * 32, 256), 256, 0, stream>>>(in_words, n_frames, H, W, Ho, Wo, lv.words, nw,
-                                                           reinterpret_cast<int*>(scratch), l == 0 ? state_words : 0);
+    k_down_mask<<<grid_for(nw, 256), 256, 0, stream>>>(in_words, pn_detail::n_words((long long)n_frames * H * W),
+                                                      n_frames, H, W, Ho, Wo, lv.words, nw,
+                                                      reinterpret_cast<int*>(scratch), l == 0 ? state_words : 0);
     PN_CHECK_LAUNCH();
     pn_detail::ScanJob& j = jobs.job[l];
     j.words = lv.words;  j.n_words = nw;  j.n_tiles = pn_detail::scan_tiles(nw);
