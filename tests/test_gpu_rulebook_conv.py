@@ -86,6 +86,30 @@ def test_rulebook_pyramid_bit_exact_vs_oracle(B, H, W, n, levels):
         prev_idx, prev_table, h, w = oidx, t, Ho, Wo
 
 
+def test_rulebook_pyramid_empty_and_fully_occupied_rasters():
+    """edge cases of the strided levels: no active site at all (every count 0, nothing written past row 0) and a
+    fully occupied raster whose width is not a multiple of 32 (every output cell active at every level; the
+    word-granular occupancy kernel has to stitch runs across row boundaries inside one word)."""
+    from pillarnet_lts_b200 import ops
+    empty = _table_from_sites(np.zeros((0, 3), np.int32), 2, 40, 24)
+    assert empty.count() == 0
+    for t, nbr in ops.rulebook_pyramid(empty, 3):
+        assert t.count() == 0 and int(t.words.abs().sum()) == 0
+    B, H, W = 2, 33, 47
+    idx = np.array([(b, y, x) for b in range(B) for y in range(H) for x in range(W)], np.int32)
+    table = _table_from_sites(idx, B, H, W)
+    assert table.count() == B * H * W
+    prev_idx, h, w = idx, H, W
+    for t, nbr_down in ops.rulebook_pyramid(table, 4):
+        oidx, onbr, (Ho, Wo) = O.rulebook_down3x3s2(prev_idx, h, w)
+        m = t.count()
+        assert m == B * Ho * Wo == len(oidx)
+        assert np.array_equal(t.coords[:m].cpu().numpy(), oidx)
+        assert np.array_equal(nbr_down[:m].cpu().numpy(), onbr)
+        assert np.array_equal(t.subm_nbr()[:m].cpu().numpy(), O.rulebook_subm3x3(oidx, Ho, Wo))
+        prev_idx, h, w = oidx, Ho, Wo
+
+
 def test_rulebook_properties_at_full_nuscenes_size():
     """size-independent properties at BASELINE size: centre tap is the identity, the table is symmetric
     (k <-> 8-k), strided outputs equal max_pool2d of the occupancy."""
