@@ -459,73 +459,119 @@ struct SweepParams {
   int use_rect[16];
 };
 
-// One warp per segment.  Removal word w (64 boxes) lives in lane w%32, slot w/32 (pre_cap <= 4096).
-// Per 64-box block: the diagonal tile is resolved serially from shared memory, then the rows of the
-// boxes kept in this block are OR-ed into the lanes' words with independent, coalesced loads.
-__global__ void __launch_bounds__(32)
+// One CTA of four warps per segment.  Warp 0 runs the greedy sweep: removal word w (64 boxes) lives in lane w%32,
+// slot w/32 (pre_cap <= 4096); per 64-box block the diagonal tile is resolved serially, then the rows of the boxes kept
+// in this block are OR-ed into the lanes' words.  The 64 mask rows of every block travel into a three-deep
+// shared-memory ring by cp.async TWO blocks ahead (speculatively: which rows are kept is not known yet; warps 1-3
+// issue, everybody waits only for the older group), so the sweep never waits on global memory.  History: one warp
+// loading the diagonal tile and then the kept rows inside the serial chain, 25 us; plain loads one block ahead, the
+// per-block barrier then waited a global round trip, 22 us; the whole matrix in shared memory up front, 50 us (most
+// frames stop after a few blocks).
+constexpr int kSweepThreads = 128;
+constexpr int kSweepRing = 3;
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(valid ? 8u : 0u) : "memory");
+}
+
+__global__ void __launch_bounds__(kSweepThreads)
 k_nms_sweep(SweepParams P, const float* __restrict__ sorted_boxes, int pre_cap,
             const int* __restrict__ sorted_count, const unsigned long long* __restrict__ mask,
             int* __restrict__ keep_idx, int post_cap, int* __restrict__ keep_count,
             float* __restrict__ det_out) {
-  const int seg = blockIdx.x, lane = threadIdx.x;
+  extern __shared__ unsigned long long s_rows[];   // [kSweepRing][64][col_blocks]
+  __shared__ int s_keep[4096];
+  __shared__ int s_done, s_kept;
+  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(sorted_count[seg], pre_cap);
   const int col_blocks = pre_cap / 64;
   const int post = min(P.post_max[seg % P.segs_per_frame], post_cap);
   const int use_rect = P.use_rect[seg % P.segs_per_frame];
   const long long base = (long long)seg * pre_cap;
-  __shared__ unsigned long long s_diag[64];
-  __shared__ int s_keep[4096];
+  const int nblk = (n + 63) / 64;
+  // words [blk, nblk) of the 64 rows of block `blk` -> ring slot blk % 3 (columns past the last box are never read;
+  // rows past the last box are zero-filled); one commit group per call, also when there is nothing to copy
+  auto fetch_block = [&](int blk, int t0, int nt) {
+    if (blk < nblk) {
+      const int rows = min(64, n - blk * 64), nwords = nblk - blk;
+      unsigned long long* dst = s_rows + (size_t)(blk % kSweepRing) * 64 * col_blocks;
+      for (int i = t0; i < 64 * nwords; i += nt) {
+        const int r = i / nwords, w = blk + (i - r * nwords);
+        const bool valid = r < rows;
+        cp_async8(dst + r * col_blocks + w, mask + (base + blk * 64 + (valid ? r : 0)) * col_blocks + w, valid);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch_block(0, tid, kSweepThreads);
+  fetch_block(1, tid, kSweepThreads);
+  if (tid == 0) { s_done = 0; s_kept = 0; }
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+  __syncthreads();
   unsigned long long remv[2] = {0ull, 0ull};
   int kept = 0;
-  const int nblk = (n + 63) / 64;
-  for (int blk = 0; blk < nblk && kept < post; ++blk) {
-    const int rows = min(64, n - blk * 64);
-    for (int r = lane; r < 64; r += 32)
-      s_diag[r] = r < rows ? mask[(base + blk * 64 + r) * col_blocks + blk] : 0ull;
-    __syncwarp();
-    unsigned long long cur = __shfl_sync(0xffffffffu, blk < 32 ? remv[0] : remv[1], blk & 31);
-    unsigned long long kept_bits = 0ull;
-    int kept_here = 0;
-    for (int r = 0; r < rows; ++r) {
-      if (!((cur >> r) & 1ull)) {
-        if (kept + kept_here < post) {
-          kept_bits |= 1ull << r;
-          if (lane == 0) s_keep[kept + kept_here] = blk * 64 + r;
-          ++kept_here;
+  for (int blk = 0; blk < nblk; ++blk) {
+    if (warp > 0) {
+      fetch_block(blk + 2, tid - 32, kSweepThreads - 32);
+    } else {
+      const unsigned long long* tile = s_rows + (size_t)(blk % kSweepRing) * 64 * col_blocks;
+      const int rows = min(64, n - blk * 64);
+      unsigned long long cur = __shfl_sync(0xffffffffu, blk < 32 ? remv[0] : remv[1], blk & 31);
+      if (rows < 64) cur |= ~0ull << rows;           // boxes past the end count as suppressed
+      // The diagonal tile is inherently serial (box r survives iff no earlier survivor suppresses it), but only the
+      // running word `cur` is loop carried: the 64 tile words are fetched by unconditional, independent loads eight
+      // at a time, so a step is shift / test / select-OR instead of a dependent shared-memory round trip.
+      unsigned long long surv = 0ull;                // survivors of this block, in order
+#pragma unroll 1
+      for (int r0 = 0; r0 < 64; r0 += 8) {
+        unsigned long long d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = tile[(r0 + j) * col_blocks + blk];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool alive = ((cur >> (r0 + j)) & 1ull) == 0ull;
+          surv |= alive ? (1ull << (r0 + j)) : 0ull;
+          cur |= alive ? d[j] : 0ull;
         }
-        cur |= s_diag[r];
       }
-    }
-    kept += kept_here;
+      unsigned long long kept_bits = 0ull;
+      int kept_here = 0;
+      while (surv && kept + kept_here < post) {      // warp-uniform
+        const int r = __ffsll((long long)surv) - 1;
+        surv &= surv - 1;
+        kept_bits |= 1ull << r;
+        if (lane == 0) s_keep[kept + kept_here] = blk * 64 + r;
+        ++kept_here;
+      }
+      kept += kept_here;
 #pragma unroll
-    for (int slot = 0; slot < 2; ++slot) {
-      const int w = lane + 32 * slot;
-      if (w > blk && w < col_blocks) {
-        // rows of the boxes kept in this block: 8 independent loads in flight per lane, then OR
-        unsigned long long acc = 0ull;
-        unsigned long long bits = kept_bits;
-        while (bits) {
-          unsigned long long v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            v[u] = 0ull;
-            if (bits) {
-              const int r = __ffsll((long long)bits) - 1;
-              bits &= bits - 1;
-              v[u] = mask[(base + blk * 64 + r) * col_blocks + w];
-            }
+      for (int slot = 0; slot < 2; ++slot) {
+        const int w = lane + 32 * slot;
+        if (w > blk && w < nblk) {
+          unsigned long long acc = 0ull, bits = kept_bits;
+          while (bits) {
+            const int r = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            acc |= tile[r * col_blocks + w];
           }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) acc |= v[u];
+          remv[slot] |= acc;
         }
-        remv[slot] |= acc;
+      }
+      if (lane == 0) {
+        s_kept = kept;
+        if (kept >= post) s_done = 1;
       }
     }
-    __syncwarp();
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // block blk+1 has landed (blk+2 may still travel)
+    __syncthreads();
+    if (s_done) break;
   }
-  __syncwarp();
-  if (lane == 0) keep_count[seg] = kept;
-  for (int k = lane; k < kept; k += 32) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  kept = s_kept;
+  if (tid == 0) keep_count[seg] = kept;
+  for (int k = tid; k < kept; k += kSweepThreads) {
     const int i = s_keep[k];
     keep_idx[(long long)seg * post_cap + k] = i;
     const float* bx = sorted_boxes + (base + i) * kBoxRec;
@@ -535,6 +581,21 @@ k_nms_sweep(SweepParams P, const float* __restrict__ sorted_boxes, int pre_cap,
     o[9] = use_rect ? bx[10] : bx[9];
     o[10] = bx[11];
   }
+}
+
+static int launch_sweep(int n_segs, const SweepParams& S, const float* sorted_boxes, int pre_cap, const int* sorted_count,
+                        const unsigned long long* mask, int* keep_idx, int post_cap, int* keep_count, float* det_out,
+                        cudaStream_t stream) {
+  const size_t smem = (size_t)kSweepRing * 64 * (pre_cap / 64) * sizeof(unsigned long long);   // 96 KB at pre_cap 4096
+  static bool configured = false;
+  if (!configured) {
+    PN_CUDA(cudaFuncSetAttribute(k_nms_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  k_nms_sweep<<<n_segs, kSweepThreads, smem, stream>>>(S, sorted_boxes, pre_cap, sorted_count, mask, keep_idx, post_cap,
+                                                      keep_count, det_out);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
 }
 
 // ---- standalone iou3d_nms_cuda drop-ins ---------------------------------------------------------
@@ -729,10 +790,8 @@ int pn_nms(int mode, int n_frames, int segs_per_frame, const float* seg_thr,
   dim3 grid(pre_cap / 64, pre_cap / 64, n_segs);
   k_nms_mask<<<grid, kMaskThreads, 0, stream>>>(M, sorted_boxes, geom, pre_cap, sorted_count, mask);
   PN_CHECK_LAUNCH();
-  k_nms_sweep<<<n_segs, 32, 0, stream>>>(S, sorted_boxes, pre_cap, sorted_count, mask, keep_idx,
-                                         post_cap, keep_count, det_out);
-  PN_CHECK_LAUNCH();
-  return PN_OK;
+  return launch_sweep(n_segs, S, sorted_boxes, pre_cap, sorted_count, mask, keep_idx, post_cap, keep_count, det_out,
+                      stream);
 }
 
 int pn_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* iou,
@@ -788,9 +847,7 @@ int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t s
   dim3 grid(cap / 64, cap / 64, 1);
   k_nms_mask<<<grid, kMaskThreads, 0, stream>>>(M, rec, geom, cap, cnt, mask);
   PN_CHECK_LAUNCH();
-  k_nms_sweep<<<1, 32, 0, stream>>>(S, rec, cap, cnt, mask, keep, cap, num_keep, det);
-  PN_CHECK_LAUNCH();
-  return PN_OK;
+  return launch_sweep(1, S, rec, cap, cnt, mask, keep, cap, num_keep, det, stream);
 }
 
 }  // extern "C"
