@@ -7,17 +7,20 @@
 // head (necks/rpn.py:147-207, bbox_heads/center_head.py:27-35,101-112).  Only the dense channel
 // contraction touches the tensor cores; the gather stays a gather.
 //
-// Structure (one persistent CTA per SM, 288 threads, warp-specialised):
-//   warps 0-3  A producers: gather 128 activation rows x 64 channels (bf16, 128 B per row) per
-//              K-chunk with 16-byte cp.async into a 128B-swizzled K-major tile (rows that are
-//              missing in the rulebook are zero-filled by cp.async src-size 0); thread 0 also
-//              issues the TMA load of the weight tile (BLOCK_N x 64, SWIZZLE_128B tensor map) and
-//              arms the stage's mbarrier with the TMA byte count.
-//   warp 8     allocates TMEM (2 x BLOCK_N fp32 columns: double-buffered accumulator); one elected
-//              lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16, kind::f16, bf16 x bf16 -> fp32) and
-//              tcgen05.commit to release smem stages / publish the accumulator.
-//   warps 4-7  epilogue: tcgen05.ld 32 lanes x 32 columns, fused scale/shift (BN+bias), residual,
-//              ReLU, convert, row-contiguous stores; overlaps with the next tile's MMAs.
+// Structure (one persistent CTA per SM, 672 threads, warp-specialised):
+//   warps 0-15  A producers: gather 128 activation rows x 64 channels (bf16, 128 B per row) per K-chunk with
+//               16-byte cp.async into a 128B-swizzled K-major tile (rows that are missing in the rulebook are
+//               zero-filled by cp.async src-size 0) and signal the stage's mbarrier with
+//               cp.async.mbarrier.arrive.noinc; thread 0 also issues the TMA load of the weight tile
+//               (BLOCK_N x 64, SWIZZLE_128B tensor map) and arms the barrier with the TMA byte count.  Rulebook
+//               rows travel global -> registers -> shared two tiles ahead.  (Opt-in PN_CONV_TMA_GATHER=1: the
+//               activations through TMA gather4 issued by 32 lanes spread over these warps; measured slower.)
+//   warp 20     allocates TMEM (2 x BLOCK_N fp32 columns: double-buffered accumulator); the warp walks the issue
+//               loop converged and one elected lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16, kind::f16,
+//               bf16 x bf16 -> fp32) and tcgen05.commit to release smem stages / publish the accumulator.
+//   warps 16-19 epilogue: tcgen05.ld 32 lanes x 32 columns, fused scale/shift (BN+bias), residual, ReLU, convert,
+//               row-contiguous stores (or the scattering store of the GEMM-form transposed conv); overlaps with
+//               the next tile's MMAs.
 // K = taps*cin is walked in 64-element chunks (zero-padded weights), so a chunk may straddle taps
 // (cin = 32) — each 16-byte piece belongs to exactly one tap because cin % 8 == 0.
 #include <cuda.h>
