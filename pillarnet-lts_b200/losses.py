@@ -25,8 +25,9 @@ class RegLoss(nn.Module):
     """per-channel masked L1 over the positive objects, normalised by their count (centernet_loss.py:9-32)"""
 
     def forward(self, output, mask, ind, target):
-        if mask.sum() == 0:
-            return output.new_zeros((1,))
+        # The reference returns zeros((1,)) when there is no positive (`if mask.sum() == 0`, a host sync per task and
+        # step); without positives every masked term below is exactly 0, so the value is the same and the step
+        # stays sync-free.
         pred = gather_feat(output, ind)
         m = mask.float().unsqueeze(2)
         loss = F.l1_loss(pred * m, target * m, reduction="none")
@@ -43,9 +44,8 @@ class FastFocalLoss(nn.Module):
         pos_pred = gather_feat(out, ind).gather(2, cat.unsqueeze(2))       # (B,M,1)
         num_pos = mask.sum()
         pos = (torch.log(pos_pred) * (1 - pos_pred).pow(2) * mask.unsqueeze(2)).sum()
-        if num_pos == 0:
-            return -neg
-        return -(pos + neg) / num_pos
+        # `if num_pos == 0: return -neg` of the reference without the host sync (pos is exactly 0 there)
+        return torch.where(num_pos == 0, -neg, -(pos + neg) / num_pos.clamp(min=1.0))
 
 
 def to_pcdet(boxes):
