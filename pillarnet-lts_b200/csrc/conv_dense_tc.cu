@@ -274,6 +274,7 @@ struct DArgs {
   // development aid (PN_DENSE_TIMELINE=1): CTA 0 records %globaltimer at its pipeline milestones
   unsigned long long* dbg;
   int dbg_mode;   // development only: bit 0 = skip the global stores, bit 1 = skip the TMEM loads
+  int tma_store;  // bf16 padded / planar output through shared memory + TMA tensor stores (tmap_o is valid)
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -300,7 +301,20 @@ struct DSmem {
   uint32_t tmem_base;
   float scale[BN];
   float shift[BN];
+  // Epilogue staging for TMA tensor stores: 32 rows x 32 bf16 columns (2 KB, SWIZZLE_64B) per epilogue warp.  A
+  // thread owns an output ROW, so its direct 16-byte stores of a warp instruction hit 32 different lines; the LSU
+  // charges per line (~2 clk each, like the gathers of conv_tcgen05.cu): 27 clk per (128 rows x column) measured,
+  // which made every short-K layer epilogue bound.  Staged, the warp issues four conflict-free STS.128 and one lane
+  // hands the 2 KB box to the TMA unit.  Only in the variants whose operand stages leave 16 KB.
+  static constexpr bool kTmaStore =
+      BN >= 32 && (size_t)SA * kSegRows * 128 + (size_t)SB * BROWS * 128 + 2048 + 8 * 2048 + 1024 <= 227 * 1024;
+  alignas(1024) uint8_t stage_out[kTmaStore ? 8 * 2048 : 16];
 };
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 
 // CL > 1: thread-block cluster of CL CTAs that work on CL consecutive row tiles of the SAME N tile; every
 // weight tile is fetched once per cluster — each CTA loads BN/CL rows and TMA-multicasts them into all CL
@@ -317,7 +331,7 @@ struct DSmem {
 template <int MT, int BN, int SA, int SB, int CL, bool BS = false, bool TWO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_constant__ CUtensorMap tmap_a_tail,
-             const __grid_constant__ CUtensorMap tmap_w, const DArgs P) {
+             const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_o, const DArgs P) {
   extern __shared__ uint8_t smem_raw[];
   static_assert(!TWO || (CL == 2 && !BS), "2-SM mode needs a cluster of exactly two CTAs");
   constexpr int BROWS = TWO ? BN / 2 : BN;
@@ -590,7 +604,9 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       if (etid == 0) PN_DBG(4);
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
-        const int q = m_tile * M_TILE + m * 128 + e * 32 + lane;
+        const int q0 = m_tile * M_TILE + m * 128 + e * 32;   // first of this warp's 32 rows
+        const bool box_ok = q0 + 32 <= P.n_pos;
+        const int q = q0 + lane;
         const bool valid = q < P.n_pos;
         const int b = valid ? q / hw_p : 0;
         const int r = q - b * hw_p;
@@ -646,6 +662,33 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
                 for (int j = 0; j < CH; ++j)
                   if (j < nvalid) op[j] = f[j];
               }
+            } else if (S::kTmaStore && CH == 32 && P.tma_store && nvalid == CH && box_ok) {
+              // all 32 lanes are here (box_ok: the warp's 32 rows exist); lane = row of the box
+              uint8_t* stg = sm.stage_out + (warp - 4) * 2048;
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous box was read
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 qv;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&qv);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[8 * j + 2 * u], f[8 * j + 2 * u + 1]);
+                // SWIZZLE_64B: 16-byte chunk index ^ address bits 7-8 = (row >> 1) & 3 for 64-byte rows
+                *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = qv;
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                int col = ocol0 + c0;
+                int row0 = q0;
+                if (P.out_group_cols > 0) {
+                  const int g = col / P.out_group_cols;
+                  col -= g * P.out_group_cols;
+                  row0 += g * P.n_pos;
+                }
+                tma_store_2d(&tmap_o, smem_u32(stg), col, row0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
             } else {
               __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + ooff;
               if (nvalid == CH && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
@@ -671,6 +714,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       else mbar_arrive(&sm.tmem_empty[acc]);
       if (etid == 0) PN_DBG(5);
     }
+    if (S::kTmaStore && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staged boxes are out
   }
   tcgen05_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA may exit while peers still signal its barriers
@@ -745,10 +789,40 @@ int get_map(const void* base, long long rows, int cols, int ld, int box_rows, CU
   return PN_OK;
 }
 
+// bf16 output matrix (rows, cols) with row stride ld for the epilogue's TMA stores: box 32 cols x 32 rows, SWIZZLE_64B
+int get_map_out(const void* base, long long rows, int cols, int ld, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  Key key{base, rows, cols, ld, -32};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return PN_OK; }
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return PN_ERR_UNSUPPORTED;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return PN_ERR_CUDA;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+  }
+  *out = m;
+  return PN_OK;
+}
+
 // `units` = work units (see the kernel); the grid is CL x min(units, co-resident clusters).
 template <int MT, int BN, int SA, int SB, int CL = 1, bool BS = false, bool TWO = false>
-int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, const DArgs& a, long long units,
-           cudaStream_t stream) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, const CUtensorMap& mo, const DArgs& a,
+           long long units, cudaStream_t stream) {
   constexpr size_t smem = sizeof(DSmem<MT, BN, SA, SB, TWO ? BN / 2 : BN>) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static_assert(CL == 1 || (BN / CL) % 8 == 0, "a weight slice must keep the 8-row swizzle period");
@@ -807,7 +881,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, 
   }
   cfg.attrs = at;
   cfg.numAttrs = n_at;
-  PN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mt, mw, a_dbg));
+  PN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mt, mw, mo, a_dbg));
   PN_CHECK_LAUNCH();
   if (timeline) {
     PN_CUDA(cudaStreamSynchronize(stream));
@@ -911,19 +985,28 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
   a.dbg = nullptr;
   a.out_group_cols = out_group_cols;
   a.in_planar = 0;
+  // epilogue through TMA tensor stores: bf16 rows of the padded (or planar) map, whole 32-column chunks
+  static const bool tma_store_enabled = [] { const char* e = getenv("PN_DENSE_TMA_STORE"); return !(e && e[0] == '0'); }();
+  CUtensorMap mo = mw;
+  a.tma_store = 0;
+  if (tma_store_enabled && out_dtype == PN_BF16 && !out_compact && cout % 32 == 0 && out_coff % 8 == 0 &&
+      out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    const long long o_rows = out_group_cols > 0 ? (long long)(cout / out_group_cols) * n_pos : n_pos;
+    if (o_rows < (1ll << 31) && get_map_out(out, o_rows, out_ld, out_ld, &mo) == PN_OK) a.tma_store = 1;
+  }
   const long long units = PN_DIVUP(m_tiles, (long long)cl) * PN_DIVUP(cout, bn);
   if (two_sm && m_tiles >= 2) {
     // half-size weight stages: the freed shared memory buys deeper pipelines
-    if (mt == 2 && bn == 256) return launch<2, 256, 3, 6, 2, false, true>(ma, mtail, mw, a, units, stream);
-    if (mt == 1 && bn == 256) return launch<1, 256, 4, 8, 2, false, true>(ma, mtail, mw, a, units, stream);
-    if (mt == 2 && bn == 128) return launch<2, 128, 4, 8, 2, false, true>(ma, mtail, mw, a, units, stream);
-    return launch<1, 128, 6, 12, 2, false, true>(ma, mtail, mw, a, units, stream);
+    if (mt == 2 && bn == 256) return launch<2, 256, 3, 6, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
+    if (mt == 1 && bn == 256) return launch<1, 256, 4, 8, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
+    if (mt == 2 && bn == 128) return launch<2, 128, 4, 8, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
+    return launch<1, 128, 6, 12, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
   }
 #define PN_DENSE_LAUNCH(MT_, BN_, SA_, SB_)                                                       \
   do {                                                                                            \
-    if (cl == 4) return launch<MT_, BN_, SA_, SB_, 4>(ma, mtail, mw, a, units, stream);           \
-    if (cl == 2) return launch<MT_, BN_, SA_, SB_, 2>(ma, mtail, mw, a, units, stream);           \
-    return launch<MT_, BN_, SA_, SB_, 1>(ma, mtail, mw, a, units, stream);                        \
+    if (cl == 4) return launch<MT_, BN_, SA_, SB_, 4>(ma, mtail, mw, mo, a, units, stream);           \
+    if (cl == 2) return launch<MT_, BN_, SA_, SB_, 2>(ma, mtail, mw, mo, a, units, stream);           \
+    return launch<MT_, BN_, SA_, SB_, 1>(ma, mtail, mw, mo, a, units, stream);                        \
   } while (0)
   if (mt == 2 && bn == 256) PN_DENSE_LAUNCH(2, 256, 2, 4);
   if (mt == 1 && bn == 256) PN_DENSE_LAUNCH(1, 256, 3, 5);
@@ -966,10 +1049,10 @@ int pn_conv_dense3x3_grouped(const void* in, int in_ld, int in_coff, int cin, in
   a.scale = scale; a.shift = shift; a.out = out; a.out_f32 = out_dtype == PN_F32; a.out_ld = out_ld;
   a.out_coff = 0; a.out_compact = out_compact; a.relu = relu; a.base_offset_mode = 0;
   a.n_groups = n_groups; a.group_tab = group_tab; a.dbg = nullptr;
-  a.out_group_cols = 0; a.in_planar = in_planar;
+  a.out_group_cols = 0; a.in_planar = in_planar; a.tma_store = 0;
   const long long tiles = PN_DIVUP(n_pos, (long long)(128 * mt)) * n_groups;
-  if (cin == BLOCK_K && n_groups <= sms) return launch<2, 16, 6, 9, 1, true>(ma, mtail, mw, a, tiles, stream);   // weights stay resident
-  return launch<2, 16, 6, 8, 1>(ma, mtail, mw, a, tiles, stream);
+  if (cin == BLOCK_K && n_groups <= sms) return launch<2, 16, 6, 9, 1, true>(ma, mtail, mw, mw, a, tiles, stream);   // weights stay resident
+  return launch<2, 16, 6, 8, 1>(ma, mtail, mw, mw, a, tiles, stream);
 }
 
 }  // extern "C"
