@@ -77,6 +77,7 @@ struct KArgs {
   int in_rows;         // allocated rows of `in` (TMA gather path: index >= in_rows reads zeros)
   int cin_shift;       // log2(cin) when cin is a power of two, else -1
   int dc_cout, dc_hp_in, dc_wp_in;   // transposed 2x2/s2 conv as one GEMM (pn_conv_args.deconv_*): 0 = off
+  int tma_store;       // bf16 output rows through shared memory + TMA tensor stores (tmap_o is valid)
   unsigned long long* dbg;   // development aid (PN_CONV_TIMELINE=1): per-CTA %globaltimer milestones
 };
 
@@ -106,7 +107,16 @@ struct Smem {
   int nbr[3][BLOCK_M * kMaxTaps];   // rulebook rows of the current tile and the next two (ring)
   float scale[BN];
   float shift[BN];
+  // Epilogue staging for TMA tensor stores (see conv_dense_tc.cu): 32 rows x 32 bf16 columns (2 KB, SWIZZLE_64B),
+  // two buffers per epilogue warp.  Here the direct row-per-thread stores cost twice: their 32 lines per warp
+  // instruction occupy the same LSU that the producers' gathers are bound by.
+  alignas(1024) uint8_t stage_out[BN >= 32 ? 4 * 2 * 2048 : 16];
 };
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 
 template <int BN>
 constexpr int tmem_cols() {
@@ -115,7 +125,8 @@ constexpr int tmem_cols() {
 
 template <int BN, int STAGES, bool TMA_A>
 __global__ void __launch_bounds__(kThreads, 1)
-k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const KArgs P) {
+k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
+          const __grid_constant__ CUtensorMap tmap_o, const KArgs P) {
   extern __shared__ uint8_t smem_raw[];
   using S = Smem<BN, STAGES>;
   S& sm = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -359,7 +370,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
     // ===================== epilogue =====================
     const int e = warp - kEpilogueWarp0;
     const int etid = threadIdx.x - kEpilogueWarp0 * 32;
-    uint32_t tcount = 0;
+    uint32_t tcount = 0, stage_k = 0;
     long long w_ss = 0, w_tfull = 0, w_body = 0;
     for (int tile = 0; tile < n_tiles; ++tile, ++tcount) {
       const int gt = tile0 + tile * tstep;
@@ -381,6 +392,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
       if (etid == 0) PN_DBG(4);
       int row = row_begin + m_tile * BLOCK_M + e * 32 + lane;
       bool row_ok = row < row_end;
+      // TMA-stored box: the warp's 32 rows must all be this CTA's live rows (a share ends on a multiple of 8 rows,
+      // so only the warp that straddles the end falls back to direct stores)
+      const bool box_ok = BN >= 32 && P.tma_store != 0 && row - lane + 32 <= row_end;
       bool border = false;
       int dc_col = 0;   // deconv mode: first output column of this N tile within its tap
       if (P.dc_cout > 0) {
@@ -471,7 +485,28 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
 #pragma unroll
               for (int j = 0; j < CH; ++j) f[j] = 0.f;
             }
-            if (nvalid == CH && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+            if (CH == 32 && box_ok && nvalid == CH) {
+              // all 32 lanes are here (box_ok: the warp's 32 rows are this CTA's live rows); lane = row of the box
+              uint8_t* stg = sm.stage_out + (e * 2 + (int)(stage_k & 1u)) * 2048;
+              ++stage_k;
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box before last was read
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 q;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[8 * j + 2 * u], f[8 * j + 2 * u + 1]);
+                // SWIZZLE_64B: 16-byte chunk index ^ address bits 7-8 = (row >> 1) & 3 for 64-byte rows
+                *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = q;
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmap_o, smem_u32(stg), P.out_coff + n0 + c0, row - lane);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            } else if (nvalid == CH && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
 #pragma unroll
               for (int j = 0; j < CH; j += 8) {
                 uint4 q;
@@ -494,6 +529,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
       if (etid == 0) PN_DBG(5);
     }
     if (etid == 0) { PN_WAIT_OUT(12, w_ss); PN_WAIT_OUT(13, w_tfull); PN_WAIT_OUT(14, w_body); PN_WAIT_OUT(15, n_tiles); }
+    if (BN >= 32 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staged boxes are out
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -573,8 +609,39 @@ int get_map(const void* base, long long rows, int cols, int ld, int box_rows, CU
   return PN_OK;
 }
 
+// bf16 output matrix (rows, cols) with row stride ld for the epilogue's TMA stores: box 32 cols x 32 rows, SWIZZLE_64B
+int get_map_out(const void* base, long long rows, int cols, int ld, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{base, rows, cols, ld, -32};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return PN_OK; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return PN_ERR_UNSUPPORTED;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return PN_ERR_CUDA;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+  }
+  *out = m;
+  return PN_OK;
+}
+
 template <int BN, int STAGES, bool TMA_A>
-int launch(const CUtensorMap& map_w, const CUtensorMap& map_a, const KArgs& ka, int grid, cudaStream_t stream) {
+int launch(const CUtensorMap& map_w, const CUtensorMap& map_a, const CUtensorMap& map_o, const KArgs& ka, int grid,
+           cudaStream_t stream) {
   constexpr size_t smem = sizeof(Smem<BN, STAGES>) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
@@ -602,7 +669,7 @@ int launch(const CUtensorMap& map_w, const CUtensorMap& map_a, const KArgs& ka, 
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  PN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<BN, STAGES, TMA_A>, map_w, map_a, ka_dbg));
+  PN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<BN, STAGES, TMA_A>, map_w, map_a, map_o, ka_dbg));
   PN_CHECK_LAUNCH();
   if (timeline) {
     PN_CUDA(cudaStreamSynchronize(stream));
@@ -736,6 +803,14 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
   ka.dc_hp_in = a->deconv_hp_in;
   ka.dc_wp_in = a->deconv_wp_in;
   ka.dbg = nullptr;
+  // epilogue through TMA tensor stores: bf16 rows written in place (no row remap), whole 32-column chunks
+  static const bool tma_store_enabled = [] { const char* e = getenv("PN_CONV_TMA_STORE"); return !(e && e[0] == '0'); }();
+  CUtensorMap map_o = map;
+  ka.tma_store = 0;
+  if (tma_store_enabled && a->out_dtype == PN_BF16 && !deconv && a->cout % 32 == 0 && a->out_coff % 8 == 0 &&
+      a->out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15u) == 0 && a->rows_cap > 0 &&
+      get_map_out(a->out, a->rows_cap, a->out_ld, a->out_ld, &map_o) == PN_OK)
+    ka.tma_store = 1;
   for (int sft = 3; sft < 16; ++sft)
     if ((1 << sft) == a->cin) ka.cin_shift = sft;
   if (a->in_rows > 0 && (long long)a->in_rows * a->in_ld * 2 >= (1ll << 32)) return PN_ERR_UNSUPPORTED;
@@ -748,22 +823,22 @@ int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
   const int grid = (int)(shares_cap < sms ? (shares_cap < 1 ? 1 : shares_cap) : sms);
   if (tma_a) {
     switch (bn) {
-      case 16: return launch<16, 8, true>(map, map_a, ka, grid, stream);
-      case 32: return launch<32, 8, true>(map, map_a, ka, grid, stream);
-      case 64: return launch<64, 8, true>(map, map_a, ka, grid, stream);
-      case 128: return launch<128, 6, true>(map, map_a, ka, grid, stream);
-      default: return launch<256, 4, true>(map, map_a, ka, grid, stream);
+      case 16: return launch<16, 8, true>(map, map_a, map_o, ka, grid, stream);
+      case 32: return launch<32, 8, true>(map, map_a, map_o, ka, grid, stream);
+      case 64: return launch<64, 8, true>(map, map_a, map_o, ka, grid, stream);
+      case 128: return launch<128, 6, true>(map, map_a, map_o, ka, grid, stream);
+      default: return launch<256, 4, true>(map, map_a, map_o, ka, grid, stream);
     }
   }
   switch (bn) {
     // Few stages on purpose: pipeline depth beyond ~4 chunks bought nothing (measured), while the shared
     // memory left to L1 lets the .ca gathers hit on the 3x reuse of activation rows between the taps of
     // horizontally adjacent outputs.
-    case 16: return launch<16, 6, false>(map, map_a, ka, grid, stream);
-    case 32: return launch<32, 6, false>(map, map_a, ka, grid, stream);
-    case 64: return launch<64, 5, false>(map, map_a, ka, grid, stream);
-    case 128: return launch<128, 4, false>(map, map_a, ka, grid, stream);
-    default: return launch<256, 4, false>(map, map_a, ka, grid, stream);
+    case 16: return launch<16, 6, false>(map, map_a, map_o, ka, grid, stream);
+    case 32: return launch<32, 6, false>(map, map_a, map_o, ka, grid, stream);
+    case 64: return launch<64, 5, false>(map, map_a, map_o, ka, grid, stream);
+    case 128: return launch<128, 4, false>(map, map_a, map_o, ka, grid, stream);
+    default: return launch<256, 4, false>(map, map_a, map_o, ka, grid, stream);
   }
 }
 
