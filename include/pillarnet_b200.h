@@ -389,6 +389,36 @@ int pn_boxes_aligned_overlap_bev(const float* boxes_a, const float* boxes_b, int
 /* keep (n) i32 device, num_keep (1) i32 device; boxes must already be score-sorted (as nms_gpu). */
 int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t scratch_bytes,
                    int* keep, int* num_keep, pn_stream_t stream);
+/* drop-in for iou3d_nms_cuda.nms_normal_gpu (iou3d_nms.cpp:162-207, kernel iou3d_nms_kernel.cu:325-380): the same
+ * greedy sweep over the axis-aligned IoU of [x, y, ., dx, dy] (heading ignored).  Same scratch as pn_nms_rotated. */
+int pn_nms_normal(const float* boxes, int n, float thr, void* scratch, size_t scratch_bytes,
+                  int* keep, int* num_keep, pn_stream_t stream);
+/* drop-in for iou3d_nms_cuda.boxes_overlap_bev_gpu (iou3d_nms.cpp:66-88, kernel iou3d_nms_kernel.cu:236-249):
+ * overlap (na, nb) f32 = BEV intersection AREA of every pair (boxes_iou3d_gpu builds the 3-D IoU from it). */
+int pn_boxes_overlap_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* overlap,
+                         pn_stream_t stream);
+
+/* ---- operator-level drop-ins for the reference's `pillar_cuda` pybind module --------------------------------------
+ * (det3d/ops/pillar_ops/src/pillar_api.cpp:10-21; headers pillar_ops_gpu.h:7-16, group_ops_gpu.h:6-12).  Not used by
+ * the fused product path (pn_pillarize / pn_pfn_scatter_max); they let det3d's own pillar_utils.py / group_utils.py
+ * run unmodified on this library through pillarnet_lts_b200.compat.pillar_cuda.
+ * scatter_max_wrapper / scatter_max_grad_wrapper map to pn_scatter_max / pn_scatter_max_grad above. */
+/* create_point_pillar_index_stack_wrapper (pillar_ops.cpp:15-36, pillar_ops_gpu.cu:13-39): pts_xy (n,2) i32 [x,y] cell
+ * coordinates, pts_batch_cnt (B) i32 points per frame; sets pillars_mask[(b*H+y)*W+x] = 1 (bool/u8, caller-zeroed)
+ * and point_pillar_index[i] = that cell id for in-range points (others keep the caller's initial value, -1). */
+int pn_compat_point_pillar_index(const int* pts_xy, const int* pts_batch_cnt, int n_points, int n_frames, int H, int W,
+                                 unsigned char* pillars_mask, int* point_pillar_index, pn_stream_t stream);
+/* create_pillar_indices_wrapper (pillar_ops.cpp:39-55, pillar_ops_gpu.cu:60-78): pillars_position (B,H,W) i32 = rank of
+ * an occupied cell or < 0; writes pillar_indices[rank] = [b, y, x]. */
+int pn_compat_pillar_indices(const int* pillars_position, int n_frames, int H, int W, int* pillar_indices,
+                             pn_stream_t stream);
+/* gather_indice_wrapper (group_ops_gpu.cu:8-17): outs[i] = indices[index[i]]. */
+int pn_compat_gather_indice(const int* index, const int* indices, int n, int* outs, pn_stream_t stream);
+/* gather_feature_wrapper / gather_feature_grad_wrapper (group_ops_gpu.cu:20-48): outs[i,:] = features[index[i],:];
+ * grad_features[index[i],:] += grad_outs[i,:] (grad_features caller-zeroed). */
+int pn_compat_gather_feature(const int* index, const float* features, int n, int c, float* outs, pn_stream_t stream);
+int pn_compat_gather_feature_grad(const int* index, const float* grad_outs, int n, int c, float* grad_features,
+                                  pn_stream_t stream);
 
 #ifdef __cplusplus
 }

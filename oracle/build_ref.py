@@ -9,6 +9,12 @@ det3d/ops/iou3d_nms/setup.py:13-14) for compute capability 10.0.  The reference'
 Outputs go only to oracle/_ref/ (git-ignored, shipped to the GPU box).
 
 `load_ref(name)` imports a prebuilt module from oracle/_ref without needing /root/reference.
+
+`stage_python()` additionally copies the handful of reference *Python* files that drive those extensions (and the numba
+CPU baseline BASELINE.json config 1 names, det3d/ops/point_cloud/point_cloud_ops.py) into oracle/_ref/py/det3d/...,
+next to package __init__ stubs written here, so the GPU box can execute the reference's own Python — as the checker of
+tests/test_gpu_compat.py and as bench.py's `cpu_baseline` — without /root/reference.  Like the .so files they are
+git-ignored build outputs, never part of the repo's history.
 """
 import glob
 import importlib.util
@@ -71,6 +77,73 @@ def load_ref(name):
     return mod
 
 
+# reference Python staged for the GPU box: relative path under /root/reference -> same path under oracle/_ref/py
+PY_FILES = [
+    "det3d/ops/pillar_ops/pillar_utils.py",
+    "det3d/ops/pillar_ops/group_utils.py",
+    "det3d/ops/pillar_ops/scatter_utils.py",
+    "det3d/ops/pillar_ops/pillar_modules.py",
+    "det3d/ops/iou3d_nms/__init__.py",
+    "det3d/ops/iou3d_nms/iou3d_nms_utils.py",
+    "det3d/ops/point_cloud/point_cloud_ops.py",
+    "det3d/core/bbox/box_torch_ops.py",
+    "det3d/core/utils/circle_nms_jit.py",
+    "det3d/models/readers/dynamic_pillar_encoder.py",
+]
+# package stubs written here (the reference's own __init__ files pull in the whole framework)
+PY_STUBS = {
+    "det3d/__init__.py": "",
+    "det3d/ops/__init__.py": "",
+    "det3d/ops/pillar_ops/__init__.py": "",
+    "det3d/ops/point_cloud/__init__.py": "",
+    "det3d/core/__init__.py": "",
+    "det3d/core/bbox/__init__.py": "",
+    "det3d/core/utils/__init__.py": "",
+    "det3d/models/__init__.py": "",
+    "det3d/models/readers/__init__.py": "",
+    # the one registry the staged reader decorates itself with (det3d/models/registry.py:3-11)
+    "det3d/models/registry.py": "class _R:\n    def register_module(self, cls):\n        return cls\nREADERS = _R()\n",
+    # container stand-in for spconv.pytorch.SparseConvTensor (pillar_modules.py:74)
+    "spconv/__init__.py": "",
+    "spconv/pytorch/__init__.py": (
+        "class SparseConvTensor:\n"
+        "    def __init__(self, features, indices, spatial_shape, batch_size):\n"
+        "        self.features, self.indices = features, indices\n"
+        "        self.spatial_shape, self.batch_size = spatial_shape, batch_size\n"),
+}
+PY_OUT = os.path.join(REF_OUT, "py")
+
+
+def stage_python():
+    import shutil
+    if not os.path.isdir(os.path.join(REFERENCE, "det3d")):
+        raise RuntimeError("reference tree not present")
+    for rel, src in PY_STUBS.items():
+        dst = os.path.join(PY_OUT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        with open(dst, "w") as fh:
+            fh.write(src)
+    for rel in PY_FILES:
+        dst = os.path.join(PY_OUT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(REFERENCE, rel), dst)
+    return PY_OUT
+
+
+def python_available():
+    return all(os.path.exists(os.path.join(PY_OUT, rel)) for rel in PY_FILES)
+
+
+def load_points_to_voxel():
+    """the reference's numba `points_to_voxel` (det3d/ops/point_cloud/point_cloud_ops.py:112-184), imported by path
+    from the staged copy"""
+    path = os.path.join(PY_OUT, "det3d/ops/point_cloud/point_cloud_ops.py")
+    spec = importlib.util.spec_from_file_location("pn_ref_point_cloud_ops", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.points_to_voxel
+
+
 def build_all(verbose=False):
     built = {}
     for name in MODULES:
@@ -79,6 +152,7 @@ def build_all(verbose=False):
             continue
         build(name, verbose=verbose)
         built[name] = so_path(name)
+    built["python"] = stage_python()
     return built
 
 

@@ -67,7 +67,43 @@ def neck_forward(neck, feats):
         x4 = neck.block_4(torch.cat([feats["conv4"], neck.top_down_54(x5)], 1))
         x3 = neck.block_3(torch.cat([feats["conv3"], neck.top_down_43(x4)], 1))
         return (x4, x3)
+    if name == "RPNV2":       # necks/rpn.py:262-272 (reads the sparse conv3 / conv4 of the S backbones, densified)
+        up = neck.deblock_4(neck.block_4(feats["conv4"]))
+        return (neck.block_3(torch.cat([feats["conv3"], up], 1)),)
+    if name == "RPNGV2":      # necks/rpn.py:428-450
+        x5 = neck.block_5(feats["conv5"])
+        x4 = neck.block_4(torch.cat([neck.reduce_4(feats["conv4"]), neck.top_down_54(x5)], 1))
+        x3 = neck.block_3(torch.cat([neck.reduce_3(feats["conv3"]), neck.top_down_43(x4)], 1))
+        return (x4, x3)
     raise NotImplementedError(name)
+
+
+def head_forward(head, bev):
+    """center_head.py:116-127 with the model's own torch containers"""
+    share = [sc(bev[k]) for k, sc in enumerate(head.share_convs)]
+    return [{name: getattr(th, name)(share[head.task_idx[t]]) for name in th.heads}
+            for t, th in enumerate(head.task_heads)]
+
+
+@torch.no_grad()
+def dense_equivalent_from_reader(model, sp):
+    """Dense-equivalent torch forward (fp32, TF32 off) from a reader output `sp` (features_f32, indices) of the model
+    under test to its head maps, on sp's device: the per-stage checker of the -m gpu whole-model parity tests."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, (H, W) = sp.batch_size, sp.spatial_shape
+    n = sp.table.count()
+    idx = sp.indices.long()
+    f = sp.features_f32[:n] if getattr(sp, "features_f32", None) is not None else sp.feat[:n].float()
+    x = torch.zeros(B, f.shape[1], H, W, device=f.device)
+    x[idx[:, 0], :, idx[:, 1], idx[:, 2]] = f
+    mask = torch.zeros(B, 1, H, W, device=f.device)
+    mask[idx[:, 0], 0, idx[:, 1], idx[:, 2]] = 1
+    feats = backbone_dense_equivalent(model.backbone, x, mask)
+    del x
+    bev = neck_forward(model.neck, feats)
+    preds = head_forward(model.bbox_head, bev)
+    return feats, bev, preds
 
 
 def nms_cfg_for_task(head, test_cfg, t):

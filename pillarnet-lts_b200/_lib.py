@@ -117,6 +117,14 @@ SIGNATURES = {
     "pn_boxes_iou_bev": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "pn_nms_rotated": (c_int, [c_void_p, c_int, c_float, c_void_p, c_size_t, c_void_p, c_void_p,
                                c_void_p]),
+    "pn_nms_normal": (c_int, [c_void_p, c_int, c_float, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "pn_boxes_overlap_bev": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "pn_compat_point_pillar_index": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                             c_void_p]),
+    "pn_compat_pillar_indices": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pn_compat_gather_indice": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "pn_compat_gather_feature": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "pn_compat_gather_feature_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -79,3 +79,23 @@ def load_checkpoint(model, filename, map_location=None, strict=False, logger=Non
         state_dict = {k[7:]: v for k, v in state_dict.items()}
     load_state_dict(model.module if hasattr(model, "module") else model, state_dict, strict, logger)
     return checkpoint
+
+
+def save_checkpoint(model, filename, optimizer=None, meta=None):
+    """det3d/torchie/trainer/checkpoint.py:235-262: writes {"meta", "state_dict" (CPU tensors, reference key names and
+    spconv-2.x layouts), "optimizer"} so a det3d trainer — or load_checkpoint above — reads the file back unchanged."""
+    if meta is None:
+        meta = {}
+    elif not isinstance(meta, dict):
+        raise TypeError("meta must be a dict or None, but got {}".format(type(meta)))
+    d = os.path.dirname(filename)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    if hasattr(model, "module"):
+        model = model.module
+    checkpoint = {"meta": meta,
+                  "state_dict": OrderedDict((k, v.detach().cpu()) for k, v in model.state_dict().items())}
+    if optimizer is not None:
+        checkpoint["optimizer"] = optimizer.state_dict()
+    torch.save(checkpoint, filename)
+    return filename

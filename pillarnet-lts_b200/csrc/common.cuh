@@ -34,6 +34,19 @@ int fail(cudaError_t e);     // records the CUDA error string, returns PN_ERR_CU
 int sm_count();              // cached multiProcessorCount of the current device
 void count_launch();         // bumps the process-wide kernel-launch counter (pn_launch_count)
 
+// cudaFuncSetAttribute(..MaxDynamicSharedMemorySize..) is a per-DEVICE function attribute: a process that drives several
+// devices must opt in on each of them.  `static PerDeviceOnce once; if (once.need()) cudaFuncSetAttribute(...)`.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 // Number of 32-bit occupancy words for a (B,H,W) raster.
 __host__ __device__ inline long long n_words(long long cells) { return (cells + 31) >> 5; }
 }  // namespace pn_detail

@@ -828,8 +828,9 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, 
   static_assert(CL == 1 || (BN / CL) % 8 == 0, "a weight slice must keep the 8-row swizzle period");
   static int max_clusters = 0;
   auto kern = k_conv_dense<MT, BN, SA, SB, CL, BS, TWO>;
+  static pn_detail::PerDeviceOnce once;
+  if (once.need()) PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (max_clusters == 0) {
-    PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int sms = pn_detail::sm_count();
     if (CL == 1) {
       max_clusters = sms;

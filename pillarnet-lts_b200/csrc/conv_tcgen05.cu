@@ -644,12 +644,10 @@ int launch(const CUtensorMap& map_w, const CUtensorMap& map_a, const CUtensorMap
            cudaStream_t stream) {
   constexpr size_t smem = sizeof(Smem<BN, STAGES>) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
+  static pn_detail::PerDeviceOnce once;
+  if (once.need())
     PN_CUDA(cudaFuncSetAttribute(k_conv_tc<BN, STAGES, TMA_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-    configured = true;
-  }
   static const bool timeline = [] { const char* e = getenv("PN_CONV_TIMELINE"); return e && e[0] == '1'; }();
   static unsigned long long* dbg_buf = nullptr;
   KArgs ka_dbg = ka;

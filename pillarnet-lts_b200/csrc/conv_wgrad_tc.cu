@@ -223,11 +223,9 @@ template <int BN, int STAGES>
 int launch(const WArgs& a, int grid, cudaStream_t stream) {
   constexpr size_t smem = sizeof(WSmem<BN, STAGES>) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
+  static pn_detail::PerDeviceOnce once;
+  if (once.need())
     PN_CUDA(cudaFuncSetAttribute(k_wgrad_tc<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   k_wgrad_tc<BN, STAGES><<<grid, kThreads, smem, stream>>>(a);
   PN_CHECK_LAUNCH();
   return PN_OK;

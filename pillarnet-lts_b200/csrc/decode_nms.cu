@@ -398,6 +398,11 @@ k_nms_mask(MaskParams P, const float* __restrict__ sorted_boxes, const float* __
   if (P.mode == 0) {
     for (int i = tid; i < cols * kGeomFloats; i += kMaskThreads)
       s_col[i] = geom[(base + cb * 64) * kGeomFloats + i];
+  } else if (P.mode == 2) {
+    for (int i = tid; i < cols; i += kMaskThreads) {
+      const float* b = sorted_boxes + (base + cb * 64 + i) * kBoxRec;
+      s_col[i * 4] = b[0]; s_col[i * 4 + 1] = b[1]; s_col[i * 4 + 2] = b[3]; s_col[i * 4 + 3] = b[4];
+    }
   } else {
     for (int i = tid; i < cols; i += kMaskThreads) {
       s_col[i * 2] = sorted_boxes[(base + cb * 64 + i) * kBoxRec + 0];
@@ -406,7 +411,24 @@ k_nms_mask(MaskParams P, const float* __restrict__ sorted_boxes, const float* __
   }
   __syncthreads();
   const int c_lo = max(cg * 16, (rb == cb) ? row_t + 1 : 0), c_hi = min(cg * 16 + 16, cols);
-  if (P.mode == 1) {
+  if (P.mode == 2) {
+    // axis-aligned IoU of [x, y, ., dx, dy] records, the arithmetic of iou3d_nms_kernel.cu:325-337 (iou_normal)
+    if (row_t < rows) {
+      const float* a = sorted_boxes + (base + rb * 64 + row_t) * kBoxRec;
+      const float ax = a[0], ay = a[1], aw = a[3], ah = a[4];
+      unsigned int lo = 0u, hi = 0u;
+      for (int c = c_lo; c < c_hi; ++c) {
+        const float bx = s_col[c * 4], by = s_col[c * 4 + 1], bw = s_col[c * 4 + 2], bh = s_col[c * 4 + 3];
+        const float left = fmaxf(ax - aw / 2, bx - bw / 2), right = fminf(ax + aw / 2, bx + bw / 2);
+        const float top = fmaxf(ay - ah / 2, by - bh / 2), bottom = fminf(ay + ah / 2, by + bh / 2);
+        const float inter = fmaxf(right - left, 0.f) * fmaxf(bottom - top, 0.f);
+        const float iou = inter / fmaxf(aw * ah + bw * bh - inter, 1e-8f);
+        if (iou > thr) { if (c < 32) lo |= 1u << c; else hi |= 1u << (c - 32); }
+      }
+      if (lo) atomicOr(&s_bits[row_t][0], lo);
+      if (hi) atomicOr(&s_bits[row_t][1], hi);
+    }
+  } else if (P.mode == 1) {
     // circle_nms: (float32 difference)^2 summed in float64, compared with <= thresh
     if (row_t < rows) {
       const float xi = sorted_boxes[(base + rb * 64 + row_t) * kBoxRec + 0];
@@ -482,7 +504,8 @@ k_nms_sweep(SweepParams P, const float* __restrict__ sorted_boxes, int pre_cap,
             float* __restrict__ det_out) {
   extern __shared__ unsigned long long s_rows[];   // [kSweepRing][64][col_blocks]
   __shared__ int s_keep[4096];
-  __shared__ int s_done, s_kept;
+  __shared__ int s_done[2], s_kept;   // s_done is double-buffered by block parity: warp 0 may already be writing the
+                                      // flag of block blk+1 while warps 1-3 still read the flag of block blk
   const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(sorted_count[seg], pre_cap);
   const int col_blocks = pre_cap / 64;
@@ -506,8 +529,10 @@ k_nms_sweep(SweepParams P, const float* __restrict__ sorted_boxes, int pre_cap,
   };
   fetch_block(0, tid, kSweepThreads);
   fetch_block(1, tid, kSweepThreads);
-  if (tid == 0) { s_done = 0; s_kept = 0; }
-  asm volatile("cp.async.wait_group 1;" ::: "memory");
+  if (tid == 0) { s_done[0] = 0; s_done[1] = 0; s_kept = 0; }
+  // cp.async groups are per thread and warp 0 issues no further copies inside the loop: every thread waits here for
+  // its own share of BOTH prelude blocks, so block 1 is complete when warp 0 reads it at blk == 1
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   unsigned long long remv[2] = {0ull, 0ull};
   int kept = 0;
@@ -560,12 +585,12 @@ k_nms_sweep(SweepParams P, const float* __restrict__ sorted_boxes, int pre_cap,
       }
       if (lane == 0) {
         s_kept = kept;
-        if (kept >= post) s_done = 1;
+        s_done[blk & 1] = kept >= post ? 1 : 0;
       }
     }
     asm volatile("cp.async.wait_group 1;" ::: "memory");   // block blk+1 has landed (blk+2 may still travel)
     __syncthreads();
-    if (s_done) break;
+    if (s_done[blk & 1]) break;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -587,11 +612,9 @@ static int launch_sweep(int n_segs, const SweepParams& S, const float* sorted_bo
                         const unsigned long long* mask, int* keep_idx, int post_cap, int* keep_count, float* det_out,
                         cudaStream_t stream) {
   const size_t smem = (size_t)kSweepRing * 64 * (pre_cap / 64) * sizeof(unsigned long long);   // 96 KB at pre_cap 4096
-  static bool configured = false;
-  if (!configured) {
+  static pn_detail::PerDeviceOnce once;   // the dynamic shared-memory opt-in is a per-device function attribute
+  if (once.need())
     PN_CUDA(cudaFuncSetAttribute(k_nms_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured = true;
-  }
   k_nms_sweep<<<n_segs, kSweepThreads, smem, stream>>>(S, sorted_boxes, pre_cap, sorted_count, mask, keep_idx, post_cap,
                                                       keep_count, det_out);
   PN_CHECK_LAUNCH();
@@ -600,6 +623,7 @@ static int launch_sweep(int n_segs, const SweepParams& S, const float* sorted_bo
 
 // ---- standalone iou3d_nms_cuda drop-ins ---------------------------------------------------------
 
+template <bool kOverlapOnly>   // true: iou3d_nms_kernel.cu:236-249 boxes_overlap_kernel (area), false: boxes_iou_bev_kernel
 __global__ void __launch_bounds__(256)
 k_boxes_iou(const float* __restrict__ A, int na, const float* __restrict__ B, int nb,
             float* __restrict__ out) {
@@ -610,7 +634,7 @@ k_boxes_iou(const float* __restrict__ A, int na, const float* __restrict__ B, in
     BoxGeom a, b;
     pn_iou::make_geom(A[i * 7], A[i * 7 + 1], A[i * 7 + 3], A[i * 7 + 4], A[i * 7 + 6], a);
     pn_iou::make_geom(B[j * 7], B[j * 7 + 1], B[j * 7 + 3], B[j * 7 + 4], B[j * 7 + 6], b);
-    out[g] = pn_iou::iou_bev(a, b);
+    out[g] = kOverlapOnly ? pn_iou::overlap_area(a, b) : pn_iou::iou_bev(a, b);
   }
 }
 
@@ -635,6 +659,7 @@ k_boxes7_to_records(const float* __restrict__ boxes, int n, float* __restrict__ 
   float* o = rec + (long long)i * kBoxRec;
   for (int d = 0; d < kBoxRec; ++d) o[d] = 0.f;
   o[0] = b[0]; o[1] = b[1]; o[2] = b[2];
+  o[3] = b[3]; o[4] = b[4];   // dx, dy (pcdet order): read by the axis-aligned mode of k_nms_mask
   BoxGeom q;
   pn_iou::make_geom(b[0], b[1], b[3], b[4], b[6], q);
   store_geom(geom + (long long)i * kGeomFloats, q);
@@ -799,7 +824,17 @@ int pn_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb,
   cudaStream_t stream = (cudaStream_t)stream_;
   PN_REQUIRE(boxes_a && boxes_b && iou && na >= 0 && nb >= 0);
   if (na == 0 || nb == 0) return PN_OK;
-  k_boxes_iou<<<grid_for((long long)na * nb, 256), 256, 0, stream>>>(boxes_a, na, boxes_b, nb, iou);
+  k_boxes_iou<false><<<grid_for((long long)na * nb, 256), 256, 0, stream>>>(boxes_a, na, boxes_b, nb, iou);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+int pn_boxes_overlap_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* overlap,
+                         pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(boxes_a && boxes_b && overlap && na >= 0 && nb >= 0);
+  if (na == 0 || nb == 0) return PN_OK;
+  k_boxes_iou<true><<<grid_for((long long)na * nb, 256), 256, 0, stream>>>(boxes_a, na, boxes_b, nb, overlap);
   PN_CHECK_LAUNCH();
   return PN_OK;
 }
@@ -816,9 +851,8 @@ int pn_boxes_aligned_overlap_bev(const float* boxes_a, const float* boxes_b, int
 }
 
 // scratch layout: records (n_cap*12 f32) | geom+mask as pn_nms | det (n_cap*11 f32) | counts (2 i32)
-int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t scratch_bytes,
-                   int* keep, int* num_keep, pn_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int nms_boxes7(int mode, const float* boxes, int n, float thr, void* scratch, size_t scratch_bytes,
+                      int* keep, int* num_keep, cudaStream_t stream) {
   PN_REQUIRE(scratch && keep && num_keep && n >= 0 && n <= 4096);
   PN_REQUIRE(boxes || n == 0);
   if (n == 0) {
@@ -840,7 +874,7 @@ int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t s
   k_boxes7_to_records<<<PN_DIVUP(n, 256), 256, 0, stream>>>(boxes, n, rec, geom, cnt);
   PN_CHECK_LAUNCH();
   MaskParams M;
-  M.mode = 0; M.segs_per_frame = 1;
+  M.mode = mode; M.segs_per_frame = 1;
   SweepParams S;
   S.segs_per_frame = 1;
   for (int i = 0; i < 16; ++i) { M.thr[i] = thr; S.post_max[i] = cap; S.use_rect[i] = 0; }
@@ -848,6 +882,16 @@ int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t s
   k_nms_mask<<<grid, kMaskThreads, 0, stream>>>(M, rec, geom, cap, cnt, mask);
   PN_CHECK_LAUNCH();
   return launch_sweep(1, S, rec, cap, cnt, mask, keep, cap, num_keep, det, stream);
+}
+
+int pn_nms_rotated(const float* boxes, int n, float thr, void* scratch, size_t scratch_bytes,
+                   int* keep, int* num_keep, pn_stream_t stream_) {
+  return nms_boxes7(0, boxes, n, thr, scratch, scratch_bytes, keep, num_keep, (cudaStream_t)stream_);
+}
+
+int pn_nms_normal(const float* boxes, int n, float thr, void* scratch, size_t scratch_bytes,
+                  int* keep, int* num_keep, pn_stream_t stream_) {
+  return nms_boxes7(2, boxes, n, thr, scratch, scratch_bytes, keep, num_keep, (cudaStream_t)stream_);
 }
 
 }  // extern "C"

@@ -449,11 +449,10 @@ int pn_pfn_scatter_max(const float* points, int point_dim, int n_points, const i
     auto smem_bf = [&](int C) { return (size_t)(((kPtThreads * point_dim + 3) & ~3) + kPtThreads * (C / 2 + 4)) * 4; };
 #define PN_PFN_BF16(C)                                                                                \
     do {                                                                                              \
-      static bool ok##C = false;                                                                      \
-      if (!ok##C) {                                                                                   \
+      static pn_detail::PerDeviceOnce ok##C;                                                          \
+      if (ok##C.need()) {                                                                             \
         PN_CUDA(cudaFuncSetAttribute(k_pfn_scatter_max_bf16<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem_bf(C) + 4096));                                        \
-        ok##C = true;                                                                                 \
       }                                                                                               \
       k_zero_rows_bf16<C><<<zero_blocks, 256, 0, stream>>>((__nv_bfloat16*)out_bf16, num_pillars, m_cap); \
       PN_CHECK_LAUNCH();                                                                              \
@@ -470,11 +469,10 @@ int pn_pfn_scatter_max(const float* points, int point_dim, int n_points, const i
   }
 #define PN_PFN_LAUNCH(C)                                                                           \
   do {                                                                                             \
-    static bool smem_ok##C = false;                                                                \
-    if (!smem_ok##C) {                                                                             \
+    static pn_detail::PerDeviceOnce smem_ok##C;                                                    \
+    if (smem_ok##C.need()) {                                                                       \
       PN_CUDA(cudaFuncSetAttribute(k_pfn_scatter_max<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,\
                                    (int)smem_pfn(C) + 4096));                                      \
-      smem_ok##C = true;                                                                           \
     }                                                                                             \
     k_zero_rows<C><<<zero_blocks, 256, 0, stream>>>(out_f32, arg, num_pillars, m_cap);             \
     PN_CHECK_LAUNCH();                                                                             \

@@ -46,9 +46,15 @@ class SingleStageDetector(nn.Module):
         self.bbox_head = build_head(bbox_head)
         self.train_cfg = train_cfg
         self.test_cfg = ConfigDict.wrap(test_cfg) if test_cfg is not None else None
-        if pretrained is not None:
-            sd = torch.load(pretrained, map_location="cpu")
-            self.load_state_dict(sd.get("state_dict", sd), strict=False)
+        self.init_weights(pretrained)
+
+    def init_weights(self, pretrained=None):
+        """detectors/single_stage.py:27-35: goes through load_checkpoint (module. prefix stripped, spconv-1.x sparse
+        weights re-laid out, `meta` objects tolerated, mismatches reported) — not a bare torch.load"""
+        if pretrained is None:
+            return
+        from .checkpoint import load_checkpoint
+        load_checkpoint(self, pretrained, map_location="cpu", strict=False)
 
     @property
     def with_neck(self):

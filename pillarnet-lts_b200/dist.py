@@ -90,15 +90,32 @@ class GradientAverager:
     """Overlapped data-parallel gradient averaging: what torch DDP does for the reference
     (det3d/torchie/apis/train.py:283-290), as explicit plumbing.  Parameters are packed (reverse registration
     order ~ backward order) into flat fp32 buckets whose slices ARE the `.grad` tensors; a bucket's
-    all-reduce is launched asynchronously (NCCL stream) the moment its last gradient has been accumulated, so
+    all-reduce is launched asynchronously (NCCL stream) once its last gradient has been accumulated, so
     the exchange of the head/neck gradients overlaps the backward of the backbone.  `finish()` waits and divides.
+
+    Collective order is FIXED: bucket k's all-reduce is issued only after buckets 0..k-1 have been issued, and
+    `finish()` flushes whatever is left in index order — so every rank issues the same sequence of collectives
+    over the same tensors even when the set of parameters that received a gradient differs between ranks (unused
+    branches), which would otherwise dead-lock or mix up buckets.  Like DDP's constructor, `__init__` broadcasts
+    rank 0's parameters (and, when `module` is given, its buffers: BN running statistics) so the replicas start
+    identical whatever their seeds.  `finish()` re-attaches a `.grad` that was detached from its bucket (e.g. by
+    `optimizer.zero_grad(set_to_none=True)` outside `train_step`), folding the stray gradient into the bucket.
     """
 
-    def __init__(self, params, bucket_mb=25, group=None):
+    def __init__(self, params, bucket_mb=25, group=None, module=None, broadcast=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
+        if broadcast and self.world > 1:
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            with torch.no_grad():
+                tensors = [p.data for p in params]
+                if module is not None:
+                    tensors += [b.data for b in module.buffers()]
+                for t in tensors:
+                    dist.broadcast(t, src=src, group=group)
         self.buckets = []          # (flat tensor, [params])
+        self._slices = []          # per bucket: [(param, offset)]
         limit = int(bucket_mb * 1024 * 1024)
         cur, size = [], 0
         for p in reversed(self.params):
@@ -110,6 +127,7 @@ class GradientAverager:
         if cur:
             self._make_bucket(cur)
         self._pending = [0] * len(self.buckets)
+        self._next = 0             # buckets [0, _next) have had their all-reduce issued this step
         self._works = []
         self._hooks = []
         for bi, (_, ps) in enumerate(self.buckets):
@@ -120,35 +138,73 @@ class GradientAverager:
     def _make_bucket(self, ps):
         n = sum(p.numel() for p in ps)
         flat = torch.zeros(n, dtype=torch.float32, device=ps[0].device)
-        off = 0
+        off, sl = 0, []
         for p in ps:
             p.grad = flat[off:off + p.numel()].view_as(p)     # gradients accumulate straight into the bucket
+            sl.append((p, off))
             off += p.numel()
         self.buckets.append((flat, list(ps)))
+        self._slices.append(sl)
+
+    def _issue_ready(self):
+        """issue, in index order, the all-reduce of every leading bucket whose gradients are complete"""
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            if self.world > 1:
+                self._works.append(dist.all_reduce(self.buckets[self._next][0], group=self.group, async_op=True))
+            self._next += 1
 
     def _make_hook(self, bi):
-        def hook(_p):
+        flat = self.buckets[bi][0]
+        offs = {id(p): off for p, off in self._slices[bi]}
+
+        def hook(p):
+            g = p.grad
+            lo = flat.data_ptr()
+            if g is not None and not (lo <= g.data_ptr() < lo + flat.numel() * 4):
+                # .grad was detached from the bucket (set_to_none / replaced): fold this step's gradient in and
+                # re-attach BEFORE the bucket can be reduced, instead of all-reducing stale zeros
+                off = offs[id(p)]
+                view = flat[off:off + p.numel()].view_as(p)
+                view.add_(g.to(view.dtype))
+                p.grad = view
             self._pending[bi] -= 1
-            if self._pending[bi] == 0 and self.world > 1:
-                self._works.append(dist.all_reduce(self.buckets[bi][0], group=self.group, async_op=True))
+            if self._pending[bi] == 0:
+                self._issue_ready()
         return hook
 
     def reset(self):
         """call before each backward (after zeroing): re-arms the per-bucket counters"""
         self._pending = [len(ps) for _, ps in self.buckets]
+        self._next = 0
         self._works = []
 
     def zero_grad(self):
+        self._reattach(fold=False)
         for flat, _ in self.buckets:
             flat.zero_()
         self.reset()
 
+    def _reattach(self, fold=True):
+        """every `.grad` must alias its bucket slice; a detached one (set_to_none / replaced tensor) is folded
+        into the bucket (fold=True: its value is a gradient of this step) and re-attached"""
+        for flat, sl in zip((b[0] for b in self.buckets), self._slices):
+            base, end = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+            for p, off in sl:
+                view = flat[off:off + p.numel()].view_as(p)
+                g = p.grad
+                if g is None or not (base <= g.data_ptr() < end):
+                    if g is not None and fold:
+                        view.add_(g.to(view.dtype))
+                    p.grad = view
+
     def finish(self):
-        """waits for the launched all-reduces, reduces buckets whose hooks did not all fire (unused
-        parameters), and turns sums into means"""
-        for bi, n in enumerate(self._pending):
-            if n != 0 and self.world > 1:
+        """flushes, in index order, the buckets not yet issued (hooks that never fired: unused parameters, or a
+        bucket waiting behind one of those), waits, and turns sums into means"""
+        self._reattach(fold=True)
+        for bi in range(self._next, len(self.buckets)):
+            if self.world > 1:
                 self._works.append(dist.all_reduce(self.buckets[bi][0], group=self.group, async_op=True))
+        self._next = len(self.buckets)
         for w in self._works:
             w.wait()
         if self.world > 1:

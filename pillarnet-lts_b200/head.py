@@ -63,6 +63,8 @@ class SepHead(nn.Module):
 
 @HEADS.register_module
 class CenterHead(nn.Module):
+    NMS_PRE_CAP = 4096   # boxes per NMS segment the device-side top-K / suppression-matrix / sweep kernels hold
+
     def __init__(self, tasks, in_channels, code_weights, common_heads=dict(), logger=None,
                  share_channel=64, reg_iou=None, pillar_size=0.1,
                  point_cloud_range=[-75.2, -75.2, -2, 75.2, 75.2, 4]):
@@ -296,7 +298,7 @@ class CenterHead(nn.Module):
         for t, ncls in enumerate(self.num_classes):
             if circle:
                 rects.append([0.0] * ncls)
-                segs.append(dict(task=t, cls=-1, pre=4096, post=int(self._per_task(nms["nms_post_max_size"], t)),
+                segs.append(dict(task=t, cls=-1, pre=self.NMS_PRE_CAP, post=int(self._per_task(nms["nms_post_max_size"], t)),
                                  thr=float(test_cfg["min_radius"][t]), use_rect=0))
             elif not multi:
                 r = test_cfg.get("rectifier", 0)
@@ -350,7 +352,12 @@ class CenterHead(nn.Module):
         B = packed[0][2][0]
         dev = packed[0][0].device
         n_segs = B * S
-        pre_cap = min(4096, (max(s["pre"] for s in segs) + 63) // 64 * 64)
+        want_pre = max(s["pre"] for s in segs)
+        if want_pre > self.NMS_PRE_CAP:
+            # the reference takes any nms_pre_max_size (box_torch_ops.py:305-306); the device-side selection and sweep
+            # hold at most NMS_PRE_CAP boxes per segment — refuse instead of silently returning different detections
+            raise NotImplementedError(f"nms_pre_max_size {want_pre} exceeds the device-side capacity {self.NMS_PRE_CAP}")
+        pre_cap = min(self.NMS_PRE_CAP, (want_pre + 63) // 64 * 64)
         post_cap = min(pre_cap, max(s["post"] for s in segs))
         cand_cap = max(p[2][1] * p[2][2] for p in packed)
         keys = torch.empty(n_segs, cand_cap, dtype=torch.int64, device=dev)
@@ -397,6 +404,13 @@ class CenterHead(nn.Module):
         (center_head.py:332-350,405-409)."""
         B, S, post_cap = plan["B"], plan["S"], plan["post_cap"]
         counts = keep_count.view(B, S).cpu().tolist()
+        if plan["mode"] == 1:
+            # circle NMS: the reference's _circle_nms (center_head.py:418-426) has no pre-NMS cap; here a segment keeps
+            # its NMS_PRE_CAP best candidates.  Say so when a frame actually had more (count is already on the device).
+            most = int(plan["cand_count"].max().item())
+            if most > plan["pre_cap"]:
+                self.logger.warning("circle NMS: %d candidates in one segment, only the %d highest-scoring were "
+                                    "considered (reference: unbounded)", most, plan["pre_cap"])
         flat = det_out.view(B * S * post_cap, 11)
         cls_off, flag = [], 0
         for n in self.num_classes:

@@ -1,0 +1,139 @@
+"""GPU: whole-model parity AT THE BENCHMARKED SIZES (VERDICT r1 missing #2 / next #1).
+
+  * nusc18  — configs/pillarnet/pillarnet_centerhead_nusc.py: 1440 x 1440 pillars, batch 1, PillarResNet18 + RPNV1,
+              six stride-8 tasks (the bench.py headline workload, same synthetic frames, same calibrated weights)
+  * waymo34 — configs/pillarnet/pillarnet34_fpn_centerhead_waymo.py: 1504 x 1504, batch 2, PillarResNet34 + RPNG,
+              stride-8 and stride-4 tasks with an iou head
+
+fp32 mode is compared stage by stage (conv1..conv5, every neck output, every head map) with the dense-equivalent
+torch restatement (oracle/cpu_path.py: SubM = conv2d * mask, strided = conv2d(s2) * max_pool(mask); cuDNN with TF32
+off), tolerance **1e-3** max-abs relative to max|ref| (north_star).  bf16 tensor-core mode is compared with the
+fp32 run of the same frames: stage errors within BF16_STAGE_TOL (rel-to-max; bf16 operands, fp32 accumulation:
+each layer re-rounds its activations to 8 mantissa bits, 2^-9 relative per element, and the error random-walks
+through ~25 (PillarNet-18) / ~40 (PillarNet-34) conv layers) and — what a user sees — the detections: boxes of the
+fp32 run re-found by the bf16 run at BEV IoU >= 0.7 with the same class.
+
+The measured numbers are written to gpurun_out/parity_fullsize_<workload>.json (copied to profiles/ per round).
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from tests.gpu_util import randomize_bn
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+FP32_TOL = 1e-3
+# bf16 mode vs the fp32 run, rel-to-max per stage.  Measured on B200 (profiles/r2_parity_fullsize_*.json):
+# sparse stages 2e-3..6e-3, dense neck 6e-3..9e-3, head maps <= 1.2e-2 (the 64-channel head branches end in
+# un-normalised 3x3 convs whose outputs are O(1) sums of 576 bf16 products).  The bound is 2x the worst measured.
+BF16_STAGE_TOL = 2.5e-2
+
+
+def _build(workload, seed=0):
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200 import configs
+    from pillarnet_lts_b200.registry import ConfigDict
+    cfg = configs.get(workload)
+    torch.manual_seed(seed)
+    model = P.build_detector(ConfigDict.wrap(cfg["model"]), None, ConfigDict.wrap(cfg["test_cfg"]))
+    randomize_bn(model, seed)
+    return model.cuda().eval(), cfg
+
+
+def _frames(cfg, n, seed0=1000):
+    from pillarnet_lts_b200 import synth
+    return [torch.from_numpy(f).cuda() for f in synth.make_batch(cfg["synth"], n, seed0)]
+
+
+def _dump(name, rec):
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, name), "w") as fh:
+        json.dump(rec, fh, indent=1)
+
+
+def _forward_stages(model, pts):
+    """product path, stage by stage: ({name: NCHW fp32 tensor}, preds, detections)"""
+    sp = model.reader(dict(points=pts))
+    feats = model.backbone(sp)
+    bev = model.neck(feats)
+    preds = model.bbox_head(bev)
+    dets = model.bbox_head.predict(dict(metadata=[{} for _ in pts]), preds, model.test_cfg)
+    stages = {}
+    for k, v in feats.items():
+        stages[k] = (v.dense() if hasattr(v, "dense") else v).float()
+    for i, b in enumerate(bev):
+        stages[f"neck{i}"] = b.float()
+    for t, p in enumerate(preds):
+        for name, v in p.items():
+            stages[f"task{t}.{name}"] = v.float()
+    return sp, stages, dets
+
+
+def _reference_stages(model, sp):
+    from oracle import cpu_path
+    feats, bev, preds = cpu_path.dense_equivalent_from_reader(model, sp)
+    stages = dict(feats)
+    for i, b in enumerate(bev):
+        stages[f"neck{i}"] = b
+    for t, p in enumerate(preds):
+        for name, v in p.items():
+            stages[f"task{t}.{name}"] = v
+    return stages
+
+
+def _run(workload, B):
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200 import agreement
+    from pillarnet_lts_b200.engine import calibrate_heatmap_bias
+    model, cfg = _build(workload)
+    frames = _frames(cfg, B)
+    P.set_precision("bf16")
+    calibrate_heatmap_bias(model, [f.cpu().numpy() for f in frames], target_cells=1500)
+    rec = {"workload": workload, "frames": B, "grid": [model.reader.height, model.reader.width],
+           "points": [int(f.shape[0]) for f in frames]}
+    with torch.no_grad():
+        P.set_precision("fp32")
+        sp, st32, det32 = _forward_stages(model, frames)
+        rec["pillars"] = sp.table.count()
+        ref = _reference_stages(model, sp)
+        rec["fp32_vs_dense_equivalent"] = {k: agreement.rel_to_max(st32[k], ref[k]) for k in ref}
+        del ref
+        torch.cuda.empty_cache()
+        P.set_precision("bf16")
+        _, st16, det16 = _forward_stages(model, frames)
+        rec["bf16_vs_fp32"] = {k: agreement.rel_to_max(st16[k], st32[k]) for k in st32}
+    torch.cuda.synchronize()
+    rec["detections_bf16_vs_fp32"] = agreement.summarize(det32, det16, iou_thr=0.7)
+    rec["detections_bf16_vs_fp32_top100"] = agreement.summarize(det32, det16, iou_thr=0.7, top=100)
+    _dump(f"parity_fullsize_{workload}.json", rec)
+    return rec
+
+
+def _check(rec):
+    for k, v in rec["fp32_vs_dense_equivalent"].items():
+        assert v <= FP32_TOL, (k, v)
+    for k, v in rec["bf16_vs_fp32"].items():
+        assert v <= BF16_STAGE_TOL, (k, v)
+    d = rec["detections_bf16_vs_fp32"]
+    assert d["n_a"] > 0 and d["n_b"] > 0
+    # random-init heads put ~1500 cells per task within a hair of the score threshold, so the *set* of kept boxes
+    # is far more sensitive than with a trained model; still >= 90 % of either run's boxes must be re-found by the
+    # other at IoU >= 0.7 with the same class, and the 100 most confident ones of every frame >= 97 %
+    assert d["recall_a_in_b"] >= 0.90 and d["recall_b_in_a"] >= 0.90, d
+    t = rec["detections_bf16_vs_fp32_top100"]
+    assert t["recall_a_in_b"] >= 0.97 and t["recall_b_in_a"] >= 0.97, t
+    assert d["max_score_delta"] <= 0.05, d
+
+
+def test_nusc18_full_size_fp32_per_stage_and_bf16_detections():
+    _check(_run("nusc18", 1))
+
+
+def test_waymo34_full_size_fp32_per_stage_and_bf16_detections():
+    _check(_run("waymo34", 2))

