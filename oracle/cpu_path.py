@@ -123,23 +123,73 @@ def nms_cfg_for_task(head, test_cfg, t):
     return base
 
 
+_p2v = None
+
+
 @torch.no_grad()
-def cpu_forward(model_cpu, frames, timings=None):
-    """frames: list of (Ni,5) float32 numpy. Returns det3d-style detections (numpy) per frame."""
+def numba_reader(rd, frames):
+    """BASELINE.json config 1 — the reference's CPU reader: numba `points_to_voxel` (hard voxelisation, z collapsed to
+    one cell; det3d/ops/point_cloud/point_cloud_ops.py:112-184, executed from the copy oracle/build_ref.py stages;
+    max_points 64, max_voxels 150000 as SURVEY §8d) per frame, then the PFN (pillar-centre offsets as
+    pillar_utils.py:51-56, Linear+BN1d+ReLU, pillar_modules.py:26-33, max over the pillar's points) on torch-CPU.
+    Returns ((pillar_features (M,C), pillar_indices (M,3) [b,y,x] int64, H, W), timings).  NOT the dynamic-pillar
+    semantics of the GPU path (caps, first-come order): a timing baseline only."""
+    global _p2v
+    if _p2v is None:
+        from . import build_ref
+        _p2v = build_ref.load_points_to_voxel()
+    pcr, ps = rd.point_cloud_range, rd.pillar_size
+    t0 = time.perf_counter()
+    vox, coors, nump, bidx = [], [], [], []
+    for b, f in enumerate(frames):
+        v, c, n = _p2v(np.ascontiguousarray(f), [ps, ps, pcr[5] - pcr[2]], list(map(float, pcr)), 64,
+                       max_voxels=150000)
+        vox.append(v), coors.append(c), nump.append(n), bidx.append(np.full(len(c), b, np.int64))
+    t1 = time.perf_counter()
+    v = torch.from_numpy(np.concatenate(vox))                      # (M, 64, D)
+    c = torch.from_numpy(np.concatenate(coors).astype(np.int64))   # (M, 3) [z, y, x]
+    n = torch.from_numpy(np.concatenate(nump).astype(np.int64))
+    M = v.shape[0]
+    valid = torch.arange(v.shape[1]).view(1, -1) < n.view(-1, 1)
+    pid = torch.arange(M).view(-1, 1).expand_as(valid)[valid]      # point -> pillar
+    pts = v[valid]                                                 # (L, D)
+    cx = c[pid, 2].float() * ps + rd.x_offset
+    cy = c[pid, 1].float() * ps + rd.y_offset
+    feat = torch.cat([(pts[:, 0] - cx).unsqueeze(1), (pts[:, 1] - cy).unsqueeze(1), pts], 1)
+    h = rd.shared_mlps(feat)
+    pf = torch.zeros(M, h.shape[1])
+    pf.index_reduce_(0, pid, h, "amax", include_self=True)
+    t2 = time.perf_counter()
+    idx = torch.stack([torch.from_numpy(np.concatenate(bidx)), c[:, 1], c[:, 2]], 1)
+    return (pf, idx, rd.height, rd.width), dict(points_to_voxel_s=t1 - t0, pfn_s=t2 - t1)
+
+
+@torch.no_grad()
+def cpu_forward(model_cpu, frames, timings=None, pillarizer="numpy"):
+    """frames: list of (Ni,5) float32 numpy. Returns det3d-style detections (numpy) per frame.
+    pillarizer: "numpy" = the dynamic-pillar oracle (comparable with the GPU path); "numba" = the reference's own
+    CPU voxeliser (bench.py's cpu_baseline: the CPU path BASELINE.json names)."""
     t0 = time.perf_counter()
     rd = model_cpu.reader.pfn_layers
     pcr, ps = rd.point_cloud_range, rd.pillar_size
-    r = O.pillarize(frames, pcr, ps, mode="cuda")
-    feat = O.point_pillar_features(r["pts"], r["pts_xy"], pcr, ps)
-    t1 = time.perf_counter()
-    h = rd.shared_mlps(torch.from_numpy(feat))
-    M = len(r["pillar_indices"])
-    pf = torch.zeros(M, h.shape[1])
-    idx = torch.from_numpy(r["point_pillar_indices"].astype(np.int64))
-    pf.index_reduce_(0, idx, h, "amax", include_self=True)
-    t2 = time.perf_counter()
-    B, H, W = len(frames), r["H"], r["W"]
-    pi = torch.from_numpy(r["pillar_indices"].astype(np.int64))
+    if pillarizer == "numba":
+        (pf, pi, H, W), tr = numba_reader(rd, frames)
+        t1 = t0 + tr["points_to_voxel_s"]
+        t2 = time.perf_counter()
+        B = len(frames)
+        r = dict(H=H, W=W, pillar_indices=pi.numpy())
+    else:
+        r = O.pillarize(frames, pcr, ps, mode="cuda")
+        feat = O.point_pillar_features(r["pts"], r["pts_xy"], pcr, ps)
+        t1 = time.perf_counter()
+        h = rd.shared_mlps(torch.from_numpy(feat))
+        M = len(r["pillar_indices"])
+        pf = torch.zeros(M, h.shape[1])
+        idx = torch.from_numpy(r["point_pillar_indices"].astype(np.int64))
+        pf.index_reduce_(0, idx, h, "amax", include_self=True)
+        t2 = time.perf_counter()
+        B, H, W = len(frames), r["H"], r["W"]
+        pi = torch.from_numpy(r["pillar_indices"].astype(np.int64))
     x = torch.zeros(B, pf.shape[1], H, W)
     x[pi[:, 0], :, pi[:, 1], pi[:, 2]] = pf
     mask = torch.zeros(B, 1, H, W)
