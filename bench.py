@@ -286,11 +286,11 @@ def parity_block(model, frames, B, pool, dev, precision):
     max|fp32| and how many detections of either run the other re-finds (same class, BEV IoU >= 0.7)."""
     import pillarnet_lts_b200 as P
     from pillarnet_lts_b200 import agreement
-    dets, maps = {}, {}
+    dets, maps, plans = {}, {}, {}
     try:
         for prec in ("fp32", precision):
             P.set_precision(prec)
-            dets[prec], maps[prec] = [], []
+            dets[prec], maps[prec], plans[prec] = [], [], []
             with torch.no_grad():
                 for i in range(pool):
                     fs = [torch.from_numpy(f).to(dev) for f in frames[i * B:(i + 1) * B]]
@@ -298,7 +298,9 @@ def parity_block(model, frames, B, pool, dev, precision):
                     preds = model.bbox_head(bev)
                     if i == 0:
                         maps[prec] = [{k: v.float().clone() for k, v in p.items()} for p in preds]
-                    dets[prec] += model.bbox_head.predict(dict(metadata=[{} for _ in fs]), preds, model.test_cfg)
+                    det_out, keep_count, plan = model.bbox_head.predict_raw(preds, model.test_cfg)
+                    dets[prec] += model.bbox_head.assemble(det_out, keep_count, plan, None)
+                    plans[prec].append(plan)
         torch.cuda.synchronize()
     finally:
         P.set_precision(precision)
@@ -308,9 +310,26 @@ def parity_block(model, frames, B, pool, dev, precision):
             e = agreement.rel_to_max(a[k], b[k])
             if e > worst:
                 worst, worst_name = e, f"task{t}.{k}"
+    cand = None
+    for pa, pb in zip(plans["fp32"], plans[precision]):
+        c = agreement.candidate_agreement(model.bbox_head, pa, pb)
+        if cand is None:
+            cand = c
+        else:
+            for k in ("n_a", "n_b", "a_in_b", "b_in_a"):
+                cand[k] += c[k]
+            cand["mean_iou"] = (cand["mean_iou"] + c["mean_iou"]) / 2   # running mean over equally sized frames
+            cand["min_iou"] = min(cand["min_iou"], c["min_iou"])
+            cand["max_score_delta"] = max(cand["max_score_delta"], c["max_score_delta"])
+    cand["recall_a_in_b"] = cand["a_in_b"] / max(1, cand["n_a"])
+    cand["recall_b_in_a"] = cand["b_in_a"] / max(1, cand["n_b"])
     return {"against": "fp32 mode of the same model on the same frames (itself within 1e-3 of the dense-equivalent torch "
                        "restatement: tests/test_gpu_fullsize.py)",
             "frames": pool * B, "head_maps_max_rel_err": worst, "worst_map": worst_name,
+            "candidates_pre_nms": cand,
+            "note": "candidates = score-sorted top-pre_max boxes handed to NMS, matched by heat-map pixel + class; "
+                    "detections = boxes kept by greedy NMS, matched at BEV IoU >= 0.7 (order-sensitive: near-tied "
+                    "scores of random-init heads reorder the sweep)",
             "detections": agreement.summarize(dets["fp32"], dets[precision], iou_thr=0.7),
             "detections_top100": agreement.summarize(dets["fp32"], dets[precision], iou_thr=0.7, top=100)}
 

@@ -64,6 +64,52 @@ def summarize(dets_a, dets_b, iou_thr=0.7, top=None):
     return tot
 
 
+def candidate_agreement(head, plan_a, plan_b):
+    """Pre-NMS agreement of two CenterHead.predict_raw runs on the same frames (the score-sorted top-`pre_max`
+    candidate boxes of every NMS segment, plan["sorted_boxes"] records [x y z w l h vx vy rot score rect label]):
+    a candidate of run A is re-found in run B when B holds a candidate of the same class whose centre lies within a
+    quarter of a head cell (i.e. the same heat-map pixel).  Reports the re-found fraction both ways, the BEV IoU of
+    the matched pairs and their score difference.  This isolates the numeric difference of the two runs from the
+    order sensitivity of greedy NMS (a near-tie in score reorders the sweep and changes which of two overlapping
+    boxes survives — with random-init heads, whose scores sit within a hair of each other, that dominates the
+    post-NMS comparison)."""
+    tot = dict(n_a=0, n_b=0, a_in_b=0, b_in_a=0, max_score_delta=0.0, min_iou=1.0)
+    iou_sum, iou_n = 0.0, 0
+    ca, cb = plan_a["sorted_count"].tolist(), plan_b["sorted_count"].tolist()
+    S = plan_a["S"]
+    for seg in range(plan_a["sorted_boxes"].shape[0]):
+        na, nb = min(ca[seg], plan_a["pre_cap"]), min(cb[seg], plan_b["pre_cap"])
+        tot["n_a"] += na
+        tot["n_b"] += nb
+        if na == 0 or nb == 0:
+            continue
+        task = plan_a["segs"][seg % S]["task"]
+        tol = 0.25 * head.task_strides[task] * float(head.pillar_size)
+        A, B = plan_a["sorted_boxes"][seg, :na], plan_b["sorted_boxes"][seg, :nb]
+        d = torch.cdist(A[:, :2].double(), B[:, :2].double())
+        same = A[:, 11].view(-1, 1) == B[:, 11].view(1, -1)
+        d = torch.where(same, d, torch.full_like(d, 1e9))
+        da, ia = d.min(1)
+        db, _ = d.min(0)
+        ok = da <= tol
+        tot["a_in_b"] += int(ok.sum())
+        tot["b_in_a"] += int((db <= tol).sum())
+        if bool(ok.any()):
+            a7 = to_pcdet(A[ok][:, :9])
+            b7 = to_pcdet(B[ia[ok]][:, :9])
+            ov = ops.boxes_aligned_overlap_bev(a7, b7)
+            area = a7[:, 3] * a7[:, 4] + b7[:, 3] * b7[:, 4] - ov
+            iou = ov / area.clamp(min=1e-8)
+            iou_sum += float(iou.sum())
+            iou_n += int(iou.numel())
+            tot["min_iou"] = min(tot["min_iou"], float(iou.min()))
+            tot["max_score_delta"] = max(tot["max_score_delta"], float((A[ok][:, 9] - B[ia[ok]][:, 9]).abs().max()))
+    tot["recall_a_in_b"] = tot["a_in_b"] / max(1, tot["n_a"])
+    tot["recall_b_in_a"] = tot["b_in_a"] / max(1, tot["n_b"])
+    tot["mean_iou"] = iou_sum / max(1, iou_n)
+    return tot
+
+
 def rel_to_max(a, b):
     """max|a-b| / max(1, max|b|): the tolerance form the parity tests state (north_star: max-abs relative to fp32)."""
     return float((a.float() - b.float()).abs().max()) / max(1.0, float(b.float().abs().max()))

@@ -232,7 +232,7 @@ class InferenceEngine:
         return out
 
 
-def calibrate_heatmap_bias(model, frames, target_cells=1500):
+def calibrate_heatmap_bias(model, frames, target_cells=1500, calibrate_rot=True):
     """Random-init heads give a degenerate candidate count (hm bias -2.19, center_head.py:19,38): shift each
     task's heat-map bias so that about `target_cells` cells per frame pass the score threshold, which is
     what a trained model feeds the NMS stage."""
@@ -252,6 +252,12 @@ def calibrate_heatmap_bias(model, frames, target_cells=1500):
             kth = torch.topk(hm, k, dim=1).values[:, -1].mean().item()
             fc = model.bbox_head.task_heads[t].hm
             fc[-1].bias.add_(logit_thr - kth)   # in-place on the Parameter: bumps ._version -> lowering refresh
+            # A trained rot head outputs (sin, cos) of unit norm; a random-init one outputs two numbers near zero, and
+            # atan2 of those turns a 1e-2 perturbation into an arbitrary heading (center_head.py:270-271).  Bias the
+            # cos channel so the decoded boxes are conditioned like a trained model's.
+            rot = getattr(model.bbox_head.task_heads[t], "rot", None)
+            if rot is not None and calibrate_rot:
+                rot[-1].bias.copy_(torch.tensor([0.0, 1.0], device=rot[-1].bias.device))
     torch.cuda.synchronize()
 
 
