@@ -224,7 +224,25 @@ typedef struct pn_conv_args {
    * [out_coff, out_coff+deconv_cout).  A quarter of the MMAs and gathers of the 4-tap gather formulation (each
    * output pixel has exactly one valid tap).  PN_IMPL_TCGEN05 only. */
   int deconv_cout, deconv_hp_in, deconv_wp_in;
+  /* What the caller knows about `nbr` (a hint: results never depend on it).  PN_NBR_SUBM_SORTED: the 3x3
+   * output-stationary table (tap = ky*3+kx) of a site set whose rows are in raster order, as pn_rulebook_subm3x3 /
+   * pn_rulebook_pyramid3x3s2 produce for the output of pn_pillarize / a strided level — then the neighbours of 128
+   * consecutive outputs under one kernel row are a short contiguous run of input rows, and PN_IMPL_TCGEN05 stages that
+   * run once per tile by TMA instead of gathering it once per tap (conv_win_tc.cu). */
+  int nbr_kind;
+  const void* nbr_plan;  /* pn_conv_window_plan(nbr) or NULL (then the gather kernel runs) */
 } pn_conv_args;
+#define PN_NBR_ANY 0
+#define PN_NBR_SUBM_SORTED 1
+
+/* Tile plans of a 3x3 rulebook for the window-staged kernel: per 128-row output tile and kernel row the start of the
+ * input-row window, the destination of every staged row under each kx, and bit masks of absent / out-of-window
+ * neighbours.  A function of (nbr, num_rows, rows_cap) only — build it once per rulebook (spconv's `indice_key`) and
+ * pass it to every conv that uses that rulebook with the same rows_cap / num_rows.  plan: 16-byte aligned device
+ * buffer of pn_conv_window_plan_bytes(rows_cap) bytes. */
+size_t pn_conv_window_plan_bytes(int rows_cap);
+int pn_conv_window_plan(const int* nbr, const int* num_rows, int rows_cap, void* plan, size_t plan_bytes,
+                        pn_stream_t stream);
 
 int pn_conv_gather(const pn_conv_args* args, int impl, pn_stream_t stream);
 /* sizeof() of the two argument structs, so a foreign binding can verify its layout. */

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpillarnet_b200.so")
 
 PN_F32, PN_BF16 = 0, 1
 PN_IMPL_SIMT, PN_IMPL_TCGEN05 = 0, 1
+PN_NBR_ANY, PN_NBR_SUBM_SORTED = 0, 1
 
 
 class ConvArgs(Structure):
@@ -29,6 +30,7 @@ class ConvArgs(Structure):
         ("num_rows", c_void_p), ("rows_cap", c_int),
         ("cin", c_int), ("cout", c_int), ("rows_hint", c_int), ("out_hp", c_int), ("out_wp", c_int), ("in_rows", c_int),
         ("deconv_cout", c_int), ("deconv_hp_in", c_int), ("deconv_wp_in", c_int),
+        ("nbr_kind", c_int), ("nbr_plan", c_void_p),
     ]
 
 
@@ -76,6 +78,8 @@ SIGNATURES = {
                                       c_void_p, c_size_t, c_void_p]),
     "pn_dense_nbr_table": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pn_conv_gather": (c_int, [POINTER(ConvArgs), c_int, c_void_p]),
+    "pn_conv_window_plan_bytes": (c_size_t, [c_int]),
+    "pn_conv_window_plan": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "pn_sizeof_conv_args": (c_size_t, []),
     "pn_sizeof_task_args": (c_size_t, []),
     "pn_conv3x3_small_cout": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,

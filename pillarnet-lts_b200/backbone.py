@@ -10,6 +10,7 @@ import torch
 from torch import nn
 
 from . import config, ops, train
+from ._lib import PN_NBR_SUBM_SORTED
 from .layers import (DenseMap, SparseConv2d, SparseReLU, SparseSequential, SubMConv2d,
                      build_norm_layer, dense_conv3x3, lower, new_dense_rows, run_conv, use_padded_layout)
 from .registry import BACKBONES
@@ -68,7 +69,8 @@ def _subm(sp, seq, relu, residual=None):
     t = sp.table
     lw = lower(conv, bn)
     out = run_conv(sp.feat, lw, t.subm_nbr(), 9, conv.in_channels, conv.out_channels, t.cap, num=t.num,
-                   relu=relu, residual=residual, rows_hint=_rows_hint(t))
+                   relu=relu, residual=residual, rows_hint=_rows_hint(t), nbr_kind=PN_NBR_SUBM_SORTED,
+                   nbr_plan=t.subm_plan() if config.get_precision() == "bf16" else None)
     return SparseConvTensor(out, t, sp.spatial_shape, sp.batch_size)
 
 
@@ -137,10 +139,15 @@ def _prefetch_rulebooks(table, n_levels):
     out = []
     with torch.cuda.stream(side):
         levels = ops.rulebook_pyramid(table, n_levels)
+        if config.get_precision() == "bf16":
+            for ot, _ in levels:
+                ot.subm_plan()           # tile plans of the level's submanifold table, off the main stream too
         ev = torch.cuda.Event()
         ev.record(side)
         for ot, nbr in levels:
-            for x in (ot.words, ot.prefix, ot.coords, ot.num, nbr, ot._nbr_subm):
+            for x in (ot.words, ot.prefix, ot.coords, ot.num, nbr, ot._nbr_subm, ot._plan_subm):
+                if x is None:
+                    continue
                 x.record_stream(main)       # allocated on the side stream, consumed on the main stream
             out.append((ot, nbr, ev))
     return out
@@ -223,6 +230,8 @@ class _PillarResNet(nn.Module):
         pre = [None, None, None]
         if not self.training and config.overlap_rulebooks():
             sp_tensor.table.subm_nbr()                      # needed at once by conv1: main stream
+            if config.get_precision() == "bf16":
+                sp_tensor.table.subm_plan()
             pre = _prefetch_rulebooks(sp_tensor.table, 3)
         x1 = _run_stage(sp_tensor, self.conv1)
         x2 = _run_stage(x1, self.conv2, pre[0])

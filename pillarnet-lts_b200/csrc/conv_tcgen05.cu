@@ -710,8 +710,15 @@ int launch(const CUtensorMap& map_w, const CUtensorMap& map_a, const CUtensorMap
 
 namespace pn_detail {
 
+int conv_win(const pn_conv_args* a, cudaStream_t stream);   // conv_win_tc.cu
+
 int conv_tcgen05(const pn_conv_args* a, cudaStream_t stream) {
   if (a->in_dtype != PN_BF16) return PN_ERR_UNSUPPORTED;
+  if (a->nbr_kind == PN_NBR_SUBM_SORTED) {
+    // raster-sorted submanifold rulebook: window-staged kernel (each input row fetched once per tile and kernel row)
+    const int rc = conv_win(a, stream);
+    if (rc != PN_ERR_UNSUPPORTED) return rc;
+  }
   if (a->taps > kMaxTaps) return PN_ERR_UNSUPPORTED;
   if (a->cin % 8 != 0 || a->in_ld % 8 != 0 || (reinterpret_cast<uintptr_t>(a->in) & 15u) != 0)
     return PN_ERR_UNSUPPORTED;

@@ -178,14 +178,15 @@ def lower_group(convs, bns, precision=None):
 
 
 def run_conv(x2d, lw, nbr, taps, cin, cout, rows_cap, *, num=None, relu=False, residual=None, out=None,
-             out_coff=0, out_dtype=None, in_ld=None, in_ptr_offset=0, rows_hint=0, out_hw_pad=None, deconv=None):
+             out_coff=0, out_dtype=None, in_ld=None, in_ptr_offset=0, rows_hint=0, out_hw_pad=None, deconv=None,
+             nbr_kind=0, nbr_plan=None):
     """One fused conv launch on channels-last rows."""
     if out is None:
         out = torch.empty(rows_cap, cout, dtype=out_dtype or x2d.dtype, device=x2d.device)
     ops.conv_gather(x2d, lw.weight, nbr, taps, cin, cout, out, in_ld=in_ld, k_pad=lw.k_pad, scale=lw.scale,
                     shift=lw.shift, residual=residual, out_coff=out_coff, relu=relu, num=num,
                     rows_cap=rows_cap, impl=config.conv_impl(), in_ptr_offset=in_ptr_offset, rows_hint=rows_hint,
-                    out_hw_pad=out_hw_pad, deconv=deconv)
+                    out_hw_pad=out_hw_pad, deconv=deconv, nbr_kind=nbr_kind, nbr_plan=nbr_plan)
     return out
 
 

@@ -27,12 +27,13 @@ class RankTable:
     coords (cap,3) int32 [b,y,x] in ascending cell order; num: device int32 scalar (1,) ; cap: host.
     """
 
-    __slots__ = ("words", "prefix", "coords", "num", "cap", "B", "H", "W", "_nbr_subm", "_train", "ready")
+    __slots__ = ("words", "prefix", "coords", "num", "cap", "B", "H", "W", "_nbr_subm", "_plan_subm", "_train", "ready")
 
     def __init__(self, words, prefix, coords, num, cap, B, H, W):
         self.words, self.prefix, self.coords, self.num = words, prefix, coords, num
         self.cap, self.B, self.H, self.W = cap, B, H, W
         self._nbr_subm = None
+        self._plan_subm = None
         self._train = None   # training-path caches (exact-size view, rulebooks): train.py
         self.ready = None    # event recorded when the table was complete (lets a side stream fork right there)
 
@@ -45,6 +46,12 @@ class RankTable:
         if self._nbr_subm is None:
             self._nbr_subm = rulebook_subm3x3(self)
         return self._nbr_subm
+
+    def subm_plan(self):
+        """cached tile plans of the submanifold table for the window-staged conv kernel (pn_conv_window_plan)"""
+        if self._plan_subm is None:
+            self._plan_subm = conv_window_plan(self.subm_nbr(), self.num, self.cap)
+        return self._plan_subm
 
 
 def pillarize(points, frame_offsets, n_frames, H, W, x0, y0, pillar_size, m_cap=None):
@@ -132,6 +139,17 @@ def rulebook_subm3x3(table):
     return nbr
 
 
+def conv_window_plan(nbr, num, rows_cap):
+    """pn_conv_window_plan: tile plans of a (rows_cap, 9) rulebook, to be passed as conv_gather(nbr_plan=...)."""
+    lib = _lib.load()
+    require_cuda(nbr)
+    nb = lib.pn_conv_window_plan_bytes(rows_cap)
+    plan = torch.empty(nb, dtype=torch.uint8, device=nbr.device)
+    check(lib.pn_conv_window_plan(ptr(nbr), ptr(num), rows_cap, ptr(plan), c_size_t(nb), stream_ptr()),
+          "pn_conv_window_plan")
+    return plan
+
+
 def rulebook_down3x3s2(table, out_cap=None):
     """Strided 3x3/s2/p1 rulebook. Returns (out RankTable, nbr (out_cap,9) int32 into input rows)."""
     lib = _lib.load()
@@ -209,7 +227,8 @@ def dense_nbr_table(mode, n_frames, H, W, stride, device, in_pad=False, out_pad=
 
 def conv_gather(inp, weight, nbr, taps, cin, cout, out, *, in_ld=None, k_pad=None, scale=None,
                 shift=None, residual=None, res_ld=None, out_ld=None, out_coff=0, relu=False, num=None,
-                rows_cap=None, impl=PN_IMPL_SIMT, in_ptr_offset=0, rows_hint=0, out_hw_pad=None, deconv=None):
+                rows_cap=None, impl=PN_IMPL_SIMT, in_ptr_offset=0, rows_hint=0, out_hw_pad=None, deconv=None,
+                nbr_kind=0, nbr_plan=None):
     """out[o, coff:coff+cout] = act((sum_t W_t . in[nbr[o,t]]) * scale + shift + residual).
     deconv = (cout_per_tap, Hp_in, Wp_in): the 2x2/s2 transposed conv as one GEMM (pn_conv_args.deconv_*).
 
@@ -243,6 +262,8 @@ def conv_gather(inp, weight, nbr, taps, cin, cout, out, *, in_ld=None, k_pad=Non
     a.out_hp, a.out_wp = (out_hw_pad if out_hw_pad is not None else (0, 0))
     a.in_rows = inp.shape[0]
     a.deconv_cout, a.deconv_hp_in, a.deconv_wp_in = deconv if deconv is not None else (0, 0, 0)
+    a.nbr_kind = int(nbr_kind)
+    a.nbr_plan = ptr(nbr_plan).value
     if residual is not None and residual.dtype != out.dtype:
         raise RuntimeError("residual dtype must match the output dtype")
     check(lib.pn_conv_gather(byref(a), impl, stream_ptr()), "pn_conv_gather")

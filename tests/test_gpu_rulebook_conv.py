@@ -303,3 +303,99 @@ def test_grouped_small_cout_conv_vs_torch():
         assert (got - want).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
         c0 += w.shape[0]
     assert bool((out[:, col:] == -9.0).all())
+
+
+# ---- window-staged submanifold kernel (conv_win_tc.cu) ---------------------------------------------------------------
+def _clustered_sites(rng, B, H, W, n):
+    """LiDAR-like occupancy: arcs + blobs, so raster neighbours exist (random sites have almost none)"""
+    ys, xs, bs = [], [], []
+    for b in range(B):
+        for r in rng.uniform(5, min(H, W) / 2 - 2, 14):
+            th = rng.uniform(0, 2 * np.pi, max(8, int(n / 14 / B)))
+            ys.append(np.clip(np.round(H / 2 + r * np.sin(th)), 0, H - 1))
+            xs.append(np.clip(np.round(W / 2 + r * np.cos(th)), 0, W - 1))
+            bs.append(np.full(len(th), b))
+        cy, cx = rng.integers(8, H - 8, 10), rng.integers(8, W - 8, 10)
+        for y0, x0 in zip(cy, cx):
+            yy, xx = np.meshgrid(np.arange(-5, 6), np.arange(-7, 8), indexing="ij")
+            keep = rng.random(yy.shape) < 0.8
+            ys.append((y0 + yy)[keep]); xs.append(np.clip((x0 + xx)[keep], 0, W - 1)); bs.append(np.full(int(keep.sum()), b))
+    idx = np.unique(np.stack([np.concatenate(bs), np.concatenate(ys), np.concatenate(xs)], 1).astype(np.int64), axis=0)
+    return idx
+
+
+@pytest.mark.parametrize("c,HW,B", [(32, 200, 2), (64, 160, 1), (128, 120, 2), (64, 40, 1)])
+def test_window_staged_subm_conv_equals_gather_kernel(c, HW, B):
+    """conv_win_tc.cu (nbr_kind = PN_NBR_SUBM_SORTED) against the gather kernel (nbr_kind = 0) and the fp32-FMA path
+    on identical bf16 operands, with residual + ReLU, partial last tiles and rows beyond the live count untouched."""
+    from pillarnet_lts_b200 import ops
+    from pillarnet_lts_b200._lib import PN_IMPL_SIMT, PN_IMPL_TCGEN05, PN_NBR_SUBM_SORTED
+    rng = np.random.default_rng(c + HW)
+    idx = _clustered_sites(rng, B, HW, HW, 6000)
+    table = _table_from_sites(idx, B, HW, HW)
+    m = table.count()
+    nbr = table.subm_nbr()
+    cap = table.cap
+    x = torch.randn(cap, c, device="cuda").to(torch.bfloat16)
+    w = torch.randn(c, 9 * c, device="cuda") * (1.0 / (9 * c) ** 0.5)
+    wp = ops.pack_weight_bf16(w.contiguous())
+    scale, shift = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+    res = torch.randn(cap, c, device="cuda").to(torch.bfloat16)
+    plan = table.subm_plan()
+    outs = {}
+    for name, impl, kind in (("simt", PN_IMPL_SIMT, 0), ("gather", PN_IMPL_TCGEN05, 0),
+                             ("window", PN_IMPL_TCGEN05, PN_NBR_SUBM_SORTED)):
+        out = torch.full((cap, c), 7.0, device="cuda", dtype=torch.bfloat16)
+        ops.conv_gather(x, wp, nbr, 9, c, c, out, scale=scale, shift=shift, residual=res, relu=True, num=table.num,
+                        rows_cap=cap, impl=impl, nbr_kind=kind, nbr_plan=plan if kind else None)
+        torch.cuda.synchronize()
+        outs[name] = out.float()
+    ref = outs["simt"]
+    assert m > 500 and bool((outs["window"][m:] == 7.0).all())          # rows past the live count are not written
+    tol = 1e-2 * max(1.0, ref.abs().max().item())                       # one bf16 ulp of the largest value
+    assert (outs["window"][:m] - ref[:m]).abs().max().item() <= tol
+    assert (outs["window"][:m] - outs["gather"][:m]).abs().max().item() <= tol
+    # same fp32 accumulation order when there is one K chunk per tap: bit-equal to the gather kernel
+    if c <= 64:
+        assert torch.equal(outs["window"][:m], outs["gather"][:m])
+    # no residual / no ReLU / no affine
+    o1 = torch.zeros(cap, c, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.zeros(cap, c, device="cuda", dtype=torch.bfloat16)
+    ops.conv_gather(x, wp, nbr, 9, c, c, o1, num=table.num, rows_cap=cap, impl=PN_IMPL_TCGEN05, nbr_kind=0)
+    ops.conv_gather(x, wp, nbr, 9, c, c, o2, num=table.num, rows_cap=cap, impl=PN_IMPL_TCGEN05,
+                    nbr_kind=PN_NBR_SUBM_SORTED, nbr_plan=plan)
+    torch.cuda.synchronize()
+    assert (o1.float() - o2.float())[:m].abs().max().item() <= 1e-2 * max(1.0, o1.float().abs().max().item())
+
+
+def test_window_staged_kernel_is_correct_for_any_rulebook():
+    """the hint never changes results: a scrambled (non-raster) rulebook sends every neighbour through the
+    out-of-window global fetch of conv_win_tc.cu; an empty site set and a one-row set run too."""
+    from pillarnet_lts_b200 import ops
+    from pillarnet_lts_b200._lib import PN_IMPL_TCGEN05, PN_NBR_SUBM_SORTED
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rows, c = 3000, 64
+    nbr = torch.randint(-1, rows, (rows, 9), device="cuda", generator=g, dtype=torch.int32)
+    nbr[torch.rand(rows, 9, device="cuda", generator=g) < 0.3] = -1
+    x = torch.randn(rows, c, device="cuda", generator=g).to(torch.bfloat16)
+    wp = ops.pack_weight_bf16((torch.randn(c, 9 * c, device="cuda", generator=g) / 24.0).contiguous())
+    outs = []
+    plan = ops.conv_window_plan(nbr, None, rows)
+    for kind in (0, PN_NBR_SUBM_SORTED):
+        out = torch.zeros(rows, c, device="cuda", dtype=torch.bfloat16)
+        ops.conv_gather(x, wp, nbr, 9, c, c, out, relu=True, impl=PN_IMPL_TCGEN05, nbr_kind=kind,
+                        nbr_plan=plan if kind else None)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    for n_live in (0, 1, 65):
+        num = torch.tensor([n_live], dtype=torch.int32, device="cuda")
+        out = torch.full((rows, c), 3.0, device="cuda", dtype=torch.bfloat16)
+        ref = torch.full((rows, c), 3.0, device="cuda", dtype=torch.bfloat16)
+        nb = nbr.clone()
+        nb[nb >= max(n_live, 1)] = -1
+        ops.conv_gather(x, wp, nb, 9, c, c, out, num=num, rows_cap=rows, impl=PN_IMPL_TCGEN05,
+                        nbr_kind=PN_NBR_SUBM_SORTED, nbr_plan=ops.conv_window_plan(nb, num, rows))
+        ops.conv_gather(x, wp, nb, 9, c, c, ref, num=num, rows_cap=rows, impl=PN_IMPL_TCGEN05, nbr_kind=0)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)

@@ -12,6 +12,7 @@
 #   launches         ncu launch list of one graph replay                 -> gpurun_out/launches.csv (+ .txt summary)
 #   ncu_mem          ncu --set full of the memory-bound kernels          -> gpurun_out/prof_mem.ncu-rep
 #   ncu_convs        ncu --set full of the conv kernels                  -> gpurun_out/prof_convs.ncu-rep
+#   timeline         per-CTA pipeline timelines + stall accounting of every conv launch -> gpurun_out/timeline.txt
 #   kbench_reader    reader kernels at scale (events)                    -> gpurun_out/kbench_reader.json
 # Every ncu step first runs the same command plain (the recipe's rule) and only profiles if that exited 0.
 mkdir -p gpurun_out
@@ -67,6 +68,9 @@ for step in "$@"; do
       [ $plain_ok -eq 1 ] && timeout 2400 ncu --profile-from-start off --set full --clock-control none --import-source on \
         -k 'regex:k_conv' -o gpurun_out/prof_convs -f $PROF_CMD > gpurun_out/ncu_convs.log 2>&1
       echo "ncu_convs rc=$?"; tail -3 gpurun_out/ncu_convs.log ;;
+    timeline)
+      timeout 600 python tools/infer_timeline.py > gpurun_out/timeline.log 2> gpurun_out/timeline.txt; echo "timeline rc=$?"
+      grep -A200 "pass 2" gpurun_out/timeline.txt | grep -A1 "conv_win\|conv_tc" | head -120 ;;
     kbench_reader)
       timeout 900 python tools/kbench_reader.py > gpurun_out/kbench_reader.log 2>&1; echo "kbench rc=$?"; tail -5 gpurun_out/kbench_reader.log ;;
     *)
