@@ -15,7 +15,7 @@
 // row ky are a CONTIGUOUS run of input rows (the outputs' x-neighbours one raster line up, on, or below; measured
 // span 128-190 rows on nuScenes/Waymo-shaped frames).  Per unit = (output tile, 64-channel chunk, ky):
 //   * one TMA box load stages the window rows [lo_ky, lo_ky + S) x chunk into shared memory (no LSU issue cost);
-//   * 12 builder warps (thread = output row, warp = row quarter x kx) read the window row that holds their neighbour
+//   * 12 builder warps (thread = output row, warp = row quarter x ky) read the window row that holds their neighbour
 //     (KU/8 LDS.128, conflict-free on the swizzled window) and write it to THEIR LANE OF TENSOR MEMORY with
 //     tcgen05.st; absent neighbours are zeros from registers, the rare neighbours outside the window come straight
 //     from global memory (always correct, whatever the rulebook looks like);
@@ -31,8 +31,8 @@
 // (pn_conv_window_plan) and streamed into shared memory one tile ahead by a bulk copy.  (First version: a mapper warp
 // inside the conv kernel — a single warp needs ~5000 clk per tile for it, 2.5 us of exposed wait per tile; measured.)
 //
-// Warp roles (576 threads, one persistent CTA per SM): 0-11 builders, 12-15 epilogue (TMEM lane quarter = warp % 4),
-// 16 MMA issuer, 17 loader (plan copies, window + weight TMA).
+// Warp roles (608 threads, one persistent CTA per SM): 0-11 builders, 12-15 epilogue (TMEM lane quarter = warp % 4),
+// 16 MMA issuer, 17 loader (plan copies, window TMA), 18 weight loader.
 #include <cuda.h>
 
 #include <climits>
@@ -48,16 +48,16 @@ namespace {
 using namespace pn_tc;
 
 constexpr int BLOCK_M = 128;
-constexpr int kWin = 192;                 // staged rows per kernel row (TMA box rows; must be <= 256)
-constexpr int kBuilderWarps = 12;         // warp w: TMEM lane quarter w % 4 (rows 32(w%4)..+31), tap kx = w / 4
-constexpr int kBuilderThreads = kBuilderWarps * 32;
+constexpr int kWin = 160;                 // staged rows per kernel row (TMA box rows; must be <= 256).  Measured spans:
+                                          // median 129, 90 % <= 143, 99 % <= 165, max 191; rows past the window are fetched
+                                          // from global memory by the builders
+constexpr int kBuilderWarps = 12;         // warp w: TMEM lane quarter w % 4 (rows 32(w%4)..+31), kernel row ky = w / 4
 constexpr int kEpilogueWarp0 = kBuilderWarps;          // 12..15 (index % 4 == TMEM lane quarter)
 constexpr int kEpilogueThreads = 128;
 constexpr int kMmaWarp = kBuilderWarps + 4;            // 16
-constexpr int kLoaderWarp = kMmaWarp + 1;              // 17
-constexpr int kThreads = (kLoaderWarp + 1) * 32;       // 576
-constexpr int kWinSlots = 3;                           // staged-window ring
-constexpr int kASlots = 2;                             // TMEM A ring, in units (3 taps each)
+constexpr int kLoaderWarp = kMmaWarp + 1;              // 17: plan copies + staged windows
+constexpr int kWeightWarp = kMmaWarp + 2;              // 18: weight tiles
+constexpr int kThreads = (kWeightWarp + 1) * 32;       // 608
 // Tile plan (bytes): src[9][128] = window row of the neighbour of output row i under tap t (0xFF absent, 0xFE outside
 // the window: fetched from global) | lo[3] + pad (int32)
 constexpr int kSrcAbsent = 0xFF, kSrcFar = 0xFE;
@@ -111,14 +111,19 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 #define PW_ACC(var) do { if (P.dbg) var += clock64() - _w0; } while (0)
 #define PW_OUT(slot, var) do { if (P.dbg) P.dbg[blockIdx.x * 16 + slot] = (unsigned long long)(var); } while (0)
 
-template <int BN, int KU, int NB>
+// RES: all 9 * n_chunks weight tiles of the layer stay resident in shared memory (loaded once per CTA; NBT = their
+// number); otherwise NBT tiles form a ring of NBT / 3 units (3 taps per barrier).  WS = staged-window ring depth,
+// AS = TMEM A ring depth in units.
+template <int BN, int KU, bool RES, int NBT, int WS, int AS>
 struct WSmem {
-  alignas(1024) uint8_t b[NB][BN * 128];                 // weight tiles, one per tap (SWIZZLE_128B, K-major)
-  alignas(1024) uint8_t win[kWinSlots][kWin * KU * 2];   // staged input windows (KU = 64: SWIZZLE_128B, 32: SWIZZLE_64B)
+  static_assert(WS % AS == 0 && AS <= 3, "a window slot must always belong to the same builder group");
+  static constexpr int NBU = RES ? 1 : NBT / 3;
+  alignas(1024) uint8_t b[NBT][BN * 128];                // weight tiles, one per tap (SWIZZLE_128B, K-major)
+  alignas(1024) uint8_t win[WS][kWin * KU * 2];          // staged input windows (KU = 64: SWIZZLE_128B, 32: SWIZZLE_64B)
   alignas(1024) uint8_t stage_out[4 * 2048];             // epilogue boxes for TMA stores (one per epilogue warp)
   alignas(16) uint8_t plan[3][kPlanBytes];               // tile plans (ring of three, copied one tile ahead)
-  alignas(8) uint64_t a_full[kASlots];
-  uint64_t a_empty[kASlots], win_full[kWinSlots], win_empty[kWinSlots], b_full[NB], b_empty[NB], map_full[3], map_empty[3];
+  alignas(8) uint64_t a_full[AS];
+  uint64_t a_empty[AS], win_full[WS], win_empty[WS], b_full[NBU], b_empty[NBU], map_full[3], map_empty[3];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   float scale[BN];
@@ -164,12 +169,14 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 
 constexpr int tmem_pow2(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int BN, int KU, int NB>
+template <int BN, int KU, bool RES, int NBT, int WS, int AS>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_in,
            const __grid_constant__ CUtensorMap tmap_o, const WArgs P) {
   extern __shared__ uint8_t smem_raw[];
-  using S = WSmem<BN, KU, NB>;
+  using S = WSmem<BN, KU, RES, NBT, WS, AS>;
+  constexpr int NBU = S::NBU;
+  constexpr int kASlots = AS, kWinSlots = WS;
   S& sm = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int KS = KU / 16;                 // MMA k-steps per tap and chunk
@@ -191,24 +198,24 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < kASlots; ++s) {
-        mbar_init(&sm.a_full[s], kBuilderWarps);
+        mbar_init(&sm.a_full[s], 4);
         mbar_init(&sm.a_empty[s], 1);
       }
       for (int s = 0; s < kWinSlots; ++s) {
         mbar_init(&sm.win_full[s], 1);
-        mbar_init(&sm.win_empty[s], kBuilderWarps);
+        mbar_init(&sm.win_empty[s], 4);
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&sm.tmem_full[s], 1);
         mbar_init(&sm.tmem_empty[s], kEpilogueThreads);
       }
-      for (int s = 0; s < NB; ++s) {
+      for (int s = 0; s < NBU; ++s) {
         mbar_init(&sm.b_full[s], 1);
         mbar_init(&sm.b_empty[s], 1);
       }
       for (int s = 0; s < 3; ++s) {
         mbar_init(&sm.map_full[s], 1);
-        mbar_init(&sm.map_empty[s], kBuilderWarps);
+        mbar_init(&sm.map_empty[s], 4 * kASlots);
       }
       fence_barrier_init();
     }
@@ -222,32 +229,48 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
   if (threadIdx.x == 0) PW_DBG(1);
 
   if (warp < kBuilderWarps) {
-    // ===================== builders: staged window -> A operand of one tap in TMEM =====================
-    // thread = output row i = 32 (warp % 4) + lane of the tile; the warp's tap is kx = warp / 4.  The row of the
-    // window that holds the neighbour is read with KU/8 16-byte loads (conflict-free on the swizzled window when the
-    // rows of neighbouring lanes are consecutive, as they are in raster order) and stored to the thread's TMEM lane.
-    const int quarter = warp & 3, kx = warp >> 2;
+    // ===================== builders: staged window -> A operands of one unit in TMEM =====================
+    // thread = output row i = 32 (warp % 4) + lane of the tile; warp group g = warp / 4 builds whole units (all three
+    // taps of a kernel row), AS units in flight at once, one per group — that hides the window / TMEM latencies a single
+    // chain per unit exposed (measured: builders and MMA warp spent half their time waiting for each other).  Per tap
+    // the thread reads the window row that holds its neighbour with KU/8 16-byte loads (conflict-free on the swizzled
+    // window when the rows of neighbouring lanes are consecutive, as they are in raster order) and stores it to its
+    // TMEM lane.
+    const int quarter = warp & 3, grp = warp >> 2;
     const int i = quarter * 32 + lane;
     const char* in_bytes = reinterpret_cast<const char*>(P.in);
     const uint32_t in_ld_bytes = (uint32_t)P.in_ld * 2u;
-    uint32_t u = 0;
     long long w_aempty = 0, w_win = 0, w_map = 0;
-    for (int tile = 0; tile < n_tiles; ++tile) {
-      const int buf = tile % 3;
-      { PW_T0(); mbar_wait(&sm.map_full[buf], (uint32_t)(tile / 3) & 1u); PW_ACC(w_map); }
-      const int row0 = row_begin + tile * BLOCK_M;
-      uint32_t src3[3];
+    // Group g owns the units u = g (mod AS): exactly the units that use TMEM A slot g, so every a_full / a_empty
+    // barrier has ONE producer group and parity waits cannot alias (a group that may run several phases ahead of a
+    // barrier it shares with others would pass a parity wait it must block on).  Groups >= AS stay idle (BN = 128 has
+    // TMEM columns for two A slots only).
+    const int upt = 3 * P.n_chunks;                       // units per tile
+    const uint32_t n_units = (uint32_t)(n_tiles * upt);
+    int cur_tile = -1, row0 = 0;
+    const uint8_t* s_plan = nullptr;
+    if (grp < kASlots) {
+      for (uint32_t u = (uint32_t)grp; u < n_units; u += kASlots) {
+        const int tile = (int)u / upt, r = (int)u - tile * upt, kc = r / 3, ky = r - kc * 3;
+        if (tile != cur_tile) {
+          if (cur_tile >= 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.map_empty[cur_tile % 3]);     // done with the previous tile's plan
+          }
+          { PW_T0(); mbar_wait(&sm.map_full[tile % 3], (uint32_t)(tile / 3) & 1u); PW_ACC(w_map); }
+          cur_tile = tile;
+          row0 = row_begin + tile * BLOCK_M;
+          s_plan = sm.plan[tile % 3];
+        }
+        const uint32_t aslot = (uint32_t)grp, aph = (u / kASlots) & 1u;
+        const uint32_t wslot = u % kWinSlots, wph = (u / kWinSlots) & 1u;
+        uint32_t src3[3];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) src3[ky] = sm.plan[buf][(ky * 3 + kx) * BLOCK_M + i];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.map_empty[buf]);    // the plan bytes this warp needs are in registers
-      for (int kc = 0; kc < P.n_chunks; ++kc) {
+        for (int kx = 0; kx < 3; ++kx) src3[kx] = s_plan[(ky * 3 + kx) * BLOCK_M + i];
+        { PW_T0(); mbar_wait(&sm.win_full[wslot], wph); PW_ACC(w_win); }
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky, ++u) {
-          const uint32_t aslot = u % kASlots, aph = (u / kASlots) & 1u;
-          const uint32_t wslot = u % kWinSlots, wph = (u / kWinSlots) & 1u;
-          { PW_T0(); mbar_wait(&sm.win_full[wslot], wph); PW_ACC(w_win); }
-          const uint32_t s = src3[ky];
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint32_t s = src3[kx];
           uint32_t v[32];
           if (s < (uint32_t)kSrcFar) {
             const uint8_t* rowp = sm.win[wslot] + s * ROWB;
@@ -270,24 +293,31 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < KU / 2; ++j) v[j] = 0u;
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.win_empty[wslot]);      // window rows are in registers
-          { PW_T0(); mbar_wait(&sm.a_empty[aslot], aph ^ 1u); PW_ACC(w_aempty); }
-          tcgen05_fence_after();
+          if (kx == 0) {
+            PW_T0(); mbar_wait(&sm.a_empty[aslot], aph ^ 1u); PW_ACC(w_aempty);
+            tcgen05_fence_after();
+          }
+          __syncwarp();     // tcgen05.st is .sync.aligned: the lanes diverged on present / far / absent above
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + A_COL0 + (aslot * 3 + kx) * ACOLS;
           if (KU == 64) tmem_st32(taddr, v); else tmem_st16(taddr, v);
-          tmem_wait_st();
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.a_full[aslot]);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.win_empty[wslot]);      // the window rows went through registers into TMEM stores
+        tmem_wait_st();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.a_full[aslot]);
+      }
+      if (cur_tile >= 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.map_empty[cur_tile % 3]);
       }
     }
     if (threadIdx.x == 0) { PW_OUT(8, w_aempty); PW_OUT(9, w_win); PW_OUT(7, w_map); }
   } else if (warp == kLoaderWarp) {
     // ===================== loader: plan copies, staged windows, weight tiles =====================
     if (lane == 0) {
-      uint32_t u = 0, g = 0;
+      uint32_t u = 0;
       const uint8_t* plan_g = P.plan + (size_t)blockIdx.x * P.tiles_per_cta * kPlanBytes;
       // plan of `tile` -> ring slot tile % 3 (free once every builder warp has read tile - 3's entries); its window
       // starts come straight from global memory so the first window load does not wait for the copy
@@ -310,14 +340,31 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
             mbar_arrive_expect_tx(&sm.win_full[slot], kWin * ROWB);
             tma_load_2d(smem_u32(sm.win[slot]), &tmap_in, kc * KU, ky == 0 ? lo0 : (ky == 1 ? lo1 : lo2),
                         &sm.win_full[slot]);
-            for (int kx = 0; kx < 3; ++kx, ++g) {
-              const uint32_t bs = g % NB, bph = (g / NB) & 1u;
-              mbar_wait(&sm.b_empty[bs], bph ^ 1u);
-              mbar_arrive_expect_tx(&sm.b_full[bs], BN * 128);
-              tma_load_2d(smem_u32(sm.b[bs]), &tmap_w, (ky * 3 + kx) * P.cin + kc * KU, 0, &sm.b_full[bs]);
-            }
           }
         }
+      }
+    }
+  } else if (warp == kWeightWarp) {
+    // ===================== weight tiles =====================
+    if (lane == 0 && n_tiles > 0) {
+      if constexpr (RES) {
+        // the whole layer fits: every tile loaded once, one barrier
+        mbar_arrive_expect_tx(&sm.b_full[0], (uint32_t)(9 * P.n_chunks) * BN * 128);
+        for (int kc = 0; kc < P.n_chunks; ++kc)
+          for (int t = 0; t < 9; ++t)
+            tma_load_2d(smem_u32(sm.b[kc * 9 + t]), &tmap_w, t * P.cin + kc * KU, 0, &sm.b_full[0]);
+      } else {
+        uint32_t u = 0;
+        for (int tile = 0; tile < n_tiles; ++tile)
+          for (int kc = 0; kc < P.n_chunks; ++kc)
+            for (int ky = 0; ky < 3; ++ky, ++u) {
+              const uint32_t bs = u % NBU, bph = (u / NBU) & 1u;
+              mbar_wait(&sm.b_empty[bs], bph ^ 1u);
+              mbar_arrive_expect_tx(&sm.b_full[bs], 3 * BN * 128);
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx)
+                tma_load_2d(smem_u32(sm.b[bs * 3 + kx]), &tmap_w, (ky * 3 + kx) * P.cin + kc * KU, 0, &sm.b_full[bs]);
+            }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -326,8 +373,11 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
     constexpr uint32_t idesc = make_idesc<BN>();
     const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_u32(sm.b[0]));
     constexpr uint32_t kBStep = (uint32_t)(BN * 128) >> 4;
-    uint32_t u = 0, bs = 0, bph = 0;
+    uint32_t u = 0;
     bool first = true;
+    if constexpr (RES) {
+      if (n_tiles > 0) mbar_wait(&sm.b_full[0], 0u);      // resident weights: one wait for the whole kernel
+    }
     long long w_afull = 0, w_bfull = 0, w_tempty = 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
       const uint32_t acc = (uint32_t)tile & 1u, acc_ph = ((uint32_t)tile >> 1) & 1u;
@@ -338,25 +388,27 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
       for (int kc = 0; kc < P.n_chunks; ++kc) {
         for (int ky = 0; ky < 3; ++ky, ++u) {
           const uint32_t aslot = u % kASlots, aph = (u / kASlots) & 1u;
+          const uint32_t bs = RES ? 0u : u % NBU, bph = (u / NBU) & 1u;
+          if constexpr (!RES) { PW_T0(); mbar_wait(&sm.b_full[bs], bph); if (!first) PW_ACC(w_bfull); }
           { PW_T0(); mbar_wait(&sm.a_full[aslot], aph); if (!first) PW_ACC(w_afull); }
-          for (int kx = 0; kx < 3; ++kx) {
-            { PW_T0(); mbar_wait(&sm.b_full[bs], bph); if (!first) PW_ACC(w_bfull); }
-            tcgen05_fence_after();
-            if (first) { if (issuer) PW_DBG(2); first = false; }
-            const uint32_t a_tmem = tmem_base + A_COL0 + (aslot * 3 + (uint32_t)kx) * ACOLS;
-            const uint64_t b_desc = b_desc0 + (uint64_t)(bs * kBStep);
-            if (issuer) {
+          tcgen05_fence_after();
+          if (first) { if (issuer) PW_DBG(2); first = false; }
+          const uint32_t b_tile0 = RES ? (uint32_t)(kc * 9 + ky * 3) : bs * 3u;
+          if (issuer) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint32_t a_tmem = tmem_base + A_COL0 + (aslot * 3 + (uint32_t)kx) * ACOLS;
+              const uint64_t b_desc = b_desc0 + (uint64_t)((b_tile0 + (uint32_t)kx) * kBStep);
 #pragma unroll
               for (int k = 0; k < KS; ++k) {
                 umma_bf16_ts(d_tmem, a_tmem + 8 * k, b_desc + 2 * k, idesc, accumulate);
                 accumulate = 1u;
               }
-              umma_commit(&sm.b_empty[bs]);
             }
-            accumulate = 1u;
-            if (++bs == NB) { bs = 0; bph ^= 1u; }
+            if constexpr (!RES) umma_commit(&sm.b_empty[bs]);
+            umma_commit(&sm.a_empty[aslot]);
           }
-          if (issuer) umma_commit(&sm.a_empty[aslot]);
+          accumulate = 1u;
         }
       }
       if (issuer) {
@@ -525,14 +577,15 @@ inline WinGeom win_geom(int rows_cap) {
   return g;
 }
 
-template <int BN, int KU, int NB>
+template <int BN, int KU, bool RES, int NBT, int WS, int AS>
 int launch(const CUtensorMap& map_w, const CUtensorMap& map_in, const CUtensorMap& map_o, const WArgs& wa, int grid,
            cudaStream_t stream) {
-  constexpr size_t smem = sizeof(WSmem<BN, KU, NB>) + 1024;
+  constexpr size_t smem = sizeof(WSmem<BN, KU, RES, NBT, WS, AS>) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static pn_detail::PerDeviceOnce once;
   if (once.need())
-    PN_CUDA(cudaFuncSetAttribute(k_conv_win<BN, KU, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PN_CUDA(cudaFuncSetAttribute(k_conv_win<BN, KU, RES, NBT, WS, AS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
   static const bool timeline = [] { const char* e = getenv("PN_CONV_TIMELINE"); return e && e[0] == '1'; }();
   static unsigned long long* dbg_buf = nullptr;
   WArgs w = wa;
@@ -552,7 +605,7 @@ int launch(const CUtensorMap& map_w, const CUtensorMap& map_in, const CUtensorMa
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  PN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_win<BN, KU, NB>, map_w, map_in, map_o, w));
+  PN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_win<BN, KU, RES, NBT, WS, AS>, map_w, map_in, map_o, w));
   PN_CHECK_LAUNCH();
   if (timeline) {
     PN_CUDA(cudaStreamSynchronize(stream));
@@ -575,9 +628,9 @@ int launch(const CUtensorMap& map_w, const CUtensorMap& map_in, const CUtensorMa
       s_w[6] += (double)q[15];
     }
     if (n > 0) {
-      fprintf(stderr, "[conv_win<%d,%d,%d> cin %d cout %d rows_cap %d grid %d busy %d] span %.1f us | setup avg %.1f | first operands "
+      fprintf(stderr, "[conv_win<%d,%d,%s> cin %d cout %d rows_cap %d grid %d busy %d] span %.1f us | setup avg %.1f | first operands "
                       "avg %.1f | mma phase avg %.1f max %.1f | last epilogue avg %.1f | CTA total avg %.1f\n",
-              BN, KU, NB, wa.cin, wa.cout, wa.rows_cap, grid, n, (t_max - t_min) / 1e3, s_setup / n / 1e3, s_first / n / 1e3,
+              BN, KU, RES ? "resident" : "streamed", wa.cin, wa.cout, wa.rows_cap, grid, n, (t_max - t_min) / 1e3, s_setup / n / 1e3, s_first / n / 1e3,
               s_mma / n / 1e3, m_mma / 1e3, s_epi / n / 1e3, s_tot / n / 1e3);
       fprintf(stderr, "    stalls per CTA (kclk; builder = warp 0): builder map %.1f, a_empty %.1f, win_full %.1f | mma a_full %.1f, b_full %.1f, "
                       "tmem_empty %.1f | tiles %.1f\n",
@@ -641,12 +694,20 @@ int conv_win(const pn_conv_args* a, cudaStream_t stream) {
       pn_tmap::get(a->out, a->rows_cap, a->out_ld, a->out_ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, &map_o) == PN_OK)
     w.tma_store = 1;
   const int grid = geo.grid;
-  if (bn == 32 && ku == 32) return launch<32, 32, 6>(map_w, map_in, map_o, w, grid, stream);
-  if (bn == 32) return launch<32, 64, 6>(map_w, map_in, map_o, w, grid, stream);
-  if (bn == 64 && ku == 32) return launch<64, 32, 6>(map_w, map_in, map_o, w, grid, stream);
-  if (bn == 64) return launch<64, 64, 6>(map_w, map_in, map_o, w, grid, stream);
-  if (ku == 32) return launch<128, 32, 6>(map_w, map_in, map_o, w, grid, stream);
-  return launch<128, 64, 6>(map_w, map_in, map_o, w, grid, stream);
+  // weights resident in shared memory when the whole layer fits beside the window ring (72 KB)
+  const bool res = (long long)9 * w.n_chunks * bn * 128 <= 72 * 1024 && w.n_chunks == 1;
+  // WS (window ring) is a multiple of AS (builder groups): a window slot is then always consumed by the same group,
+  // which keeps every parity wait within one phase of its barrier.
+  if (res) {
+    if (bn == 32 && ku == 32) return launch<32, 32, true, 9, 6, 3>(map_w, map_in, map_o, w, grid, stream);
+    if (bn == 32) return launch<32, 64, true, 9, 6, 3>(map_w, map_in, map_o, w, grid, stream);
+    if (bn == 64 && ku == 32) return launch<64, 32, true, 9, 6, 3>(map_w, map_in, map_o, w, grid, stream);
+    if (bn == 64) return launch<64, 64, true, 9, 6, 3>(map_w, map_in, map_o, w, grid, stream);
+  }
+  if (bn == 32) return launch<32, 64, false, 6, 6, 3>(map_w, map_in, map_o, w, grid, stream);
+  if (bn == 64) return launch<64, 64, false, 6, 6, 3>(map_w, map_in, map_o, w, grid, stream);
+  if (ku == 32) return launch<128, 32, false, 6, 4, 2>(map_w, map_in, map_o, w, grid, stream);
+  return launch<128, 64, false, 6, 4, 2>(map_w, map_in, map_o, w, grid, stream);
 }
 
 }  // namespace pn_detail
