@@ -98,6 +98,7 @@ struct WArgs {
   int cin;
   int cout;
   int tma_store;
+  int tma_res;           // residual rows through TMA boxes (tmap_r is valid)
   unsigned long long* dbg;
 };
 
@@ -121,10 +122,11 @@ struct WSmem {
   alignas(1024) uint8_t b[NBT][BN * 128];                // weight tiles, one per tap (SWIZZLE_128B, K-major)
   alignas(1024) uint8_t win[WS][kWin * KU * 2];          // staged input windows (KU = 64: SWIZZLE_128B, 32: SWIZZLE_64B)
   alignas(1024) uint8_t stage_out[4 * 2048];             // epilogue boxes for TMA stores (one per epilogue warp)
+  alignas(1024) uint8_t stage_res[4][BN >= 32 ? BN / 32 : 1][2048];   // residual boxes (32 rows x 32 cols, SWIZZLE_64B)
   alignas(16) uint8_t plan[3][kPlanBytes];               // tile plans (ring of three, copied one tile ahead)
   alignas(8) uint64_t a_full[AS];
   uint64_t a_empty[AS], win_full[WS], win_empty[WS], b_full[NBU], b_empty[NBU], map_full[3], map_empty[3];
-  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t tmem_full[2], tmem_empty[2], res_full[4];
   uint32_t tmem_base;
   float scale[BN];
   float shift[BN];
@@ -172,7 +174,7 @@ constexpr int tmem_pow2(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ?
 template <int BN, int KU, bool RES, int NBT, int WS, int AS>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_in,
-           const __grid_constant__ CUtensorMap tmap_o, const WArgs P) {
+           const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r, const WArgs P) {
   extern __shared__ uint8_t smem_raw[];
   using S = WSmem<BN, KU, RES, NBT, WS, AS>;
   constexpr int NBU = S::NBU;
@@ -188,6 +190,10 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
   if (threadIdx.x == 0) PW_DBG(0);
   pdl_launch_dependents();
   pdl_wait();                                 // everything below depends on the predecessor's outputs
+  // the window starts of this CTA's first tile do not depend on the live row count: their load travels together with it
+  int4 lo_first = make_int4(0, 0, 0, 0);
+  if (warp == kLoaderWarp && lane == 0)
+    lo_first = __ldg(reinterpret_cast<const int4*>(P.plan + (size_t)blockIdx.x * P.tiles_per_cta * kPlanBytes + kPlanLo));
   const int rows = P.num_rows ? min(*P.num_rows, P.rows_cap) : P.rows_cap;
   // balanced schedule (as conv_tcgen05.cu): equal contiguous row shares, walked in 128-row tiles
   const int share = win_share(rows, (int)gridDim.x);
@@ -213,6 +219,7 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
         mbar_init(&sm.b_full[s], 1);
         mbar_init(&sm.b_empty[s], 1);
       }
+      for (int s = 0; s < 4; ++s) mbar_init(&sm.res_full[s], 1);
       for (int s = 0; s < 3; ++s) {
         mbar_init(&sm.map_full[s], 1);
         mbar_init(&sm.map_empty[s], 4 * kASlots);
@@ -329,7 +336,11 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
         lo = __ldg(reinterpret_cast<const int4*>(plan_g + (size_t)tile * kPlanBytes + kPlanLo));
       };
       int4 lo_next = make_int4(0, 0, 0, 0);
-      if (n_tiles > 0) prefetch_plan(0, lo_next);
+      if (n_tiles > 0) {
+        int4 dummy;
+        prefetch_plan(0, dummy);
+        lo_next = lo_first;
+      }
       for (int tile = 0; tile < n_tiles; ++tile) {
         const int lo0 = lo_next.x, lo1 = lo_next.y, lo2 = lo_next.z;
         if (tile + 1 < n_tiles) prefetch_plan(tile + 1, lo_next);
@@ -427,14 +438,31 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
       sm.shift[i] = (i < P.cout && P.shift) ? __ldg(P.shift + i) : 0.f;
     }
     named_bar_sync(2, kEpilogueThreads);
+    uint32_t res_ph = 0u;
     for (int tile = 0; tile < n_tiles; ++tile) {
       const uint32_t acc = (uint32_t)tile & 1u, acc_ph = ((uint32_t)tile >> 1) & 1u;
+      const int row = row_begin + tile * BLOCK_M + e * 32 + lane;
+      const bool row_ok = row < row_end;
+      const bool full_box = BN >= 32 && row - lane + 32 <= row_end;     // the warp's 32 rows are all live rows of this CTA
+      const bool box_ok = full_box && P.tma_store != 0;
+      // Residual rows of this tile travel as TMA boxes while the tile's MMAs are still running: a thread owns a row, so
+      // direct loads touch 32 different lines per warp instruction and sat on the critical path after tmem_full
+      // (measured: residual layers 2.5 us slower than their twins, MMA warp waiting on tmem_empty).
+      const bool res_box = full_box && P.tma_res != 0 && P.residual != nullptr;
+      if (res_box) {
+        if (lane == 0) {
+          constexpr int NCH = BN >= 32 ? BN / 32 : 1;
+          mbar_arrive_expect_tx(&sm.res_full[e], NCH * 2048);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+            tma_load_2d(smem_u32(sm.stage_res[e][c]), &tmap_r, c * 32, row, &sm.res_full[e]);
+        }
+        __syncwarp();
+      }
       mbar_wait_relaxed(&sm.tmem_full[acc], acc_ph);
       tcgen05_fence_after();
       if (etid == 0) PW_DBG(4);
-      const int row = row_begin + tile * BLOCK_M + e * 32 + lane;
-      const bool row_ok = row < row_end;
-      const bool box_ok = BN >= 32 && P.tma_store != 0 && row - lane + 32 <= row_end;
+      if (res_box) { mbar_wait(&sm.res_full[e], res_ph); res_ph ^= 1u; }
       constexpr int CH = BN < 32 ? 16 : 32;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
@@ -451,7 +479,20 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
           __nv_bfloat16* op = P.out + (long long)row * P.out_ld + P.out_coff + c0;
           if (P.residual) {
             const __nv_bfloat16* rp = P.residual + (long long)row * P.res_ld + c0;
-            if (nvalid == CH && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
+            if (CH == 32 && res_box) {
+              const uint8_t* rb = sm.stage_res[e][c0 / 32];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4*>(rb + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int w2 = 0; w2 < 4; ++w2) {
+                  const float2 ff = __bfloat1622float2(h[w2]);
+                  f[8 * j + 2 * w2] += ff.x;
+                  f[8 * j + 2 * w2 + 1] += ff.y;
+                }
+              }
+            } else if (nvalid == CH && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
 #pragma unroll
               for (int j = 0; j < CH; j += 8) {
                 const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
@@ -578,8 +619,8 @@ inline WinGeom win_geom(int rows_cap) {
 }
 
 template <int BN, int KU, bool RES, int NBT, int WS, int AS>
-int launch(const CUtensorMap& map_w, const CUtensorMap& map_in, const CUtensorMap& map_o, const WArgs& wa, int grid,
-           cudaStream_t stream) {
+int launch(const CUtensorMap& map_w, const CUtensorMap& map_in, const CUtensorMap& map_o, const CUtensorMap& map_r,
+           const WArgs& wa, int grid, cudaStream_t stream) {
   constexpr size_t smem = sizeof(WSmem<BN, KU, RES, NBT, WS, AS>) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static pn_detail::PerDeviceOnce once;
@@ -605,7 +646,7 @@ int launch(const CUtensorMap& map_w, const CUtensorMap& map_in, const CUtensorMa
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  PN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_win<BN, KU, RES, NBT, WS, AS>, map_w, map_in, map_o, w));
+  PN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_win<BN, KU, RES, NBT, WS, AS>, map_w, map_in, map_o, map_r, w));
   PN_CHECK_LAUNCH();
   if (timeline) {
     PN_CUDA(cudaStreamSynchronize(stream));
@@ -693,21 +734,27 @@ int conv_win(const pn_conv_args* a, cudaStream_t stream) {
       (reinterpret_cast<uintptr_t>(a->out) & 15u) == 0 &&
       pn_tmap::get(a->out, a->rows_cap, a->out_ld, a->out_ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, &map_o) == PN_OK)
     w.tma_store = 1;
+  CUtensorMap map_r = map_w;
+  w.tma_res = 0;
+  if (tma_store_enabled && a->residual != nullptr && a->cout % 32 == 0 && a->res_ld % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0 &&
+      pn_tmap::get(a->residual, a->rows_cap, a->cout, a->res_ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, &map_r) == PN_OK)
+    w.tma_res = 1;
   const int grid = geo.grid;
   // weights resident in shared memory when the whole layer fits beside the window ring (72 KB)
   const bool res = (long long)9 * w.n_chunks * bn * 128 <= 72 * 1024 && w.n_chunks == 1;
   // WS (window ring) is a multiple of AS (builder groups): a window slot is then always consumed by the same group,
   // which keeps every parity wait within one phase of its barrier.
   if (res) {
-    if (bn == 32 && ku == 32) return launch<32, 32, true, 9, 6, 3>(map_w, map_in, map_o, w, grid, stream);
-    if (bn == 32) return launch<32, 64, true, 9, 6, 3>(map_w, map_in, map_o, w, grid, stream);
-    if (bn == 64 && ku == 32) return launch<64, 32, true, 9, 6, 3>(map_w, map_in, map_o, w, grid, stream);
-    if (bn == 64) return launch<64, 64, true, 9, 6, 3>(map_w, map_in, map_o, w, grid, stream);
+    if (bn == 32 && ku == 32) return launch<32, 32, true, 9, 6, 3>(map_w, map_in, map_o, map_r, w, grid, stream);
+    if (bn == 32) return launch<32, 64, true, 9, 6, 3>(map_w, map_in, map_o, map_r, w, grid, stream);
+    if (bn == 64 && ku == 32) return launch<64, 32, true, 9, 6, 3>(map_w, map_in, map_o, map_r, w, grid, stream);
+    if (bn == 64) return launch<64, 64, true, 9, 6, 3>(map_w, map_in, map_o, map_r, w, grid, stream);
   }
-  if (bn == 32) return launch<32, 64, false, 6, 6, 3>(map_w, map_in, map_o, w, grid, stream);
-  if (bn == 64) return launch<64, 64, false, 6, 6, 3>(map_w, map_in, map_o, w, grid, stream);
-  if (ku == 32) return launch<128, 32, false, 6, 4, 2>(map_w, map_in, map_o, w, grid, stream);
-  return launch<128, 64, false, 6, 4, 2>(map_w, map_in, map_o, w, grid, stream);
+  if (bn == 32) return launch<32, 64, false, 6, 6, 3>(map_w, map_in, map_o, map_r, w, grid, stream);
+  if (bn == 64) return launch<64, 64, false, 6, 6, 3>(map_w, map_in, map_o, map_r, w, grid, stream);
+  if (ku == 32) return launch<128, 32, false, 6, 4, 2>(map_w, map_in, map_o, map_r, w, grid, stream);
+  return launch<128, 64, false, 6, 4, 2>(map_w, map_in, map_o, map_r, w, grid, stream);
 }
 
 }  // namespace pn_detail
