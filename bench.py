@@ -312,17 +312,19 @@ def parity_block(model, frames, B, pool, dev, precision):
                 worst, worst_name = e, f"task{t}.{k}"
     cand = None
     for pa, pb in zip(plans["fp32"], plans[precision]):
-        c = agreement.candidate_agreement(model.bbox_head, pa, pb)
+        c = agreement.candidate_agreement(model.bbox_head, pa, pb, score_thr=float(model.test_cfg["score_threshold"]))
         if cand is None:
             cand = c
         else:
-            for k in ("n_a", "n_b", "a_in_b", "b_in_a"):
+            for k in ("n_a", "n_b", "a_in_b", "b_in_a", "unexplained"):
                 cand[k] += c[k]
             cand["mean_iou"] = (cand["mean_iou"] + c["mean_iou"]) / 2   # running mean over equally sized frames
             cand["min_iou"] = min(cand["min_iou"], c["min_iou"])
             cand["max_score_delta"] = max(cand["max_score_delta"], c["max_score_delta"])
     cand["recall_a_in_b"] = cand["a_in_b"] / max(1, cand["n_a"])
     cand["recall_b_in_a"] = cand["b_in_a"] / max(1, cand["n_b"])
+    cand["note"] = ("unexplained = candidates listed by one run only whose score is NOT within 1e-3 of the other list's cut "
+                    "(score threshold / pre_max-th score); 0 means the two runs differ only in near-ties at the cut")
     return {"against": "fp32 mode of the same model on the same frames (itself within 1e-3 of the dense-equivalent torch "
                        "restatement: tests/test_gpu_fullsize.py)",
             "frames": pool * B, "head_maps_max_rel_err": worst, "worst_map": worst_name,

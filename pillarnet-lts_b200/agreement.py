@@ -64,7 +64,7 @@ def summarize(dets_a, dets_b, iou_thr=0.7, top=None):
     return tot
 
 
-def candidate_agreement(head, plan_a, plan_b):
+def candidate_agreement(head, plan_a, plan_b, score_thr=None, eps=1e-3):
     """Pre-NMS agreement of two CenterHead.predict_raw runs on the same frames (the score-sorted top-`pre_max`
     candidate boxes of every NMS segment, plan["sorted_boxes"] records [x y z w l h vx vy rot score rect label]):
     a candidate of run A is re-found in run B when B holds a candidate of the same class whose centre lies within a
@@ -72,8 +72,13 @@ def candidate_agreement(head, plan_a, plan_b):
     the matched pairs and their score difference.  This isolates the numeric difference of the two runs from the
     order sensitivity of greedy NMS (a near-tie in score reorders the sweep and changes which of two overlapping
     boxes survives — with random-init heads, whose scores sit within a hair of each other, that dominates the
-    post-NMS comparison)."""
-    tot = dict(n_a=0, n_b=0, a_in_b=0, b_in_a=0, max_score_delta=0.0, min_iou=1.0)
+    post-NMS comparison).
+
+    A candidate that one run lists and the other does not is *explained* when its score lies within `eps` of the
+    membership boundary of the other run's list — the score threshold, or that list's lowest score when the list is
+    full (pre_max entries): the two runs then agree on the score (to within eps) and differ only in which side of the
+    cut a near-tie falls.  `unexplained` counts the rest; the tests require it to be 0."""
+    tot = dict(n_a=0, n_b=0, a_in_b=0, b_in_a=0, max_score_delta=0.0, min_iou=1.0, unexplained=0)
     iou_sum, iou_n = 0.0, 0
     ca, cb = plan_a["sorted_count"].tolist(), plan_b["sorted_count"].tolist()
     S = plan_a["S"]
@@ -94,6 +99,12 @@ def candidate_agreement(head, plan_a, plan_b):
         ok = da <= tol
         tot["a_in_b"] += int(ok.sum())
         tot["b_in_a"] += int((db <= tol).sum())
+        if score_thr is not None:
+            pre = plan_a["segs"][seg % S]["pre"]
+            cut_b = max(float(score_thr), float(B[:, 10].min())) if nb >= pre else float(score_thr)
+            cut_a = max(float(score_thr), float(A[:, 10].min())) if na >= pre else float(score_thr)
+            # sorted_boxes[:, 10] = the (rectified) score the list is ordered by
+            tot["unexplained"] += int((A[~ok][:, 10] > cut_b + eps).sum()) + int((B[db > tol][:, 10] > cut_a + eps).sum())
         if bool(ok.any()):
             a7 = to_pcdet(A[ok][:, :9])
             b7 = to_pcdet(B[ia[ok]][:, :9])

@@ -159,4 +159,23 @@ __device__ __forceinline__ bool surely_disjoint(const BoxGeom& a, const BoxGeom&
   return dx * dx + dy * dy > R * R * 1.001f;
 }
 
+// Sharper conservative test on the same contract: separating axis over the four box axes with every half extent
+// taken as half size + MARGIN (g.mx, g.my) and 0.1 m of slack.  Boxes this far apart have no crossing edges and no
+// corner inside the other's margin box, so the reference arithmetic yields cnt == 0 => overlap 0.  The circle test
+// above lets every pair within ~(ra + rb) through to the exact evaluation — for 4 x 2 m boxes that is 5x the area a
+// box really covers, and the exact evaluations were what k_nms_mask spent its time on (28 us at 6 x 1000 boxes).
+// NaN / inf geometry fails every comparison => "not disjoint" => exact path.
+__device__ __forceinline__ bool surely_disjoint_sat(const BoxGeom& a, const BoxGeom& b) {
+  const float kSlack = 0.1f;
+  const float dx = b.cx - a.cx, dy = b.cy - a.cy;
+  // axes: u = (ic, -is), v = (is, ic) (ic = cos(heading), is = -sin(heading))
+  const float c = fabsf(a.ic * b.ic + a.is * b.is);        // |cos(ha - hb)|
+  const float s = fabsf(a.ic * b.is - a.is * b.ic);        // |sin(ha - hb)|
+  const float da_u = fabsf(dx * a.ic - dy * a.is), da_v = fabsf(dx * a.is + dy * a.ic);
+  const float db_u = fabsf(dx * b.ic - dy * b.is), db_v = fabsf(dx * b.is + dy * b.ic);
+  const float k = 1.001f;
+  return da_u > (a.mx + b.mx * c + b.my * s + kSlack) * k || da_v > (a.my + b.mx * s + b.my * c + kSlack) * k ||
+         db_u > (b.mx + a.mx * c + a.my * s + kSlack) * k || db_v > (b.my + a.mx * s + a.my * c + kSlack) * k;
+}
+
 }  // namespace pn_iou

@@ -112,7 +112,8 @@ def _run(workload, B):
         _, st16, det16, plan16 = _forward_stages(model, frames)
         rec["bf16_vs_fp32"] = {k: agreement.rel_to_max(st16[k], st32[k]) for k in st32}
     torch.cuda.synchronize()
-    rec["candidates_bf16_vs_fp32"] = agreement.candidate_agreement(model.bbox_head, plan32, plan16)
+    rec["candidates_bf16_vs_fp32"] = agreement.candidate_agreement(model.bbox_head, plan32, plan16,
+                                                                   score_thr=float(model.test_cfg["score_threshold"]))
     rec["detections_bf16_vs_fp32"] = agreement.summarize(det32, det16, iou_thr=0.7)
     rec["detections_bf16_vs_fp32_top100"] = agreement.summarize(det32, det16, iou_thr=0.7, top=100)
     _dump(f"parity_fullsize_{workload}.json", rec)
@@ -124,13 +125,16 @@ def _check(rec):
         assert v <= FP32_TOL, (k, v)
     for k, v in rec["bf16_vs_fp32"].items():
         assert v <= BF16_STAGE_TOL, (k, v)
-    # what the decode stage hands to NMS: the score-sorted top-`pre_max` candidates of every segment.  Same heat-map
-    # pixel + same class in both runs for >= 97 % of them (the rest sit at the score-threshold / pre_max boundary),
-    # and the matched boxes are the same boxes (BEV IoU), with the same scores
+    # what the decode stage hands to NMS: the score-sorted top-`pre_max` candidates of every segment.  The same
+    # heat-map pixel + class is listed by both runs for most of them (measured 72-92 %: random-init heads put thousands
+    # of pixels within 1e-4 of the score threshold / of the pre_max-th score, so set membership is a coin flip there);
+    # EVERY candidate only one run lists must be such a boundary case (score within 1e-3 of the other list's cut), and
+    # the matched pairs are the same boxes (BEV IoU) with the same scores
     c = rec["candidates_bf16_vs_fp32"]
     assert c["n_a"] > 1000 and c["n_b"] > 1000
-    assert c["recall_a_in_b"] >= 0.97 and c["recall_b_in_a"] >= 0.97, c
-    assert c["mean_iou"] >= 0.97 and c["max_score_delta"] <= 2e-3, c
+    assert c["recall_a_in_b"] >= 0.6 and c["recall_b_in_a"] >= 0.6, c
+    assert c["unexplained"] == 0, c
+    assert c["mean_iou"] >= 0.97 and c["min_iou"] >= 0.5 and c["max_score_delta"] <= 1e-3, c
     # after greedy NMS: reported, and only sanity-checked — with random-init heads the scores of a segment sit within
     # a hair of each other, a bf16-sized perturbation reorders the sweep, and which of two overlapping boxes survives
     # flips (measured r2: 57 % of the kept boxes coincide at IoU >= 0.7 while their scores agree to 4e-5); a trained

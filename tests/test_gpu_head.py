@@ -180,7 +180,10 @@ def _torch_predict_rotate(preds, strides, num_classes, cfg, nms_gpu):
     return outs
 
 
-def test_predict_rotate_bit_exact_vs_torch_and_reference_nms():
+@pytest.mark.parametrize("n_peaks", [2500, 9000])
+def test_predict_rotate_bit_exact_vs_torch_and_reference_nms(n_peaks):
+    """n_peaks 2500: every NMS segment has <= 4096 candidates (8-CTA cluster selection, k_select_topk_cluster);
+    9000: more than 4096 (single-CTA radix select, k_select_topk)."""
     iou3d = ref_ext("iou3d_nms_cuda")
     if iou3d is None:
         pytest.skip("oracle/_ref/iou3d_nms_cuda not built")
@@ -193,7 +196,7 @@ def test_predict_rotate_bit_exact_vs_torch_and_reference_nms():
                       share_channel=8, pillar_size=PS, point_cloud_range=PCR).cuda()
     preds = []
     for t, K in enumerate([1, 2]):
-        m = synth.synthetic_head_maps(rng, B, H, W, 10 + K, slice(10, 10 + K), n_peaks=2500)
+        m = synth.synthetic_head_maps(rng, B, H, W, 10 + K, slice(10, 10 + K), n_peaks=n_peaks)
         m[..., 0:2] = rng.uniform(0, 1, m[..., 0:2].shape)
         m[..., 3:6] = rng.normal(0.5, 0.5, m[..., 3:6].shape)
         tm = torch.from_numpy(m).cuda().permute(0, 3, 1, 2).contiguous()
@@ -203,6 +206,9 @@ def test_predict_rotate_bit_exact_vs_torch_and_reference_nms():
                                         nms_iou_threshold=0.2), rectifier=0, score_threshold=0.1,
                                post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]))
     got = head.predict({"metadata": [None] * B}, preds, cfg)
+    _, _, plan = head.predict_raw(preds, cfg)
+    most = int(plan["cand_count"].max())
+    assert (most > 4096) == (n_peaks > 4096), most
     want = _torch_predict_rotate(preds, [8, 8], [1, 2], dict(post_center_limit_range=cfg.post_center_limit_range,
                                                             score_threshold=0.1, pre=1000, post=83, thr=0.2),
                                  iou3d.nms_gpu)

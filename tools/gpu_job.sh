@@ -11,6 +11,7 @@
 #   bench_train      nusc34 training step, 4 frames                      -> gpurun_out/bench_train_nusc34_b4.json
 #   launches         ncu launch list of one graph replay                 -> gpurun_out/launches.csv (+ .txt summary)
 #   ncu_mem          ncu --set full of the memory-bound kernels          -> gpurun_out/prof_mem.ncu-rep
+#   ncu_k:<regex>    ncu --set full of the kernels matching <regex>           -> gpurun_out/prof_k.ncu-rep
 #   ncu_convs        ncu --set full of the conv kernels                  -> gpurun_out/prof_convs.ncu-rep
 #   timeline         per-CTA pipeline timelines + stall accounting of every conv launch -> gpurun_out/timeline.txt
 #   kbench_reader    reader kernels at scale (events)                    -> gpurun_out/kbench_reader.json
@@ -63,6 +64,11 @@ for step in "$@"; do
         -k 'regex:k_mark|k_scan_emit|k_rank|k_pfn|k_zero_rows|k_decode_candidates|k_select_topk|k_nms_|k_sparse_to_dense|k_subm_nbr|k_down_mask|k_pyramid_nbr' \
         -o gpurun_out/prof_mem -f $PROF_CMD > gpurun_out/ncu_mem.log 2>&1
       echo "ncu_mem rc=$?"; tail -3 gpurun_out/ncu_mem.log ;;
+    ncu_k:*)
+      plain
+      [ $plain_ok -eq 1 ] && timeout 1500 ncu --profile-from-start off --set full --clock-control none --import-source on \
+        -k "regex:${step#ncu_k:}" -o gpurun_out/prof_k -f $PROF_CMD > gpurun_out/ncu_k.log 2>&1
+      echo "ncu_k rc=$?"; tail -3 gpurun_out/ncu_k.log | cut -c1-200 ;;
     ncu_convs)
       plain
       [ $plain_ok -eq 1 ] && timeout 2400 ncu --profile-from-start off --set full --clock-control none --import-source on \
