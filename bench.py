@@ -174,7 +174,11 @@ def conv_breakdown(engine, reps=3):
         for _ in range(inner[0]):
             r = orig(inp, weight, nbr, taps, cin, cout, out, **kw)
         e.record()
-        recs.append((taps, cin, cout, kw.get("rows_cap") or out.shape[0], kw.get("num"), s, e, "k_conv_tc", nbr,
+        # window-staged kernel (conv_win_tc.cu) when the caller passed tile plans for a raster-sorted submanifold
+        # rulebook and the layer fits it (cout <= 128); gather kernel (conv_tcgen05.cu) otherwise
+        kname = "k_conv_win" if (kw.get("nbr_plan") is not None and kw.get("nbr_kind") and cout <= 128
+                                 and inp.dtype == torch.bfloat16 and out.dtype == torch.bfloat16) else "k_conv_tc"
+        recs.append((taps, cin, cout, kw.get("rows_cap") or out.shape[0], kw.get("num"), s, e, kname, nbr,
                      kw.get("deconv")))
         return r
 
@@ -499,8 +503,9 @@ def run_gpu(args):
         tf_peak_name = peaks["source"] + (" (burst bf16: kernels timed in isolation at max SM clock)" if at_max
                                           else " (sustained bf16: SM clock below max during the run)")
         fams = {}
+        fam_of = {"k_conv_win": "sparse convs (k_conv_win + k_conv_tc)", "k_conv_tc": "sparse convs (k_conv_win + k_conv_tc)"}
         for r in breakdown:
-            f = fams.setdefault(r["kernel"], dict(us=0.0, flop=0.0, launches=0, bytes=0))
+            f = fams.setdefault(fam_of.get(r["kernel"], r["kernel"]), dict(us=0.0, flop=0.0, launches=0, bytes=0))
             f["us"] += r["total_us_per_pass"]
             f["flop"] += r["flop"] * r["launches_per_pass"]
             f["launches"] += r["launches_per_pass"]
@@ -515,11 +520,14 @@ def run_gpu(args):
         top = breakdown[0]
         flop_total = sum(r["flop"] * r["launches_per_pass"] for r in breakdown)
         nusc_b1 = args.workload == "nusc18" and B == 1
-        traffic, traffic_src = _ncu_family_traffic(fam["kernel"]) if nusc_b1 else (None, None)
+        traffic, traffic_src = (_ncu_family_traffic("k_conv_win" if fam["kernel"].startswith("sparse") else fam["kernel"])
+                                if nusc_b1 else (None, None))
         top_traffic, top_traffic_src = _ncu_traffic(top) if nusc_b1 else (None, None)
         # `roofline` = the kernel FAMILY with the largest share of the step (all its launches: sum of 2*P*Cin*Cout over
         # sum of durations); `best_shape` = the single conv shape with the largest share, for comparison
-        roof = {"bound": "tensor", "kernel": fam["kernel"] + " (tcgen05 implicit-GEMM conv, all launches of the family)",
+        roof = {"bound": "tensor", "kernel": fam["kernel"] + " (tcgen05 implicit-GEMM convs, all launches of the family; the "
+                                                             "sparse family also holds the strided and the two dense gather "
+                                                             "convs that share k_conv_tc)",
                 "achieved": fam["tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": fam["frac"],
                 "peak_source": tf_peak_name, "launches_per_step": fam["launches_per_pass"],
                 "avg_us": fam["total_us_per_pass"] / fam["launches_per_pass"], "share_of_step": fam["share_of_step"],
@@ -605,8 +613,8 @@ def run_train(args):
     torch.manual_seed(0)
     model = P.build_detector(ConfigDict.wrap(cfg["model"]), cfg["train_cfg"], ConfigDict.wrap(cfg["test_cfg"]))
     model = model.to(dev).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
-    avg = GradientAverager(list(model.parameters()), bucket_mb=25) if world > 1 else None
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, capturable=not args.train_eager)
+    avg = GradientAverager(list(model.parameters()), bucket_mb=25, module=model) if world > 1 else None
     pool = 4
     rng = np.random.default_rng(7 + rank)
     H, W = model.reader.height, model.reader.width
@@ -625,20 +633,35 @@ def run_train(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    eng = None
+    if not args.train_eager:
+        # sync-free step as two CUDA graphs (train.TrainEngine): fixed input buffers, live row counts on the device
+        cap = int(max(b["points_batched"][0].shape[0] for b in batches) * 1.02) + 1024
+        eng = train.TrainEngine(model, opt, B, cap, batches[0], averager=avg).prepare(warmup=3)
+        l0 = lib.pn_launch_count()
+        with torch.cuda.stream(eng.stream), torch.no_grad():
+            pass
+        step = lambda i: eng.step(batches[i % pool])
+        stream = eng.stream
+    else:
+        step = lambda i: train.train_step(model, batches[i % pool], opt, avg)
+        stream = torch.cuda.current_stream()
     for i in range(max(args.warmup, 3)):
-        loss = train.train_step(model, batches[i % pool], opt, avg)
+        loss = step(i)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = lib.pn_launch_count()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
+    s.record(stream)
     for i in range(args.steps):
-        loss = train.train_step(model, batches[i % pool], opt, avg)
-    e.record()
+        loss = step(i)
+    e.record(stream)
     barrier()
     gpu_ms = s.elapsed_time(e)
     launches = lib.pn_launch_count() - l0
+    if eng is not None:
+        launches = eng.launches_per_step * args.steps
     clocks = sampler.stop()
     t = torch.tensor([gpu_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -654,7 +677,10 @@ def run_train(args):
             "config": {"workload": f"{args.workload}-train: {B} frames/GPU (~{n_pts} pts/frame), AdamW, synthetic targets, "
                                    f"random-init weights; inputs larger than L2 (activations ~GBs per step)",
                        "frames_per_step_per_gpu": B, "precision": args.precision,
-                       "host_syncs": "one per rulebook (exact row counts), as the reference"},
+                       "mode": ("eager, exactly sized rows, one host sync per rulebook (as the reference)" if args.train_eager
+                                else "TrainEngine: forward+loss+backward and the optimiser step as two CUDA graphs, no "
+                                     "host sync; input batch copied device-to-device into fixed buffers inside the "
+                                     "timed region")},
             "clocks": clocks, "gpu_launches": int(launches), "loss_last": float(loss),
             "e2e": None, "roofline": None, "cpu_baseline": None,
         }
@@ -783,6 +809,8 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=1)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--hm-cells", type=int, default=1500)
+    ap.add_argument("--train-eager", action="store_true",
+                    help="--mode train: the eager, exactly sized path (host syncs) instead of the CUDA-graph TrainEngine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the fp32-vs-bf16 parity block (outside the timed region)")
     ap.add_argument("--sustain-s", type=float, default=2.5,

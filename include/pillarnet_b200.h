@@ -313,6 +313,38 @@ int pn_conv_wgrad(const void* x, int x_dtype, int x_ld, const void* dy, int dy_d
                   pn_stream_t stream);
 
 /* f32 -> bf16 weight packing with zero padding of K to k_pad (multiple of 64). */
+/* ---- training: batch-statistics BatchNorm over the live rows of a sparse feature matrix (bn_train.cu) -------------
+ * Replaces nn.BatchNorm1d(+ residual add + ReLU) in train mode on `.features` (backbones/base.py:155-213) with the row
+ * count kept on the device (num_rows; NULL => rows_cap).  dtype = PN_F32 | PN_BF16 for x / y / dy / dx / residual.
+ * c must be a power of two <= 256 for the two *_stats entry points. */
+/* sums (2c f32, zeroed here): sum x, sum x^2 over rows < *num_rows */
+int pn_bn_stats(const void* x, int dtype, int x_ld, const int* num_rows, int rows_cap, int c, float* sums,
+                pn_stream_t stream);
+/* mean, rstd = 1/sqrt(var_biased + eps), scale = gamma*rstd, shift = beta - mean*scale (all (c) f32); when
+ * running_mean/var are given they are updated in place as torch does (momentum, unbiased variance) */
+int pn_bn_finalize(const float* sums, const int* num_rows, int rows_cap, int c, const float* gamma, const float* beta,
+                   float eps, float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
+                   float* scale, float* shift, pn_stream_t stream);
+/* out[r,:] = act(x[r,:]*scale + shift + residual[r,:]) for r < *num_rows (the other rows of the capacity are
+ * neither read nor written: every consumer on the path masks by the same count) */
+int pn_bn_apply(const void* x, int dtype, int x_ld, const float* scale, const float* shift, const void* residual,
+                int res_ld, int relu, const int* num_rows, int rows_cap, int c, void* out, int out_ld,
+                pn_stream_t stream);
+/* g = dy * (y > 0 if relu); sums (2c f32, zeroed here): sum g, sum g * xhat  with xhat = (x - mean) * rstd
+ * (these are d beta and d gamma) */
+int pn_bn_bwd_stats(const void* dy, int dtype, int dy_ld, const void* y, int y_ld, const void* x, int x_ld,
+                    const float* mean, const float* rstd, int relu, const int* num_rows, int rows_cap, int c,
+                    float* sums, pn_stream_t stream);
+/* dx = gamma*rstd*(g - sums[0:c]/n - xhat*sums[c:2c]/n); dres (may be NULL) = g; rows < *num_rows only */
+int pn_bn_bwd_apply(const void* dy, int dtype, int dy_ld, const void* y, int y_ld, const void* x, int x_ld,
+                    const float* mean, const float* rstd, const float* gamma, const float* sums, int relu,
+                    const int* num_rows, int rows_cap, int c, void* dx, int dx_ld, void* dres, int dres_ld,
+                    pn_stream_t stream);
+/* backward of pn_sparse_to_dense / SparseConvTensor.dense(): out[r,:] = dense[b,y,x,:] at coords[r] = [b,y,x] of a
+ * compact (B,H,W,dense_ld) NHWC map; rows < *num_rows only */
+int pn_dense_to_sparse(const void* dense, int dtype, int dense_ld, const int* coords, const int* num_rows, int rows_cap,
+                       int H, int W, int c, void* out, int out_ld, pn_stream_t stream);
+
 int pn_conv_pack_weight_bf16(const float* w_f32, int cout, int k, int k_pad, void* w_bf16,
                              pn_stream_t stream);
 /* rows x cols cast (first *num_rows rows when num_rows != NULL). */

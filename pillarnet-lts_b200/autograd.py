@@ -96,3 +96,92 @@ class SparseConvFunction(Function):
 
 
 sparse_conv = SparseConvFunction.apply
+
+
+# ---- sync-free (CUDA-graph capturable) training nodes -----------------------------------------------------------------
+
+class StaticRulebook:
+    """Capacity-sized rulebook with device-resident row counts: nbr (cap_out, taps) output-stationary, nbr_t
+    (cap_in, taps) input-stationary; plan / plan_t = tile plans of the window-staged kernel (bf16, submanifold only)."""
+
+    __slots__ = ("nbr", "nbr_t", "num_in", "num_out", "cap_in", "cap_out", "taps", "plan", "plan_t", "kind")
+
+    def __init__(self, nbr, nbr_t, num_in, num_out, cap_in, cap_out, plan=None, plan_t=None, kind=0, taps=9):
+        self.nbr, self.nbr_t, self.num_in, self.num_out = nbr, nbr_t, num_in, num_out
+        self.cap_in, self.cap_out, self.taps, self.plan, self.plan_t, self.kind = cap_in, cap_out, taps, plan, plan_t, kind
+
+
+class SparseConvBNFunction(Function):
+    """y = act(BN_batch(conv(x) + bias) + residual) on capacity-sized rows with the live counts on the device:
+    SparseSequential(SubMConv2d | SparseConv2d, BN1d[, SparseReLU]) (+ the block's residual add and ReLU) of
+    backbones/base.py:145-213 in train mode as ONE autograd node — conv (pn_conv_gather), batch statistics, normalise
+    + residual + ReLU (pn_bn_*), and their backward: BN backward, data gradient (gather conv on the input-stationary
+    rulebook), weight gradient (pn_conv_wgrad).  No host synchronisation anywhere."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, residual, rb, bn, relu):
+        cout, cin = weight.shape[0], weight.shape[-1]
+        act = config.act_dtype()
+        xq = x.detach().to(act).contiguous()
+        wq = _pack(weight.detach().reshape(cout, rb.taps * cin))
+        xc = torch.empty(rb.cap_out, cout, dtype=act, device=x.device)
+        ops.conv_gather(xq, wq, rb.nbr, rb.taps, cin, cout, xc, k_pad=wq.shape[1],
+                        shift=bias.detach().float().contiguous() if bias is not None else None, num=rb.num_out,
+                        rows_cap=rb.cap_out, impl=config.conv_impl(), nbr_kind=rb.kind, nbr_plan=rb.plan)
+        res = residual.detach().to(act).contiguous() if residual is not None else None
+        y, mean, rstd = ops.bn_train_forward(xc, rb.num_out, gamma.detach().float(), beta.detach().float(),
+                                             bn.running_mean, bn.running_var, bn.eps, bn.momentum, res, relu)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        ctx.save_for_backward(xq, weight, xc, y, mean, rstd, gamma)
+        ctx.rb, ctx.relu, ctx.has_bias, ctx.has_res = rb, relu, bias is not None, residual is not None
+        ctx.x_dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xq, weight, xc, y, mean, rstd, gamma = ctx.saved_tensors
+        rb = ctx.rb
+        cout, cin = weight.shape[0], weight.shape[-1]
+        act = config.act_dtype()
+        dconv, dres, dgamma, dbeta = ops.bn_train_backward(dy, y, xc, mean, rstd, gamma.detach().float(), ctx.relu,
+                                                           rb.num_out, ctx.has_res)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wt = _pack(weight.detach().reshape(cout, rb.taps, cin).permute(2, 1, 0).reshape(cin, rb.taps * cout))
+            dx = torch.empty(rb.cap_in, cin, dtype=act, device=dy.device)
+            ops.conv_gather(dconv, wt, rb.nbr_t, rb.taps, cout, cin, dx, k_pad=wt.shape[1], num=rb.num_in,
+                            rows_cap=rb.cap_in, impl=config.conv_impl(), nbr_kind=rb.kind, nbr_plan=rb.plan_t)
+            dx = dx.to(ctx.x_dtype)
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_wgrad(xq, dconv, rb.nbr, rb.taps, cin, cout, num=rb.num_out, rows=rb.cap_out,
+                                impl=config.conv_impl()).view(weight.shape).to(weight.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            # a bias in front of a batch-statistics BN has no gradient: sum_r dconv[r] = -gamma*rstd*(sum_r xhat)*(..)/n
+            # and sum_r xhat = 0 (the dynamic path's dy.sum(0) is that zero plus rounding noise)
+            db = torch.zeros(cout, dtype=weight.dtype, device=dy.device)
+        return dx, dw, db, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), dres, None, None, None
+
+
+sparse_conv_bn = SparseConvBNFunction.apply
+
+
+class DenseFromSparseFunction(Function):
+    """SparseConvTensor.dense() (PillarResNet.py:139) with a device-resident row count: forward pn_sparse_to_dense,
+    backward pn_dense_to_sparse."""
+
+    @staticmethod
+    def forward(ctx, feat, table):
+        C = feat.shape[1]
+        rows = ops.sparse_to_dense(feat.detach().contiguous(), table, C)
+        ctx.table, ctx.C = table, C
+        return rows.view(table.B, table.H, table.W, C).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        t = ctx.table
+        rows = g.permute(0, 2, 3, 1).contiguous().view(t.B * t.H * t.W, ctx.C)
+        return ops.dense_to_sparse(rows, t, ctx.C), None
+
+
+dense_from_sparse_static = DenseFromSparseFunction.apply

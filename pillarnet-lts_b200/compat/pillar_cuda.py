@@ -89,7 +89,6 @@ def scatter_max_grad_wrapper(grad_out, arg, grad_src):
     _i32(arg)
     _f32(grad_out, grad_src)
     M, C = arg.shape
-    num = torch.tensor([M], dtype=torch.int32).to(arg.device, non_blocking=True)
-    check(_lib.load().pn_scatter_max_grad(ptr(grad_out), ptr(arg), ptr(num), M, C, ptr(grad_src), stream_ptr()),
+    check(_lib.load().pn_scatter_max_grad(ptr(grad_out), ptr(arg), ptr(None), M, C, ptr(grad_src), stream_ptr()),
           "pn_scatter_max_grad")
     return 1

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(256)
 k_scatter_max_grad(const float* __restrict__ grad_out, const int* __restrict__ arg,
                    const int* __restrict__ num_rows, int m_cap, int C,
                    float* __restrict__ grad_src) {
-  const int n = min(*num_rows, m_cap);
+  const int n = num_rows ? min(*num_rows, m_cap) : m_cap;
   const long long total = (long long)n * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -502,7 +502,7 @@ int pn_pfn_scatter_max(const float* points, int point_dim, int n_points, const i
 int pn_scatter_max_grad(const float* grad_out, const int* arg, const int* num_pillars, int m_cap,
                         int c_out, float* grad_src, pn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  PN_REQUIRE(grad_out && arg && num_pillars && grad_src && c_out > 0);
+  PN_REQUIRE(grad_out && arg && grad_src && c_out > 0);   // num_pillars may be NULL: all m_cap rows (arg < 0 = none)
   if (m_cap == 0) return PN_OK;
   const int sms = pn_detail::sm_count();
   if (sms <= 0) return PN_ERR_CUDA;

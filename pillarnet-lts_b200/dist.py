@@ -127,6 +127,7 @@ class GradientAverager:
         if cur:
             self._make_bucket(cur)
         self._pending = [0] * len(self.buckets)
+        self.defer = False         # True: hooks only count (captured backward); finish() issues every all-reduce
         self._next = 0             # buckets [0, _next) have had their all-reduce issued this step
         self._works = []
         self._hooks = []
@@ -148,6 +149,8 @@ class GradientAverager:
 
     def _issue_ready(self):
         """issue, in index order, the all-reduce of every leading bucket whose gradients are complete"""
+        if self.defer:
+            return
         while self._next < len(self.buckets) and self._pending[self._next] == 0:
             if self.world > 1:
                 self._works.append(dist.all_reduce(self.buckets[self._next][0], group=self.group, async_op=True))
@@ -201,6 +204,8 @@ class GradientAverager:
         """flushes, in index order, the buckets not yet issued (hooks that never fired: unused parameters, or a
         bucket waiting behind one of those), waits, and turns sums into means"""
         self._reattach(fold=True)
+        if self.defer:
+            self._next = 0         # a replayed (captured) backward does not run the hooks: reduce every bucket here
         for bi in range(self._next, len(self.buckets)):
             if self.world > 1:
                 self._works.append(dist.all_reduce(self.buckets[bi][0], group=self.group, async_op=True))

@@ -464,7 +464,7 @@ class CenterHead(nn.Module):
                 anno = torch.cat((p["reg"], p["height"], p["dim"], p["rot"]), dim=-1)
                 target_box = target_box[..., [0, 1, 2, 3, 4, 5, -2, -1]]
             box_loss = self.crit_reg(anno, mask, ind, target_box)
-            loc_loss = (box_loss * box_loss.new_tensor(self.code_weights)).sum()
+            loc_loss = (box_loss * losses.device_const(list(self.code_weights), box_loss.device)).sum()
             loss = hm_loss * train_cfg["hm_weight"] + loc_loss * train_cfg["bbox_weight"]
             ret = {"hm_loss": hm_loss.detach(), "loc_loss": loc_loss, "loc_loss_elem": box_loss.detach(),
                    "num_positive": mask.float().sum()}

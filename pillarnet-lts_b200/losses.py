@@ -68,21 +68,43 @@ def boxes_aligned_iou3d(boxes_a, boxes_b):
     return inter / torch.clamp(va + vb - inter, min=1e-6)
 
 
+def _positives(mask, pred_box, box_gt):
+    """(weights (B*M,) f32, pred (B*M,7), gt (B*M,7)) with every slot kept (static shapes, no host sync): the slots
+    without an object get a copy of their own prediction as target — finite IoU terms whose weight is 0."""
+    w = mask.reshape(-1).float()
+    p = pred_box.reshape(-1, pred_box.shape[-1])
+    g = box_gt.reshape(-1, box_gt.shape[-1])
+    g = torch.where(w.unsqueeze(1) > 0, g, p.detach())
+    return w, p, g
+
+
 class IouLoss(nn.Module):
-    """L1 between the IoU head and 2*IoU3D(pred, gt)-1 on the positives (centernet_loss.py:70-96)"""
+    """L1 between the IoU head and 2*IoU3D(pred, gt)-1 on the positives (centernet_loss.py:70-96).  The reference
+    returns zeros((1,)) when `mask.sum() == 0` (a host sync) and compacts the positives with a boolean index (another);
+    here every slot is evaluated and weighted by the mask: the same value, shape-static."""
 
     def forward(self, iou_pred, mask, ind, box_pred, box_gt):
-        if mask.sum() == 0:
-            return iou_pred.new_zeros((1,))
-        mask = mask.bool()
-        pred = gather_feat(iou_pred, ind)[mask]
-        pred_box = gather_feat(box_pred, ind)
-        target = 2 * boxes_aligned_iou3d(pred_box[mask], box_gt[mask]) - 1
-        return F.l1_loss(pred, target, reduction="sum") / (mask.sum() + 1e-4)
+        w, p, g = _positives(mask, gather_feat(box_pred, ind), box_gt)
+        pred = gather_feat(iou_pred, ind).reshape(-1, 1)
+        target = 2 * boxes_aligned_iou3d(p, g) - 1
+        return ((pred - target).abs() * w.unsqueeze(1)).sum() / (w.sum() + 1e-4)
+
+
+_const_cache = {}
+
+
+def device_const(values, device, dtype=torch.float32):
+    """small constant tensors are uploaded once per device: a host->device copy of a Python list inside the step would
+    break CUDA-graph capture of the training step"""
+    key = (tuple(map(tuple, values)) if values and isinstance(values[0], (list, tuple)) else tuple(values), str(device), dtype)
+    t = _const_cache.get(key)
+    if t is None:
+        t = _const_cache[key] = torch.tensor(values, dtype=dtype).to(device)
+    return t
 
 
 def _corners(center, dim):
-    norm = torch.tensor([[-0.5, -0.5], [-0.5, 0.5], [0.5, 0.5], [0.5, -0.5]], dtype=torch.float32, device=dim.device)
+    norm = device_const([[-0.5, -0.5], [-0.5, 0.5], [0.5, 0.5], [0.5, -0.5]], dim.device)
     return dim.view(-1, 1, 2) * norm.view(1, 4, 2) + center.view(-1, 1, 2)
 
 
@@ -136,9 +158,6 @@ class IouRegLoss(nn.Module):
         self.bbox3d_iou_func = funcs[type]
 
     def forward(self, box_pred, mask, ind, box_gt):
-        if mask.sum() == 0:
-            return box_pred.new_zeros((1,))
-        mask = mask.bool()
-        pred_box = gather_feat(box_pred, ind)
-        iou = self.bbox3d_iou_func(pred_box[mask], box_gt[mask])
-        return (1.0 - iou).sum() / (mask.sum() + 1e-4)
+        w, p, g = _positives(mask, gather_feat(box_pred, ind), box_gt)
+        iou = self.bbox3d_iou_func(p, g)
+        return ((1.0 - iou) * w).sum() / (w.sum() + 1e-4)

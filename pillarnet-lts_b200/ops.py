@@ -435,8 +435,7 @@ def scatter_max_grad_flat(grad_out, arg, n_points):
     M, C = arg.shape
     grad_out = grad_out.float().contiguous()
     grad_src = torch.zeros(n_points, C, dtype=torch.float32, device=grad_out.device)
-    num = torch.tensor([M], dtype=torch.int32).to(grad_out.device)
-    check(lib.pn_scatter_max_grad(ptr(grad_out), ptr(arg), ptr(num), M, C, ptr(grad_src), stream_ptr()),
+    check(lib.pn_scatter_max_grad(ptr(grad_out), ptr(arg), ptr(None), M, C, ptr(grad_src), stream_ptr()),
           "pn_scatter_max_grad")
     return grad_src
 
@@ -523,3 +522,61 @@ def merge_sweeps(raw, sweep_offsets, transforms, time_lags, min_distance=1.0, n_
                               ptr(out_base), ptr(out), out.shape[0], ptr(n_total), ptr(scratch), c_size_t(sb),
                               stream_ptr()), "pn_merge_sweeps")
     return out, n_total
+
+
+# ---- training: batch-statistics BN on the live rows (bn_train.cu), sync-free -----------------------------------------
+
+def bn_train_forward(x, num, gamma, beta, running_mean, running_var, eps, momentum, residual=None, relu=False):
+    """y = act(BN_batch(x) + residual) over the rows < *num (the rows of the capacity beyond them are left untouched);
+    running statistics are updated in place like nn.BatchNorm1d in train mode.  Returns (y, mean, rstd)."""
+    lib = _lib.load()
+    require_cuda(x)
+    rows_cap, C = x.shape
+    dev = x.device
+    sums = torch.empty(2 * C, dtype=torch.float32, device=dev)
+    stats = torch.empty(4, C, dtype=torch.float32, device=dev)     # mean, rstd, scale, shift
+    check(lib.pn_bn_stats(ptr(x), _DT[x.dtype], x.stride(0), ptr(num), rows_cap, C, ptr(sums), stream_ptr()),
+          "pn_bn_stats")
+    check(lib.pn_bn_finalize(ptr(sums), ptr(num), rows_cap, C, ptr(gamma), ptr(beta), c_float(eps), c_float(momentum),
+                             ptr(running_mean), ptr(running_var), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]),
+                             ptr(stats[3]), stream_ptr()), "pn_bn_finalize")
+    y = torch.empty(rows_cap, C, dtype=x.dtype, device=dev)
+    if residual is not None and residual.dtype != x.dtype:
+        raise RuntimeError("residual dtype must match x")
+    check(lib.pn_bn_apply(ptr(x), _DT[x.dtype], x.stride(0), ptr(stats[2]), ptr(stats[3]), ptr(residual),
+                          residual.stride(0) if residual is not None else 0, 1 if relu else 0, ptr(num), rows_cap, C,
+                          ptr(y), y.stride(0), stream_ptr()), "pn_bn_apply")
+    return y, stats[0], stats[1]
+
+
+def bn_train_backward(dy, y, x, mean, rstd, gamma, relu, num, want_dres):
+    """Returns (dx, dres | None, dgamma (C) f32, dbeta (C) f32)."""
+    lib = _lib.load()
+    require_cuda(dy, x)
+    rows_cap, C = x.shape
+    dev = x.device
+    dy = dy.contiguous()
+    if dy.dtype != x.dtype:
+        dy = dy.to(x.dtype)
+    sums = torch.empty(2 * C, dtype=torch.float32, device=dev)
+    check(lib.pn_bn_bwd_stats(ptr(dy), _DT[x.dtype], dy.stride(0), ptr(y), y.stride(0) if y is not None else 0, ptr(x),
+                              x.stride(0), ptr(mean), ptr(rstd), 1 if relu else 0, ptr(num), rows_cap, C, ptr(sums),
+                              stream_ptr()), "pn_bn_bwd_stats")
+    dx = torch.empty(rows_cap, C, dtype=x.dtype, device=dev)
+    dres = torch.empty(rows_cap, C, dtype=x.dtype, device=dev) if want_dres else None
+    check(lib.pn_bn_bwd_apply(ptr(dy), _DT[x.dtype], dy.stride(0), ptr(y), y.stride(0) if y is not None else 0, ptr(x),
+                              x.stride(0), ptr(mean), ptr(rstd), ptr(gamma), ptr(sums), 1 if relu else 0, ptr(num),
+                              rows_cap, C, ptr(dx), dx.stride(0), ptr(dres), dres.stride(0) if want_dres else 0,
+                              stream_ptr()), "pn_bn_bwd_apply")
+    return dx, dres, sums[C:], sums[:C]
+
+
+def dense_to_sparse(dense_rows, table, C):
+    """rows (cap, C) of a compact NHWC map (B*H*W, ld) at the table's sites (rows beyond the live count untouched)"""
+    lib = _lib.load()
+    require_cuda(dense_rows)
+    out = torch.empty(table.cap, C, dtype=dense_rows.dtype, device=dense_rows.device)
+    check(lib.pn_dense_to_sparse(ptr(dense_rows), _DT[dense_rows.dtype], dense_rows.stride(0), ptr(table.coords),
+                                 ptr(table.num), table.cap, table.H, table.W, C, ptr(out), out.stride(0), stream_ptr()),
+          "pn_dense_to_sparse")
+    return out

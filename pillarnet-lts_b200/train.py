@@ -12,8 +12,23 @@ import torch
 import torch.nn.functional as F
 
 from . import config, ops
-from .autograd import Rulebook, scatter_max, sparse_conv
+from ._lib import PN_NBR_SUBM_SORTED
+from .autograd import (Rulebook, StaticRulebook, dense_from_sparse_static, scatter_max, sparse_conv, sparse_conv_bn)
 from .sparse import SparseConvTensor
+
+# Static mode: every tensor of the step has a capacity-derived shape and the live row counts stay on the device, so the
+# whole step (forward, loss, backward, optimiser) is free of host synchronisation and can be captured in a CUDA graph
+# (TrainEngine).  The dynamic mode below sizes every matrix exactly and reads the counts back, like the reference.
+_static = False
+
+
+def set_static(on):
+    global _static
+    _static = bool(on)
+
+
+def is_static():
+    return _static
 
 
 def _exact(table):
@@ -56,9 +71,47 @@ def autocast_ctx():
 
 # ---- reader ---------------------------------------------------------------------------------------
 
+def _masked_bn_relu(h, valid, bn):
+    """BatchNorm1d (batch statistics over the rows with valid == 1, running stats updated as torch does) + ReLU, written
+    with shape-static torch ops so it needs no compaction of the valid rows."""
+    w = valid.to(h.dtype).unsqueeze(1)
+    n = w.sum().clamp(min=1.0)
+    mean = (h * w).sum(0) / n
+    d = (h - mean) * w
+    var = (d * d).sum(0) / n
+    y = (h - mean) * torch.rsqrt(var + bn.eps) * bn.weight + bn.bias
+    with torch.no_grad():
+        m = bn.momentum
+        bn.running_mean.mul_(1 - m).add_(mean.detach() * m)
+        bn.running_var.mul_(1 - m).add_(var.detach() * (n / (n - 1).clamp(min=1.0)) * m)
+        bn.num_batches_tracked.add_(1)
+    return F.relu(y)
+
+
+def _reader_forward_static(pfn, points, frame_offsets, batch_size):
+    table, point_pillar = ops.pillarize(points, frame_offsets, batch_size, pfn.height, pfn.width,
+                                        pfn.point_cloud_range[0], pfn.point_cloud_range[1], pfn.pillar_size)
+    feats = ops.point_features(points, pfn.point_cloud_range[0], pfn.point_cloud_range[1], pfn.pillar_size,
+                               pfn.x_offset, pfn.y_offset)
+    # points past the live count (the tail of the capacity) were not visited by pn_pillarize: index -1 like the
+    # out-of-range ones
+    live = frame_offsets[batch_size:batch_size + 1]
+    point_pillar = torch.where(torch.arange(points.shape[0], device=points.device, dtype=torch.int32) < live,
+                               point_pillar, torch.full_like(point_pillar, -1))
+    h = pfn.shared_mlps[0](feats)                               # Linear on every point of the capacity
+    h = _masked_bn_relu(h.float(), point_pillar >= 0, pfn.shared_mlps[1])
+    pooled = scatter_max(h.contiguous(), point_pillar, table.cap)   # index -1 is skipped
+    sp = SparseConvTensor(pooled.to(config.act_dtype()), table, (pfn.height, pfn.width), batch_size)
+    sp._count = table.cap
+    sp.point_pillar = point_pillar
+    return sp
+
+
 def reader_forward(pfn, points, frame_offsets, batch_size):
     """PillarMaxPooling.forward in train mode (pillar_modules.py:56-74): the MLP is torch (autograd),
     pillarization / point features / scatter-max (+ its backward) are library kernels."""
+    if _static:
+        return _reader_forward_static(pfn, points, frame_offsets, batch_size)
     table, point_pillar = ops.pillarize(points, frame_offsets, batch_size, pfn.height, pfn.width,
                                         pfn.point_cloud_range[0], pfn.point_cloud_range[1], pfn.pillar_size)
     ex = _exact(table)
@@ -85,7 +138,34 @@ def conv_bn(feat, conv, bn, rb, relu, residual=None):
     return F.relu(y) if relu else y
 
 
+def _subm_rulebook_static(table):
+    if table._train is None:
+        table._train = {}
+    rb = table._train.get("subm_static")
+    if rb is None:
+        nbr = table.subm_nbr()
+        # a submanifold rulebook is its own transpose with the taps mirrored: nbr_t[i,t] = nbr[i,8-t]
+        nbr_t = nbr.flip(1).contiguous()
+        bf16 = config.get_precision() == "bf16"
+        plan = table.subm_plan() if bf16 else None
+        plan_t = ops.conv_window_plan(nbr_t, table.num, table.cap) if bf16 else None
+        rb = StaticRulebook(nbr, nbr_t, table.num, table.num, table.cap, table.cap, plan, plan_t, PN_NBR_SUBM_SORTED)
+        table._train["subm_static"] = rb
+    return rb
+
+
+def _down_rulebook_static(table):
+    out_table, nbr = ops.rulebook_down3x3s2(table)
+    nbr_t = ops.rulebook_transpose(nbr, table.cap, out_table.num)
+    return out_table, StaticRulebook(nbr, nbr_t, table.num, out_table.num, table.cap, out_table.cap)
+
+
 def subm_block(sp, seq, relu, residual=None):
+    if _static:
+        rb = _subm_rulebook_static(sp.table)
+        conv, bn = seq[0], seq[1]
+        out = sparse_conv_bn(sp.feat, conv.weight, conv.bias, bn.weight, bn.bias, residual, rb, bn, relu)
+        return _wrap(out, sp.table, sp)
     rb = subm_rulebook(sp.table)
     out = conv_bn(sp.feat, seq[0], seq[1], rb, relu, residual)
     return _wrap(out, sp.table, sp)
@@ -98,6 +178,10 @@ def _wrap(feat, table, like):
 
 
 def down_block(sp, conv, bn):
+    if _static:
+        out_table, rb = _down_rulebook_static(sp.table)
+        out = sparse_conv_bn(sp.feat, conv.weight, conv.bias, bn.weight, bn.bias, None, rb, bn, True)
+        return _wrap(out, out_table, sp)
     out_table, rb = down_rulebook(sp.table)
     out = conv_bn(sp.feat, conv, bn, rb, relu=True)
     return _wrap(out, out_table, sp)
@@ -105,6 +189,8 @@ def down_block(sp, conv, bn):
 
 def dense_from_sparse(sp):
     """differentiable SparseConvTensor.dense() (PillarResNet.py:139): (B,C,H,W)"""
+    if _static:
+        return dense_from_sparse_static(sp.feat, sp.table)
     t = sp.table
     c = t.coords.long()
     d = sp.feat.new_zeros(t.B, t.H, t.W, sp.feat.shape[1])
@@ -174,3 +260,114 @@ def train_step(model, example, optimizer, averager=None):
         averager.finish()
     optimizer.step()
     return loss.detach()
+
+
+class TrainEngine:
+    """The whole training step of BASELINE config 4 without host synchronisation, as two CUDA graphs:
+
+        graph A: zero the gradients, forward (reader, sparse backbone, dense conv5 / neck / head), loss, backward
+        (data-parallel runs: one bucketed NCCL all-reduce of the flat gradient buffers, dist.GradientAverager)
+        graph B: the optimiser step (a `capturable=True` torch optimiser)
+
+    Inputs live in fixed buffers sized by a capacity (points, frame offsets, the target tensors of
+    CenterHead.loss); `step(example)` copies a batch in and replays.  Everything in between uses capacity-derived
+    shapes with the live counts on the device (set_static above).  The reference synchronises the host several times
+    per layer (`.item()` at pillar_utils.py:45, spconv's indice-pair counts, `mask.sum() == 0` in the losses) and
+    issues ~5000 launches per step from Python.
+
+        eng = TrainEngine(model, optimizer, n_frames=4, points_cap=1_200_000, example=first_batch).prepare()
+        loss = eng.step(batch)        # device scalar
+    """
+
+    TARGET_KEYS = ("hm", "ind", "mask", "cat", "anno_box", "gt_box")
+
+    def __init__(self, model, optimizer, n_frames, points_cap, example, averager=None, point_dim=5, use_graph=True):
+        self.model, self.opt, self.avg = model.train(), optimizer, averager
+        self.B, self.cap = n_frames, int(points_cap)
+        self.dev = next(model.parameters()).device
+        self.points = torch.zeros(self.cap, point_dim, dtype=torch.float32, device=self.dev)
+        self.offsets = torch.zeros(n_frames + 1, dtype=torch.int32, device=self.dev)
+        self.targets = {k: [t.clone() for t in example[k]] for k in self.TARGET_KEYS if k in example}
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.use_graph = use_graph
+        self.graph_fb = self.graph_opt = None
+        self.loss = None
+        self.load(example)
+
+    def load(self, example):
+        """copies one batch into the fixed input buffers (async on the engine stream)"""
+        pts, off = example["points_batched"]
+        n = pts.shape[0]
+        if n > self.cap:
+            raise RuntimeError(f"{n} points exceed the engine capacity {self.cap}")
+        with torch.cuda.stream(self.stream):
+            self.points[:n].copy_(pts, non_blocking=True)
+            self.offsets.copy_(off, non_blocking=True)
+            for k, lst in self.targets.items():
+                for dst, src in zip(lst, example[k]):
+                    dst.copy_(src, non_blocking=True)
+
+    def _example(self):
+        ex = {"points_batched": (self.points, self.offsets), "points": None, "metadata": [None] * self.B}
+        ex.update(self.targets)
+        return ex
+
+    def _forward_backward(self):
+        if self.avg is not None:
+            self.avg.zero_grad()
+        else:
+            # None, not zeros: autograd then writes each gradient instead of accumulating into it (saves a fill and an
+            # add per parameter, ~1200 launches); under capture the new gradient tensors come from the graph's private
+            # pool at fixed addresses, which the optimiser graph captured right after sees
+            self.opt.zero_grad(set_to_none=True)
+        losses = self.model(self._example(), return_loss=True)
+        loss = sum(l.sum() for l in losses["loss"])
+        loss.backward()
+        return loss.detach()
+
+    def prepare(self, warmup=3):
+        """eager warm-up steps (allocator, lowering caches, optimiser state) on the engine stream, then capture"""
+        set_static(True)
+        if self.avg is not None:
+            self.avg.defer = True          # gradients are reduced after the captured backward, in bucket order
+        with torch.cuda.stream(self.stream):
+            for _ in range(max(1, warmup)):
+                self.loss = self._forward_backward()
+                if self.avg is not None:
+                    self.avg.finish()
+                self.opt.step()
+            self.stream.synchronize()
+            from . import _lib
+            l0 = _lib.load().pn_launch_count()
+            self.loss = self._forward_backward()       # one more eager pass, counted: the library kernels of a step
+            if self.avg is not None:
+                self.avg.finish()
+            self.opt.step()
+            self.stream.synchronize()
+            self.launches_per_step = int(_lib.load().pn_launch_count() - l0)
+            if self.use_graph:
+                self.graph_fb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_fb, stream=self.stream):
+                    self.loss = self._forward_backward()
+                self.graph_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_opt, stream=self.stream):
+                    self.opt.step()
+        self.stream.synchronize()
+        return self
+
+    def step(self, example=None):
+        """one training step; returns the summed loss (device scalar, valid once the engine stream has reached it)"""
+        if example is not None:
+            self.load(example)
+        with torch.cuda.stream(self.stream):
+            if self.graph_fb is not None:
+                self.graph_fb.replay()
+            else:
+                self.loss = self._forward_backward()
+            if self.avg is not None:
+                self.avg.finish()
+            if self.graph_opt is not None:
+                self.graph_opt.replay()
+            else:
+                self.opt.step()
+        return self.loss

@@ -230,3 +230,200 @@ def test_assign_label_gpu_vs_reference_golden(golden_dir):
             np.testing.assert_allclose(out["anno_box"][t][f].cpu().numpy(), g[f"f{f}_t{t}_anno_box"], rtol=2e-6, atol=2e-7)
     # the targets plug into the loss
     assert out["hm"][1].shape == (3, 160, 160, 2) and out["ind"][0].dtype == torch.int64
+
+
+# ---- sync-free (CUDA-graph) training path: fused batch-stat BN kernels, static shapes, TrainEngine --------------------
+def _small_train_setup(seed, precision, n_pts=20000, max_objs=40):
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200 import configs, train
+    P.set_precision(precision)
+    torch.manual_seed(seed)
+    cfg = configs.get("nusc18")
+    cfg["model"]["reader"]["pc_range"] = [-24.0, -24.0, -5.0, 24.0, 24.0, 3.0]
+    cfg["model"]["bbox_head"]["point_cloud_range"] = [-24.0, -24.0, -5.0, 24.0, 24.0, 3.0]
+    cfg["model"]["neck"]["layer_nums"] = [1, 1]
+    model = P.build_detector(cfg["model"], train_cfg=cfg["train_cfg"], test_cfg=cfg["test_cfg"]).cuda().train()
+    rng = np.random.default_rng(seed)
+    batches = []
+    for _ in range(3):
+        pts, off = batch_points([rand_points(rng, n_pts, -26.0, 26.0) for _ in range(2)])   # some points out of range
+        ex = {"points_batched": (pts, off), "points": None, "metadata": [None, None]}
+        ex.update(train.synthetic_targets(model.bbox_head, 2, 640, 640, rng, max_objs=max_objs))
+        batches.append(ex)
+    return model, cfg, batches
+
+
+def _grads(model):
+    return {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(1e-6, b.abs().max().item())
+
+
+def _pre_bn_biases(model):
+    """conv biases in front of a batch-statistics BN: their gradient is mathematically zero (BN removes the mean), what
+    either path computes for them is rounding noise"""
+    names = set()
+    for mn, m in model.named_modules():
+        kids = list(m.children()) if isinstance(m, torch.nn.Sequential) else []
+        for a, b in zip(kids, kids[1:]):
+            if isinstance(b, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)) and getattr(a, "bias", None) is not None:
+                names.add(f"{mn}.{kids.index(a)}.bias" if mn else f"{kids.index(a)}.bias")
+    return names
+
+
+def _grad_errors(got, want, skip=()):
+    """(relative L2 error of the concatenated gradient vector, worst per-tensor max-abs error relative to the tensor's
+    largest gradient over the weight tensors with >= 512 elements)"""
+    keys = [k for k in want if k not in skip]
+    g = torch.cat([got[k].reshape(-1) for k in keys])
+    w = torch.cat([want[k].reshape(-1) for k in keys])
+    l2 = ((g - w).norm() / w.norm()).item()
+    worst = max((_rel(got[k], want[k]), k) for k in keys if want[k].numel() >= 512)
+    return l2, worst
+
+
+def test_bn_train_kernels_vs_torch_batch_norm():
+    """pn_bn_stats / finalize / apply / bwd_stats / bwd_apply vs nn.BatchNorm1d (train) + add + ReLU under autograd on
+    the live rows; rows beyond the device-resident count do not enter the statistics."""
+    from pillarnet_lts_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    cap, n, C = 5000, 3777, 64
+    num = torch.tensor([n], dtype=torch.int32, device="cuda")
+    x = torch.randn(cap, C, device="cuda", generator=g) * 2 + 0.5
+    res = torch.randn(cap, C, device="cuda", generator=g)
+    dy = torch.randn(cap, C, device="cuda", generator=g)
+    bn = torch.nn.BatchNorm1d(C, eps=1e-3, momentum=0.01).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.2)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    xr, rr = x[:n].clone().requires_grad_(True), res[:n].clone().requires_grad_(True)
+    want = torch.relu(bn(xr) + rr)
+    want.backward(dy[:n])
+    y, mean, rstd = ops.bn_train_forward(x, num, bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps, bn.momentum, res, True)
+    dx, dres, dgamma, dbeta = ops.bn_train_backward(dy, y, x, mean, rstd, bn.weight.detach(), True, num, True)
+    torch.cuda.synchronize()
+    assert _rel(y[:n], want.detach()) <= 1e-5
+    assert _rel(dx[:n], xr.grad) <= 1e-4 and _rel(dres[:n], rr.grad) <= 1e-6
+    assert _rel(dgamma, bn.weight.grad) <= 1e-4 and _rel(dbeta, bn.bias.grad) <= 1e-4
+    assert _rel(rm, bn.running_mean) <= 1e-5 and _rel(rv, bn.running_var) <= 1e-5
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-2), ("bf16", 1e-1)])
+def test_static_training_path_matches_dynamic_path(precision, tol):
+    """same parameters, same batch: the sync-free path (capacity-sized rows, fused BN kernels, masked PFN) gives the head
+    maps and the parameter gradients of the exactly sized path (torch BatchNorm1d on compacted rows).  The probe loss is
+    LINEAR in the head maps (fixed random weights): CenterHead's L1 terms have sign discontinuities, which turn a
+    rounding-level difference of the predictions into O(1/num_pos) jumps of the gradient and make a per-step
+    comparison of two correct bf16 paths meaningless (the real loss is compared in fp32 against the dense-equivalent
+    autograd model below)."""
+    from pillarnet_lts_b200 import train
+    model, cfg, batches = _small_train_setup(5, precision)
+    ex = batches[0]
+    out = {}
+    probe = None
+    try:
+        for mode in (False, True):
+            train.set_static(mode)
+            model.zero_grad(set_to_none=True)
+            bev, _ = model.extract_feat(dict(points_batched=ex["points_batched"], points=None))
+            preds = model.bbox_head(bev)
+            if probe is None:
+                g = torch.Generator(device="cuda").manual_seed(9)
+                probe = [{k: torch.randn(v.shape, device="cuda", generator=g) for k, v in p.items()} for p in preds]
+            loss = sum((p[k].float() * w[k]).sum() for p, w in zip(preds, probe) for k in p) / 1000.0
+            loss.backward()
+            out[mode] = (float(loss.detach()), _grads(model), [{k: v.detach().float().clone() for k, v in p.items()} for p in preds])
+    finally:
+        train.set_static(False)
+    assert abs(out[True][0] - out[False][0]) <= tol * max(1.0, abs(out[False][0]))
+    assert set(out[True][1]) == set(out[False][1])
+    # Tolerances: each operator is pinned tightly on its own (BN kernels 1e-5 / 1e-4 above, conv fwd / dgrad / wgrad
+    # 1e-4 in fp32); through ~25 batch-norm layers in TRAIN mode a 1e-6 difference in one conv output is amplified
+    # (rstd up to 1/sqrt(eps) = 31 per layer on low-variance channels, ReLU masks flipping near zero): measured fp32
+    # head maps agree to ~1e-3 and the full gradient vector to 6e-3 relative L2 — between ANY two implementations,
+    # e.g. this path and cuDNN through the dense-equivalent model below.  A wiring bug gives O(1).
+    l2, worst = _grad_errors(out[True][1], out[False][1], skip=_pre_bn_biases(model))
+    fwd = max(_rel(a[k], b[k]) for a, b in zip(out[True][2], out[False][2]) for k in a)
+    if precision == "fp32":
+        assert fwd <= 5e-3 and l2 <= tol * 2 and worst[0] <= 0.3, (fwd, l2, worst)
+    else:
+        # bf16: the same amplification acts on 4e-3 roundings — head maps within 5e-2, while the gradient of the FIRST
+        # layers (backward through every BN of the net) differs by tens of percent between two correct bf16 paths
+        # (measured l2 0.49).  Only the wiring is asserted here (the gradient vectors point the same way); the bf16
+        # kernels are pinned per operator in the tests above.
+        g = torch.cat([v.reshape(-1) for k, v in out[True][1].items()])
+        w = torch.cat([out[False][1][k].reshape(-1) for k in out[True][1]])
+        cos = float((g * w).sum() / (g.norm() * w.norm()))
+        assert fwd <= 5e-2 and cos >= 0.7, (fwd, cos, l2)
+
+
+def test_whole_step_gradients_vs_dense_equivalent_autograd():
+    """gradients of EVERY backbone / neck / head parameter from the library's training path (fp32
+    mode: gather conv fwd / dgrad / wgrad kernels + fused BN kernels) against torch autograd through the dense-equivalent
+    model (oracle/dense_train.py: F.conv2d + batch-norm over the active rows), same reader output, same loss."""
+    from oracle import dense_train
+    from pillarnet_lts_b200 import train
+    model, cfg, batches = _small_train_setup(6, "fp32", n_pts=12000, max_objs=30)
+    ex = batches[0]
+    try:
+        train.set_static(True)
+        model.zero_grad(set_to_none=True)
+        sp = model.reader(dict(points_batched=ex["points_batched"]))
+        feat_leaf = sp.feat.detach().clone().requires_grad_(True)
+        sp.feat = feat_leaf
+        feats = model.backbone(sp)
+        bev = model.neck(feats)
+        preds = model.bbox_head(bev)
+        loss = sum(l.sum() for l in model.bbox_head.loss(ex, preds, cfg["train_cfg"])["loss"])
+        loss.backward()
+        got = _grads(model)
+        got_feat = feat_leaf.grad.clone()
+        n = sp.table.count()
+    finally:
+        train.set_static(False)
+    model.zero_grad(set_to_none=True)
+    leaf = feat_leaf.detach()[:n].clone().requires_grad_(True)
+    want_loss = dense_train.loss_dense_equivalent(model, leaf, sp.table.coords[:n], 2, sp.table.H, sp.table.W, ex,
+                                                  cfg["train_cfg"])
+    want_loss.backward()
+    want = _grads(model)
+    assert abs(float(loss) - float(want_loss)) <= 1e-3 * abs(float(want_loss))
+    assert _rel(got_feat[:n], leaf.grad) <= 2e-2
+    skip = _pre_bn_biases(model) | {k for k in want if k.startswith("reader.")}
+    assert len([k for k in want if k not in skip]) > 100
+    l2, worst = _grad_errors(got, want, skip=skip)
+    assert l2 <= 2e-2 and worst[0] <= 0.2, (l2, worst)
+
+
+def test_train_engine_graph_replay_matches_eager_steps():
+    """TrainEngine (two CUDA graphs, fixed input buffers) against eager steps of the same static path from the same
+    initial state: the loss curves agree (fp32 atomics in the statistics kernels reorder sums, hence not bit-equal) and
+    the loss goes down."""
+    import copy
+    from pillarnet_lts_b200 import train
+    model, cfg, batches = _small_train_setup(7, "bf16")
+    model2 = copy.deepcopy(model)
+    cap = max(b["points_batched"][0].shape[0] for b in batches) + 1000
+    try:
+        opt = torch.optim.AdamW(model.parameters(), lr=2e-4, capturable=True)
+        eng = train.TrainEngine(model, opt, 2, cap, batches[0]).prepare(warmup=2)
+        got = []
+        for i in range(6):
+            loss = eng.step(batches[i % 3])
+            eng.stream.synchronize()            # the step runs on the engine's stream
+            got.append(float(loss))
+        train.set_static(True)
+        opt2 = torch.optim.AdamW(model2.parameters(), lr=2e-4, capturable=True)
+        eng2 = train.TrainEngine(model2, opt2, 2, cap, batches[0], use_graph=False).prepare(warmup=2)
+        want = []
+        for i in range(6):
+            loss = eng2.step(batches[i % 3])
+            eng2.stream.synchronize()
+            want.append(float(loss))
+    finally:
+        train.set_static(False)
+    assert all(np.isfinite(got)) and all(np.isfinite(want))
+    assert max(abs(a - b) / abs(b) for a, b in zip(got, want)) <= 5e-2, (got, want)
+    assert got[-1] < got[0]

@@ -51,7 +51,7 @@ for step in "$@"; do
       timeout 900 python bench.py --workload waymo34 --frames-per-step 1 --steps 30 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/bench_waymo34_b1.json 2>> gpurun_out/bench_waymo_err.log
       echo "waymo b1 rc=$?"; cut -c1-300 gpurun_out/bench_waymo34_b1.json ;;
     bench_train)
-      timeout 900 python bench.py --mode train --workload nusc34 --frames-per-step 4 --steps 10 --warmup 3 > gpurun_out/bench_train_nusc34_b4.json 2> gpurun_out/bench_train_err.log
+      timeout 900 python bench.py --mode train --workload nusc34 --frames-per-step 4 --steps 20 --warmup 3 > gpurun_out/bench_train_nusc34_b4.json 2> gpurun_out/bench_train_err.log
       echo "train rc=$?"; cut -c1-400 gpurun_out/bench_train_nusc34_b4.json; tail -3 gpurun_out/bench_train_err.log ;;
     launches)
       plain

@@ -1,9 +1,8 @@
-"""torch.profiler breakdown of one training step (where the time goes: our kernels vs cuDNN vs elementwise vs host)."""
+"""CUPTI breakdown of one training step as the TrainEngine replays it (two CUDA graphs): per-kernel device time."""
 import argparse
 import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch
@@ -15,15 +14,16 @@ from pillarnet_lts_b200 import configs, synth, train  # noqa: E402
 from pillarnet_lts_b200.registry import ConfigDict  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--workload", default="nusc18")
-ap.add_argument("--frames", type=int, default=2)
+ap.add_argument("--workload", default="nusc34")
+ap.add_argument("--frames", type=int, default=4)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--out", default="gpurun_out/prof_train.json")
 args = ap.parse_args()
 dev = torch.device("cuda")
 cfg = configs.get(args.workload)
 torch.manual_seed(0)
 model = P.build_detector(ConfigDict.wrap(cfg["model"]), cfg["train_cfg"], ConfigDict.wrap(cfg["test_cfg"])).to(dev).train()
-opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+opt = torch.optim.AdamW(model.parameters(), lr=1e-4, capturable=True)
 rng = np.random.default_rng(0)
 B = args.frames
 fs = synth.make_batch(cfg["synth"], B, 100)
@@ -31,40 +31,26 @@ offs = np.cumsum([0] + [len(f) for f in fs]).astype(np.int32)
 ex = {"points_batched": (torch.from_numpy(np.concatenate(fs)).to(dev), torch.from_numpy(offs).to(dev)), "points": None,
       "metadata": [None] * B}
 ex.update(train.synthetic_targets(model.bbox_head, B, model.reader.height, model.reader.width, rng, device=dev))
+eng = train.TrainEngine(model, opt, B, ex["points_batched"][0].shape[0] + 1024, ex).prepare(warmup=3)
 for _ in range(3):
-    train.train_step(model, ex, opt)
+    eng.step(ex)
 torch.cuda.synchronize()
-
-
-def timed(fn):
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    r = fn()
-    torch.cuda.synchronize()
-    return r, (time.perf_counter() - t0) * 1e3
-
-
-stages = {}
-opt.zero_grad(set_to_none=True)
-sp, stages["reader_fwd"] = timed(lambda: model.reader(dict(points_batched=ex["points_batched"])))
-feats, stages["backbone_fwd"] = timed(lambda: model.backbone(sp))
-bev, stages["neck_fwd"] = timed(lambda: model.neck(feats))
-preds, stages["head_fwd"] = timed(lambda: model.bbox_head(bev))
-losses, stages["loss"] = timed(lambda: model.bbox_head.loss(ex, preds, model.train_cfg))
-loss = sum(l.sum() for l in losses["loss"])
-_, stages["backward"] = timed(lambda: loss.backward())
-_, stages["optimizer"] = timed(lambda: opt.step())
-print("stage wall ms (sync on both sides):", json.dumps({k: round(v, 2) for k, v in stages.items()}))
-
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(args.steps):
-        train.train_step(model, ex, opt)
+        eng.step(ex)
     torch.cuda.synchronize()
-ka = prof.key_averages()
-rows = sorted([(k.key, getattr(k, "device_time_total", 0.0) / args.steps, k.count / args.steps) for k in ka
-               if getattr(k, "device_time_total", 0.0) > 0 and k.device_type.name == "CUDA"], key=lambda r: -r[1])
+agg = {}
+for e in prof.events():
+    if e.device_type.name != "CUDA":
+        continue
+    a = agg.setdefault(e.name, [0.0, 0])
+    a[0] += e.device_time
+    a[1] += 1
+rows = sorted(((k, v[0] / args.steps, v[1] / args.steps) for k, v in agg.items()), key=lambda r: -r[1])
 tot = sum(r[1] for r in rows)
-print(f"CUDA kernel time per step: {tot / 1e3:.2f} ms over {sum(r[2] for r in rows):.0f} launches")
-for name, us, n in rows[:40]:
-    print(f"{us:10.1f} us {100 * us / tot:5.1f}%  n={n:6.1f}  {name[:110]}")
+print(f"kernel time per step {tot / 1e3:.2f} ms over {sum(r[2] for r in rows):.0f} launches")
+for name, us, n in rows[:45]:
+    print(f"{us:10.1f} us {100 * us / tot:5.1f}%  n={n:6.1f}  {name[:120]}")
+os.makedirs(os.path.dirname(args.out), exist_ok=True)
+json.dump([dict(kernel=k[:160], us_per_step=u, launches=n) for k, u, n in rows], open(args.out, "w"), indent=0)
