@@ -490,6 +490,31 @@ def run_gpu(args):
         step_resident(0)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+    # ---- extra: the other two B200 configurations of BASELINE.json, measured by every driver run -------------------
+    # (config 3: PillarNet-34 Waymo, 8 frames per step STRONG-scaled over the ranks; config 4: PillarNet-34 nuScenes
+    # training step, 4 frames per GPU, NCCL gradient all-reduce).  Outside the headline's timed regions.
+    extra = None
+    if not args.no_extra and not args.profile_pass:
+        extra = {}
+        try:
+            per = max(1, 8 // world)
+            r3 = measure_infer_resident("waymo34", per, 12, 3, args.precision, world, rank, dev)
+            extra["config3_waymo34_8_frames_strong_scaled"] = {
+                "value": r3["value"], "unit": "frames/s", "ms_per_step": r3["ms_per_step"], "frames_per_step_total": per * world,
+                "frames_per_step_per_gpu": per, "scaling": "strong" if world <= 8 else "weak",
+                "what": "device-resident frames/s, CUDA-graph replay, L2 flushed between steps, max over ranks"}
+        except Exception as ex:                                   # the headline must survive a failure here
+            extra["config3_waymo34_8_frames_strong_scaled"] = {"error": repr(ex)[:300]}
+        try:
+            r4 = measure_train("nusc34", 4, 8, 3, args.precision, world, rank, dev)
+            extra["config4_nusc34_training_4_frames_per_gpu"] = {
+                "value": r4["value"], "unit": "frames/s", "ms_per_step": r4["ms_per_step"], "launches_per_step": r4["launches"] // 8,
+                "scaling": "weak", "loss_last": r4["loss_last"],
+                "what": "TrainEngine step (forward+loss+backward graph, gradient all-reduce, optimiser graph), "
+                        "max over ranks"}
+        except Exception as ex:
+            extra["config4_nusc34_training_4_frames_per_gpu"] = {"error": repr(ex)[:300]}
+        P.set_precision(args.precision)
     line = None
     if rank == 0:
         peaks = _peaks()
@@ -575,6 +600,7 @@ def run_gpu(args):
             "model_tflops": flop_total / step_us / 1e6,
             "stages_us": stages,
             "cpu_baseline": cpu,
+            "extra": extra,
         }
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         tag = "_prof" if args.profile_pass else ""
@@ -588,32 +614,20 @@ def run_gpu(args):
 
 
 # ---------------------------------------------------------------------------------------------------
-def run_train(args):
-    """BASELINE config 4: one data-parallel training step (reader + sparse backbone forward/backward on the
-    library's kernels, dense neck/head + loss in PyTorch, overlapped NCCL gradient all-reduce)."""
+def measure_train(workload, B, steps, warmup, precision, world, rank, dev, eager=False):
+    """one data-parallel training configuration (BASELINE config 4): returns a dict of results (every rank)"""
     import torch.distributed as dist
     import pillarnet_lts_b200 as P
     from pillarnet_lts_b200 import _lib, configs, train
     from pillarnet_lts_b200.dist import GradientAverager
     from pillarnet_lts_b200.registry import ConfigDict
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-    P.set_precision(args.precision)
+    P.set_precision(precision)
     lib = _lib.load()
-    B = args.frames_per_step
-    cfg = configs.get(args.workload)
+    cfg = configs.get(workload)
     torch.manual_seed(0)
     model = P.build_detector(ConfigDict.wrap(cfg["model"]), cfg["train_cfg"], ConfigDict.wrap(cfg["test_cfg"]))
     model = model.to(dev).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, capturable=not args.train_eager)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, capturable=not eager)
     avg = GradientAverager(list(model.parameters()), bucket_mb=25, module=model) if world > 1 else None
     pool = 4
     rng = np.random.default_rng(7 + rank)
@@ -634,54 +648,131 @@ def run_train(args):
         torch.cuda.synchronize()
 
     eng = None
-    if not args.train_eager:
+    if not eager:
         # sync-free step as two CUDA graphs (train.TrainEngine): fixed input buffers, live row counts on the device
         cap = int(max(b["points_batched"][0].shape[0] for b in batches) * 1.02) + 1024
         eng = train.TrainEngine(model, opt, B, cap, batches[0], averager=avg).prepare(warmup=3)
-        l0 = lib.pn_launch_count()
-        with torch.cuda.stream(eng.stream), torch.no_grad():
-            pass
         step = lambda i: eng.step(batches[i % pool])
         stream = eng.stream
     else:
         step = lambda i: train.train_step(model, batches[i % pool], opt, avg)
         stream = torch.cuda.current_stream()
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(warmup, 3)):
         loss = step(i)
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index or 0)
     sampler.start()
     l0 = lib.pn_launch_count()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record(stream)
-    for i in range(args.steps):
+    for i in range(steps):
         loss = step(i)
     e.record(stream)
     barrier()
     gpu_ms = s.elapsed_time(e)
     launches = lib.pn_launch_count() - l0
     if eng is not None:
-        launches = eng.launches_per_step * args.steps
+        launches = eng.launches_per_step * steps
     clocks = sampler.stop()
     t = torch.tensor([gpu_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     gpu_ms = t.item()
+    res = dict(value=steps * B * world / (gpu_ms / 1e3), ms_per_step=gpu_ms / steps, launches=int(launches),
+               loss_last=float(loss), clocks=clocks, n_pts=n_pts, train_state=train.is_static())
+    train.set_static(False)
+    del eng, model, opt, batches
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_infer_resident(workload, B, steps, warmup, precision, world, rank, dev):
+    """device-resident frames/s of one inference configuration, frames sharded rank-major (i -> rank i % world); used
+    for the strong-scaling leg of BASELINE config 3 (8 Waymo-shaped frames per step over all ranks)"""
+    import torch.distributed as dist
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200.engine import InferenceEngine, calibrate_heatmap_bias
+    P.set_precision(precision)
+    model, cfg = build_model(workload, dev)
+    pool = 4
+    frames = [make_frames(cfg["synth"], 1, seed0=3000 + (j * world + rank))[0] for j in range(pool * B)]
+    calibrate_heatmap_bias(model, frames[:B], target_cells=1500)
+    cap = int(max(sum(len(f) for f in frames[i * B:(i + 1) * B]) for i in range(pool)) * 1.05) + 1024
+    eng = InferenceEngine(model, B, cap, device=dev)
+    eng.upload(eng.stage_host(frames[:B]))
+    eng.prepare(warmup=2)
+    dev_batches = []
+    for i in range(pool):
+        fs = frames[i * B:(i + 1) * B]
+        offs = np.cumsum([0] + [len(f) for f in fs]).astype(np.int32)
+        dev_batches.append((torch.from_numpy(np.concatenate(fs)).to(dev), torch.from_numpy(offs).to(dev)))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(i):
+        p, o = dev_batches[i % pool]
+        with torch.cuda.stream(eng.stream):
+            eng.points[:p.shape[0]].copy_(p, non_blocking=True)
+            eng.offsets.copy_(o, non_blocking=True)
+        eng.launch()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(warmup, 3)):
+        step(i)
+    barrier()
+    ev = []
+    for i in range(steps):
+        with torch.cuda.stream(eng.stream):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(eng.stream)
+        step(i)
+        with torch.cuda.stream(eng.stream):
+            e.record(eng.stream)
+        ev.append((s, e))
+    barrier()
+    gpu_ms = sum(s.elapsed_time(e) for s, e in ev)
+    t = torch.tensor([gpu_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gpu_ms = t.item()
+    del eng, model, dev_batches, flush
+    torch.cuda.empty_cache()
+    return dict(value=steps * B * world / (gpu_ms / 1e3), ms_per_step=gpu_ms / steps, frames_per_step_per_gpu=B)
+
+
+def run_train(args):
+    """BASELINE config 4: one data-parallel training step (reader + sparse backbone forward/backward on the
+    library's kernels, dense neck/head + loss in PyTorch, NCCL gradient all-reduce)."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.frames_per_step
+    r = measure_train(args.workload, B, args.steps, args.warmup, args.precision, world, rank, dev, eager=args.train_eager)
     if rank == 0:
-        value = args.steps * B * world / (gpu_ms / 1e3)
         line = {
             "metric": "frames/s (training step: reader + sparse backbone fwd/bwd, dense neck/head + loss, grad all-reduce)",
-            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": gpu_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "value": r["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-train: {B} frames/GPU (~{n_pts} pts/frame), AdamW, synthetic targets, "
+            "config": {"workload": f"{args.workload}-train: {B} frames/GPU (~{r['n_pts']} pts/frame), AdamW, synthetic targets, "
                                    f"random-init weights; inputs larger than L2 (activations ~GBs per step)",
                        "frames_per_step_per_gpu": B, "precision": args.precision,
                        "mode": ("eager, exactly sized rows, one host sync per rulebook (as the reference)" if args.train_eager
                                 else "TrainEngine: forward+loss+backward and the optimiser step as two CUDA graphs, no "
                                      "host sync; input batch copied device-to-device into fixed buffers inside the "
                                      "timed region")},
-            "clocks": clocks, "gpu_launches": int(launches), "loss_last": float(loss),
+            "clocks": r["clocks"], "gpu_launches": r["launches"], "loss_last": r["loss_last"],
             "e2e": None, "roofline": None, "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)
@@ -812,6 +903,8 @@ def main():
     ap.add_argument("--train-eager", action="store_true",
                     help="--mode train: the eager, exactly sized path (host syncs) instead of the CUDA-graph TrainEngine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the extra block (config 3 strong scaling, config 4 training step)")
     ap.add_argument("--no-parity", action="store_true", help="skip the fp32-vs-bf16 parity block (outside the timed region)")
     ap.add_argument("--sustain-s", type=float, default=2.5,
                     help="length of the back-to-back sustained leg in seconds (0 disables; reported as value_sustained)")

@@ -17,7 +17,7 @@
 #   kbench_reader    reader kernels at scale (events)                    -> gpurun_out/kbench_reader.json
 # Every ncu step first runs the same command plain (the recipe's rule) and only profiles if that exited 0.
 mkdir -p gpurun_out
-PROF_CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-parity --sustain-s 0 --profile-pass"
+PROF_CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-parity --no-extra --sustain-s 0 --profile-pass"
 plain_ok=0
 plain() {
   if [ $plain_ok -eq 0 ]; then
@@ -40,7 +40,7 @@ for step in "$@"; do
       timeout 1200 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_nusc18.json 2> gpurun_out/bench_err.log
       echo "bench rc=$?"; cut -c1-400 gpurun_out/bench_nusc18.json; tail -3 gpurun_out/bench_err.log ;;
     bench_quick)
-      timeout 900 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-parity --sustain-s 0 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick_err.log
+      timeout 900 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-parity --no-extra --sustain-s 0 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick_err.log
       echo "bench rc=$?"; cut -c1-300 gpurun_out/bench_quick.json; tail -3 gpurun_out/bench_quick_err.log ;;
     bench_ref)
       timeout 1200 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_ref_err.log
