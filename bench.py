@@ -606,7 +606,7 @@ def run_gpu(args):
         tag = "_prof" if args.profile_pass else ""
         with open(os.path.join(ROOT, "gpurun_out", f"breakdown_{args.workload}_n{world}{tag}.json"), "w") as fh:
             json.dump({"convs": breakdown, "stages_us": stages, "conv_launches_per_pass": n_conv}, fh, indent=1)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -775,7 +775,7 @@ def run_train(args):
             "clocks": r["clocks"], "gpu_launches": r["launches"], "loss_last": r["loss_last"],
             "e2e": None, "roofline": None, "cpu_baseline": None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -885,10 +885,34 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """stdout carries exactly ONE JSON line (the driver parses it).  Libraries write there too (NCCL prints its version
+    banner at NCCL_DEBUG >= VERSION, which launchers set): from here on file descriptor 1 points at stderr and the
+    result line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
