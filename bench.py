@@ -175,8 +175,8 @@ def conv_breakdown(engine, reps=3):
             r = orig(inp, weight, nbr, taps, cin, cout, out, **kw)
         e.record()
         # window-staged kernel (conv_win_tc.cu) when the caller passed tile plans for a raster-sorted submanifold
-        # rulebook and the layer fits it (cout <= 128); gather kernel (conv_tcgen05.cu) otherwise
-        kname = "k_conv_win" if (kw.get("nbr_plan") is not None and kw.get("nbr_kind") and cout <= 128
+        # rulebook and the layer fits it (cout <= 256); gather kernel (conv_tcgen05.cu) otherwise
+        kname = "k_conv_win" if (kw.get("nbr_plan") is not None and kw.get("nbr_kind") and cout <= 256
                                  and inp.dtype == torch.bfloat16 and out.dtype == torch.bfloat16) else "k_conv_tc"
         recs.append((taps, cin, cout, kw.get("rows_cap") or out.shape[0], kw.get("num"), s, e, kname, nbr,
                      kw.get("deconv")))

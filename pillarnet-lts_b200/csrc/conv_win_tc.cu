@@ -67,10 +67,10 @@ static_assert(kPlanBytes % 16 == 0, "bulk copy granularity");
 static_assert(kWin <= kSrcFar, "window offsets must fit the byte map");
 
 // Row partition shared by the plan kernel and the conv kernel: CTA c of `grid` owns rows [begin, end), walked in
-// 128-row tiles.  Equal contiguous shares (multiple of 8 rows, >= 64), as conv_tcgen05.cu.
+// 128-row tiles.  Equal contiguous shares (multiple of 8 rows, at least one tile), as conv_tcgen05.cu.
 __host__ __device__ inline int win_share(int rows, int grid) {
   const int s = (((rows + grid - 1) / grid) + 7) & ~7;
-  return s < 64 ? 64 : s;
+  return s < BLOCK_M ? BLOCK_M : s;   // never less than one full tile: an MMA costs the same for 64 rows as for 128
 }
 
 template <int BN>
@@ -84,6 +84,9 @@ struct WArgs {
   const int* nbr;
   const uint8_t* plan;   // tile plans of pn_conv_window_plan: [grid][tiles_per_cta][kPlanBytes]
   int tiles_per_cta;
+  int plan_grid;         // row shares the plan was built for (win_geom)
+  int n_split;           // CTAs per output-column block: CTA c computes columns [BN * (c % n_split), +BN) of the row
+                         // shares c / n_split + k * ceil(plan_grid / n_split), k < n_split
   int n_chunks;          // cin / KU
   const float* scale;
   const float* shift;
@@ -118,6 +121,7 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 template <int BN, int KU, bool RES, int NBT, int WS, int AS>
 struct WSmem {
   static_assert(WS % AS == 0 && AS <= 3, "a window slot must always belong to the same builder group");
+  static_assert(BN <= 128, "wider layers are split into 128-column blocks across CTAs (WArgs::n_split)");
   static constexpr int NBU = RES ? 1 : NBT / 3;
   alignas(1024) uint8_t b[NBT][BN * 128];                // weight tiles, one per tap (SWIZZLE_128B, K-major)
   alignas(1024) uint8_t win[WS][kWin * KU * 2];          // staged input windows (KU = 64: SWIZZLE_128B, 32: SWIZZLE_64B)
@@ -190,16 +194,29 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
   if (threadIdx.x == 0) PW_DBG(0);
   pdl_launch_dependents();
   pdl_wait();                                 // everything below depends on the predecessor's outputs
+  // Column split (wide layers with few rows: 61 row tiles of a 256-channel layer leave 87 SMs idle and the busy ones
+  // MMA-bound; two CTAs per row share, one per 128-column half, halve that): CTA c owns column block c % n_split.
+  const int col_blk = (int)blockIdx.x % P.n_split, share_a = (int)blockIdx.x / P.n_split;
+  const int share_b = share_a + (P.plan_grid + P.n_split - 1) / P.n_split;      // second row share of a split CTA
+  const int col0 = col_blk * BN, cout_l = min(BN, P.cout - col0);
   // the window starts of this CTA's first tile do not depend on the live row count: their load travels together with it
   int4 lo_first = make_int4(0, 0, 0, 0);
   if (warp == kLoaderWarp && lane == 0)
-    lo_first = __ldg(reinterpret_cast<const int4*>(P.plan + (size_t)blockIdx.x * P.tiles_per_cta * kPlanBytes + kPlanLo));
+    lo_first = __ldg(reinterpret_cast<const int4*>(P.plan + (size_t)share_a * P.tiles_per_cta * kPlanBytes + kPlanLo));
   const int rows = P.num_rows ? min(*P.num_rows, P.rows_cap) : P.rows_cap;
   // balanced schedule (as conv_tcgen05.cu): equal contiguous row shares, walked in 128-row tiles
-  const int share = win_share(rows, (int)gridDim.x);
-  const int row_begin = min(rows, (int)blockIdx.x * share);
-  const int row_end = min(rows, row_begin + share);
-  const int n_tiles = (row_end - row_begin + BLOCK_M - 1) / BLOCK_M;
+  const int share = win_share(rows, P.plan_grid);
+  const int beg_a = min(rows, share_a * share), end_a = min(rows, beg_a + share);
+  const int tiles_a = (end_a - beg_a + BLOCK_M - 1) / BLOCK_M;
+  const bool has_b = P.n_split > 1 && share_b < P.plan_grid;
+  const int beg_b = has_b ? min(rows, share_b * share) : rows, end_b = has_b ? min(rows, beg_b + share) : rows;
+  const int n_tiles = tiles_a + (end_b - beg_b + BLOCK_M - 1) / BLOCK_M;
+  // tile t of this CTA: first row, end of its share, plan record
+  auto tile_row0 = [&](int t) { return t < tiles_a ? beg_a + t * BLOCK_M : beg_b + (t - tiles_a) * BLOCK_M; };
+  auto tile_end = [&](int t) { return t < tiles_a ? end_a : end_b; };
+  auto tile_plan = [&](int t) {
+    return P.plan + ((size_t)(t < tiles_a ? share_a : share_b) * P.tiles_per_cta + (t < tiles_a ? t : t - tiles_a)) * kPlanBytes;
+  };
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -266,7 +283,7 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
           }
           { PW_T0(); mbar_wait(&sm.map_full[tile % 3], (uint32_t)(tile / 3) & 1u); PW_ACC(w_map); }
           cur_tile = tile;
-          row0 = row_begin + tile * BLOCK_M;
+          row0 = tile_row0(tile);
           s_plan = sm.plan[tile % 3];
         }
         const uint32_t aslot = (uint32_t)grp, aph = (u / kASlots) & 1u;
@@ -325,15 +342,15 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
     // ===================== loader: plan copies, staged windows, weight tiles =====================
     if (lane == 0) {
       uint32_t u = 0;
-      const uint8_t* plan_g = P.plan + (size_t)blockIdx.x * P.tiles_per_cta * kPlanBytes;
       // plan of `tile` -> ring slot tile % 3 (free once every builder warp has read tile - 3's entries); its window
       // starts come straight from global memory so the first window load does not wait for the copy
       auto prefetch_plan = [&](int tile, int4& lo) {
         const int buf = tile % 3;
         mbar_wait(&sm.map_empty[buf], ((uint32_t)(tile / 3) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&sm.map_full[buf], kPlanBytes);
-        bulk_copy_g2s(smem_u32(sm.plan[buf]), plan_g + (size_t)tile * kPlanBytes, kPlanBytes, &sm.map_full[buf]);
-        lo = __ldg(reinterpret_cast<const int4*>(plan_g + (size_t)tile * kPlanBytes + kPlanLo));
+        const uint8_t* plan_g = tile_plan(tile);
+        bulk_copy_g2s(smem_u32(sm.plan[buf]), plan_g, kPlanBytes, &sm.map_full[buf]);
+        lo = __ldg(reinterpret_cast<const int4*>(plan_g + kPlanLo));
       };
       int4 lo_next = make_int4(0, 0, 0, 0);
       if (n_tiles > 0) {
@@ -363,7 +380,7 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
         mbar_arrive_expect_tx(&sm.b_full[0], (uint32_t)(9 * P.n_chunks) * BN * 128);
         for (int kc = 0; kc < P.n_chunks; ++kc)
           for (int t = 0; t < 9; ++t)
-            tma_load_2d(smem_u32(sm.b[kc * 9 + t]), &tmap_w, t * P.cin + kc * KU, 0, &sm.b_full[0]);
+            tma_load_2d(smem_u32(sm.b[kc * 9 + t]), &tmap_w, t * P.cin + kc * KU, col0, &sm.b_full[0]);
       } else {
         uint32_t u = 0;
         for (int tile = 0; tile < n_tiles; ++tile)
@@ -374,7 +391,7 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
               mbar_arrive_expect_tx(&sm.b_full[bs], 3 * BN * 128);
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx)
-                tma_load_2d(smem_u32(sm.b[bs * 3 + kx]), &tmap_w, (ky * 3 + kx) * P.cin + kc * KU, 0, &sm.b_full[bs]);
+                tma_load_2d(smem_u32(sm.b[bs * 3 + kx]), &tmap_w, (ky * 3 + kx) * P.cin + kc * KU, col0, &sm.b_full[bs]);
             }
       }
     }
@@ -434,14 +451,14 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
     const int e = warp - kEpilogueWarp0;
     const int etid = threadIdx.x - kEpilogueWarp0 * 32;
     for (int i = etid; i < BN; i += kEpilogueThreads) {
-      sm.scale[i] = (i < P.cout && P.scale) ? __ldg(P.scale + i) : 1.f;
-      sm.shift[i] = (i < P.cout && P.shift) ? __ldg(P.shift + i) : 0.f;
+      sm.scale[i] = (i < cout_l && P.scale) ? __ldg(P.scale + col0 + i) : 1.f;
+      sm.shift[i] = (i < cout_l && P.shift) ? __ldg(P.shift + col0 + i) : 0.f;
     }
     named_bar_sync(2, kEpilogueThreads);
     uint32_t res_ph = 0u;
     for (int tile = 0; tile < n_tiles; ++tile) {
       const uint32_t acc = (uint32_t)tile & 1u, acc_ph = ((uint32_t)tile >> 1) & 1u;
-      const int row = row_begin + tile * BLOCK_M + e * 32 + lane;
+      const int row = tile_row0(tile) + e * 32 + lane, row_end = tile_end(tile);
       const bool row_ok = row < row_end;
       const bool full_box = BN >= 32 && row - lane + 32 <= row_end;     // the warp's 32 rows are all live rows of this CTA
       const bool box_ok = full_box && P.tma_store != 0;
@@ -455,7 +472,7 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
           mbar_arrive_expect_tx(&sm.res_full[e], NCH * 2048);
 #pragma unroll
           for (int c = 0; c < NCH; ++c)
-            tma_load_2d(smem_u32(sm.stage_res[e][c]), &tmap_r, c * 32, row, &sm.res_full[e]);
+            tma_load_2d(smem_u32(sm.stage_res[e][c]), &tmap_r, col0 + c * 32, row, &sm.res_full[e]);
         }
         __syncwarp();
       }
@@ -466,19 +483,19 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
       constexpr int CH = BN < 32 ? 16 : 32;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
-        if (c0 >= P.cout) break;   // warp-uniform
+        if (c0 >= cout_l) break;   // warp-uniform
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * BN + c0;
         if (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         tmem_wait_ld();
         if (row_ok) {
-          const int nvalid = min(CH, P.cout - c0);
+          const int nvalid = min(CH, cout_l - c0);
           float f[CH];
 #pragma unroll
           for (int j = 0; j < CH; ++j) f[j] = fmaf(__uint_as_float(v[j]), sm.scale[c0 + j], sm.shift[c0 + j]);
-          __nv_bfloat16* op = P.out + (long long)row * P.out_ld + P.out_coff + c0;
+          __nv_bfloat16* op = P.out + (long long)row * P.out_ld + P.out_coff + col0 + c0;
           if (P.residual) {
-            const __nv_bfloat16* rp = P.residual + (long long)row * P.res_ld + c0;
+            const __nv_bfloat16* rp = P.residual + (long long)row * P.res_ld + col0 + c0;
             if (CH == 32 && res_box) {
               const uint8_t* rb = sm.stage_res[e][c0 / 32];
 #pragma unroll
@@ -529,7 +546,7 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmap_o, smem_u32(stg), P.out_coff + c0, row - lane);
+              tma_store_2d(&tmap_o, smem_u32(stg), P.out_coff + col0 + c0, row - lane);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           } else if (nvalid == CH && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
@@ -611,7 +628,7 @@ struct WinGeom {
 };
 inline WinGeom win_geom(int rows_cap) {
   const int sms = pn_detail::sm_count();
-  const long long shares = PN_DIVUP((long long)rows_cap, 64ll);
+  const long long shares = PN_DIVUP((long long)rows_cap, (long long)BLOCK_M);
   WinGeom g;
   g.grid = (int)(shares < sms ? (shares < 1 ? 1 : shares) : sms);
   g.tiles_per_cta = PN_DIVUP(win_share(rows_cap, g.grid), BLOCK_M);
@@ -696,8 +713,11 @@ int conv_win(const pn_conv_args* a, cudaStream_t stream) {
   const int ku = a->cin == 32 ? 32 : 64;
   if (a->cin % ku != 0 || a->in_ld % 8 != 0 || (reinterpret_cast<uintptr_t>(a->in) & 15u) != 0) return PN_ERR_UNSUPPORTED;
   if (a->k_pad % 64 != 0 || (reinterpret_cast<uintptr_t>(a->weight) & 15u) != 0) return PN_ERR_UNSUPPORTED;
-  if (a->cout > 128 || a->cout % 8 != 0) return PN_ERR_UNSUPPORTED;
+  if (a->cout > 256 || a->cout % 8 != 0) return PN_ERR_UNSUPPORTED;
+  if (a->cout > 128 && ku != 64) return PN_ERR_UNSUPPORTED;
   if ((long long)a->in_rows * a->in_ld * 2 >= (1ll << 32)) return PN_ERR_UNSUPPORTED;
+  // 256 output channels: two CTAs per row share, one per 128-column half.  (One 256-wide tile per CTA measured 18-20 us
+  // against 13 us on the 7.8k-row stage-4 layers: 61 busy SMs, each MMA-bound.)
   const int bn = a->cout <= 32 ? 32 : a->cout <= 64 ? 64 : 128;
   CUtensorMap map_w, map_in, map_o;
   int rc = pn_tmap::get(a->weight, a->cout, a->k_pad, a->k_pad, 64, bn, CU_TENSOR_MAP_SWIZZLE_128B, &map_w);
@@ -713,6 +733,8 @@ int conv_win(const pn_conv_args* a, cudaStream_t stream) {
   if (geo.grid <= 0) return PN_ERR_CUDA;
   w.plan = reinterpret_cast<const uint8_t*>(a->nbr_plan);
   w.tiles_per_cta = geo.tiles_per_cta;
+  w.plan_grid = geo.grid;
+  w.n_split = PN_DIVUP(a->cout, bn);
   w.n_chunks = a->cin / ku;
   w.scale = a->scale;
   w.shift = a->shift;
@@ -740,7 +762,7 @@ int conv_win(const pn_conv_args* a, cudaStream_t stream) {
       (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0 &&
       pn_tmap::get(a->residual, a->rows_cap, a->cout, a->res_ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, &map_r) == PN_OK)
     w.tma_res = 1;
-  const int grid = geo.grid;
+  const int grid = PN_DIVUP(geo.grid, w.n_split) * w.n_split;
   // weights resident in shared memory when the whole layer fits beside the window ring (72 KB)
   const bool res = (long long)9 * w.n_chunks * bn * 128 <= 72 * 1024 && w.n_chunks == 1;
   // WS (window ring) is a multiple of AS (builder groups): a window slot is then always consumed by the same group,

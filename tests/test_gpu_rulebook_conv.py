@@ -324,7 +324,7 @@ def _clustered_sites(rng, B, H, W, n):
     return idx
 
 
-@pytest.mark.parametrize("c,HW,B", [(32, 200, 2), (64, 160, 1), (128, 120, 2), (64, 40, 1)])
+@pytest.mark.parametrize("c,HW,B", [(32, 200, 2), (64, 160, 1), (128, 120, 2), (64, 40, 1), (256, 96, 2)])
 def test_window_staged_subm_conv_equals_gather_kernel(c, HW, B):
     """conv_win_tc.cu (nbr_kind = PN_NBR_SUBM_SORTED) against the gather kernel (nbr_kind = 0) and the fp32-FMA path
     on identical bf16 operands, with residual + ReLU, partial last tiles and rows beyond the live count untouched."""
