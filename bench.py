@@ -38,6 +38,8 @@ def _peaks():
 
 def _conv_bytes(r):
     """algorithmic bytes of one conv launch: bf16 activations in and out once, weights once"""
+    if r.get("bytes") is not None:          # grouped head convs: n_groups planar 64-channel maps in, f32 columns out
+        return int(r["bytes"])
     return int(2 * r["rows"] * (r["cin"] + r["cout"]) + 2 * r["taps"] * r["cin"] * r["cout"])
 
 
@@ -178,8 +180,7 @@ def conv_breakdown(engine, reps=3):
         # rulebook and the layer fits it (cout <= 256); gather kernel (conv_tcgen05.cu) otherwise
         kname = "k_conv_win" if (kw.get("nbr_plan") is not None and kw.get("nbr_kind") and cout <= 256
                                  and inp.dtype == torch.bfloat16 and out.dtype == torch.bfloat16) else "k_conv_tc"
-        recs.append((taps, cin, cout, kw.get("rows_cap") or out.shape[0], kw.get("num"), s, e, kname, nbr,
-                     kw.get("deconv")))
+        recs.append((taps, cin, cout, kw.get("rows_cap") or out.shape[0], kw.get("num"), s, e, kname, nbr, None))
         return r
 
     model = engine.model
@@ -223,12 +224,27 @@ def conv_breakdown(engine, reps=3):
             r = orig_grouped(inp, in_coff, cin, n_groups, n_frames, H, W, weight, shift, group_tab, out, **kw)
         e.record()
         # useful FLOPs: every group maps cin channels to its own few outputs (sum = packed output columns)
-        recs.append((9, cin, int(out.shape[1]), n_frames * H * W, None, s, e, "k_conv_dense_grouped", None, None))
+        recs.append((9, cin, int(out.shape[1]), n_frames * H * W, None, s, e, "k_conv_dense_grouped", None,
+                     inp.numel() * 2 + out.numel() * 4 + weight.numel() * 2))
+        return r
+
+    orig_shift = ops.conv_dense3x3_grouped_shift
+
+    def timed_shift(inp, n_groups, n_frames, H, W, weight, shift, group_tab, out):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(inner[0]):
+            r = orig_shift(inp, n_groups, n_frames, H, W, weight, shift, group_tab, out)
+        e.record()
+        # same useful FLOPs as the implicit-GEMM form it replaces; the kernel itself is bound by reading `inp` once
+        recs.append((9, 64, int(out.shape[1]), n_frames * H * W, None, s, e, "k_conv_shift", None,
+                     inp.numel() * 2 + out.numel() * 4 + weight.numel() * 2))
         return r
 
     ops.conv_gather = timed
     ops.conv_dense3x3, ops.conv3x3_small_cout = timed_dense, timed_small
     ops.conv_dense3x3_grouped = timed_grouped
+    ops.conv_dense3x3_grouped_shift = timed_shift
     try:
         with torch.cuda.stream(engine.stream), torch.no_grad():
             for rep in range(reps + 1):
@@ -253,10 +269,11 @@ def conv_breakdown(engine, reps=3):
         ops.conv_gather = orig
         ops.conv_dense3x3, ops.conv3x3_small_cout = orig_dense, orig_small
         ops.conv_dense3x3_grouped = orig_grouped
+        ops.conv_dense3x3_grouped_shift = orig_shift
     per_pass = recs[recs_start:]
     shapes = {}
     pair_cache = {}
-    for taps, cin, cout, rows_cap, num, s, e, kname, nbr, deconv in recs:
+    for taps, cin, cout, rows_cap, num, s, e, kname, nbr, abytes in recs:
         rows = rows_cap if num is None else min(int(num.item()), rows_cap)
         # rulebook pairs P = present neighbours (SURVEY §8d counts a sparse conv as 2*P*Cin*Cout, not rows*taps: the
         # zero-filled taps of absent neighbours are not work)
@@ -268,14 +285,14 @@ def conv_breakdown(engine, reps=3):
         else:
             pairs = rows * taps
         key = (taps, cin, cout, rows, kname, pairs)
-        d = shapes.setdefault(key, dict(us=0.0, n=0))
+        d = shapes.setdefault(key, dict(us=0.0, n=0, bytes=abytes))
         d["us"] += s.elapsed_time(e) * 1e3 / 4
         d["n"] += 1
     out = []
     for (taps, cin, cout, rows, kname, pairs), d in shapes.items():
         flop = 2.0 * pairs * cin * cout
         avg = d["us"] / d["n"]
-        out.append(dict(kernel=kname, taps=taps, cin=cin, cout=cout, rows=rows, pairs=pairs,
+        out.append(dict(kernel=kname, taps=taps, cin=cin, cout=cout, rows=rows, pairs=pairs, bytes=d["bytes"],
                         launches_per_pass=d["n"], avg_us=avg, flop=flop,
                         tflops=flop / avg / 1e6, tflops_zero_filled=2.0 * rows * taps * cin * cout / avg / 1e6,
                         total_us_per_pass=d["us"]))
@@ -538,6 +555,7 @@ def run_gpu(args):
         families = [dict(kernel=k, launches_per_pass=f["launches"], total_us_per_pass=f["us"],
                          share_of_step=f["us"] / step_us, tflops=f["flop"] / f["us"] / 1e6,
                          frac=f["flop"] / f["us"] / 1e6 / tf_peak,
+                         algorithmic_gbs=f["bytes"] / f["us"] / 1e3,
                          algorithmic_bytes_per_launch=int(f["bytes"] / max(1, f["launches"])))
                     for k, f in fams.items()]
         families.sort(key=lambda r: -r["total_us_per_pass"])

@@ -285,6 +285,19 @@ int pn_conv_dense3x3_grouped(const void* in, int in_ld, int in_coff, int cin, in
                              const int* group_tab, void* out, int out_dtype, int out_ld, int out_compact,
                              int relu, int in_planar, pn_stream_t stream);
 
+/* The same grouped last conv (center_head.py:34-35: Conv2d(64, cout <= 3, 3, padding=1, bias=True) of every branch) as
+ * ONE 1x1 GEMM per branch plus nine shifted sums: out[q, c] = bias[c] + sum_tap Y[q + off(tap), 3 tap + c] with
+ * Y = h_g * W'_g (N = 27 of 32).  Reads the planar intermediate once (HBM bound) where the implicit-GEMM form is bound
+ * by N = 16 MMAs.  bf16 tensor-core mode only; the fp32 twin stays pn_conv3x3_small_cout.
+ *   in: bf16 [(n_groups * n_pos), 64], n_pos = n_frames*(H+2)*(W+2), borders zero (pn_conv_dense3x3 with
+ *       out_group_cols = 64); weight: bf16 [n_groups*32][64], row g*32 + 3*tap + c = W_g[c, :, tap], unused rows zero;
+ *   shift: f32 [n_groups*4] biases (NULL: none); group_tab: int32 [n_groups][2] = {first output column, cout <= 3};
+ *   out: f32 compact rows (n_frames*H*W, out_ld).
+ * PN_ERR_UNSUPPORTED when W + 3 > 256 (a shift must stay within two 128-row tiles). */
+int pn_conv_dense3x3_grouped_shift(const void* in, int n_groups, int n_frames, int H, int W, const void* weight,
+                                   const float* shift, const int* group_tab, float* out, int out_ld,
+                                   pn_stream_t stream);
+
 /* Training targets on the GPU (SURVEY §8 f rank 1): AssignLabel of the reference's data pipeline
  * (det3d/datasets/pipelines/preprocess.py:248-317) for ONE task: per object the Gaussian radius
  * (center_utils.py:16-38), the heat-map patch (draw_umich_gaussian, :48-64) and the regression targets.

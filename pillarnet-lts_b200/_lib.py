@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpillarnet_b200.so")
 PN_F32, PN_BF16 = 0, 1
 PN_IMPL_SIMT, PN_IMPL_TCGEN05 = 0, 1
 PN_NBR_ANY, PN_NBR_SUBM_SORTED = 0, 1
+PN_ERR_UNSUPPORTED = 4
 
 
 class ConvArgs(Structure):
@@ -89,6 +90,8 @@ SIGNATURES = {
     "pn_conv_dense3x3_grouped": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                          c_void_p]),
+    "pn_conv_dense3x3_grouped_shift": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_int, c_void_p]),
     "pn_bn_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "pn_bn_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -163,9 +163,17 @@ class CenterHead(nn.Module):
                 hc = two_level[0][2][0].out_channels
                 if inter.pad and hc % 64 == 0 and inter.coff == 0:
                     # tensor-core grouped conv on the padded layout (reads the intermediate 3x, not 9x)
-                    wg, sg, tab = self._final_groups_tc(fi, entries, slot, t_off, hc)
-                    ops.conv_dense3x3_grouped(inter.rows, 0, hc, len(entries), feat.B, feat.H, feat.W, wg, sg, tab,
-                                              all_rows, out_compact=True, in_planar=planar)
+                    # planar 64-channel intermediate, <= 3 outputs per branch, map narrow enough for the halo:
+                    # 1x1 GEMM + nine shifted sums (conv_shift_tc.cu), else the implicit-GEMM grouped conv
+                    if (planar and hc == 64 and feat.W + 3 <= 256
+                            and all(e[2][-1].out_channels <= 3 for e in entries)):
+                        ws, bs, tab = self._final_groups_shift(fi, entries, slot, t_off, hc)
+                        ops.conv_dense3x3_grouped_shift(inter.rows, len(entries), feat.B, feat.H, feat.W, ws, bs, tab,
+                                                        all_rows)
+                    else:
+                        wg, sg, tab = self._final_groups_tc(fi, entries, slot, t_off, hc)
+                        ops.conv_dense3x3_grouped(inter.rows, 0, hc, len(entries), feat.B, feat.H, feat.W, wg, sg,
+                                                  tab, all_rows, out_compact=True, in_planar=planar)
                 else:
                     groups, wbuf = self._final_groups(fi, entries, slot, t_off, hc)
                     ops.conv3x3_small_cout(inter.rows, inter.rows.stride(0), hc, feat.B, feat.H, feat.W, groups,
@@ -234,6 +242,41 @@ class CenterHead(nn.Module):
         tabd = torch.tensor(tab, dtype=torch.int32).to(dev)
         cache[fi] = (key, wg, b, tabd)
         return wg, b, tabd
+
+    def _final_groups_shift(self, fi, entries, slot, t_off, hc):
+        """bf16 [G*32][64] weights (row g*32 + 3*tap + c = W_g[c, :, tap]), f32 [G*4] biases and the device
+        {out column, cout} table for pn_conv_dense3x3_grouped_shift (cached on parameter versions)"""
+        finals = [e[2][-1] for e in entries]
+        key = tuple((f.weight.data_ptr(), f.weight._version, f.bias.data_ptr(), f.bias._version) for f in finals)
+        cache = self.__dict__.setdefault("_pn_final_groups_shift", {})
+        hit = cache.get(fi)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2], hit[3]
+        G = len(entries)
+        dev = finals[0].weight.device
+        w = torch.zeros(G, 9, 3, hc, dtype=torch.float32, device=dev)
+        b = torch.zeros(G, 4, dtype=torch.float32, device=dev)
+        tab = [[0, 0] for _ in range(G)]
+        for t, name, fc in entries:
+            g = slot[id(fc)]
+            f = fc[-1]
+            c = f.out_channels
+            th = self.task_heads[t]
+            col = t_off[t]
+            for nm in th.heads:
+                if nm == name:
+                    break
+                col += th.heads[nm][0]
+            # (cout, cin, 3, 3) -> (tap = 3 dy + dx, cout, cin)
+            w[g, :, :c] = f.weight.detach().float().permute(2, 3, 0, 1).reshape(9, c, hc)
+            b[g, :c] = f.bias.detach().float()
+            tab[g] = [col, c]
+        w32 = torch.zeros(G, 32, hc, dtype=torch.float32, device=dev)
+        w32[:, :27] = w.reshape(G, 27, hc)
+        ws = w32.reshape(G * 32, hc).to(torch.bfloat16).contiguous()
+        tabd = torch.tensor(tab, dtype=torch.int32).to(dev)
+        cache[fi] = (key, ws, b.reshape(-1).contiguous(), tabd)
+        return ws, cache[fi][2], tabd
 
     def _final_groups(self, fi, entries, slot, t_off, hc):
         """device descriptors + packed fp32 weights of all final convs on feature `fi` (cached on versions)"""

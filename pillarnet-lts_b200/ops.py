@@ -302,6 +302,18 @@ def conv_dense3x3_grouped(inp, in_coff, cin, n_groups, n_frames, H, W, weight, s
     return out
 
 
+def conv_dense3x3_grouped_shift(inp, n_groups, n_frames, H, W, weight, shift, group_tab, out):
+    """the grouped last conv of the CenterHead branches as one 1x1 GEMM per branch + nine shifted sums (C header);
+    raises NotImplementedError when the map is too wide for the kernel's halo (callers fall back to the grouped conv)"""
+    lib = _lib.load()
+    rc = lib.pn_conv_dense3x3_grouped_shift(ptr(inp), n_groups, n_frames, H, W, ptr(weight), ptr(shift), ptr(group_tab),
+                                            ptr(out), out.stride(0), stream_ptr())
+    if rc == _lib.PN_ERR_UNSUPPORTED:
+        raise NotImplementedError("pn_conv_dense3x3_grouped_shift: map too wide")
+    check(rc, "pn_conv_dense3x3_grouped_shift")
+    return out
+
+
 def pack_weight_bf16(w_f32_2d, k_pad=None):
     """(Cout,K) f32 -> (Cout,k_pad) bf16 with K zero-padded to a multiple of 64."""
     lib = _lib.load()

@@ -149,6 +149,66 @@ def test_planar_intermediate_layout_matches_interleaved():
     assert float(out_a.abs().max()) > 0.1
 
 
+@pytest.mark.parametrize("B,H,W,G", [(2, 23, 31, 5), (1, 180, 180, 36), (3, 7, 5, 3), (1, 40, 253, 2), (2, 64, 64, 150)])
+def test_grouped_last_conv_as_gemm_plus_shifted_sums(B, H, W, G):
+    """pn_conv_dense3x3_grouped_shift (1x1 GEMM per branch + nine shifted sums) on the planar padded intermediate vs
+    F.conv2d on the same bf16 operands (2e-3 rel-to-max: fp32 accumulation, different summation order) and vs the
+    implicit-GEMM grouped kernel; strips with halos, several frames, more branches than SMs, columns outside the
+    groups untouched; maps wider than the halo are refused."""
+    from pillarnet_lts_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + H + G)
+    hc = 64
+    x = (torch.randn(G, B, H, W, hc, device="cuda", generator=g)).relu().to(torch.bfloat16)
+    n_pos = B * (H + 2) * (W + 2)
+    planar = torch.stack([_pad_rows(x[i]) for i in range(G)]).reshape(G * n_pos, hc).contiguous()
+    couts = [(1, 2, 3)[i % 3] for i in range(G)]
+    ws = [torch.randn(c, hc, 3, 3, device="cuda", generator=g) * 0.1 for c in couts]
+    bs = [torch.randn(c, device="cuda", generator=g) for c in couts]
+    w32 = torch.zeros(G, 32, hc, device="cuda")
+    b4 = torch.zeros(G, 4, device="cuda")
+    wf = torch.zeros(G * 16, 9 * hc, device="cuda")
+    bf = torch.zeros(G * 16, device="cuda")
+    tab, col = [], 2
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        c = w.shape[0]
+        w32[i, :27] = torch.nn.functional.pad(w.permute(2, 3, 0, 1).reshape(9, c, hc), (0, 0, 0, 3 - c)).reshape(27, hc)
+        b4[i, :c] = b
+        wf[i * 16:i * 16 + c] = w.permute(0, 2, 3, 1).reshape(c, -1)
+        bf[i * 16:i * 16 + c] = b
+        tab.append([col, c])
+        col += c
+    wsh = w32.reshape(G * 32, hc).to(torch.bfloat16).contiguous()
+    tabd = torch.tensor(tab, dtype=torch.int32).cuda()
+    out = torch.full((B * H * W, col + 3), -9.0, device="cuda")
+    ops.conv_dense3x3_grouped_shift(planar, G, B, H, W, wsh, b4.reshape(-1).contiguous(), tabd, out)
+    ref = torch.full((B * H * W, col + 3), -9.0, device="cuda")
+    ops.conv_dense3x3_grouped(planar, 0, hc, G, B, H, W, ops.pack_weight_bf16(wf), bf, tabd, ref, out_compact=True,
+                              in_planar=True)
+    torch.cuda.synchronize()
+    assert bool((out[:, :2] == -9.0).all()) and bool((out[:, col:] == -9.0).all())
+    c0 = 2
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        c = w.shape[0]
+        wq = w.to(torch.bfloat16).float()
+        want = F.conv2d(x[i].float().permute(0, 3, 1, 2), wq, b, padding=1).permute(0, 2, 3, 1)
+        got = out[:, c0:c0 + c].view(B, H, W, c)
+        tol = 2e-3 * max(1.0, want.abs().max().item())
+        assert (got - want).abs().max().item() <= tol, i
+        assert (got - ref[:, c0:c0 + c].view(B, H, W, c)).abs().max().item() <= tol, i
+        c0 += c
+
+
+def test_grouped_shift_refuses_maps_wider_than_its_halo():
+    from pillarnet_lts_b200 import ops
+    G, B, H, W, hc = 1, 1, 4, 300, 64
+    planar = torch.zeros(G * B * (H + 2) * (W + 2), hc, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(NotImplementedError):
+        ops.conv_dense3x3_grouped_shift(planar, G, B, H, W, torch.zeros(32, hc, device="cuda", dtype=torch.bfloat16),
+                                        torch.zeros(4, device="cuda"), torch.tensor([[0, 1]], dtype=torch.int32).cuda(),
+                                        torch.zeros(B * H * W, 1, device="cuda"))
+
+
 @pytest.mark.parametrize("B,H,W,cin,cout,coff,width", [(1, 12, 9, 64, 64, 0, 64), (2, 45, 45, 256, 256, 256, 512),
                                                         (1, 90, 90, 256, 128, 8, 136), (1, 5, 7, 128, 48, 0, 48)])
 def test_deconv2x2_gemm_form_vs_torch_and_gather_form(B, H, W, cin, cout, coff, width):

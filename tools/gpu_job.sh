@@ -14,6 +14,7 @@
 #   ncu_k:<regex>    ncu --set full of the kernels matching <regex>           -> gpurun_out/prof_k.ncu-rep
 #   ncu_convs        ncu --set full of the conv kernels                  -> gpurun_out/prof_convs.ncu-rep
 #   timeline         per-CTA pipeline timelines + stall accounting of every conv launch -> gpurun_out/timeline.txt
+#   kbench_head      the CenterHead conv pair in isolation (events)      -> gpurun_out/kbench_head.json
 #   kbench_reader    reader kernels at scale (events)                    -> gpurun_out/kbench_reader.json
 # Every ncu step first runs the same command plain (the recipe's rule) and only profiles if that exited 0.
 mkdir -p gpurun_out
@@ -77,6 +78,8 @@ for step in "$@"; do
     timeline)
       timeout 600 python tools/infer_timeline.py > gpurun_out/timeline.log 2> gpurun_out/timeline.txt; echo "timeline rc=$?"
       grep -A200 "pass 2" gpurun_out/timeline.txt | grep -A1 "conv_win\|conv_tc" | head -120 ;;
+    kbench_head)
+      timeout 300 python tools/kbench_head.py 2>&1 | tail -5 ;;
     kbench_reader)
       timeout 900 python tools/kbench_reader.py > gpurun_out/kbench_reader.log 2>&1; echo "kbench rc=$?"; tail -5 gpurun_out/kbench_reader.log ;;
     *)
