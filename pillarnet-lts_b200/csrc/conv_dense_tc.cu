@@ -30,8 +30,15 @@
 namespace {
 
 constexpr int BLOCK_K = 64;
-constexpr int kThreads = 384;            // warps 0-2: producers + MMA, 3: idle, 4-11: epilogue
-constexpr int kEpilogueThreads = 256;    // 8 warps: two per TMEM lane quarter, each takes every other column chunk
+constexpr int kThreads = 640;            // warps 0-2: producers + MMA, 3: idle, 4-19: epilogue
+// 16 epilogue warps: four per TMEM lane quarter, each takes every fourth 32-column chunk.  Measured with per-phase
+// clocks (8 warps): a 32x32 chunk cost ~1800 clk of a warp's time, its ~250 instructions issuing at one per ~7 clk
+// (two warps per scheduler, dependent chains, TMEM / shared-memory latencies), so every short-K layer ran at the
+// epilogue's pace (64 -> 2304 head conv: 94 us, 62 us with the stores compiled out).  Latency is hidden with warps,
+// not with software pipelining: 102 registers per thread leave no room for a prefetched second chunk anyway.
+constexpr int kEpilogueWarps = 16;
+constexpr int kEpilogueThreads = kEpilogueWarps * 32;
+constexpr int kColSets = kEpilogueWarps / 4;
 constexpr int kTailRows = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -299,16 +306,16 @@ struct DSmem {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
-  float scale[BN];
-  float shift[BN];
+  alignas(16) float2 ss[BN];       // {scale, shift} per output column of the current N tile, read two columns per LDS.128:
+                                   // a broadcast LDS.32 costs the shared-memory pipe a full wavefront, like 128 useful bytes
   // Epilogue staging for TMA tensor stores: 32 rows x 32 bf16 columns (2 KB, SWIZZLE_64B) per epilogue warp.  A
   // thread owns an output ROW, so its direct 16-byte stores of a warp instruction hit 32 different lines; the LSU
   // charges per line (~2 clk each, like the gathers of conv_tcgen05.cu): 27 clk per (128 rows x column) measured,
   // which made every short-K layer epilogue bound.  Staged, the warp issues four conflict-free STS.128 and one lane
   // hands the 2 KB box to the TMA unit.  Only in the variants whose operand stages leave 16 KB.
   static constexpr bool kTmaStore =
-      BN >= 32 && (size_t)SA * kSegRows * 128 + (size_t)SB * BROWS * 128 + 2048 + 8 * 2048 + 1024 <= 227 * 1024;
-  alignas(1024) uint8_t stage_out[kTmaStore ? 8 * 2048 : 16];
+      BN >= 32 && (size_t)SA * kSegRows * 128 + (size_t)SB * BROWS * 128 + 2048 + kEpilogueWarps * 2048 + 2 * BN * 4 + 1024 <= 227 * 1024;
+  alignas(1024) uint8_t stage_out[kTmaStore ? kEpilogueWarps * 2048 : 16];
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -575,7 +582,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int e = (warp - 4) & 3;          // TMEM lane quarter this warp may access (warp id % 4)
-    const int half = (warp - 4) >> 2;      // which of the two interleaved column-chunk sets
+    const int cset = (warp - 4) >> 2;      // which of the kColSets interleaved column-chunk sets
     const int etid = threadIdx.x - 4 * 32;
     const int hw_p = P.Hp * P.Wp;
     uint32_t tcount = 0;
@@ -595,8 +602,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       named_bar_sync(2, kEpilogueThreads);
       for (int i = etid; i < BN; i += kEpilogueThreads) {
         const bool ok = nbase + i < cout_t;
-        sm.scale[i] = (ok && P.scale) ? __ldg(P.scale + n0 + i) : 1.f;
-        sm.shift[i] = (ok && P.shift) ? __ldg(P.shift + n0 + i) : 0.f;
+        sm.ss[i] = make_float2((ok && P.scale) ? __ldg(P.scale + n0 + i) : 1.f, (ok && P.shift) ? __ldg(P.shift + n0 + i) : 0.f);
       }
       named_bar_sync(2, kEpilogueThreads);
       mbar_wait_relaxed(&sm.tmem_full[acc], acc_ph);
@@ -618,32 +624,33 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
           store = valid && !border;
           orow = ((long long)b * (P.Hp - 2) + (y - 1)) * (P.Wp - 2) + (x - 1);
         }
-        // software-pipelined over column chunks: the TMEM load of chunk c+1 is in flight while chunk c is
-        // converted and stored (tcgen05.wait::ld only covers loads issued before it)
         constexpr int CH = BN < 32 ? 16 : 32;
         const int n_ch = min(BN, cout_t - nbase + CH - 1) / CH;   // warp-uniform number of live chunks
         const uint32_t tbase = tmem_base + ((uint32_t)(e * 32) << 16) + acc * ACC_COLS + m * BN;
-        uint32_t v[32], w[32];
-        if (half < n_ch && !(P.dbg_mode & 2)) {
-          if (CH == 32) tmem_ld32(tbase + half * CH, v); else tmem_ld16(tbase + half * CH, v);
-        }
 #pragma unroll 1
-        for (int ci = half; ci < n_ch; ci += 2) {
+        for (int ci = cset; ci < n_ch; ci += kColSets) {
           const int c0 = ci * CH;
-          if (!(P.dbg_mode & 2)) tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < CH; ++j) w[j] = v[j];
-          if (ci + 2 < n_ch && !(P.dbg_mode & 2)) {
-            if (CH == 32) tmem_ld32(tbase + c0 + 2 * CH, v); else tmem_ld16(tbase + c0 + 2 * CH, v);
+          uint32_t w[32];
+          if (!(P.dbg_mode & 2)) {
+            if (CH == 32) tmem_ld32(tbase + c0, w); else tmem_ld16(tbase + c0, w);
+            tmem_wait_ld();
           }
           if (store && !(P.dbg_mode & 1)) {
             const int nvalid = min(CH, cout_t - (nbase + c0));
             float f[32];
+            const float4* ss4 = reinterpret_cast<const float4*>(&sm.ss[c0]);   // c0 % 16 == 0: 16-byte aligned
+            const bool affine = P.scale != nullptr || P.shift != nullptr;
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              float t = fmaf(__uint_as_float(w[j]), sm.scale[c0 + j], sm.shift[c0 + j]);
-              if (P.relu) t = fmaxf(t, 0.f);
-              f[j] = (border && !P.out_compact) ? 0.f : t;
+            for (int j = 0; j < CH; j += 2) {
+              float t0 = __uint_as_float(w[j]), t1 = __uint_as_float(w[j + 1]);
+              if (affine) {
+                const float4 s2 = ss4[j >> 1];
+                t0 = fmaf(t0, s2.x, s2.y);
+                t1 = fmaf(t1, s2.z, s2.w);
+              }
+              if (P.relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
+              f[j] = (border && !P.out_compact) ? 0.f : t0;
+              f[j + 1] = (border && !P.out_compact) ? 0.f : t1;
             }
             long long ooff = orow * P.out_ld + ocol0 + c0;
             if (P.out_group_cols > 0) {   // planar output: a CH-wide chunk never straddles two maps (gc % CH == 0)
@@ -998,10 +1005,10 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
   const long long units = PN_DIVUP(m_tiles, (long long)cl) * PN_DIVUP(cout, bn);
   if (two_sm && m_tiles >= 2) {
     // half-size weight stages: the freed shared memory buys deeper pipelines
-    if (mt == 2 && bn == 256) return launch<2, 256, 3, 6, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
-    if (mt == 1 && bn == 256) return launch<1, 256, 4, 8, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
-    if (mt == 2 && bn == 128) return launch<2, 128, 4, 8, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
-    return launch<1, 128, 6, 12, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
+    if (mt == 2 && bn == 256) return launch<2, 256, 3, 5, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
+    if (mt == 1 && bn == 256) return launch<1, 256, 4, 7, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
+    if (mt == 2 && bn == 128) return launch<2, 128, 4, 6, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
+    return launch<1, 128, 6, 10, 2, false, true>(ma, mtail, mw, mo, a, units, stream);
   }
 #define PN_DENSE_LAUNCH(MT_, BN_, SA_, SB_)                                                       \
   do {                                                                                            \
@@ -1009,10 +1016,11 @@ int pn_conv_dense3x3(const void* in, int in_ld, int in_coff, int cin, int n_fram
     if (cl == 2) return launch<MT_, BN_, SA_, SB_, 2>(ma, mtail, mw, mo, a, units, stream);           \
     return launch<MT_, BN_, SA_, SB_, 1>(ma, mtail, mw, mo, a, units, stream);                        \
   } while (0)
-  if (mt == 2 && bn == 256) PN_DENSE_LAUNCH(2, 256, 2, 4);
-  if (mt == 1 && bn == 256) PN_DENSE_LAUNCH(1, 256, 3, 5);
-  if (mt == 2 && bn == 128) PN_DENSE_LAUNCH(2, 128, 3, 6);
-  PN_DENSE_LAUNCH(1, 128, 4, 8);
+  // stage counts leave 32 KB for the epilogue's staging boxes (one 2 KB box per epilogue warp)
+  if (mt == 2 && bn == 256) PN_DENSE_LAUNCH(2, 256, 2, 3);
+  if (mt == 1 && bn == 256) PN_DENSE_LAUNCH(1, 256, 3, 4);
+  if (mt == 2 && bn == 128) PN_DENSE_LAUNCH(2, 128, 3, 5);
+  PN_DENSE_LAUNCH(1, 128, 4, 7);
 #undef PN_DENSE_LAUNCH
 }
 

@@ -14,12 +14,12 @@
 // nuScenes head) — HBM bound.
 //
 // Work unit = (branch g, strip of consecutive 128-row tiles): the branch's 4 KB weight tile stays resident, tiles are
-// walked in order, Y tiles land in a ring of six in shared memory (column-major: lanes = consecutive rows, conflict
+// walked in order, Y tiles land in a ring of eight in shared memory (column-major: lanes = consecutive rows, conflict
 // free) and tile t is summed once t+2 has arrived (|off| <= Wp + 1 <= 256 rows).  A strip recomputes two halo tiles on
 // each side (4 of ~65).
 //
-// Warp roles (384 threads, one persistent CTA per SM): 0 = TMA producer, 1 = TMEM owner + MMA issuer, 4-7 = drain
-// (TMEM -> Y ring), 8-11 = shifted sums + bias -> compact f32 output rows.
+// Warp roles (512 threads, one persistent CTA per SM): 0 = TMA producer, 1 = TMEM owner + MMA issuer, 4-7 = drain
+// (TMEM -> Y ring), 8-15 = shifted sums + bias -> compact f32 output rows (two groups of four, alternate tiles).
 #include <cuda.h>
 
 #include <cstdio>
@@ -38,10 +38,10 @@ constexpr int KC = 64;             // input channels (one 128-byte swizzle row)
 constexpr int NCOL = 32;           // GEMM N: 27 used columns (tap-major, 3 output slots per tap)
 constexpr int CP = 3;              // output slots per tap
 constexpr int NY = 9 * CP;
-constexpr int kStages = 8;         // input tiles in flight (16 KB each)
+constexpr int kStages = 6;         // input tiles in flight (16 KB each)
 constexpr int kHalo = 2;           // halo tiles on each side of a strip: covers |off| <= 256 rows
-constexpr int kYSlots = 2 * kHalo + 2;
-constexpr int kThreads = 384;
+constexpr int kYSlots = 2 * kHalo + 4;   // two sum groups at tiles t, t+1 hold t-2 .. t+3; two more for the drain to run ahead
+constexpr int kThreads = 512;
 constexpr int kDrainWarp0 = 4, kSumWarp0 = 8;
 
 struct SArgs {
@@ -51,12 +51,18 @@ struct SArgs {
   const int* group_tab;    // [n_groups][2] = {first output column, cout}
   float* out;              // compact rows b*H*W + (y-1)*W + (x-1)
   int out_ld;
+  unsigned long long* dbg; // PN_SHIFT_TIMELINE=1: per-CTA stall clocks [grid][16]
 };
+
+// stall accounting (debug launches only): clocks spent in a wait, summed per role by one lane
+#define SW_T0() const long long _w0 = P.dbg ? clock64() : 0
+#define SW_ACC(var) do { if (P.dbg) var += clock64() - _w0; } while (0)
+#define SW_OUT(slot, var) do { if (P.dbg) P.dbg[blockIdx.x * 16 + slot] = (unsigned long long)(var); } while (0)
 
 struct SSmem {
   alignas(1024) uint8_t h[kStages][TM * 128];
   alignas(1024) uint8_t w[2][NCOL * 128];
-  alignas(16) float y[NY][kYSlots * TM];     // Y ring, column-major: tile with ring counter c at positions (c % 6) * 128 + row
+  alignas(16) float y[NY][kYSlots * TM];     // Y ring, column-major: tile with ring counter c at positions (c % kYSlots) * 128 + row
   alignas(8) uint64_t h_full[kStages];
   uint64_t h_empty[kStages], w_full[2], w_empty[2], tmem_full[2], tmem_empty[2], y_full[kYSlots], y_empty[kYSlots];
   uint32_t tmem_base;
@@ -75,7 +81,7 @@ k_conv_shift(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
         mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], 1);
         mbar_init(&sm.tmem_full[s], 1); mbar_init(&sm.tmem_empty[s], 128);
       }
-      for (int s = 0; s < kYSlots; ++s) { mbar_init(&sm.y_full[s], 128); mbar_init(&sm.y_empty[s], 128); }
+      for (int s = 0; s < kYSlots; ++s) { mbar_init(&sm.y_full[s], 128); mbar_init(&sm.y_empty[s], 256); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -99,6 +105,8 @@ k_conv_shift(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0, uc = 0;
+      long long w_hempty = 0;
+      const long long t_begin = P.dbg ? clock64() : 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         int g, t0, n;
         unit_range(u, g, t0, n);
@@ -113,17 +121,20 @@ k_conv_shift(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
         const int row_base = g * P.n_pos + (t0 - kHalo) * TM;
         for (int i = 0; i < n; ++i, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-          mbar_wait(&sm.h_empty[s], ph ^ 1u);
+          { SW_T0(); mbar_wait(&sm.h_empty[s], ph ^ 1u); SW_ACC(w_hempty); }
           mbar_arrive_expect_tx(&sm.h_full[s], TM * 128);
           tma_load_2d(smem_u32(sm.h[s]), &tmap_h, 0, row_base + i * TM, &sm.h_full[s]);
         }
       }
+      SW_OUT(0, w_hempty); SW_OUT(1, (P.dbg ? clock64() : 0) - t_begin); SW_OUT(2, it);
     }
   } else if (warp == 1) {
     const bool issuer = elect_one();
     // M = 128, N = 32, bf16 x bf16 -> f32, both operands K-major
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     uint32_t it = 0, uc = 0;
+    long long w_tempty = 0, w_hfull = 0;
+    const long long t_begin = P.dbg ? clock64() : 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       int g, t0, n;
       unit_range(u, g, t0, n);
@@ -134,8 +145,8 @@ k_conv_shift(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
       for (int i = 0; i < n; ++i, ++it) {
         const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
         const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
-        mbar_wait(&sm.tmem_empty[acc], aph ^ 1u);
-        mbar_wait(&sm.h_full[s], ph);
+        { SW_T0(); mbar_wait(&sm.tmem_empty[acc], aph ^ 1u); SW_ACC(w_tempty); }
+        { SW_T0(); mbar_wait(&sm.h_full[s], ph); SW_ACC(w_hfull); }
         tcgen05_fence_after();
         if (issuer) {
           const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(sm.h[s]));
@@ -151,37 +162,46 @@ k_conv_shift(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
       __syncwarp();
       ++uc;
     }
+    if (issuer) { SW_OUT(3, w_tempty); SW_OUT(4, w_hfull); SW_OUT(5, (P.dbg ? clock64() : 0) - t_begin); }
   } else if (warp >= kDrainWarp0 && warp < kDrainWarp0 + 4) {
     // ===================== drain: accumulator (row = TMEM lane) -> Y ring, column-major =====================
     const int quarter = warp & 3, r = quarter * 32 + lane;
     uint32_t it = 0;
+    long long w_tfull = 0, w_yempty = 0;
+    const long long t_begin = P.dbg ? clock64() : 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       int g, t0, n;
       unit_range(u, g, t0, n);
       for (int i = 0; i < n; ++i, ++it) {
         const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
         const uint32_t ys = it % kYSlots, yph = (it / kYSlots) & 1u;
-        mbar_wait(&sm.tmem_full[acc], aph);
+        { SW_T0(); mbar_wait(&sm.tmem_full[acc], aph); SW_ACC(w_tfull); }
         tcgen05_fence_after();
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * NCOL, v);
         tmem_wait_ld();
         tcgen05_fence_before();
         mbar_arrive(&sm.tmem_empty[acc]);
-        mbar_wait(&sm.y_empty[ys], yph ^ 1u);
+        { SW_T0(); mbar_wait(&sm.y_empty[ys], yph ^ 1u); SW_ACC(w_yempty); }
 #pragma unroll
         for (int j = 0; j < NY; ++j) sm.y[j][ys * TM + r] = __uint_as_float(v[j]);
         mbar_arrive(&sm.y_full[ys]);       // release: the sum warps' acquire wait orders these stores before their loads
       }
     }
+    if (warp == kDrainWarp0 && lane == 0) { SW_OUT(6, w_tfull); SW_OUT(7, w_yempty); SW_OUT(8, (P.dbg ? clock64() : 0) - t_begin); }
   } else if (warp >= kSumWarp0) {
-    // ===================== shifted sums: thread = row of the tile =====================
-    const int r = (warp - kSumWarp0) * 32 + lane;
+    // ===================== shifted sums: thread = row of the tile, two warp groups take alternate tiles ==========
+    // (one group alone: ~660 clk of dependent index math + 27 LDS per tile on one warp per scheduler; measured with
+    // PN_SHIFT_TIMELINE, it paced the whole ring.)  Both groups release every tile: group p is done with tile k once its
+    // own sum of tile k+1 or k+2 has finished.
+    const int grp = (warp - kSumWarp0) >> 2, r = ((warp - kSumWarp0) & 3) * 32 + lane;
     constexpr int kRing = kYSlots * TM;
     int off[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) off[t] = (t / 3 - 1) * P.Wp + (t % 3 - 1);
-    uint32_t it = 0;
+    uint32_t it0 = 0;                 // ring counter of the unit's tile 0
+    long long w_yfull = 0;
+    const long long t_begin = P.dbg ? clock64() : 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       int g, t0, n;
       unit_range(u, g, t0, n);
@@ -190,45 +210,50 @@ k_conv_shift(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__
       float bias[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) bias[c] = (c < cout && P.shift) ? __ldg(P.shift + 4 * g + c) : 0.f;
-      // (frame, y, x) of this thread's row in the first real tile; advanced by 128 positions per tile
-      int q = t0 * TM + r;
+      // (frame, y, x) of this thread's row in the group's first tile; advanced by two tiles per step
+      int q = (t0 + grp) * TM + r;
       int b = q / (P.Hp * P.Wp), y = (q - b * P.Hp * P.Wp) / P.Wp, x = q - (b * P.Hp + y) * P.Wp;
-      for (int i = 0; i < n; ++i, ++it) {
-        // tile i has arrived (and, in order, every tile before it): tile ti = i - kHalo has its whole neighbourhood
-        mbar_wait(&sm.y_full[it % kYSlots], (it / kYSlots) & 1u);
-        const int ti = i - kHalo;
-        if (ti >= kHalo) {
-          if (q < P.n_pos && y >= 1 && y <= P.H && x >= 1 && x <= P.W) {
-            float a[CP];
+      int rel = 0;                    // next tile (unit-relative) this group has to release
+      for (int t = kHalo + grp; t < n - kHalo; t += 2) {
+        // tile t + kHalo has arrived (and, in order, every tile before it): tile t has its whole neighbourhood
+        const uint32_t cw = it0 + (uint32_t)(t + kHalo);
+        { SW_T0(); mbar_wait(&sm.y_full[cw % kYSlots], (cw / kYSlots) & 1u); SW_ACC(w_yfull); }
+        if (q < P.n_pos && y >= 1 && y <= P.H && x >= 1 && x <= P.W) {
+          float a[CP];
 #pragma unroll
-            for (int c = 0; c < CP; ++c) a[c] = bias[c];
-            const int pos0 = (int)((it - kHalo) % kYSlots) * TM + r;      // ring position of this row
+          for (int c = 0; c < CP; ++c) a[c] = bias[c];
+          const int pos0 = (int)((it0 + (uint32_t)t) % kYSlots) * TM + r;      // ring position of this row
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              int pos = pos0 + off[t];                                      // |off| <= 2 tiles < ring
-              pos += pos < 0 ? kRing : 0;
-              pos -= pos >= kRing ? kRing : 0;
-              const float* yp = &sm.y[t * CP][pos];
-#pragma unroll
-              for (int c = 0; c < CP; ++c)
-                if (c < cout) a[c] += yp[c * kRing];
-            }
-            float* op = P.out + ((long long)(b * P.H + (y - 1)) * P.W + (x - 1)) * P.out_ld + col;
+          for (int k = 0; k < 9; ++k) {
+            int pos = pos0 + off[k];                                            // |off| <= 2 tiles < ring
+            pos += pos < 0 ? kRing : 0;
+            pos -= pos >= kRing ? kRing : 0;
+            const float* yp = &sm.y[k * CP][pos];
 #pragma unroll
             for (int c = 0; c < CP; ++c)
-              if (c < cout) op[c] = a[c];
+              if (c < cout) a[c] += yp[c * kRing];
           }
-          q += TM;
-          x += TM;
-          while (x >= P.Wp) { x -= P.Wp; ++y; }
-          while (y >= P.Hp) { y -= P.Hp; ++b; }
-          // tile ti - kHalo is not needed any more
-          mbar_arrive(&sm.y_empty[(it - 2 * kHalo) % kYSlots]);
+          float* op = P.out + ((long long)(b * P.H + (y - 1)) * P.W + (x - 1)) * P.out_ld + col;
+#pragma unroll
+          for (int c = 0; c < CP; ++c)
+            if (c < cout) op[c] = a[c];
         }
+        q += 2 * TM;
+        x += 2 * TM;
+        while (x >= P.Wp) { x -= P.Wp; ++y; }
+        while (y >= P.Hp) { y -= P.Hp; ++b; }
+        // this group's next sum is tile t + 2, which reads tiles >= t: everything below is released
+        for (; rel < t; ++rel) mbar_arrive(&sm.y_empty[(it0 + (uint32_t)rel) % kYSlots]);
       }
-      // the last 2 * kHalo tiles of the unit were never released inside the loop
-      for (int k = 2 * kHalo; k >= 1; --k) mbar_arrive(&sm.y_empty[(it - k) % kYSlots]);
+      // unit end: the remaining tiles, once they have been written (an arrival must land in the phase of ITS use of the slot)
+      {
+        const uint32_t cw = it0 + (uint32_t)(n - 1);
+        SW_T0(); mbar_wait(&sm.y_full[cw % kYSlots], (cw / kYSlots) & 1u); SW_ACC(w_yfull);
+      }
+      for (; rel < n; ++rel) mbar_arrive(&sm.y_empty[(it0 + (uint32_t)rel) % kYSlots]);
+      it0 += (uint32_t)n;
     }
+    if (warp == kSumWarp0 && lane == 0) { SW_OUT(9, w_yfull); SW_OUT(10, (P.dbg ? clock64() : 0) - t_begin); }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -274,6 +299,14 @@ int pn_conv_dense3x3_grouped_shift(const void* in, int n_groups, int n_frames, i
   a.strip_tiles = PN_DIVUP(a.tiles_total, strips);
   a.strips = PN_DIVUP(a.tiles_total, a.strip_tiles);
   a.shift = shift; a.group_tab = group_tab; a.out = out; a.out_ld = out_ld;
+  a.dbg = nullptr;
+  static const bool timeline = [] { const char* e = getenv("PN_SHIFT_TIMELINE"); return e && e[0] == '1'; }();
+  static unsigned long long* dbg_buf = nullptr;
+  if (timeline) {
+    if (!dbg_buf) PN_CUDA(cudaMalloc(&dbg_buf, 16 * 1024 * sizeof(unsigned long long)));
+    PN_CUDA(cudaMemsetAsync(dbg_buf, 0, 16 * 1024 * sizeof(unsigned long long), stream));
+    a.dbg = dbg_buf;
+  }
   const int units = n_groups * a.strips;
   constexpr size_t smem = sizeof(SSmem) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
@@ -292,6 +325,20 @@ int pn_conv_dense3x3_grouped_shift(const void* in, int n_groups, int n_frames, i
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   PN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_shift, mh, mw, a));
   PN_CHECK_LAUNCH();
+  if (timeline) {
+    PN_CUDA(cudaStreamSynchronize(stream));
+    static unsigned long long t[16 * 1024];
+    PN_CUDA(cudaMemcpy(t, dbg_buf, sizeof(t), cudaMemcpyDeviceToHost));
+    const int n = (int)cfg.gridDim.x < 1024 ? (int)cfg.gridDim.x : 1024;
+    double s[11] = {0};
+    for (int c = 0; c < n; ++c)
+      for (int k = 0; k < 11; ++k) s[k] += (double)t[c * 16 + k] / n;
+    fprintf(stderr, "[conv_shift groups %d strips %d x %d tiles, grid %d] per CTA (kclk): tiles %.1f | producer total %.1f, "
+                    "h_empty %.1f | mma total %.1f, tmem_empty %.1f, h_full %.1f | drain total %.1f, tmem_full %.1f, y_empty "
+                    "%.1f | sum total %.1f, y_full %.1f\n",
+            n_groups, a.strips, a.strip_tiles, n, s[2], s[1] / 1e3, s[0] / 1e3, s[5] / 1e3, s[3] / 1e3, s[4] / 1e3, s[8] / 1e3,
+            s[6] / 1e3, s[7] / 1e3, s[10] / 1e3, s[9] / 1e3);
+  }
   return PN_OK;
 }
 

@@ -51,9 +51,30 @@ def timeit(fn, reps=20):
 res = {}
 res["conv1_64_to_2304_planar"] = timeit(lambda: ops.conv_dense3x3(rows, 0, 64, B, H, W, w1, G * hc, planar, scale=sc, shift=sh,
                                                                   relu=True, out_group_cols=hc))
+res["conv1 without scale/shift"] = timeit(lambda: ops.conv_dense3x3(rows, 0, 64, B, H, W, w1, G * hc, planar, relu=True,
+                                                                    out_group_cols=hc))
 res["last_conv_shift"] = timeit(lambda: ops.conv_dense3x3_grouped_shift(planar, G, B, H, W, w32, b4, tabd, out))
 res["last_conv_grouped_implicit_gemm"] = timeit(lambda: ops.conv_dense3x3_grouped(planar, 0, hc, G, B, H, W, wg, bg, tabd, out,
                                                                                   out_compact=True, in_planar=True))
+
+
+def pair(n_chunks):
+    """the pair in n_chunks branch chunks through ONE chunk-sized intermediate buffer (stays in L2 when small enough)"""
+    gc = G // n_chunks
+    buf = planar[:gc * n_pos]
+
+    def run():
+        for k in range(n_chunks):
+            ops.conv_dense3x3(rows, 0, 64, B, H, W, w1[k * gc * hc:(k + 1) * gc * hc], gc * hc, buf,
+                              scale=sc[k * gc * hc:(k + 1) * gc * hc], shift=sh[k * gc * hc:(k + 1) * gc * hc], relu=True,
+                              out_group_cols=hc)
+            ops.conv_dense3x3_grouped_shift(buf, gc, B, H, W, w32[k * gc * 32:(k + 1) * gc * 32], b4[k * gc * 4:(k + 1) * gc * 4],
+                                            tabd[k * gc:(k + 1) * gc], out)
+    return run
+
+
+for nc in (1,):
+    res[f"pair_in_{nc}_chunks"] = timeit(pair(nc))
 bytes_in = planar.numel() * 2
 for k, (med, best) in res.items():
     print(f"{k:36s} median {med:7.1f} us  best {best:7.1f} us   ({bytes_in / med / 1e3:7.0f} GB/s of the intermediate)")
