@@ -25,7 +25,7 @@ def main():
         rows = torch.randn((H + 2) * (H + 2), cin, device="cuda").to(torch.bfloat16)
         w = ops.pack_weight_bf16(torch.randn(cout, 9 * cin, device="cuda") * 0.02)
         out = torch.empty((H + 2) * (H + 2), cout, device="cuda", dtype=torch.bfloat16)
-        for hint in (0, 1, 2, 3, 4, 0x801, 0x802, 0x803, 0x804, 0x401, 0x402, 0x403, 0x404):   # 0x8xx: no cluster, 0x4xx: cluster 4
+        for hint in (0, 1, 2, 3, 4, 0x1001, 0x1002, 0x1003, 0x1004, 0x203):   # 0x1xxx: cta_group::2 pair, 0x2xx: weight multicast over 2
             if (hint & 0xF) in (1, 2) and cout <= 128:
                 continue
             us = timeit(lambda: ops.conv_dense3x3(rows, 0, cin, 1, H, H, w, cout, out, relu=True, tile_hint=hint))
