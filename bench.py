@@ -589,7 +589,9 @@ def run_gpu(args):
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": gpu_ms / args.steps, "ms_per_frame": gpu_ms / args.steps / B,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (three bf16 tensor-core products per fp32 product, fp32 "
+                                                "accumulate and activations)"}.get(args.precision, "f32"),
+            "data": "synthetic",
             "config": {"workload": f"{args.workload}: PillarNet inference, batch {B}/GPU, synthetic "
                                    f"{cfg['synth']}-shaped frames (~{int(np.mean([len(f) for f in frames]))} pts), "
                                    f"random-init weights, hm bias calibrated to ~{args.hm_cells} candidate cells/task",
@@ -940,7 +942,9 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train: BASELINE config 4 (training step); not the headline metric")
     ap.add_argument("--frames-per-step", type=int, default=1)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3"],
+                    help="bf16: the fast mode (headline); bf16x3: split-bf16 tensor-core mode at fp32-grade accuracy; "
+                         "fp32: FMA kernels (validation)")
     ap.add_argument("--hm-cells", type=int, default=1500)
     ap.add_argument("--train-eager", action="store_true",
                     help="--mode train: the eager, exactly sized path (host syncs) instead of the CUDA-graph TrainEngine")

@@ -366,6 +366,14 @@ int pn_cast_f32_to_bf16(const float* in, int in_ld, void* out, int out_ld, int c
 int pn_cast_bf16_to_f32(const void* in, int in_ld, float* out, int out_ld, int cols,
                         const int* num_rows, int rows_cap, pn_stream_t stream);
 
+/* Split-bf16 ("bf16x3") input for a tensor-core conv at fp32-grade accuracy: out (rows, 3*cols) bf16 =
+ * [hi | lo | hi] of in[:, :cols] (f32, row stride in_ld), hi = bf16(x), lo = bf16(x - hi).  With weights laid out
+ * [hi_w | hi_w | lo_w] per tap (cin' = 3*cin) pn_conv_gather (PN_IMPL_TCGEN05, f32 output) then accumulates
+ * hi*hi + lo*hi + hi*lo in fp32: ~2^-17 relative per product, against 2^-9 of the plain bf16 mode.  Rows at or above
+ * *num_rows (when given) are not written. */
+int pn_split_bf16x3(const float* in, int in_ld, void* out, int cols, const int* num_rows, int rows_cap,
+                    pn_stream_t stream);
+
 /* SparseConvTensor.dense() (spconv) in NHWC: out[(b*H+y)*W+x, coff..coff+C) = feat[rank] or 0.
  * out_padded != 0: rows index the zero-padded map (b*(H+2)+y+1)*(W+2)+x+1, borders written as 0. */
 int pn_sparse_to_dense(const void* feat, int dtype, int feat_ld, const uint32_t* occ_words,

@@ -106,6 +106,7 @@ SIGNATURES = {
     "pn_conv_pack_weight_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pn_cast_f32_to_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pn_cast_bf16_to_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "pn_split_bf16x3": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "pn_sparse_to_dense": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                    c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pn_decode_candidates": (c_int, [POINTER(TaskArgs), c_int, c_int, c_int, c_float, POINTER(c_float),

@@ -149,6 +149,28 @@ k_cast_rows(const TI* __restrict__ in, int in_ld, TO* __restrict__ out, int out_
   }
 }
 
+// f32 row -> [hi | lo | hi] bf16 with hi = bf16(x), lo = bf16(x - hi): the input side of the split-bf16 tensor-core
+// mode (x * w ~= hi_x * hi_w + lo_x * hi_w + hi_x * lo_w against weights laid out [hi | hi | lo] per tap; the dropped
+// lo * lo term and the rounding of the lo parts are ~2^-17 relative).
+__global__ void __launch_bounds__(256)
+k_split_bf16x3(const float* __restrict__ in, int in_ld, __nv_bfloat16* __restrict__ out, int cols,
+               const int* __restrict__ num_rows, int rows_cap) {
+  const int rows = num_rows ? min(*num_rows, rows_cap) : rows_cap;
+  const long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float x = in[r * in_ld + c];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    __nv_bfloat16* o = out + r * 3ll * cols + c;
+    o[0] = hi;
+    o[cols] = lo;
+    o[2 * cols] = hi;
+  }
+}
+
 // Dense-driven densify: one thread per (pixel, 8-byte chunk); absent pixels get zeros, so no memset
 // and every output byte is written exactly once, coalesced along channels.  pad = 1: the output rows
 // are the zero-padded (H+2, W+2) map (borders written as zeros).
@@ -266,6 +288,17 @@ int pn_cast_bf16_to_f32(const void* in, int in_ld, float* out, int out_ld, int c
   if (rows_cap == 0) return PN_OK;
   k_cast_rows<__nv_bfloat16, float><<<grid_for((long long)rows_cap * cols, 256), 256, 0, stream>>>(
       (const __nv_bfloat16*)in, in_ld, out, out_ld, cols, num_rows, rows_cap);
+  PN_CHECK_LAUNCH();
+  return PN_OK;
+}
+
+int pn_split_bf16x3(const float* in, int in_ld, void* out, int cols, const int* num_rows, int rows_cap,
+                    pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(in && out && cols > 0 && rows_cap >= 0);
+  if (rows_cap == 0) return PN_OK;
+  k_split_bf16x3<<<grid_for((long long)rows_cap * cols, 256), 256, 0, stream>>>(in, in_ld, (__nv_bfloat16*)out, cols,
+                                                                                 num_rows, rows_cap);
   PN_CHECK_LAUNCH();
   return PN_OK;
 }

@@ -128,6 +128,16 @@ def invalidate(module):
             m.__dict__.pop(k, None)
 
 
+def split_weight_bf16x3(w2d, cin):
+    """(Cout, taps*cin) f32 -> (Cout, k_pad) bf16 with every tap laid out [hi_w | hi_w | lo_w] (3*cin columns): the
+    partner of ops.split_bf16x3's [hi_x | lo_x | hi_x] rows, so one bf16 GEMM sums hi*hi + lo*hi + hi*lo."""
+    cout = w2d.shape[0]
+    w = w2d.reshape(cout, -1, cin)
+    hi = w.to(torch.bfloat16).float()
+    lo = (w - hi).to(torch.bfloat16).float()
+    return ops.pack_weight_bf16(torch.cat([hi, hi, lo], dim=2).reshape(cout, -1).contiguous())
+
+
 class Lowered:
     __slots__ = ("weight", "k_pad", "scale", "shift", "key")
 
@@ -149,6 +159,8 @@ def lower(conv, bn, precision=None):
     lw = Lowered()
     if precision == "bf16":
         lw.weight = ops.pack_weight_bf16(w2d)
+    elif precision == "bf16x3":
+        lw.weight = split_weight_bf16x3(w2d, conv.in_channels)
     else:
         lw.weight = w2d
     lw.k_pad = lw.weight.shape[1]
@@ -183,6 +195,16 @@ def run_conv(x2d, lw, nbr, taps, cin, cout, rows_cap, *, num=None, relu=False, r
     """One fused conv launch on channels-last rows."""
     if out is None:
         out = torch.empty(rows_cap, cout, dtype=out_dtype or x2d.dtype, device=x2d.device)
+    if config.get_precision() == "bf16x3":
+        # fp32 rows in and out; the conv itself on the tensor cores over split-bf16 operands (three bf16 products per
+        # fp32 product).  Rows are split for this launch only (6 bytes per value written, then gathered).
+        if deconv is not None or x2d.dtype != torch.float32 or out.dtype != torch.float32:
+            raise RuntimeError("bf16x3 mode runs fp32 rows through the gather conv")
+        xs = ops.split_bf16x3(x2d, cin, col0=in_ptr_offset)
+        ops.conv_gather(xs, lw.weight, nbr, taps, 3 * cin, cout, out, k_pad=lw.k_pad, scale=lw.scale, shift=lw.shift,
+                        residual=residual, out_coff=out_coff, relu=relu, num=num, rows_cap=rows_cap,
+                        impl=config.conv_impl(), rows_hint=rows_hint, out_hw_pad=out_hw_pad)
+        return out
     ops.conv_gather(x2d, lw.weight, nbr, taps, cin, cout, out, in_ld=in_ld, k_pad=lw.k_pad, scale=lw.scale,
                     shift=lw.shift, residual=residual, out_coff=out_coff, relu=relu, num=num,
                     rows_cap=rows_cap, impl=config.conv_impl(), in_ptr_offset=in_ptr_offset, rows_hint=rows_hint,

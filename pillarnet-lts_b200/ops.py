@@ -341,6 +341,19 @@ def cast_rows(inp, dtype, num=None):
     return out
 
 
+def split_bf16x3(inp, cols, col0=0, num=None):
+    """(rows, ld) f32 -> (rows, 3*cols) bf16 [hi | lo | hi] of columns [col0, col0 + cols) (C header)."""
+    lib = _lib.load()
+    require_cuda(inp)
+    if inp.dtype != torch.float32:
+        raise RuntimeError("split_bf16x3 wants f32 rows")
+    rows = inp.shape[0]
+    out = torch.empty(rows, 3 * cols, dtype=torch.bfloat16, device=inp.device)
+    check(lib.pn_split_bf16x3(c_void_p(inp.data_ptr() + 4 * col0), inp.stride(0), ptr(out), cols, ptr(num), rows,
+                              stream_ptr()), "pn_split_bf16x3")
+    return out
+
+
 def sparse_to_dense(feat, table, C, out=None, out_coff=0, padded=False):
     """NHWC densify: returns (B*H*W, out_ld) rows whose [coff,coff+C) columns hold the features
     (padded: (B*(H+2)*(W+2), out_ld) rows of the zero-bordered map)."""

@@ -108,6 +108,10 @@ def _run(workload, B):
         rec["fp32_vs_dense_equivalent"] = {k: agreement.rel_to_max(st32[k], ref[k]) for k in ref}
         del ref
         torch.cuda.empty_cache()
+        P.set_precision("bf16x3")
+        _, stx3, _, _ = _forward_stages(model, frames)
+        rec["bf16x3_vs_fp32"] = {k: agreement.rel_to_max(stx3[k], st32[k]) for k in st32}
+        del stx3
         P.set_precision("bf16")
         _, st16, det16, plan16 = _forward_stages(model, frames)
         rec["bf16_vs_fp32"] = {k: agreement.rel_to_max(st16[k], st32[k]) for k in st32}
@@ -122,6 +126,8 @@ def _run(workload, B):
 
 def _check(rec):
     for k, v in rec["fp32_vs_dense_equivalent"].items():
+        assert v <= FP32_TOL, (k, v)
+    for k, v in rec["bf16x3_vs_fp32"].items():       # split-bf16 tensor-core mode: the fp32 bar
         assert v <= FP32_TOL, (k, v)
     for k, v in rec["bf16_vs_fp32"].items():
         assert v <= BF16_STAGE_TOL, (k, v)

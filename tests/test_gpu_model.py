@@ -150,6 +150,37 @@ def test_bf16_mode_within_stated_tolerance_and_detector_runs():
         assert d["label_preds"].dtype == torch.int64
 
 
+@pytest.mark.parametrize("backbone", ["PillarResNet18", "PillarResNet34"])
+def test_split_bf16_tensor_core_mode_meets_the_fp32_tolerance(backbone):
+    """precision "bf16x3": every conv on tcgen05 over split-bf16 operands (hi*hi + lo*hi + hi*lo, fp32 accumulate)
+    against the dense-equivalent torch model — the same 1e-3 bar as the fp32 FMA mode, on the tensor cores."""
+    import pillarnet_lts_b200 as P
+    model = _model(backbone)
+    pts = _frames(2)
+    try:
+        with torch.no_grad():
+            P.set_precision("fp32")
+            sp32 = model.reader(dict(points=pts))
+            rf, r5, rbev, rpreds = _dense_reference(model, sp32)
+            P.set_precision("bf16x3")
+            sp = model.reader(dict(points=pts))
+            feats = model.backbone(sp)
+            bev = model.neck(feats)
+            preds = model.bbox_head(bev)
+        torch.cuda.synchronize()
+    finally:
+        P.set_precision("bf16")
+    worst = 0.0
+    for name in ("conv1", "conv2", "conv3"):
+        worst = max(worst, _rel(feats[name].dense(), rf[name]))
+    worst = max(worst, _rel(feats["conv4"], rf["conv4"]), _rel(feats["conv5"], r5), _rel(bev[0], rbev))
+    for p, rp in zip(preds, rpreds):
+        for k in rp:
+            worst = max(worst, _rel(p[k], rp[k]))
+    print(f"bf16x3 vs dense-equivalent torch, worst stage rel-to-max: {worst:.3g}")
+    assert worst <= 1e-3
+
+
 def test_frames_are_independent_batch_equals_single():
     """frame sharding contract: a frame's detections do not depend on its batch-mates."""
     import pillarnet_lts_b200 as P
