@@ -110,7 +110,9 @@ def candidate_agreement(head, plan_a, plan_b, score_thr=None, eps=1e-3):
             b7 = to_pcdet(B[ia[ok]][:, :9])
             ov = ops.boxes_aligned_overlap_bev(a7, b7)
             area = a7[:, 3] * a7[:, 4] + b7[:, 3] * b7[:, 4] - ov
-            iou = ov / area.clamp(min=1e-8)
+            # (nearly) coincident boxes: the fp32 polygon clipping can return slightly more than the true overlap when
+            # edges coincide, which makes the union vanish — the ratio is capped at 1
+            iou = (ov / area.clamp(min=1e-8)).clamp(max=1.0)
             iou_sum += float(iou.sum())
             iou_n += int(iou.numel())
             tot["min_iou"] = min(tot["min_iou"], float(iou.min()))
