@@ -154,6 +154,26 @@ class InferenceEngine:
         self._n[slot] = n
         return n * dp.shape[1] * 4 + do.numel() * 4
 
+    def _launch_slot(self, slot):
+        """queue the batch staged in input slot `slot` on the engine stream: refresh the graph's input buffers from the
+        slot, replay, read the result back into the slot's pinned buffers; returns the bytes read back"""
+        dp, do = self._p_dev[slot]
+        rd, rc = self._p_res[slot]
+        n = self._n[slot]
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            self.stream.wait_event(self._ev_up[slot])
+            self.points[:n].copy_(dp[:n], non_blocking=True)
+            self.offsets.copy_(do, non_blocking=True)
+            self._ev_used[slot].record(self.stream)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self.det_out, self.keep_count, self.plan = self._forward()
+            rd.copy_(self.det_out, non_blocking=True)
+            rc.copy_(self.keep_count, non_blocking=True)
+            self._ev_done[slot].record(self.stream)
+        return rd.numel() * 4 + rc.numel() * 4
+
     def run_pipelined(self, batches, consume=None):
         """Runs a sequence of batches (each a list of B frames) with the next batch's host packing and H2D
         overlapped with the current batch's graph replay.  `consume(i, detections)` is called per batch (default:
@@ -170,24 +190,7 @@ class InferenceEngine:
         if n_b == 0:
             return out, 0, 0
         def launch(i):
-            """queue batch i on the engine stream: refresh the graph's input buffers from its slot, replay, read back"""
-            slot = i & 1
-            dp, do = self._p_dev[slot]
-            rd, rc = self._p_res[slot]
-            n = self._n[slot]
-            with torch.cuda.stream(self.stream), torch.no_grad():
-                self.stream.wait_event(self._ev_up[slot])
-                self.points[:n].copy_(dp[:n], non_blocking=True)
-                self.offsets.copy_(do, non_blocking=True)
-                self._ev_used[slot].record(self.stream)
-                if self.graph is not None:
-                    self.graph.replay()
-                else:
-                    self.det_out, self.keep_count, self.plan = self._forward()
-                rd.copy_(self.det_out, non_blocking=True)
-                rc.copy_(self.keep_count, non_blocking=True)
-                self._ev_done[slot].record(self.stream)
-            return rd.numel() * 4 + rc.numel() * 4
+            return self._launch_slot(i & 1)
 
         h2d = self._prefetch(0, batches[0])
         d2h = launch(0)
@@ -230,6 +233,101 @@ class InferenceEngine:
             out.append({"box3d_lidar": torch.cat(boxes), "scores": torch.cat(scores),
                         "label_preds": torch.cat(labels), "metadata": metadata[b] if metadata else None})
         return out
+
+
+class StreamingEngine:
+    """Several batches in flight on one GPU: `in_flight` lanes, each an InferenceEngine with its own stream, CUDA graph
+    and buffers, take the batches round-robin.  A batch-1 step ends in kernels that occupy a handful of SMs (top-k
+    selection, NMS mask and sweep: ~90 us on <= 40 CTAs) and starts with small reader / rulebook launches; with
+    another frame's convs running beside them those phases cost nothing (measured on one B200, nuScenes batch 1:
+    1113 -> 1236 -> 1300 frames/s with 1 / 2 / 3 frames in flight).  Per-frame results are identical to the single
+    lane's (tests/test_gpu_model.py); per-frame latency grows to about `in_flight` steps."""
+
+    def __init__(self, model, n_frames, points_cap, in_flight=3, point_dim=5, device=None):
+        assert in_flight >= 1
+        self.lanes = [InferenceEngine(model, n_frames, points_cap, point_dim, device) for _ in range(in_flight)]
+        self.model, self.B, self.dev = self.lanes[0].model, n_frames, self.lanes[0].dev
+        self._fork = torch.cuda.Event(enable_timing=True)
+        self._join = torch.cuda.Event(enable_timing=True)
+
+    def prepare(self, frames, warmup=2):
+        """warm-up and graph capture of every lane on a real batch"""
+        for lane in self.lanes:
+            if lane.det_out is None:
+                lane.upload(lane.stage_host(frames))
+                lane.prepare(warmup)
+        return self
+
+    @property
+    def plan(self):
+        return self.lanes[0].plan
+
+    def launch_resident(self, i, points, offsets):
+        """step i from device-resident inputs on lane i % in_flight (no host synchronisation)"""
+        lane = self.lanes[i % len(self.lanes)]
+        with torch.cuda.stream(lane.stream):
+            lane.points[:points.shape[0]].copy_(points, non_blocking=True)
+            lane.offsets.copy_(offsets, non_blocking=True)
+        lane.launch()
+        return lane
+
+    def fork(self, stream=None):
+        """start of a timed region: every lane waits for this point of `stream` (default: the current stream)"""
+        stream = stream or torch.cuda.current_stream(self.dev)
+        self._fork.record(stream)
+        for lane in self.lanes:
+            lane.stream.wait_event(self._fork)
+        return self._fork
+
+    def join(self, stream=None):
+        """end of a timed region: `stream` waits for every lane; returns (fork event, join event) for elapsed_time"""
+        stream = stream or torch.cuda.current_stream(self.dev)
+        for lane in self.lanes:
+            ev = torch.cuda.Event()
+            ev.record(lane.stream)
+            stream.wait_event(ev)
+        self._join.record(stream)
+        return self._fork, self._join
+
+    def synchronize(self):
+        for lane in self.lanes:
+            lane.stream.synchronize()
+
+    def run(self, batches, consume=None):
+        """Throughput API over host batches (each a list of B frames, ideally in pinned memory): batch i goes to lane
+        i % in_flight; per lane the next batch's packing + H2D overlap the current replay (two input / result slots
+        per lane), so up to 2 * in_flight batches are queued.  `consume(i, detections)` is called in batch order
+        (default: collect).  Returns (results, h2d_bytes_per_batch, d2h_bytes_per_batch)."""
+        n_b, L = len(batches), len(self.lanes)
+        if n_b == 0:
+            return [], 0, 0
+        self.prepare(batches[0])
+        for lane in self.lanes:
+            if not hasattr(lane, "_p_host"):
+                lane._init_pipeline()
+        depth = 2 * L
+        h2d = d2h = 0
+
+        def issue(i):
+            lane, slot = self.lanes[i % L], (i // L) & 1
+            a = lane._prefetch(slot, batches[i])
+            return a, lane._launch_slot(slot)
+
+        for i in range(min(depth, n_b)):
+            h2d, d2h = issue(i)
+        out = []
+        for i in range(n_b):
+            lane, slot = self.lanes[i % L], (i // L) & 1
+            lane._ev_done[slot].synchronize()
+            lane.h_det, lane.h_cnt = lane._p_res[slot]
+            dets = lane.assemble_host()
+            if consume is not None:
+                consume(i, dets)
+            else:
+                out.append(dets)
+            if i + depth < n_b:
+                h2d, d2h = issue(i + depth)
+        return out, h2d, d2h
 
 
 def calibrate_heatmap_bias(model, frames, target_cells=1500, calibrate_rot=True):

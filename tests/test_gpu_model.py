@@ -332,6 +332,44 @@ def test_engine_graph_replay_equals_eager_and_serves_smaller_frames():
         assert torch.equal(r[0]["scores"], want[0]["scores"]) and torch.equal(r[0]["box3d_lidar"], want[0]["box3d_lidar"])
 
 
+def test_several_frames_in_flight_return_the_single_lane_detections():
+    """StreamingEngine: three lanes (own stream, graph, buffers) take the frames round-robin and run concurrently;
+    every frame's detections equal the single-lane engine's bit for bit, in order, for frames of different sizes."""
+    import pillarnet_lts_b200 as P
+    from pillarnet_lts_b200.engine import InferenceEngine, StreamingEngine
+    P.set_precision("bf16")
+    model = _model()
+    a, b = _frames(2)
+    pool = [a.cpu().pin_memory(), b.cpu().pin_memory(), a[:5000].cpu().contiguous().pin_memory(),
+            b[1000:9000].cpu().contiguous().pin_memory()]
+    cap = max(f.shape[0] for f in pool) + 100
+    single = InferenceEngine(model, 1, cap)
+    want = [single.infer([f]) for f in pool]
+    multi = StreamingEngine(model, 1, cap, in_flight=3)
+    seq = [[pool[i % 4]] for i in range(17)]
+    res, h2d, d2h = multi.run(seq)
+    assert len(res) == 17 and h2d > 0 and d2h > 0
+    for i, r in enumerate(res):
+        w = want[i % 4]
+        assert torch.equal(r[0]["scores"], w[0]["scores"]), i
+        assert torch.equal(r[0]["box3d_lidar"], w[0]["box3d_lidar"]), i
+        assert torch.equal(r[0]["label_preds"], w[0]["label_preds"]), i
+    assert sum(r[0]["scores"].shape[0] for r in res) > 0
+    # device-resident stepping with a timed fork / join
+    dev = [(f.cuda(), torch.tensor([0, f.shape[0]], dtype=torch.int32, device="cuda")) for f in pool]
+    multi.fork()
+    lanes = [multi.launch_resident(i, *dev[i % 4]) for i in range(6)]
+    e0, e1 = multi.join()
+    torch.cuda.synchronize()
+    assert e0.elapsed_time(e1) > 0
+    for i in (3, 4, 5):                     # the last three steps are still in the lanes' output buffers
+        lane = lanes[i]
+        lane.download()
+        lane.stream.synchronize()
+        got = lane.assemble_host()
+        assert torch.equal(got[0]["scores"], want[i % 4][0]["scores"]), i
+
+
 # ---- neck / backbone variants that 4 of the 7 configs/pillarnet/*.py use (VERDICT r1 missing #3) ---------------------
 def _variant_model(backbone, neck, seed=0):
     """small-grid versions of configs/pillarnet/pillarnet{,34}_centerhead_s4_waymo.py (PillarResNet18S/34S + RPNV2,
