@@ -298,6 +298,34 @@ int pn_conv_dense3x3_grouped_shift(const void* in, int n_groups, int n_frames, i
                                    const float* shift, const int* group_tab, float* out, int out_ld,
                                    pn_stream_t stream);
 
+/* ---- Pillar R-CNN second stage, inference path ------------------------------------------------
+ * Rulebook of spconv's SparseConv2d(k = s, stride = s, padding = 0) (lateral layers of
+ * det3d/models/second_stage/bev_interpolation.py:66-72): output grid (H_in / s, W_in / s), cell active iff any input of
+ * its s x s block is; nbr (out_m_cap, s*s) int32, tap ky*s + kx reads input (s*oy + ky, s*ox + kx) or -1.
+ * Same mask / prefix / coords / device-count conventions as pn_rulebook_down3x3s2; scratch =
+ * pn_rulebook_down_scratch_bytes(n_frames, H_in / s, W_in / s). */
+int pn_rulebook_block(const uint32_t* in_words, const int* in_prefix, int n_frames, int H_in, int W_in, int s,
+                      uint32_t* out_words, int* out_prefix, int* out_coords, int* out_num_rows, int out_m_cap,
+                      int* nbr, void* scratch, size_t scratch_bytes, pn_stream_t stream);
+
+/* RoI grid points + bilinear interpolation of an NHWC map (bev_interpolation.py:85-123, box_torch_ops.py:159-251,
+ * center_utils.py:91-120) in one launch.  rois (n_rois, roi_ld) f32 [x, y, z, dx, dy, dz, ...] with the yaw at column
+ * ry_col; RoI r belongs to frame r / rois_per_frame.  feat: rows of a (n_frames, H, W) map (feat_padded: the zero-bordered
+ * (H+2, W+2) layout), channels [feat_coff, +C) of rows with stride feat_ld, f32 or bf16; cell = bev_stride * pillar_size.
+ * out (n_rois, grid_size^2, C) in feat's dtype; points_out (n_rois, grid_size^2, 2) f32 or NULL.  Point order = the
+ * reference's (x index major). */
+int pn_roi_grid_bilinear(const float* rois, int roi_ld, int ry_col, int n_rois, int rois_per_frame, int grid_size,
+                         const void* feat, int feat_dtype, int feat_ld, int feat_coff, int n_frames, int H, int W,
+                         int feat_padded, int C, float x0, float y0, float cell, float* points_out, void* out,
+                         pn_stream_t stream);
+
+/* RoI head output -> refined boxes (roi_head_template.py:189-219) and fused scores / validity
+ * (detectors/pillar_rcnn.py:141-170): boxes (n, code_size) = rotate_z(reg + [0,0,0, roi dims, yaw, ...], yaw) + centre,
+ * scores = sqrt(sigmoid(cls) * roi_score), valid = (label != 0) & (dims > 0).  roi_labels: int64 or NULL. */
+int pn_roi_refine(const float* rois, int roi_ld, const float* reg, int code_size, const float* cls,
+                  const float* roi_scores, const long long* roi_labels, int n_rois, float* boxes, float* scores,
+                  unsigned char* valid, pn_stream_t stream);
+
 /* Training targets on the GPU (SURVEY §8 f rank 1): AssignLabel of the reference's data pipeline
  * (det3d/datasets/pipelines/preprocess.py:248-317) for ONE task: per object the Gaussian radius
  * (center_utils.py:16-38), the heat-map patch (draw_umich_gaussian, :48-64) and the regression targets.

@@ -8,11 +8,12 @@ Importable as `pillarnet_lts_b200` (see the repo-root shim of that name; the dir
   sparse.py, layers.py, reader.py, backbone.py, neck.py, head.py, detector.py
              host-side mirror of det3d's reader / backbone / neck / head / detector interfaces
   registry.py  det3d-style registries + config loader so configs/pillarnet/*.py build unchanged
+  second_stage.py, roi_head.py  Pillar R-CNN second stage, inference path (BEV fusion, RoI grid pooling, RoI head)
   synth.py   seeded synthetic LiDAR frames; dist.py frame sharding + detection gather
 """
 from . import _lib  # noqa: F401
 from .config import get_precision, set_precision  # noqa: F401
-from . import reader, backbone, neck, head, detector  # noqa: F401  (fills the registries)
+from . import reader, backbone, neck, head, detector, second_stage, roi_head  # noqa: F401  (fills the registries)
 from .registry import (Config, build_detector, build_from_cfg, READERS, BACKBONES, NECKS, HEADS,  # noqa: F401
                        DETECTORS)
 

@@ -117,6 +117,51 @@ k_down_nbr(const uint32_t* __restrict__ in_words, const int* __restrict__ in_pre
   }
 }
 
+// Non-overlapping strided conv, kernel = stride = s (spconv SparseConv2d(k=s, stride=s, padding=0), the lateral
+// layers of the second stage: det3d/models/second_stage/bev_interpolation.py:66-72): output cell (oy, ox) of the
+// (H / s, W / s) grid is active iff any input cell of its s x s block is; tap k = ky*s + kx reads (s*oy + ky, s*ox + kx).
+__global__ void __launch_bounds__(256)
+k_block_mask(const uint32_t* __restrict__ in_words, int n_frames, int H, int W, int s, int Ho, int Wo,
+             uint32_t* __restrict__ out_words, long long n_out_words, int* __restrict__ scan_state, int n_state) {
+  pn_detail::zero_scan_state(scan_state, n_state);
+  const long long cells = (long long)n_frames * Ho * Wo;
+  // thread = output cell, the warp's ballot is the output word (grid covers whole words: blockDim % 32 == 0)
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_out_words * 32;
+       c += (long long)gridDim.x * blockDim.x) {
+    bool on = false;
+    if (c < cells) {
+      const int b = (int)(c / ((long long)Ho * Wo));
+      const int r = (int)(c - (long long)b * Ho * Wo);
+      const int oy = r / Wo, ox = r - oy * Wo;
+      for (int ky = 0; ky < s && !on; ++ky) {
+        const long long base = ((long long)b * H + (long long)s * oy + ky) * W + (long long)s * ox;
+        for (int kx = 0; kx < s; ++kx) {
+          const long long bit = base + kx;
+          if ((__ldg(in_words + (bit >> 5)) >> (bit & 31)) & 1u) { on = true; break; }
+        }
+      }
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0) out_words[c >> 5] = word;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_block_nbr(const uint32_t* __restrict__ in_words, const int* __restrict__ in_prefix, int H, int W, int s,
+            const int* __restrict__ out_coords, const int* __restrict__ out_num_rows, int out_m_cap,
+            int* __restrict__ nbr) {
+  const int n = min(*out_num_rows, out_m_cap);
+  const int taps = s * s;
+  const long long total = (long long)n * taps;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(t / taps), k = (int)(t - (long long)o * taps);
+    const int b = __ldg(out_coords + 3 * o), oy = __ldg(out_coords + 3 * o + 1), ox = __ldg(out_coords + 3 * o + 2);
+    const int yy = s * oy + k / s, xx = s * ox + k % s;
+    nbr[t] = pn_rank_of(in_words, in_prefix, (b * H + yy) * W + xx);
+  }
+}
+
 // Both neighbour tables of every strided level in one launch: for output row o of level l, tap k reads
 // (2oy-1+ky, 2ox-1+kx) of level l-1 (strided conv) and (oy+ky-1, ox+kx-1) of level l (submanifold convs).
 struct NbrLevel {
@@ -253,6 +298,29 @@ int pn_rulebook_down3x3s2(const uint32_t* in_words, const int* in_prefix, const 
   if (out_m_cap > 0) {
     k_down_nbr<<<grid_for((long long)out_m_cap * 9, 256), 256, 0, stream>>>(
         in_words, in_prefix, H_in, W_in, out_coords, out_num_rows, out_m_cap, nbr);
+    PN_CHECK_LAUNCH();
+  }
+  return PN_OK;
+}
+
+int pn_rulebook_block(const uint32_t* in_words, const int* in_prefix, int n_frames, int H_in, int W_in, int s,
+                      uint32_t* out_words, int* out_prefix, int* out_coords, int* out_num_rows, int out_m_cap,
+                      int* nbr, void* scratch, size_t scratch_bytes, pn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PN_REQUIRE(in_words && in_prefix && out_words && out_prefix && out_coords && out_num_rows && nbr && scratch);
+  PN_REQUIRE(n_frames >= 1 && s >= 1 && s <= 8 && H_in >= s && W_in >= s && out_m_cap >= 0);
+  const int Ho = H_in / s, Wo = W_in / s;       // floor((H - s) / s) + 1
+  const long long nw = pn_detail::n_words((long long)n_frames * Ho * Wo);
+  if (scratch_bytes < pn_detail::scan_scratch_bytes(nw)) return PN_ERR_WORKSPACE;
+  k_block_mask<<<grid_for(nw * 32, 256), 256, 0, stream>>>(in_words, n_frames, H_in, W_in, s, Ho, Wo, out_words, nw,
+                                                          reinterpret_cast<int*>(scratch), pn_detail::scan_state_words(nw));
+  PN_CHECK_LAUNCH();
+  int rc = pn_detail::mask_scan_emit(out_words, out_prefix, nw, Ho * Wo, Wo, out_coords, out_m_cap, out_num_rows,
+                                     scratch, scratch_bytes, stream, /*state_is_zero=*/true);
+  if (rc != PN_OK) return rc;
+  if (out_m_cap > 0) {
+    k_block_nbr<<<grid_for((long long)out_m_cap * s * s, 256), 256, 0, stream>>>(in_words, in_prefix, H_in, W_in, s,
+                                                                               out_coords, out_num_rows, out_m_cap, nbr);
     PN_CHECK_LAUNCH();
   }
   return PN_OK;

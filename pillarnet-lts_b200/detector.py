@@ -8,7 +8,8 @@ neck / bbox_head from their cfg dicts through the registries, regroups test_cfg 
 import torch
 from torch import nn
 
-from .registry import DETECTORS, ConfigDict, build_backbone, build_head, build_neck, build_reader
+from .registry import (DETECTORS, ConfigDict, build_backbone, build_detector, build_head, build_neck,
+                       build_reader)
 
 
 def set_by_task_cfg(test_cfg, task_num_classes):
@@ -93,9 +94,107 @@ class PillarNet(SingleStageDetector):
             return self.bbox_head.loss(example, preds, self.train_cfg)
         return self.bbox_head.predict(example, preds, self.test_cfg)
 
+    def forward_two_stage(self, example, return_loss=True, **kwargs):
+        """detectors/pillarnet.py:51-82: first-stage detections plus the maps the second stage pools from"""
+        batch_size = len(example["metadata"]) if "metadata" in example else len(example["points"])
+        data = dict(points=example["points"], batch_size=batch_size)
+        if "points_batched" in example:
+            data["points_batched"] = example["points_batched"]
+        bev_features, backbone_features = self.extract_feat(data)
+        preds = self.bbox_head(bev_features)
+        if return_loss:
+            raise NotImplementedError("two-stage training is outside the inference path")
+        boxes = self.bbox_head.predict(example, preds, self.test_cfg)
+        return boxes, bev_features, backbone_features, None
+
     @torch.no_grad()
     def forward_device(self, points, frame_offsets):
         """Sync-free inference: (det_out, keep_count, plan) — see CenterHead.predict_raw."""
         bev_features, _ = self.extract_feat(dict(points_batched=(points, frame_offsets)))
         preds = self.bbox_head(bev_features)
         return self.bbox_head.predict_raw(preds, self.test_cfg)
+
+
+@DETECTORS.register_module
+class PillarRCNN(nn.Module):
+    """detectors/pillar_rcnn.py:9-170, inference path: first stage -> RoIs (padded to NMS_POST_MAXSIZE) -> second-stage
+    modules -> point head -> RoI head -> post-processing.  Same constructor kwargs and module tree (`single_det`,
+    `second_stage`, `point_head`, `roi_head`) as the reference, so its checkpoints load."""
+
+    def __init__(self, first_stage_cfg, second_stage_modules, roi_head, freeze=False, point_head=None,
+                 train_cfg=None, test_cfg=None, pretrained=None, **kwargs):
+        super().__init__()
+        from .registry import build_point_head, build_roi_head, build_second_stage_module
+        self.single_det = build_detector(first_stage_cfg, train_cfg=train_cfg, test_cfg=test_cfg)
+        if freeze:
+            for p in self.single_det.parameters():
+                p.requires_grad = False
+            self.single_det.eval()
+        self.bbox_head = self.single_det.bbox_head
+        self.test_cfg = self.single_det.test_cfg
+        self.num_classes = sum(self.single_det.num_classes)
+        first = dict(backbone_channels=self.single_det.backbone.backbone_channels,
+                     backbone_strides=self.single_det.backbone.backbone_strides)
+        self.second_stage = nn.ModuleList()
+        for m in second_stage_modules:
+            m = dict(m)
+            m.update(first)
+            self.second_stage.append(build_second_stage_module(m))
+        self.point_head = build_point_head(point_head) if point_head is not None else None
+        self.roi_head = build_roi_head(roi_head)
+        if pretrained is not None:
+            from .checkpoint import load_checkpoint
+            load_checkpoint(self, pretrained, map_location="cpu", strict=False)
+
+    def reorder_first_stage_prediction(self, first_pred, example):
+        """pillar_rcnn.py:50-83: per-frame detections -> fixed-size (B, NMS_POST_MAXSIZE, .) RoI tensors, labels + 1"""
+        B = len(first_pred)
+        D = first_pred[0]["box3d_lidar"].shape[1]
+        n_max = self.single_det.NMS_POST_MAXSIZE
+        dev = first_pred[0]["box3d_lidar"].device
+        rois = torch.zeros(B, n_max, D, dtype=torch.float32, device=dev)
+        roi_scores = torch.zeros(B, n_max, dtype=torch.float32, device=dev)
+        roi_labels = torch.zeros(B, n_max, dtype=torch.long, device=dev)
+        for i in range(B):
+            boxes = first_pred[i]["box3d_lidar"]
+            n = boxes.shape[0]
+            if self.roi_head.code_size == 9:
+                boxes = boxes[:, [0, 1, 2, 3, 4, 5, 8, 6, 7]]
+            rois[i, :n] = boxes
+            roi_labels[i, :n] = first_pred[i]["label_preds"] + 1
+            roi_scores[i, :n] = first_pred[i]["scores"]
+        example["rois"], example["roi_labels"], example["roi_scores"] = rois, roi_labels, roi_scores
+        example["has_class_labels"] = True
+        return example
+
+    def second_stage_forward(self, example):
+        """everything after the first stage: needs rois / roi_scores / roi_labels, bev_feature, backbone_features"""
+        for module in self.second_stage:
+            example = module(example)
+        if self.point_head is not None:
+            example = self.point_head(example)
+        return self.roi_head(example, training=False)
+
+    def forward(self, example, return_loss=True, **kwargs):
+        if return_loss:
+            raise NotImplementedError("PillarRCNN: only the inference path is implemented")
+        batch_size = len(example["metadata"]) if "metadata" in example else len(example["points"])
+        example["batch_size"] = batch_size
+        preds, bev_features, backbone_features, _ = self.single_det.forward_two_stage(example, False, **kwargs)
+        example["bev_feature"] = bev_features[-1]
+        example["backbone_features"] = backbone_features
+        example = self.reorder_first_stage_prediction(preds, example)
+        return self.post_process(self.second_stage_forward(example))
+
+    def post_process(self, batch_dict):
+        """pillar_rcnn.py:141-170 (score fusion + validity mask computed by pn_roi_refine)"""
+        out = []
+        for i in range(batch_dict["batch_size"]):
+            boxes = batch_dict["batch_box_preds"][i]
+            if boxes.shape[-1] == 9:
+                boxes = boxes[:, [0, 1, 2, 3, 4, 5, 7, 8, 6]]
+            mask = batch_dict["refined_valid"][i]
+            out.append({"box3d_lidar": boxes[mask], "scores": batch_dict["refined_scores"][i][mask],
+                        "label_preds": batch_dict["roi_labels"][i][mask] - 1,
+                        "metadata": batch_dict["metadata"][i] if "metadata" in batch_dict else None})
+        return out

@@ -23,8 +23,8 @@ class _SparseConvBase(nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1,
                  bias=True, indice_key=None):
         super().__init__()
-        if kernel_size != 3 or dilation != 1:
-            raise NotImplementedError("only 3x3, dilation 1 sparse convs are on the PillarNet hot path")
+        if dilation != 1:
+            raise NotImplementedError("only dilation 1 sparse convs are on the PillarNet hot path")
         self.in_channels, self.out_channels = in_channels, out_channels
         self.kernel_size, self.stride, self.padding, self.indice_key = kernel_size, stride, padding, indice_key
         # spconv 2.x layout (Cout, kH, kW, Cin); checkpoint.py:78-87
@@ -46,14 +46,23 @@ class _SparseConvBase(nn.Module):
 class SubMConv2d(_SparseConvBase):
     """spconv.pytorch.SubMConv2d container (backbones/base.py:43-52)."""
 
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1,
+                 bias=True, indice_key=None):
+        if kernel_size != 3:
+            raise NotImplementedError("only 3x3 submanifold convs are supported")
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, bias, indice_key)
+
 
 class SparseConv2d(_SparseConvBase):
-    """spconv.pytorch.SparseConv2d container (PillarResNet.py:87,95,103); stride 2, padding 1."""
+    """spconv.pytorch.SparseConv2d container: 3x3 / stride 2 / padding 1 (PillarResNet.py:87,95,103) or the
+    non-overlapping kernel = stride = s, padding 0 of the second stage's lateral layers
+    (second_stage/bev_interpolation.py:66-72)."""
 
     def __init__(self, in_channels, out_channels, kernel_size=3, stride=2, padding=1, dilation=1,
                  bias=False, indice_key=None):
-        if stride != 2 or padding != 1:
-            raise NotImplementedError("only stride 2 / padding 1 strided sparse convs are supported")
+        block = kernel_size == stride and padding == 0 and 1 <= stride <= 8
+        if not block and not (kernel_size == 3 and stride == 2 and padding == 1):
+            raise NotImplementedError("strided sparse convs: 3x3 / stride 2 / padding 1, or kernel = stride <= 8 / padding 0")
         super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, bias, indice_key)
 
 
@@ -79,6 +88,8 @@ def build_norm_layer(cfg, num_features):
         layer = nn.BatchNorm2d(num_features, **cfg)
     elif t == "BN1d":
         layer = nn.BatchNorm1d(num_features, **cfg)
+    elif t == "LN":
+        layer = nn.LayerNorm(num_features, **cfg)
     else:
         raise NotImplementedError(f"norm type {t}")
     return t.lower(), layer
@@ -99,6 +110,10 @@ def weight_matrix(conv):
         return conv.weight.detach().permute(1, 2, 3, 0).reshape(conv.out_channels, -1)
     if isinstance(conv, nn.Conv2d):
         return conv.weight.detach().permute(0, 2, 3, 1).reshape(conv.out_channels, -1)
+    if isinstance(conv, nn.Conv1d) and conv.kernel_size == (1,):        # the RoI head's per-RoI "FC" layers
+        return conv.weight.detach().reshape(conv.out_channels, -1)
+    if isinstance(conv, nn.Linear):
+        return conv.weight.detach()
     raise TypeError(type(conv))
 
 
@@ -160,7 +175,7 @@ def lower(conv, bn, precision=None):
     if precision == "bf16":
         lw.weight = ops.pack_weight_bf16(w2d)
     elif precision == "bf16x3":
-        lw.weight = split_weight_bf16x3(w2d, conv.in_channels)
+        lw.weight = split_weight_bf16x3(w2d, conv.in_features if isinstance(conv, nn.Linear) else conv.in_channels)
     else:
         lw.weight = w2d
     lw.k_pad = lw.weight.shape[1]

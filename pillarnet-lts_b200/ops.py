@@ -172,6 +172,63 @@ def rulebook_down3x3s2(table, out_cap=None):
     return RankTable(words, prefix, coords, num, out_cap, table.B, Ho, Wo), nbr
 
 
+def rulebook_block(table, s, out_cap=None):
+    """SparseConv2d(k = s, stride = s) rulebook (pn_rulebook_block): (out RankTable on the (H // s, W // s) grid,
+    nbr (out_cap, s*s) int32 into the input rows)."""
+    lib = _lib.load()
+    dev = table.coords.device
+    Ho, Wo = table.H // s, table.W // s
+    if out_cap is None:
+        out_cap = max(1, min(table.cap, table.B * Ho * Wo))     # blocks do not overlap: at most one output per input
+    nw = lib.pn_mask_words(table.B, Ho, Wo)
+    words, prefix = _i32(nw, device=dev), _i32(nw, device=dev)
+    coords, num = _i32(out_cap, 3, device=dev), _i32(1, device=dev)
+    nbr = _i32(out_cap, s * s, device=dev)
+    sb = lib.pn_rulebook_down_scratch_bytes(table.B, Ho, Wo)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
+    check(lib.pn_rulebook_block(ptr(table.words), ptr(table.prefix), table.B, table.H, table.W, s, ptr(words),
+                                ptr(prefix), ptr(coords), ptr(num), out_cap, ptr(nbr), ptr(scratch), c_size_t(sb),
+                                stream_ptr()), "pn_rulebook_block")
+    return RankTable(words, prefix, coords, num, out_cap, table.B, Ho, Wo), nbr
+
+
+def roi_grid_bilinear(rois, grid_size, feat_rows, n_frames, H, W, C, x0, y0, cell, feat_coff=0, padded=False,
+                      want_points=True):
+    """rois (B, N, >=7) f32 -> (features (B, N, G*G, C) in feat's dtype, points (B, N, G*G, 2) f32 or None): RoI grid
+    points + bilinear interpolation of the NHWC map rows (pn_roi_grid_bilinear)."""
+    lib = _lib.load()
+    require_cuda(rois, feat_rows)
+    B, N, D = rois.shape
+    if rois.dtype != torch.float32 or not rois.is_contiguous() or B != n_frames:
+        raise RuntimeError("rois must be a contiguous (B, N, D) float32 tensor")
+    P = grid_size * grid_size
+    out = torch.empty(B, N, P, C, dtype=feat_rows.dtype, device=rois.device)
+    pts = torch.empty(B, N, P, 2, dtype=torch.float32, device=rois.device) if want_points else None
+    check(lib.pn_roi_grid_bilinear(ptr(rois), D, D - 1, B * N, N, grid_size, ptr(feat_rows),   # yaw = rois[:, -1] as the reference
+                                   _DT[feat_rows.dtype], feat_rows.stride(0), feat_coff, n_frames, H, W,
+                                   1 if padded else 0, C, c_float(_f32(x0)), c_float(_f32(y0)), c_float(_f32(cell)),
+                                   ptr(pts), ptr(out), stream_ptr()), "pn_roi_grid_bilinear")
+    return out, pts
+
+
+def roi_refine(rois, reg, cls, roi_scores, roi_labels):
+    """(boxes (B, N, code), scores (B, N), valid (B, N) bool) from the RoI head's outputs (pn_roi_refine)."""
+    lib = _lib.load()
+    require_cuda(rois, reg, cls, roi_scores)
+    B, N, D = rois.shape
+    code = reg.shape[-1]
+    reg = reg.reshape(B * N, code).float().contiguous()
+    cls = cls.reshape(B * N).float().contiguous()
+    roi_scores = roi_scores.reshape(B * N).float().contiguous()
+    labels = roi_labels.reshape(B * N).to(torch.int64).contiguous() if roi_labels is not None else None
+    boxes = torch.empty(B, N, code, dtype=torch.float32, device=rois.device)
+    scores = torch.empty(B, N, dtype=torch.float32, device=rois.device)
+    valid = torch.empty(B, N, dtype=torch.uint8, device=rois.device)
+    check(lib.pn_roi_refine(ptr(rois.contiguous()), D, ptr(reg), code, ptr(cls), ptr(roi_scores), ptr(labels), B * N,
+                            ptr(boxes), ptr(scores), ptr(valid), stream_ptr()), "pn_roi_refine")
+    return boxes, scores, valid.bool()
+
+
 def rulebook_pyramid(table, n_levels):
     """All strided levels below `table` in n_levels + 2 launches (pn_rulebook_pyramid3x3s2).
     Returns [(out RankTable with its submanifold table attached, nbr_down (cap,9))] per level — the same

@@ -86,6 +86,9 @@ BACKBONES = Registry("backbone")
 NECKS = Registry("neck")
 HEADS = Registry("head")
 DETECTORS = Registry("detector")
+SECOND_STAGE = Registry("second_stage")     # det3d/models/registry.py:9-11 (Pillar R-CNN)
+ROI_HEAD = Registry("roi_head")
+POINT_HEAD = Registry("point_head")
 
 
 def build_reader(cfg):
@@ -102,6 +105,18 @@ def build_neck(cfg):
 
 def build_head(cfg):
     return build_from_cfg(cfg, HEADS)
+
+
+def build_second_stage_module(cfg):
+    return build_from_cfg(cfg, SECOND_STAGE)
+
+
+def build_point_head(cfg):
+    return build_from_cfg(cfg, POINT_HEAD)
+
+
+def build_roi_head(cfg):
+    return build_from_cfg(cfg, ROI_HEAD)
 
 
 def build_detector(cfg, train_cfg=None, test_cfg=None):

@@ -12,6 +12,11 @@ Fixtures (all small .npz):
   sweeps.npz             datasets/pipelines/loading.py:102-141 key frame + sweeps (remove_close, transform, time lag)
   neck_head_forward.npz  det3d/models/necks/rpn.py:137-207 RPNV1 + center_head.py:116-127 forward (torch CPU)
   set_by_task_cfg.json   det3d/core/utils/center_utils.py:229-274 on the Waymo FPN test_cfg
+  second_stage.npz       det3d/models/second_stage/bev_interpolation.py:162-308 BEVStrideFeature (two variants: the shipped
+                         config's stride-1 laterals, and out_stride 2 with stride-2 transposed convs),
+                         roi_heads/roi_mix_head.py:83-122 RoIMIXHead.forward(training=False),
+                         point_heads/point_head_simple.py:68-96 PointHead.forward,
+                         detectors/pillar_rcnn.py:141-170 PillarRCNN.post_process (torch CPU)
 """
 import json
 import logging
@@ -354,6 +359,89 @@ def gen_neck_head():
     np.savez_compressed(os.path.join(HERE, "neck_head_forward.npz"), **save)
 
 
+def _randomise_bn(module):
+    for m in module.modules():
+        if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.1)
+
+
+def gen_second_stage():
+    from det3d.models.second_stage.bev_interpolation import BEVStrideFeature
+    from det3d.models.roi_heads.roi_mix_head import RoIMIXHead
+    from det3d.models.point_heads.point_head_simple import PointHead
+    from det3d.models.detectors.pillar_rcnn import PillarRCNN
+    torch.manual_seed(21)
+    rng = np.random.default_rng(21)
+    ps, pcr = 0.4, [-12.8, -12.8, -2.0, 12.8, 12.8, 4.0]          # 64 x 64 pillars; stride-4 map 16 x 16
+    chans = {"conv1": 32, "conv2": 64, "conv3": 128, "conv4": 256}
+    strides = {"conv1": 1, "conv2": 2, "conv3": 4, "conv4": 8}
+    B, N = 2, 14
+    save = {"pillar_size": np.float32(ps), "pc_range": np.asarray(pcr, np.float32)}
+    rois = np.zeros((B, N, 7), np.float32)
+    for b in range(B):
+        r = rand_boxes(rng, N, spread=11.0)
+        r[-3:] = 0.0                                                # padded slots of reorder_first_stage_prediction
+        r[0, :2] = [12.5, -12.7]                                    # a RoI hanging over the map border (clamped corners)
+        rois[b] = r
+    roi_scores = rng.uniform(0.05, 0.95, (B, N)).astype(np.float32)
+    roi_labels = rng.integers(1, 4, (B, N)).astype(np.int64)
+    roi_scores[:, -3:], roi_labels[:, -3:] = 0.0, 0
+    save.update(rois=rois, roi_scores=roi_scores, roi_labels=roi_labels)
+    conv2 = torch.randn(B, 64, 32, 32) * (torch.rand(B, 1, 32, 32) > 0.6)
+    conv3 = torch.randn(B, 128, 16, 16) * (torch.rand(B, 1, 16, 16) > 0.4)
+    bev = torch.randn(B, 128, 16, 16)
+    save.update(conv2=conv2.numpy(), conv3=conv3.numpy(), bev=bev.numpy())
+    mcfg = Config(dict(CLASS_AGNOSTIC=True, SHARED_FC=[32, 32], CLS_FC=[32, 32], REG_FC=[32, 32], DP_RATIO=0.3,
+                       TARGET_CONFIG=dict(ROI_PER_IMAGE=128, FG_RATIO=0.5, SAMPLE_ROI_BY_EACH_CLASS=True,
+                                          CLS_SCORE_TYPE="roi_iou", CLS_FG_THRESH=0.7, CLS_BG_THRESH=0.25,
+                                          CLS_BG_THRESH_LO=0.1, HARD_BG_RATIO=0.8, REG_FG_THRESH=0.5),
+                       LOSS_CONFIG=dict(CLS_LOSS="BinaryCrossEntropy", REG_LOSS="L1",
+                                        LOSS_WEIGHTS={"rcnn_cls_weight": 1.0, "rcnn_reg_weight": 1.0,
+                                                      "code_weights": [1.0] * 7})))
+    pcfg = Config(dict(CLASS_AGNOSTIC=True, CLS_FC=[32, 32], TARGET_CONFIG=dict(GT_EXTRA_WIDTH=[0.2, 0.2, 0.2]),
+                       LOSS_CONFIG=dict(LOSS_REG="smooth-l1", LOSS_WEIGHTS={"point_cls_weight": 1.0})))
+    variants = {
+        # the shipped config: out_stride 4, lateral conv3 with stride 1 (ConvTranspose2d k = 1)
+        "a": dict(feature_sources=["conv3"], out_stride=4),
+        # out_stride 2: top-down and conv3 lateral are ConvTranspose2d(k = 2, stride = 2), conv2 lateral k = 1
+        "b": dict(feature_sources=["conv2", "conv3"], out_stride=2),
+    }
+    for tag, v in variants.items():
+        torch.manual_seed(100 + ord(tag))
+        mod = BEVStrideFeature(grid_size=7, in_channels=128, share_channels=64, pillar_size=ps, pc_range=pcr,
+                               backbone_channels=chans, backbone_strides=strides, **v)
+        head = RoIMIXHead(in_channels=64, model_cfg=mcfg, num_class=1, code_size=7, mixer_type="", num_patches=49)
+        phead = PointHead(in_channels=64, num_class=1, model_cfg=pcfg)
+        for m in (mod, head, phead):
+            _randomise_bn(m)
+            m.eval()
+        torch.nn.init.normal_(head.reg_layers[-1].weight, mean=0, std=0.05)     # visible residuals
+        example = {"rois": torch.from_numpy(rois.copy()), "roi_scores": torch.from_numpy(roi_scores.copy()),
+                   "roi_labels": torch.from_numpy(roi_labels.copy()), "bev_feature": bev,
+                   "backbone_features": {"conv2": conv2, "conv3": conv3}, "batch_size": B,
+                   "metadata": [None] * B}
+        with torch.no_grad():
+            example = mod.forward(example)
+            save[f"{tag}.roi_features"] = example["roi_features"].numpy().copy()
+            save[f"{tag}.point_coords"] = example["point_coords"].numpy().copy()
+            example = phead(example)
+            save[f"{tag}.point_cls_scores"] = example["point_cls_scores"].numpy().copy()
+            out = head(example, training=False)
+            save[f"{tag}.batch_cls_preds"] = out["batch_cls_preds"].numpy().copy()
+            save[f"{tag}.batch_box_preds"] = out["batch_box_preds"].numpy().copy()
+            dets = PillarRCNN.post_process(None, out)
+        for i, d in enumerate(dets):
+            for k in ("box3d_lidar", "scores", "label_preds"):
+                save[f"{tag}.det{i}.{k}"] = d[k].numpy().copy()
+        for name, m in (("second_stage", mod), ("roi_head", head), ("point_head", phead)):
+            for k, t in m.state_dict().items():
+                save[f"{tag}.{name}.{k}"] = t.numpy()
+    np.savez_compressed(os.path.join(HERE, "second_stage.npz"), **save)
+
+
 def gen_cfg():
     cfg = Config.fromfile("/root/reference/configs/pillarnet/pillarnet34_fpn_centerhead_waymo.py")
     out = set_by_task_cfg(cfg.test_cfg, [1, 2])
@@ -370,5 +458,6 @@ if __name__ == "__main__":
     gen_assign_label()
     gen_sweeps()
     gen_neck_head()
+    gen_second_stage()
     gen_cfg()
     print("golden fixtures written to", HERE)
