@@ -92,8 +92,31 @@ class _BEVFusion(nn.Module):
             return DenseMap(d, t.batch_size, t.table.H, t.table.W, t.feat.shape[1], 0, 1 if use_padded_layout() else 0)
         return DenseMap.from_nchw(t)
 
+    def _fused_map_stride1(self, bev_feature, backbone_features):
+        """every transposed conv has k = stride = 1 (the shipped config): each is a 1x1 GEMM over the rows of its input
+        map, written straight into its channel slice of the concatenated (padded) map — no shuffle, cat or pad copies"""
+        srcs = [(self._as_map(bev_feature), self.top_down_conv)]
+        for k, src in enumerate(self.lat_conv_name):
+            srcs.append((self._as_map(backbone_features[src]), self.lat_conv[k]))
+        x0 = srcs[0][0]
+        cout = self.top_down_conv[0].out_channels
+        for m, _ in srcs:
+            if (m.B, m.H, m.W, m.pad) != (x0.B, x0.H, x0.W, x0.pad):
+                raise RuntimeError("second-stage feature maps disagree")
+        cat = torch.empty(x0.n_rows, cout * len(srcs), dtype=x0.rows.dtype, device=x0.rows.device)
+        for k, (m, seq) in enumerate(srcs):
+            run_conv(m.rows, _lower_deconv_ks(seq[0], seq[1]), None, 1, m.C, cout, m.n_rows, relu=True, out=cat,
+                     out_coff=k * cout, in_ld=m.rows.stride(0), in_ptr_offset=m.coff,
+                     out_hw_pad=(x0.H + 2, x0.W + 2) if x0.pad else None)      # border rows stay zero
+        x = DenseMap(cat, x0.B, x0.H, x0.W, cat.shape[1], 0, x0.pad)
+        return dense_conv3x3(x, self.fusion_conv[0], self.fusion_conv[1], relu=True)
+
     def fused_map(self, bev_feature, backbone_features):
         """-> DenseMap of the fusion conv's output (B, H_out, W_out, share_channels)"""
+        if (config.get_precision() != "bf16x3" and self.top_down_conv[0].kernel_size == (1, 1)
+                and all(t == "dense" and self.lat_conv[k][0].kernel_size == (1, 1)
+                        for k, t in enumerate(self.lat_tensor_type))):
+            return self._fused_map_stride1(bev_feature, backbone_features)
         parts = [deconv_ks(self._as_map(bev_feature), self.top_down_conv[0], self.top_down_conv[1])]
         for k, src in enumerate(self.lat_conv_name):
             cur = backbone_features[src]
