@@ -193,31 +193,11 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
   static_assert(A_COL0 + kASlots * 3 * ACOLS <= 512, "TMEM budget");
   if (threadIdx.x == 0) PW_DBG(0);
   pdl_launch_dependents();
-  pdl_wait();                                 // everything below depends on the predecessor's outputs
   // Column split (wide layers with few rows: 61 row tiles of a 256-channel layer leave 87 SMs idle and the busy ones
   // MMA-bound; two CTAs per row share, one per 128-column half, halve that): CTA c owns column block c % n_split.
   const int col_blk = (int)blockIdx.x % P.n_split, share_a = (int)blockIdx.x / P.n_split;
   const int share_b = share_a + (P.plan_grid + P.n_split - 1) / P.n_split;      // second row share of a split CTA
   const int col0 = col_blk * BN, cout_l = min(BN, P.cout - col0);
-  // the window starts of this CTA's first tile do not depend on the live row count: their load travels together with it
-  int4 lo_first = make_int4(0, 0, 0, 0);
-  if (warp == kLoaderWarp && lane == 0)
-    lo_first = __ldg(reinterpret_cast<const int4*>(P.plan + (size_t)share_a * P.tiles_per_cta * kPlanBytes + kPlanLo));
-  const int rows = P.num_rows ? min(*P.num_rows, P.rows_cap) : P.rows_cap;
-  // balanced schedule (as conv_tcgen05.cu): equal contiguous row shares, walked in 128-row tiles
-  const int share = win_share(rows, P.plan_grid);
-  const int beg_a = min(rows, share_a * share), end_a = min(rows, beg_a + share);
-  const int tiles_a = (end_a - beg_a + BLOCK_M - 1) / BLOCK_M;
-  const bool has_b = P.n_split > 1 && share_b < P.plan_grid;
-  const int beg_b = has_b ? min(rows, share_b * share) : rows, end_b = has_b ? min(rows, beg_b + share) : rows;
-  const int n_tiles = tiles_a + (end_b - beg_b + BLOCK_M - 1) / BLOCK_M;
-  // tile t of this CTA: first row, end of its share, plan record
-  auto tile_row0 = [&](int t) { return t < tiles_a ? beg_a + t * BLOCK_M : beg_b + (t - tiles_a) * BLOCK_M; };
-  auto tile_end = [&](int t) { return t < tiles_a ? end_a : end_b; };
-  auto tile_plan = [&](int t) {
-    return P.plan + ((size_t)(t < tiles_a ? share_a : share_b) * P.tiles_per_cta + (t < tiles_a ? t : t - tiles_a)) * kPlanBytes;
-  };
-
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < kASlots; ++s) {
@@ -250,6 +230,36 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
+  // Programmatic dependent launch: everything above (barriers, TMEM) and the resident weights below are independent of
+  // the predecessor, so they overlap its tail; the row count, the plan and every activation are read after the wait.
+  if constexpr (RES) {
+    if (warp == kWeightWarp && lane == 0) {
+      mbar_arrive_expect_tx(&sm.b_full[0], (uint32_t)(9 * P.n_chunks) * BN * 128);
+      for (int kc = 0; kc < P.n_chunks; ++kc)
+        for (int t = 0; t < 9; ++t)
+          tma_load_2d(smem_u32(sm.b[kc * 9 + t]), &tmap_w, t * P.cin + kc * KU, col0, &sm.b_full[0]);
+    }
+  }
+  pdl_wait();
+  // the window starts of this CTA's first tile do not depend on the live row count: their load travels together with it
+  int4 lo_first = make_int4(0, 0, 0, 0);
+  if (warp == kLoaderWarp && lane == 0)
+    lo_first = __ldg(reinterpret_cast<const int4*>(P.plan + (size_t)share_a * P.tiles_per_cta * kPlanBytes + kPlanLo));
+  const int rows = P.num_rows ? min(*P.num_rows, P.rows_cap) : P.rows_cap;
+  // balanced schedule (as conv_tcgen05.cu): equal contiguous row shares, walked in 128-row tiles
+  const int share = win_share(rows, P.plan_grid);
+  const int beg_a = min(rows, share_a * share), end_a = min(rows, beg_a + share);
+  const int tiles_a = (end_a - beg_a + BLOCK_M - 1) / BLOCK_M;
+  const bool has_b = P.n_split > 1 && share_b < P.plan_grid;
+  const int beg_b = has_b ? min(rows, share_b * share) : rows, end_b = has_b ? min(rows, beg_b + share) : rows;
+  const int n_tiles = tiles_a + (end_b - beg_b + BLOCK_M - 1) / BLOCK_M;
+  // tile t of this CTA: first row, end of its share, plan record
+  auto tile_row0 = [&](int t) { return t < tiles_a ? beg_a + t * BLOCK_M : beg_b + (t - tiles_a) * BLOCK_M; };
+  auto tile_end = [&](int t) { return t < tiles_a ? end_a : end_b; };
+  auto tile_plan = [&](int t) {
+    return P.plan + ((size_t)(t < tiles_a ? share_a : share_b) * P.tiles_per_cta + (t < tiles_a ? t : t - tiles_a)) * kPlanBytes;
+  };
+
   if (threadIdx.x == 0) PW_DBG(1);
 
   if (warp < kBuilderWarps) {
@@ -374,14 +384,13 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
     }
   } else if (warp == kWeightWarp) {
     // ===================== weight tiles =====================
+    if constexpr (RES) {
+      // resident weights were requested before the dependency wait (above); a CTA without tiles still has to see them
+      // land before it may exit
+      if (lane == 0 && n_tiles == 0) mbar_wait(&sm.b_full[0], 0u);
+    }
     if (lane == 0 && n_tiles > 0) {
-      if constexpr (RES) {
-        // the whole layer fits: every tile loaded once, one barrier
-        mbar_arrive_expect_tx(&sm.b_full[0], (uint32_t)(9 * P.n_chunks) * BN * 128);
-        for (int kc = 0; kc < P.n_chunks; ++kc)
-          for (int t = 0; t < 9; ++t)
-            tma_load_2d(smem_u32(sm.b[kc * 9 + t]), &tmap_w, t * P.cin + kc * KU, col0, &sm.b_full[0]);
-      } else {
+      if constexpr (!RES) {
         uint32_t u = 0;
         for (int tile = 0; tile < n_tiles; ++tile)
           for (int kc = 0; kc < P.n_chunks; ++kc)
