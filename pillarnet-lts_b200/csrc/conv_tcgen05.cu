@@ -134,9 +134,23 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
   constexpr int TCOLS = tmem_cols<BN>();
   if (threadIdx.x == 0) PN_DBG(0);
   pdl_launch_dependents();   // our successor may be scheduled; it waits for this grid's completion itself
-  // Everything below reads the predecessor's results (live row count, rulebook, activations) or overwrites buffers
-  // it may still read.  Waiting first lets the producers fetch their first rulebook rows while the MMA warp sets
-  // up barriers and TMEM (programmatic launch itself is worth < 1 % here: the graph replay hides launch latency).
+  // Barriers and TMEM do not depend on the predecessor: set up while its last CTAs are still running.  Everything
+  // after the wait reads its results (live row count, rulebook, activations) or overwrites buffers it may still read.
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&sm.full[s], TMA_A ? 1 : kProducerThreads + 1);
+        mbar_init(&sm.empty[s], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&sm.tmem_full[i], 1);
+        mbar_init(&sm.tmem_empty[i], kEpilogueThreads);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<TCOLS>(&sm.tmem_base);
+  }
   pdl_wait();
   const int rows = P.num_rows ? min(*P.num_rows, P.rows_cap) : P.rows_cap;
   const int n_n_tiles = (P.cout + BN - 1) / BN;
@@ -191,7 +205,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
     }
   };
   if (warp < kProducerWarps) {
-    // in flight while the MMA warp initialises barriers and allocates TMEM
     if constexpr (TMA_A) {
       fetch_rows(0, ra0);
     } else {
@@ -200,21 +213,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
     }
   }
 
-  if (warp == kMmaWarp) {
-    if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) {
-        mbar_init(&sm.full[s], TMA_A ? 1 : kProducerThreads + 1);
-        mbar_init(&sm.empty[s], 1);
-      }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&sm.tmem_full[i], 1);
-        mbar_init(&sm.tmem_empty[i], kEpilogueThreads);
-      }
-      fence_barrier_init();
-    }
-    __syncwarp();
-    tmem_alloc<TCOLS>(&sm.tmem_base);
-  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
