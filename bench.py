@@ -624,6 +624,8 @@ def run_gpu(args):
                 "peak_source": tf_peak_name, "launches_per_step": fam["launches_per_pass"],
                 "avg_us": fam["total_us_per_pass"] / fam["launches_per_pass"], "share_of_step": fam["share_of_step"],
                 "flops": "2*P*Cin*Cout with P = rulebook pairs actually present (dense convs: P = 9*pixels)",
+                "share_basis": "share_of_step = kernel time / the one_in_flight step (one pass of one frame); with steps "
+                               "in flight the conv families, which fill every SM, add up to the whole step",
                 "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, family mean)",
                 "traffic_source": traffic_src, "algorithmic_bytes": fam["algorithmic_bytes_per_launch"],
                 "families": families,
