@@ -635,6 +635,53 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
             if (CH == 32) tmem_ld32(tbase + c0, w); else tmem_ld16(tbase + c0, w);
             tmem_wait_ld();
           }
+          // Fast path (every bf16 padded / planar output of the neck and head): the warp's 32 rows exist, the chunk is
+          // whole -> folded affine, ReLU and the bf16 pack in one pass (cvt.rn.relu.bf16x2), border rows zeroed on the
+          // packed words, four conflict-free STS.128 into the warp's staging box, one TMA tensor store.
+          if (S::kTmaStore && CH == 32 && P.tma_store && box_ok && !P.out_f32 && cout_t - (nbase + c0) >= CH &&
+              !(P.dbg_mode & 1)) {
+            const float4* ss4 = reinterpret_cast<const float4*>(&sm.ss[c0]);   // c0 % 16 == 0: 16-byte aligned
+            const bool affine = P.scale != nullptr || P.shift != nullptr;
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float t0 = __uint_as_float(w[2 * j]), t1 = __uint_as_float(w[2 * j + 1]);
+              if (affine) {
+                const float4 s2 = ss4[j];
+                t0 = fmaf(t0, s2.x, s2.y);
+                t1 = fmaf(t1, s2.z, s2.w);
+              }
+              if (P.relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(t1), "f"(t0));
+              else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(t1), "f"(t0));
+            }
+            if (border) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = 0u;
+            }
+            uint8_t* stg = sm.stage_out + (warp - 4) * 2048;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous box was read
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // SWIZZLE_64B: 16-byte chunk index ^ address bits 7-8 = (row >> 1) & 3 for 64-byte rows
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              int col = ocol0 + c0;
+              int row0 = q0;
+              if (P.out_group_cols > 0) {
+                const int g = col / P.out_group_cols;
+                col -= g * P.out_group_cols;
+                row0 += g * P.n_pos;
+              }
+              tma_store_2d(&tmap_o, smem_u32(stg), col, row0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            continue;
+          }
           if (store && !(P.dbg_mode & 1)) {
             const int nvalid = min(CH, cout_t - (nbase + c0));
             float f[32];
@@ -668,33 +715,6 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
 #pragma unroll
                 for (int j = 0; j < CH; ++j)
                   if (j < nvalid) op[j] = f[j];
-              }
-            } else if (S::kTmaStore && CH == 32 && P.tma_store && nvalid == CH && box_ok) {
-              // all 32 lanes are here (box_ok: the warp's 32 rows exist); lane = row of the box
-              uint8_t* stg = sm.stage_out + (warp - 4) * 2048;
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous box was read
-              __syncwarp();
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 qv;
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&qv);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[8 * j + 2 * u], f[8 * j + 2 * u + 1]);
-                // SWIZZLE_64B: 16-byte chunk index ^ address bits 7-8 = (row >> 1) & 3 for 64-byte rows
-                *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = qv;
-              }
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              __syncwarp();
-              if (lane == 0) {
-                int col = ocol0 + c0;
-                int row0 = q0;
-                if (P.out_group_cols > 0) {
-                  const int g = col / P.out_group_cols;
-                  col -= g * P.out_group_cols;
-                  row0 += g * P.n_pos;
-                }
-                tma_store_2d(&tmap_o, smem_u32(stg), col, row0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               }
             } else {
               __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + ooff;
