@@ -105,8 +105,8 @@ struct Smem {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   int nbr[3][BLOCK_M * kMaxTaps];   // rulebook rows of the current tile and the next two (ring)
-  float scale[BN];
-  float shift[BN];
+  alignas(16) float2 ss[BN];   // {scale, shift} per output column, read two columns per LDS.128 (a broadcast LDS.32
+                               // costs the shared-memory pipe a full wavefront)
   // Epilogue staging for TMA tensor stores (see conv_dense_tc.cu): 32 rows x 32 bf16 columns (2 KB, SWIZZLE_64B),
   // two buffers per epilogue warp.  Here the direct row-per-thread stores cost twice: their 32 lines per warp
   // instruction occupy the same LSU that the producers' gathers are bound by.
@@ -379,8 +379,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
       named_bar_sync(2, kEpilogueThreads);
       for (int i = etid; i < BN; i += kEpilogueThreads) {
         const int n = n0 + i;
-        sm.scale[i] = (n < P.cout && P.scale) ? __ldg(P.scale + n) : 1.f;
-        sm.shift[i] = (n < P.cout && P.shift) ? __ldg(P.shift + n) : 0.f;
+        sm.ss[i] = make_float2((n < P.cout && P.scale) ? __ldg(P.scale + n) : 1.f,
+                               (n < P.cout && P.shift) ? __ldg(P.shift + n) : 0.f);
       }
       named_bar_sync(2, kEpilogueThreads);
       const long long _e1 = P.dbg ? clock64() : 0;
@@ -425,7 +425,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
           const int nvalid = min(CH, P.cout - (n0 + c0));
           float f[CH];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) f[j] = fmaf(__uint_as_float(v[j]), sm.scale[c0 + j], sm.shift[c0 + j]);
+          for (int j = 0; j < CH; j += 2) {
+            const float4 s2 = *reinterpret_cast<const float4*>(&sm.ss[c0 + j]);      // c0, j even: 16-byte aligned
+            f[j] = fmaf(__uint_as_float(v[j]), s2.x, s2.y);
+            f[j + 1] = fmaf(__uint_as_float(v[j + 1]), s2.z, s2.w);
+          }
           const long long ooff = (long long)row * P.out_ld + P.out_coff + (n0 - dc_col) + c0;
           if (P.out_f32) {
             float* op = reinterpret_cast<float*>(P.out) + ooff;

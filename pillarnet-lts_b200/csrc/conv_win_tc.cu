@@ -132,8 +132,8 @@ struct WSmem {
   uint64_t a_empty[AS], win_full[WS], win_empty[WS], b_full[NBU], b_empty[NBU], map_full[3], map_empty[3];
   uint64_t tmem_full[2], tmem_empty[2], res_full[4];
   uint32_t tmem_base;
-  float scale[BN];
-  float shift[BN];
+  alignas(16) float2 ss[BN];   // {scale, shift} per output column, read two columns per LDS.128 (a broadcast LDS.32
+                               // costs the shared-memory pipe a full wavefront)
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -460,8 +460,8 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
     const int e = warp - kEpilogueWarp0;
     const int etid = threadIdx.x - kEpilogueWarp0 * 32;
     for (int i = etid; i < BN; i += kEpilogueThreads) {
-      sm.scale[i] = (i < cout_l && P.scale) ? __ldg(P.scale + col0 + i) : 1.f;
-      sm.shift[i] = (i < cout_l && P.shift) ? __ldg(P.shift + col0 + i) : 0.f;
+      sm.ss[i] = make_float2((i < cout_l && P.scale) ? __ldg(P.scale + col0 + i) : 1.f,
+                             (i < cout_l && P.shift) ? __ldg(P.shift + col0 + i) : 0.f);
     }
     named_bar_sync(2, kEpilogueThreads);
     uint32_t res_ph = 0u;
@@ -501,7 +501,11 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
           const int nvalid = min(CH, cout_l - c0);
           float f[CH];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) f[j] = fmaf(__uint_as_float(v[j]), sm.scale[c0 + j], sm.shift[c0 + j]);
+          for (int j = 0; j < CH; j += 2) {
+            const float4 s2 = *reinterpret_cast<const float4*>(&sm.ss[c0 + j]);      // c0, j even: 16-byte aligned
+            f[j] = fmaf(__uint_as_float(v[j]), s2.x, s2.y);
+            f[j + 1] = fmaf(__uint_as_float(v[j + 1]), s2.z, s2.w);
+          }
           __nv_bfloat16* op = P.out + (long long)row * P.out_ld + P.out_coff + col0 + c0;
           if (P.residual) {
             const __nv_bfloat16* rp = P.residual + (long long)row * P.res_ld + col0 + c0;
