@@ -387,7 +387,8 @@ def run_gpu(args):
     cap = int(max(sum(len(f) for f in frames[i * B:(i + 1) * B]) for i in range(pool)) * 1.05) + 1024
     # `in_flight` lanes (stream + CUDA graph + buffers each) take the steps round-robin; lane 0 alone serves the
     # one-step-at-a-time legs (per-kernel breakdown, classic flushed timing, profiling pass)
-    n_lanes = 1 if args.profile_pass else max(1, args.in_flight)
+    in_flight = args.in_flight if args.in_flight > 0 else (3 if B <= 2 else 1)
+    n_lanes = 1 if args.profile_pass else in_flight
     seng = StreamingEngine(model, B, cap, in_flight=n_lanes, device=dev)
     seng.prepare(frames[:B], warmup=2)
     eng = seng.lanes[0]
@@ -1011,8 +1012,10 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train: BASELINE config 4 (training step); not the headline metric")
     ap.add_argument("--frames-per-step", type=int, default=1)
-    ap.add_argument("--in-flight", type=int, default=3,
-                    help="steps in flight per GPU (StreamingEngine lanes); 1 = one step at a time with L2 flushes")
+    ap.add_argument("--in-flight", type=int, default=0,
+                    help="steps in flight per GPU (StreamingEngine lanes); 1 = one step at a time with L2 flushes; "
+                         "0 = auto: 3 for steps of one or two frames (whose tail kernels leave most SMs idle), 1 for "
+                         "larger batches (measured: waymo34 batch 8 gains nothing)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3"],
                     help="bf16: the fast mode (headline); bf16x3: split-bf16 tensor-core mode at fp32-grade accuracy; "
                          "fp32: FMA kernels (validation)")
