@@ -186,6 +186,44 @@ class PillarRCNN(nn.Module):
         example = self.reorder_first_stage_prediction(preds, example)
         return self.post_process(self.second_stage_forward(example))
 
+    @torch.no_grad()
+    def forward_device(self, points, frame_offsets):
+        """Sync-free inference (CUDA-graph capturable): every NMS slot of the first stage is a RoI — slot k of segment
+        s of frame b, valid iff k < keep_count[b, s] — instead of the reference's compacted-then-padded list, so nothing
+        is read back on the host; invalid slots carry label 0 and come out with valid = False, exactly as the padded
+        slots of `reorder_first_stage_prediction` do.  Returns (boxes (B, N, code), scores (B, N), labels (B, N) int64
+        zero-based, valid (B, N) bool) with N = segments * post_cap; the valid rows are the detections `forward`
+        returns (same values, segment-major order)."""
+        det = self.single_det
+        bev_features, backbone_features = det.extract_feat(dict(points_batched=(points, frame_offsets)))
+        preds = det.bbox_head(bev_features)
+        det_out, keep_count, plan = det.bbox_head.predict_raw(preds, det.test_cfg)
+        B, S, post_cap = plan["B"], plan["S"], plan["post_cap"]
+        head = det.bbox_head
+        d = det_out.view(B, S, post_cap, 11)
+        live = torch.arange(post_cap, device=d.device).view(1, 1, post_cap) < keep_count.view(B, S, 1)
+        cls_off, flag = [], 0
+        for n in head.num_classes:
+            cls_off.append(flag)
+            flag += n
+        from .losses import device_const           # cached device constant: no host-to-device copy inside a capture
+        off = device_const(tuple(cls_off[seg["task"]] for seg in plan["segs"]), d.device, torch.int64).view(1, S, 1)
+        if self.roi_head.code_size == 9:
+            boxes = d[..., [0, 1, 2, 3, 4, 5, 8, 6, 7]]
+        else:
+            boxes = torch.cat([d[..., :6], d[..., 8:9]], -1)
+        zero = torch.zeros((), dtype=d.dtype, device=d.device)
+        example = {
+            "batch_size": B,
+            "rois": torch.where(live.unsqueeze(-1), boxes, zero).reshape(B, S * post_cap, -1).contiguous(),
+            "roi_scores": torch.where(live, d[..., 9], zero).reshape(B, S * post_cap),
+            "roi_labels": torch.where(live, d[..., 10].to(torch.int64) + off + 1,
+                                      torch.zeros((), dtype=torch.int64, device=d.device)).reshape(B, S * post_cap),
+            "bev_feature": bev_features[-1], "backbone_features": backbone_features, "has_class_labels": True,
+        }
+        out = self.second_stage_forward(example)
+        return out["batch_box_preds"], out["refined_scores"], example["roi_labels"] - 1, out["refined_valid"]
+
     def post_process(self, batch_dict):
         """pillar_rcnn.py:141-170 (score fusion + validity mask computed by pn_roi_refine)"""
         out = []

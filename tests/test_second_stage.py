@@ -261,6 +261,20 @@ def test_pillar_rcnn_detector_runs_end_to_end_and_refines_the_first_stage_boxes(
             assert len(dets) == 2
             for d in dets:
                 assert d["box3d_lidar"].shape[1] == 7 and d["scores"].shape[0] == d["box3d_lidar"].shape[0]
+            # the sync-free path (every NMS slot a RoI, validity on the device) returns the same detections
+            offs = torch.tensor([0, frames[0].shape[0], frames[0].shape[0] + frames[1].shape[0]], dtype=torch.int32, device=dev)
+            boxes_d, scores_d, labels_d, valid_d = model.forward_device(torch.cat(frames), offs)
+            torch.cuda.synchronize()
+            for i, d in enumerate(dets):
+                m = valid_d[i]
+                assert int(m.sum()) == d["scores"].shape[0]
+                got = torch.cat([boxes_d[i][m], scores_d[i][m][:, None], labels_d[i][m][:, None].float()], 1)
+                want = torch.cat([d["box3d_lidar"], d["scores"][:, None], d["label_preds"][:, None].float()], 1)
+                # same rows in a different order: sort both lexicographically by (label, score, x)
+                def canon(t):
+                    key = t[:, -1] * 1e6 + t[:, -2] * 1e3 + t[:, 0] * 1e-3
+                    return t[torch.argsort(key)]
+                assert _rel(canon(got), canon(want)) <= (1e-5 if precision == "fp32" else 1e-3), (precision, i)
             if precision != "fp32":
                 continue
             # oracle on the same first-stage outputs
