@@ -492,6 +492,9 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       constexpr uint32_t kBStep = (uint32_t)(BROWS * 128) >> 4;
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tcount = 0;
       bool first_tap = true, a_ahead = false, b_ahead = false;
+      long long w_fa = 0, w_fb = 0, w_te = 0;          // PN_DENSE_TIMELINE: clocks the MMA warp waited for operands / TMEM
+#define DW_T0() const long long _w0 = P.dbg ? clock64() : 0
+#define DW_ACC(v) do { if (P.dbg) v += clock64() - _w0; } while (0)
       const bool look_ahead = (P.dbg_mode & 8) == 0;   // PN_DENSE_DBGMODE=8 disables it (A/B measurements)
       if (BS && unit0 < n_tiles) {
         mbar_wait(&sm.full_b[0], 0);
@@ -500,13 +503,13 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       for (int tile = unit0; tile < n_tiles; tile += unit_step, ++tcount) {
         const uint32_t acc = NACC == 2 ? (tcount & 1u) : 0u;
         const uint32_t acc_ph = NACC == 2 ? ((tcount >> 1) & 1u) : (tcount & 1u);
-        mbar_wait(&sm.tmem_empty[acc], acc_ph ^ 1u);
+        { DW_T0(); mbar_wait(&sm.tmem_empty[acc], acc_ph ^ 1u); DW_ACC(w_te); }
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         int dy = rot % 3;                       // kernel row of this step (the walk is rotated per CTA)
         const bool more_tiles = tile + unit_step < n_tiles;
         for (int u = 0; u < n_u; ++u) {
-          if (!a_ahead) mbar_wait(&sm.full_a[sa], pha);
+          if (!a_ahead) { DW_T0(); mbar_wait(&sm.full_a[sa], pha); DW_ACC(w_fa); }
           a_ahead = false;
           const uint64_t a_stage = a_desc0 + (uint64_t)(sa * kAStep);
 #pragma unroll
@@ -516,7 +519,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
               b_stage = b_desc0 + (uint64_t)((uint32_t)(dy * 3 + dx) * kBStep);   // resident weight slot of this tap
               if (dx == 0) tcgen05_fence_after();
             } else {
-              if (!b_ahead) mbar_wait(&sm.full_b[sb], phb);
+              if (!b_ahead) { DW_T0(); mbar_wait(&sm.full_b[sb], phb); DW_ACC(w_fb); }
               b_ahead = false;
               tcgen05_fence_after();
               b_stage = b_desc0 + (uint64_t)(sb * kBStep);
@@ -535,12 +538,12 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
                   if (look_ahead && !(u == n_u - 1 && dx == 2 && !more_tiles)) {
                     if constexpr (!BS) {
                       const uint32_t sbn = sb + 1 == SB ? 0u : sb + 1, phbn = sb + 1 == SB ? phb ^ 1u : phb;
-                      mbar_wait(&sm.full_b[sbn], phbn);
+                      { DW_T0(); mbar_wait(&sm.full_b[sbn], phbn); DW_ACC(w_fb); }
                       b_ahead = true;
                     }
                     if (dx == 2) {
                       const uint32_t san = sa + 1 == SA ? 0u : sa + 1, phan = sa + 1 == SA ? pha ^ 1u : pha;
-                      mbar_wait(&sm.full_a[san], phan);
+                      { DW_T0(); mbar_wait(&sm.full_a[san], phan); DW_ACC(w_fa); }
                       a_ahead = true;
                     }
                   }
@@ -577,6 +580,11 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
         }
         __syncwarp();
       }
+      if (issuer && P.dbg) {
+        P.dbg[blockIdx.x * 16 + 8] = w_fa; P.dbg[blockIdx.x * 16 + 9] = w_fb; P.dbg[blockIdx.x * 16 + 10] = w_te;
+      }
+#undef DW_T0
+#undef DW_ACC
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -922,11 +930,14 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, 
       if (t[c * 16 + 6] > t_max) t_max = t[c * 16 + 6];
     }
     double s_start = 0, s_first = 0, s_mma = 0, s_epi = 0, s_tot = 0, m_start = 0, m_mma = 0, m_tot = 0, m_epi = 0;
+    double s_w[3] = {0, 0, 0};
+    int n_issuers = 0;
     for (int c = 0; c < n; ++c) {
       const unsigned long long* q = t + c * 16;
       const double st = (double)(q[0] - t_min), fi = (double)(q[2] - q[1]), mm = (double)(q[3] - q[2]),
                    ep = (double)(q[5] - q[4]), to = (double)(q[6] - q[0]);
       s_start += st; s_first += fi; s_mma += mm; s_epi += ep; s_tot += to;
+      if (q[8] + q[9] + q[10] > 0) { ++n_issuers; for (int k = 0; k < 3; ++k) s_w[k] += (double)q[8 + k]; }
       if (st > m_start) m_start = st;
       if (mm > m_mma) m_mma = mm;
       if (to > m_tot) m_tot = to;
@@ -937,6 +948,9 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mt, const CUtensorMap& mw, 
                     "max %.1f\n",
             MT, BN, SA, SB, CL, n, units, (t_max - t_min) / 1e3, s_start / n / 1e3, m_start / 1e3, s_first / n / 1e3,
             s_mma / n / 1e3, m_mma / 1e3, s_epi / n / 1e3, m_epi / 1e3, s_tot / n / 1e3, m_tot / 1e3);
+    if (n_issuers > 0)
+      fprintf(stderr, "    MMA warp waits per issuing CTA (kclk): full_a %.1f, full_b %.1f, tmem_empty %.1f\n",
+              s_w[0] / n_issuers / 1e3, s_w[1] / n_issuers / 1e3, s_w[2] / n_issuers / 1e3);
   }
   return PN_OK;
 }
