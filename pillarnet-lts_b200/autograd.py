@@ -185,3 +185,37 @@ class DenseFromSparseFunction(Function):
 
 
 dense_from_sparse_static = DenseFromSparseFunction.apply
+
+
+class DenseBNFunction(Function):
+    """nn.BatchNorm2d in train mode (+ the ReLU behind it) on a channels-last (B, C, H, W) map as one autograd node on the
+    row kernels of csrc/bn_train.cu (a dense NHWC map is a (B*H*W, C) row matrix): statistics + finalize (running stats
+    updated in place like torch) + apply, and the two-kernel backward.  Replaces PyTorch's four channels-last BN kernels
+    + a separate ReLU per layer of the dense conv5 / neck / head in the static training path (det3d/models/necks/rpn.py:
+    172-185, center_head.py:27-33 in train mode)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, relu):
+        B, C, H, W = x.shape
+        rows = x.permute(0, 2, 3, 1)
+        if not rows.is_contiguous():
+            rows = rows.contiguous()
+        rows = rows.view(B * H * W, C)
+        y, mean, rstd = ops.bn_train_forward(rows, None, gamma.detach().float(), beta.detach().float(), bn.running_mean,
+                                             bn.running_var, bn.eps, bn.momentum, None, relu)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        ctx.save_for_backward(rows, y if relu else None, mean, rstd, gamma)
+        ctx.relu, ctx.shape = relu, (B, C, H, W)
+        return y.view(B, H, W, C).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        rows, y, mean, rstd, gamma = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        dr = dy.permute(0, 2, 3, 1)
+        if not dr.is_contiguous():
+            dr = dr.contiguous()
+        dx, _, dgamma, dbeta = ops.bn_train_backward(dr.view(B * H * W, C), y, rows, mean, rstd, gamma.detach().float(),
+                                                     ctx.relu, None, False)
+        return (dx.view(B, H, W, C).permute(0, 3, 1, 2), dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None, None)

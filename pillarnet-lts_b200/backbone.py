@@ -246,7 +246,7 @@ class _PillarResNet(nn.Module):
                 with train.autocast_ctx():
                     d4 = train.dense_from_sparse(x4)
                     feats["conv4"] = d4
-                    feats["conv5"] = self.conv5(d4)
+                    feats["conv5"] = train.run_dense_seq(self.conv5, d4)
             return feats
         if self.DENSE:
             # x_conv4.dense() lands in the left half of a 2C-wide buffer so the neck's channel concat

@@ -109,10 +109,10 @@ class CenterHead(nn.Module):
         """center_head.py:116-127 with the torch modules themselves (training: cuDNN + autograd)"""
         rets = []
         with train.autocast_ctx():
-            share = [sc(x[k]) for k, sc in enumerate(self.share_convs)]
+            share = [train.run_dense_seq(sc, x[k]) for k, sc in enumerate(self.share_convs)]
             for idx, task in enumerate(self.task_heads):
                 feat = share[self.task_idx[idx]]
-                rets.append({name: getattr(task, name)(feat) for name in task.heads})
+                rets.append({name: train.run_dense_seq(getattr(task, name), feat) for name in task.heads})
         return rets
 
     def forward(self, x):

@@ -92,8 +92,9 @@ class RPNV1(_RPNBase):
         """necks/rpn.py:196-207 with the torch modules themselves (training: cuDNN + autograd)"""
         with train.autocast_ctx():
             x4, x5 = train.to_dense(f["conv4"]), train.to_dense(f["conv5"])
-            up = self.deblock_5(self.block_5(x5))
-            return tuple([self.block_4(torch.cat([x4, up], dim=1))])
+            run = train.run_dense_seq
+            up = run(self.deblock_5, run(self.block_5, x5))
+            return tuple([run(self.block_4, torch.cat([x4, up], dim=1))])
 
     def forward(self, pillar_features, **kwargs):
         if self.training:
@@ -126,8 +127,9 @@ class RPNV2(_RPNBase):
         """necks/rpn.py:262-272"""
         with train.autocast_ctx():
             x3, x4 = train.to_dense(f["conv3"]), train.to_dense(f["conv4"])
-            up = self.deblock_4(self.block_4(x4))
-            return tuple([self.block_3(torch.cat([x3, up], dim=1))])
+            run = train.run_dense_seq
+            up = run(self.deblock_4, run(self.block_4, x4))
+            return tuple([run(self.block_3, torch.cat([x3, up], dim=1))])
 
     def forward(self, pillar_features, **kwargs):
         if self.training:
@@ -165,9 +167,10 @@ class RPNG(_RPNBase):
         """necks/rpn.py:336-355"""
         with train.autocast_ctx():
             x3, x4, x5 = (train.to_dense(f[k]) for k in ("conv3", "conv4", "conv5"))
-            x5 = self.block_5(x5)
-            x4 = self.block_4(torch.cat([x4, self.top_down_54(x5)], dim=1))
-            x3 = self.block_3(torch.cat([x3, self.top_down_43(x4)], dim=1))
+            run = train.run_dense_seq
+            x5 = run(self.block_5, x5)
+            x4 = run(self.block_4, torch.cat([x4, run(self.top_down_54, x5)], dim=1))
+            x3 = run(self.block_3, torch.cat([x3, run(self.top_down_43, x4)], dim=1))
             return tuple([x4, x3])
 
     def forward(self, pillar_features, **kwargs):
@@ -220,9 +223,10 @@ class RPNGV2(_RPNBase):
         """necks/rpn.py:428-450"""
         with train.autocast_ctx():
             x3, x4, x5 = (train.to_dense(f[k]) for k in ("conv3", "conv4", "conv5"))
-            x5 = self.block_5(x5)
-            x4 = self.block_4(torch.cat([self.reduce_4(x4), self.top_down_54(x5)], dim=1))
-            x3 = self.block_3(torch.cat([self.reduce_3(x3), self.top_down_43(x4)], dim=1))
+            run = train.run_dense_seq
+            x5 = run(self.block_5, x5)
+            x4 = run(self.block_4, torch.cat([run(self.reduce_4, x4), run(self.top_down_54, x5)], dim=1))
+            x3 = run(self.block_3, torch.cat([run(self.reduce_3, x3), run(self.top_down_43, x4)], dim=1))
             return tuple([x4, x3])
 
     def forward(self, pillar_features, **kwargs):

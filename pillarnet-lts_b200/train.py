@@ -31,6 +31,31 @@ def is_static():
     return _static
 
 
+def run_dense_seq(seq, x):
+    """A Sequential of the dense conv5 / neck / head in TRAIN mode: convs (and anything else) run as PyTorch modules under
+    autograd (cuDNN); in the static path every BatchNorm2d and the ReLU behind it run as one node on the library's BN
+    kernels (autograd.DenseBNFunction) when the map is bf16 / f32 with C % 8 == 0."""
+    from torch import nn
+    from .autograd import DenseBNFunction
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if (_static and isinstance(m, nn.BatchNorm2d) and m.training and m.track_running_stats and m.affine
+                and m.momentum is not None and x.is_cuda and x.dtype in (torch.bfloat16, torch.float32)
+                and x.shape[1] % 8 == 0):
+            relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+            x = DenseBNFunction.apply(x, m.weight, m.bias, m, relu)
+            i += 2 if relu else 1
+        elif isinstance(m, nn.Sequential):
+            x = run_dense_seq(m, x)
+            i += 1
+        else:
+            x = m(x)
+            i += 1
+    return x
+
+
 def _exact(table):
     """RankTable view with cap == live rows (one host sync, cached on the table)."""
     ex = table._train.get("exact") if table._train is not None else None
