@@ -310,6 +310,52 @@ def test_bn_train_kernels_vs_torch_batch_norm():
     assert _rel(rm, bn.running_mean) <= 1e-5 and _rel(rv, bn.running_var) <= 1e-5
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_dense_bn_relu_node_vs_torch_batch_norm_2d(dtype, tol):
+    """autograd.DenseBNFunction (BatchNorm2d in train mode + ReLU on a channels-last map, library BN kernels) vs
+    nn.BatchNorm2d + ReLU under torch autograd: outputs, input / weight / bias gradients, running statistics and
+    num_batches_tracked; a Sequential with nested blocks through train.run_dense_seq."""
+    import copy
+    from pillarnet_lts_b200 import train
+    from pillarnet_lts_b200.autograd import DenseBNFunction
+    g = torch.Generator(device="cuda").manual_seed(12)
+    B, C, H, W = 2, 64, 23, 31
+    x = (torch.randn(B, C, H, W, device="cuda", generator=g) * 2 + 0.3).to(dtype).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(B, C, H, W, device="cuda", generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+    bn = torch.nn.BatchNorm2d(C, eps=1e-3, momentum=0.01).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.2)
+    bn2 = copy.deepcopy(bn)
+    xr = x.clone().requires_grad_(True)
+    want = torch.relu(bn(xr.float())).to(dtype)
+    want.backward(dy)
+    xg = x.clone().requires_grad_(True)
+    got = DenseBNFunction.apply(xg, bn2.weight, bn2.bias, bn2, True)
+    got.backward(dy)
+    torch.cuda.synchronize()
+    assert _rel(got.float(), want.float()) <= tol
+    assert _rel(xg.grad.float(), xr.grad.float()) <= 5 * tol
+    assert _rel(bn2.weight.grad, bn.weight.grad) <= 5 * tol and _rel(bn2.bias.grad, bn.bias.grad) <= 5 * tol
+    assert _rel(bn2.running_mean, bn.running_mean) <= 1e-4 and _rel(bn2.running_var, bn.running_var) <= 1e-3
+    assert int(bn2.num_batches_tracked) == int(bn.num_batches_tracked) == 1
+    # a nested Sequential (conv, BN, ReLU, block(conv, BN, ReLU)): the fused nodes replace the BN + ReLU pairs only in the
+    # static path, and both paths agree
+    torch.manual_seed(3)
+    seq = torch.nn.Sequential(torch.nn.Conv2d(C, 32, 3, padding=1, bias=False), torch.nn.BatchNorm2d(32, eps=1e-3), torch.nn.ReLU(),
+                              torch.nn.Sequential(torch.nn.Conv2d(32, 32, 3, padding=1, bias=False),
+                                                  torch.nn.BatchNorm2d(32, eps=1e-3, momentum=0.01), torch.nn.ReLU())).cuda().train()
+    seq = seq.to(memory_format=torch.channels_last)
+    xin = x.float()
+    ref = seq(xin)
+    try:
+        train.set_static(True)
+        out = train.run_dense_seq(copy.deepcopy(seq), xin)
+    finally:
+        train.set_static(False)
+    assert _rel(out, ref) <= 1e-4
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-2), ("bf16", 1e-1)])
 def test_static_training_path_matches_dynamic_path(precision, tol):
     """same parameters, same batch: the sync-free path (capacity-sized rows, fused BN kernels, masked PFN) gives the head
