@@ -195,7 +195,10 @@ class DenseBNFunction(Function):
     172-185, center_head.py:27-33 in train mode)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, bn, relu):
+    def forward(ctx, x, gamma, beta, bn, relu, conv_bias=None):
+        """conv_bias: bias of the conv that produced x, NOT yet added (batch normalisation removes a per-channel shift
+        exactly, so the add — and the (B, H, W) reduction of its gradient — are skipped; only the running mean sees
+        it).  Its gradient is exactly zero."""
         B, C, H, W = x.shape
         rows = x.permute(0, 2, 3, 1)
         if not rows.is_contiguous():
@@ -205,8 +208,11 @@ class DenseBNFunction(Function):
                                              bn.running_var, bn.eps, bn.momentum, None, relu)
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
+        if conv_bias is not None:
+            bn.running_mean.add_(conv_bias.detach().to(bn.running_mean.dtype), alpha=bn.momentum)
         ctx.save_for_backward(rows, y if relu else None, mean, rstd, gamma)
         ctx.relu, ctx.shape = relu, (B, C, H, W)
+        ctx.bias_like = conv_bias
         return y.view(B, H, W, C).permute(0, 3, 1, 2)
 
     @staticmethod
@@ -218,4 +224,5 @@ class DenseBNFunction(Function):
             dr = dr.contiguous()
         dx, _, dgamma, dbeta = ops.bn_train_backward(dr.view(B * H * W, C), y, rows, mean, rstd, gamma.detach().float(),
                                                      ctx.relu, None, False)
-        return (dx.view(B, H, W, C).permute(0, 3, 1, 2), dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None, None)
+        dbias = torch.zeros_like(ctx.bias_like) if ctx.bias_like is not None else None
+        return (dx.view(B, H, W, C).permute(0, 3, 1, 2), dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None, None, dbias)

@@ -38,10 +38,23 @@ def run_dense_seq(seq, x):
     from torch import nn
     from .autograd import DenseBNFunction
     mods = list(seq)
+
+    def fusable_bn(m, x):
+        return (_static and isinstance(m, nn.BatchNorm2d) and m.training and m.track_running_stats and m.affine
+                and m.momentum is not None and x.is_cuda and x.shape[1] % 8 == 0)
+
     i = 0
     while i < len(mods):
         m = mods[i]
-        if (_static and isinstance(m, nn.BatchNorm2d) and m.training and m.track_running_stats and m.affine
+        if (isinstance(m, nn.Conv2d) and m.bias is not None and m.padding_mode == "zeros" and i + 1 < len(mods)
+                and isinstance(mods[i + 1], nn.BatchNorm2d) and m.out_channels % 8 == 0 and fusable_bn(mods[i + 1], x)):
+            # conv + bias followed by batch statistics: the bias add and the reduction of its gradient are dropped
+            bn = mods[i + 1]
+            y = torch.nn.functional.conv2d(x, m.weight, None, m.stride, m.padding, m.dilation, m.groups)
+            relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+            x = DenseBNFunction.apply(y, bn.weight, bn.bias, bn, relu, m.bias)
+            i += 3 if relu else 2
+        elif (_static and isinstance(m, nn.BatchNorm2d) and m.training and m.track_running_stats and m.affine
                 and m.momentum is not None and x.is_cuda and x.dtype in (torch.bfloat16, torch.float32)
                 and x.shape[1] % 8 == 0):
             relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)

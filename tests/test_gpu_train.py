@@ -342,18 +342,27 @@ def test_dense_bn_relu_node_vs_torch_batch_norm_2d(dtype, tol):
     # a nested Sequential (conv, BN, ReLU, block(conv, BN, ReLU)): the fused nodes replace the BN + ReLU pairs only in the
     # static path, and both paths agree
     torch.manual_seed(3)
-    seq = torch.nn.Sequential(torch.nn.Conv2d(C, 32, 3, padding=1, bias=False), torch.nn.BatchNorm2d(32, eps=1e-3), torch.nn.ReLU(),
+    seq = torch.nn.Sequential(torch.nn.Conv2d(C, 32, 3, padding=1, bias=True), torch.nn.BatchNorm2d(32, eps=1e-3), torch.nn.ReLU(),
                               torch.nn.Sequential(torch.nn.Conv2d(32, 32, 3, padding=1, bias=False),
                                                   torch.nn.BatchNorm2d(32, eps=1e-3, momentum=0.01), torch.nn.ReLU())).cuda().train()
     seq = seq.to(memory_format=torch.channels_last)
     xin = x.float()
+    with torch.no_grad():
+        seq[0].bias.normal_(0, 0.5)
+    seq2 = copy.deepcopy(seq)
     ref = seq(xin)
+    ref.sum().backward()
     try:
         train.set_static(True)
-        out = train.run_dense_seq(copy.deepcopy(seq), xin)
+        out = train.run_dense_seq(seq2, xin)
     finally:
         train.set_static(False)
+    out.sum().backward()
     assert _rel(out, ref) <= 1e-4
+    # the conv bias in front of the batch norm is not added (BN removes it); the running mean still tracks it
+    assert _rel(seq2[1].running_mean, seq[1].running_mean) <= 1e-4 and _rel(seq2[1].running_var, seq[1].running_var) <= 1e-3
+    assert float(seq2[0].bias.grad.abs().max()) == 0.0 and float(seq[0].bias.grad.abs().max()) <= 1e-3
+    assert _rel(seq2[0].weight.grad, seq[0].weight.grad) <= 1e-3
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-2), ("bf16", 1e-1)])
