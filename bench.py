@@ -717,7 +717,8 @@ def measure_train(workload, B, steps, warmup, precision, world, rank, dev, eager
     torch.manual_seed(0)
     model = P.build_detector(ConfigDict.wrap(cfg["model"]), cfg["train_cfg"], ConfigDict.wrap(cfg["test_cfg"]))
     model = model.to(dev).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, capturable=not eager)
+    # fused multi-tensor AdamW: one kernel per parameter group instead of a dozen foreach passes over 515 tensors
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, capturable=not eager, fused=True)
     avg = GradientAverager(list(model.parameters()), bucket_mb=25, module=model) if world > 1 else None
     pool = 4
     rng = np.random.default_rng(7 + rank)

@@ -23,7 +23,7 @@ dev = torch.device("cuda")
 cfg = configs.get(args.workload)
 torch.manual_seed(0)
 model = P.build_detector(ConfigDict.wrap(cfg["model"]), cfg["train_cfg"], ConfigDict.wrap(cfg["test_cfg"])).to(dev).train()
-opt = torch.optim.AdamW(model.parameters(), lr=1e-4, capturable=True)
+opt = torch.optim.AdamW(model.parameters(), lr=1e-4, capturable=True, fused=True)
 rng = np.random.default_rng(0)
 B = args.frames
 fs = synth.make_batch(cfg["synth"], B, 100)
