@@ -202,6 +202,18 @@ def require_cuda(*tensors):
             raise RuntimeError("pillarnet_b200 ops need contiguous tensors")
 
 
+def require_cuda_rows(*tensors):
+    """CUDA (rows, C) matrices whose rows are contiguous (a column slice of a wider matrix is fine: the ops take the
+    row stride)."""
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("pillarnet_b200 ops need CUDA tensors (no CPU fallback)")
+        if t.dim() != 2 or t.stride(1) != 1:
+            raise RuntimeError("pillarnet_b200 ops need (rows, C) matrices with contiguous rows")
+
+
 def farr(values):
     return (c_float * len(values))(*[float(v) for v in values])
 

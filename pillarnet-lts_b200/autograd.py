@@ -200,10 +200,11 @@ class DenseBNFunction(Function):
         exactly, so the add — and the (B, H, W) reduction of its gradient — are skipped; only the running mean sees
         it).  Its gradient is exactly zero."""
         B, C, H, W = x.shape
-        rows = x.permute(0, 2, 3, 1)
-        if not rows.is_contiguous():
+        # channels-last maps and channel slices of them flatten to a (B*H*W, C) row view (row stride = all channels of
+        # the parent) without a copy; anything else is copied
+        rows = x.permute(0, 2, 3, 1).reshape(B * H * W, C)
+        if rows.stride(1) != 1 or rows.stride(0) % 8 != 0 or rows.data_ptr() % 16 != 0:
             rows = rows.contiguous()
-        rows = rows.view(B * H * W, C)
         y, mean, rstd = ops.bn_train_forward(rows, None, gamma.detach().float(), beta.detach().float(), bn.running_mean,
                                              bn.running_var, bn.eps, bn.momentum, None, relu)
         if bn.num_batches_tracked is not None:

@@ -110,10 +110,43 @@ class CenterHead(nn.Module):
         rets = []
         with train.autocast_ctx():
             share = [train.run_dense_seq(sc, x[k]) for k, sc in enumerate(self.share_convs)]
+            if train.is_static():
+                return self._forward_train_grouped(share)
             for idx, task in enumerate(self.task_heads):
                 feat = share[self.task_idx[idx]]
                 rets.append({name: train.run_dense_seq(getattr(task, name), feat) for name in task.heads})
         return rets
+
+    def _forward_train_grouped(self, share):
+        """Static training path: the first-level convs of ALL branches on a shared feature run as ONE conv (weights
+        concatenated along Cout, as the inference path does) — one cuDNN fprop / dgrad / wgrad instead of one triple per
+        branch, and the feature's gradient comes out of one dgrad instead of being accumulated branch by branch; the
+        output is split per branch (autograd concatenates the branch gradients once), each branch's BatchNorm2d + ReLU
+        runs on its channel slice in place (library BN kernels, row stride = all channels), then the small last convs."""
+        from .autograd import DenseBNFunction
+        rets = [dict() for _ in self.task_heads]
+        for fi, feat in enumerate(share):
+            tids = [t for t in range(len(self.task_heads)) if self.task_idx[t] == fi]
+            entries = [(t, name, getattr(self.task_heads[t], name)) for t in tids for name in self.task_heads[t].heads]
+            two = [e for e in entries if len(e[2]) == 4 and isinstance(e[2][1], nn.BatchNorm2d) and e[2][1].training
+                   and e[2][0].out_channels % 8 == 0]
+            hcs = {e[2][0].out_channels for e in two}
+            if len(two) >= 2 and len(hcs) == 1 and all(e[2][0].kernel_size == (3, 3) and e[2][0].padding == (1, 1)
+                                                       for e in two):
+                hc = hcs.pop()
+                w1 = torch.cat([e[2][0].weight for e in two], 0)
+                y = torch.nn.functional.conv2d(feat, w1, None, padding=1)          # biases: dropped in front of the BN
+                for (t, name, fc), part in zip(two, y.split(hc, dim=1)):
+                    h = DenseBNFunction.apply(part, fc[1].weight, fc[1].bias, fc[1], True, fc[0].bias)
+                    rets[t][name] = fc[3](h)
+                done = {id(e[2]) for e in two}
+            else:
+                done = set()
+            for t, name, fc in entries:
+                if id(fc) not in done:
+                    rets[t][name] = train.run_dense_seq(fc, feat)
+        # the reference's dict order per task (center_head.py:43-50: iteration over self.heads)
+        return [{name: rets[t][name] for name in self.task_heads[t].heads} for t in range(len(self.task_heads))]
 
     def forward(self, x):
         assert len(x) == len(self.share_convs)

@@ -612,7 +612,7 @@ def bn_train_forward(x, num, gamma, beta, running_mean, running_var, eps, moment
     """y = act(BN_batch(x) + residual) over the rows < *num (the rows of the capacity beyond them are left untouched);
     running statistics are updated in place like nn.BatchNorm1d in train mode.  Returns (y, mean, rstd)."""
     lib = _lib.load()
-    require_cuda(x)
+    _lib.require_cuda_rows(x, residual)
     rows_cap, C = x.shape
     dev = x.device
     sums = torch.empty(2 * C, dtype=torch.float32, device=dev)
@@ -634,10 +634,11 @@ def bn_train_forward(x, num, gamma, beta, running_mean, running_var, eps, moment
 def bn_train_backward(dy, y, x, mean, rstd, gamma, relu, num, want_dres):
     """Returns (dx, dres | None, dgamma (C) f32, dbeta (C) f32)."""
     lib = _lib.load()
-    require_cuda(dy, x)
+    _lib.require_cuda_rows(x, y)
     rows_cap, C = x.shape
     dev = x.device
     dy = dy.contiguous()
+    require_cuda(dy)
     if dy.dtype != x.dtype:
         dy = dy.to(x.dtype)
     sums = torch.empty(2 * C, dtype=torch.float32, device=dev)
