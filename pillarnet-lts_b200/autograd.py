@@ -227,3 +227,28 @@ class DenseBNFunction(Function):
                                                      ctx.relu, None, False)
         dbias = torch.zeros_like(ctx.bias_like) if ctx.bias_like is not None else None
         return (dx.view(B, H, W, C).permute(0, 3, 1, 2), dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None, None, dbias)
+
+
+class RowBNFunction(Function):
+    """nn.BatchNorm1d in train mode (+ ReLU) over the first *num rows of a (rows, C) matrix (device-resident count) on the
+    library's BN kernels — the PFN's BatchNorm over the in-range points once they are compacted to a prefix
+    (det3d/models/readers/pillar_modules.py:26-33 in train mode).  Rows past the count are left as they are in the output
+    buffer (zeros) and get zero gradient."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, relu, num):
+        x = x.contiguous()
+        y, mean, rstd = ops.bn_train_forward(x, num, gamma.detach().float(), beta.detach().float(), bn.running_mean,
+                                             bn.running_var, bn.eps, bn.momentum, None, relu)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        ctx.save_for_backward(x, y if relu else None, mean, rstd, gamma, num)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, rstd, gamma, num = ctx.saved_tensors
+        dx, _, dgamma, dbeta = ops.bn_train_backward(dy, y, x, mean, rstd, gamma.detach().float(), ctx.relu, num, False,
+                                                     zero_tail=True)      # the Linear's backward reads every row
+        return dx, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None, None, None

@@ -631,8 +631,9 @@ def bn_train_forward(x, num, gamma, beta, running_mean, running_var, eps, moment
     return y, stats[0], stats[1]
 
 
-def bn_train_backward(dy, y, x, mean, rstd, gamma, relu, num, want_dres):
-    """Returns (dx, dres | None, dgamma (C) f32, dbeta (C) f32)."""
+def bn_train_backward(dy, y, x, mean, rstd, gamma, relu, num, want_dres, zero_tail=False):
+    """Returns (dx, dres | None, dgamma (C) f32, dbeta (C) f32).  zero_tail: the rows of dx at or above *num are zeros
+    (for consumers that read the whole capacity, e.g. a torch matmul) instead of unwritten."""
     lib = _lib.load()
     _lib.require_cuda_rows(x, y)
     rows_cap, C = x.shape
@@ -645,7 +646,7 @@ def bn_train_backward(dy, y, x, mean, rstd, gamma, relu, num, want_dres):
     check(lib.pn_bn_bwd_stats(ptr(dy), _DT[x.dtype], dy.stride(0), ptr(y), y.stride(0) if y is not None else 0, ptr(x),
                               x.stride(0), ptr(mean), ptr(rstd), 1 if relu else 0, ptr(num), rows_cap, C, ptr(sums),
                               stream_ptr()), "pn_bn_bwd_stats")
-    dx = torch.empty(rows_cap, C, dtype=x.dtype, device=dev)
+    dx = (torch.zeros if zero_tail else torch.empty)(rows_cap, C, dtype=x.dtype, device=dev)
     dres = torch.empty(rows_cap, C, dtype=x.dtype, device=dev) if want_dres else None
     check(lib.pn_bn_bwd_apply(ptr(dy), _DT[x.dtype], dy.stride(0), ptr(y), y.stride(0) if y is not None else 0, ptr(x),
                               x.stride(0), ptr(mean), ptr(rstd), ptr(gamma), ptr(sums), 1 if relu else 0, ptr(num),

@@ -136,9 +136,27 @@ def _reader_forward_static(pfn, points, frame_offsets, batch_size):
     live = frame_offsets[batch_size:batch_size + 1]
     point_pillar = torch.where(torch.arange(points.shape[0], device=points.device, dtype=torch.int32) < live,
                                point_pillar, torch.full_like(point_pillar, -1))
-    h = pfn.shared_mlps[0](feats)                               # Linear on every point of the capacity
-    h = _masked_bn_relu(h.float(), point_pillar >= 0, pfn.shared_mlps[1])
-    pooled = scatter_max(h.contiguous(), point_pillar, table.cap)   # index -1 is skipped
+    bn = pfn.shared_mlps[1]
+    if isinstance(bn, torch.nn.BatchNorm1d) and bn.track_running_stats and bn.affine and bn.momentum is not None:
+        # The in-range points are moved to a prefix (stable; the others fill the tail) with shape-static index math, so
+        # the BatchNorm + ReLU over them is the library's fused row kernel with a device-resident count instead of ~40
+        # masked elementwise / reduction passes over the (capacity, 32) matrix.  The pooling is order independent.
+        from .autograd import RowBNFunction
+        valid = point_pillar >= 0
+        n_pts = points.shape[0]
+        c_valid = torch.cumsum(valid, 0, dtype=torch.int32)
+        live_valid = c_valid[-1:].contiguous()                      # (1,) int32 on the device
+        pos = torch.arange(1, n_pts + 1, device=points.device, dtype=torch.int32)
+        dest = torch.where(valid, c_valid - 1, n_pts - (pos - c_valid)).long()     # a permutation of 0..n_pts-1
+        feats_c = torch.empty_like(feats).index_copy_(0, dest, feats)
+        pp_c = torch.empty_like(point_pillar).index_copy_(0, dest, point_pillar)
+        h = pfn.shared_mlps[0](feats_c)                             # Linear on every point of the capacity
+        h = RowBNFunction.apply(h.float(), bn.weight, bn.bias, bn, True, live_valid)
+        pooled = scatter_max(h, pp_c, table.cap)                    # index -1 (the tail) is skipped
+    else:
+        h = pfn.shared_mlps[0](feats)                               # Linear on every point of the capacity
+        h = _masked_bn_relu(h.float(), point_pillar >= 0, bn)
+        pooled = scatter_max(h.contiguous(), point_pillar, table.cap)   # index -1 is skipped
     sp = SparseConvTensor(pooled.to(config.act_dtype()), table, (pfn.height, pfn.width), batch_size)
     sp._count = table.cap
     sp.point_pillar = point_pillar
