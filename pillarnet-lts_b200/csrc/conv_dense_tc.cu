@@ -616,6 +616,7 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
       mbar_wait_relaxed(&sm.tmem_full[acc], acc_ph);
       tcgen05_fence_after();
       if (etid == 0) PN_DBG(4);
+      bool released = false;   // the accumulator goes back to the MMA warp once this thread's last chunk is in registers
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
         const int q0 = m_tile * M_TILE + m * 128 + e * 32;   // first of this warp's 32 rows
@@ -642,6 +643,12 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
           if (!(P.dbg_mode & 2)) {
             if (CH == 32) tmem_ld32(tbase + c0, w); else tmem_ld16(tbase + c0, w);
             tmem_wait_ld();
+          }
+          if (m == MT - 1 && ci + kColSets >= n_ch) {
+            tcgen05_fence_before();
+            if constexpr (TWO) mbar_arrive_cluster(map_to_cta(&sm.tmem_empty[acc], 0));   // the leader's MMA thread waits
+            else mbar_arrive(&sm.tmem_empty[acc]);
+            released = true;
           }
           // Fast path (every bf16 padded / planar output of the neck and head): the warp's 32 rows exist, the chunk is
           // whole -> folded affine, ReLU and the bf16 pack in one pass (cvt.rn.relu.bf16x2), border rows zeroed on the
@@ -744,9 +751,11 @@ k_conv_dense(const __grid_constant__ CUtensorMap tmap_a_main, const __grid_const
           }
         }
       }
-      tcgen05_fence_before();
-      if constexpr (TWO) mbar_arrive_cluster(map_to_cta(&sm.tmem_empty[acc], 0));   // the leader's MMA thread waits
-      else mbar_arrive(&sm.tmem_empty[acc]);
+      if (!released) {         // a warp without a chunk of this tile
+        tcgen05_fence_before();
+        if constexpr (TWO) mbar_arrive_cluster(map_to_cta(&sm.tmem_empty[acc], 0));
+        else mbar_arrive(&sm.tmem_empty[acc]);
+      }
       if (etid == 0) PN_DBG(5);
     }
     if (S::kTmaStore && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staged boxes are out

@@ -490,6 +490,11 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
       if (etid == 0) PW_DBG(4);
       if (res_box) { mbar_wait(&sm.res_full[e], res_ph); res_ph ^= 1u; }
       constexpr int CH = BN < 32 ? 16 : 32;
+      // the accumulator is handed back to the MMA warp as soon as this thread's LAST chunk of it sits in registers —
+      // not after that chunk has been converted and stored (the 64-channel layers had the MMA warp waiting 20-30 % of
+      // its time on tmem_empty)
+      const int c0_last = cout_l > 0 ? ((min(BN, cout_l) - 1) / CH) * CH : -1;
+      if (c0_last < 0) { tcgen05_fence_before(); mbar_arrive(&sm.tmem_empty[acc]); }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         if (c0 >= cout_l) break;   // warp-uniform
@@ -497,6 +502,7 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
         const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * BN + c0;
         if (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         tmem_wait_ld();
+        if (c0 == c0_last) { tcgen05_fence_before(); mbar_arrive(&sm.tmem_empty[acc]); }
         if (row_ok) {
           const int nvalid = min(CH, cout_l - c0);
           float f[CH];
@@ -578,8 +584,6 @@ k_conv_win(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ C
           }
         }
       }
-      tcgen05_fence_before();
-      mbar_arrive(&sm.tmem_empty[acc]);
       if (etid == 0) PW_DBG(5);
     }
     if (BN >= 32 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
